@@ -1,0 +1,125 @@
+/*
+ * ocgcn.h — C ABI of the B200-native GraphCNN hot path (libocgcn.so).
+ *
+ * Every entry point replaces a piece of the OpenChem reference (paths relative to the reference root):
+ *
+ *   ocgcn_encoder_forward   <- GraphCNNEncoder.forward          openchem/modules/encoders/gcn_encoder.py:38-53
+ *                              (per layer GraphConvolution.forward openchem/layers/gcn.py:33-42, tanh :43,
+ *                               neighbour max-pool :44-50, dense/tanh/sum/tanh readout :51-53)
+ *   ocgcn_encoder_backward  <- autograd of the above (the reference has no explicit backward)
+ *   ocgcn_layer_forward     <- GraphConvolution.forward          openchem/layers/gcn.py:33-42
+ *   ocgcn_layer_backward    <- autograd of GraphConvolution.forward (dX, dW, db, dgamma, dbeta)
+ *   ocgcn_query_workspace   <- (implicit) the temporaries autograd keeps alive in the reference
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer on the current CUDA device unless noted;
+ *   - the caller owns every buffer (inputs, outputs, grads, running stats, workspaces); the library never
+ *     allocates device memory and keeps no per-call state;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no device synchronisation inside;
+ *   - thread-safe / re-entrant (DataParallel drives one replica per host thread, run.py:238);
+ *   - return value: 0 = OK, otherwise an OCGCN_E* code (ocgcn_status_string gives text). No C++ exceptions
+ *     cross the boundary. There is NO CPU fallback: host pointers are the caller's error.
+ */
+#ifndef OCGCN_H_
+#define OCGCN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCGCN_MAX_LAYERS 16
+#define OCGCN_MAX_ATOMS 256 /* arg-max indices are stored as u8 */
+
+/* precision classes (encoder_params['precision']) */
+#define OCGCN_FP32 0 /* exact fp32 FFMA products, fp32 accumulate               (1e-5 class) */
+#define OCGCN_TF32 1 /* tensor-core products, split operands in the forward     (1e-2 class) */
+#define OCGCN_BF16 2 /* tensor-core products, split operands in the forward     (1e-2 class) */
+
+/* status codes */
+#define OCGCN_OK 0
+#define OCGCN_EINVAL 1      /* bad shape / null pointer / bad enum */
+#define OCGCN_EUNSUPPORTED 2 /* size or mode outside what the kernels implement */
+#define OCGCN_EALIGN 3      /* misaligned pointer */
+#define OCGCN_EARCH 4       /* not an sm_100 device */
+#define OCGCN_ECUDA 5       /* a CUDA call failed (see ocgcn_last_cuda_error) */
+
+typedef struct ocgcn_desc {
+  int32_t B;                       /* molecules in the batch                                  */
+  int32_t N;                       /* padded atoms per molecule (tensor dim 1), <= 256        */
+  int32_t L;                       /* graph-conv layers (1 for the layer_* entry points)      */
+  int32_t E;                       /* encoder_dim (dense/readout width); unused by layer_*    */
+  int32_t F[OCGCN_MAX_LAYERS + 1]; /* F[0] = input_size, F[l] = hidden_size[l-1]              */
+  int32_t mode;                    /* OCGCN_FP32 / OCGCN_TF32 / OCGCN_BF16                     */
+  int32_t training;                /* 1: batch statistics + running-stat update; 0: running   */
+  int32_t has_bias;                /* GraphConvolution(bias=...)                              */
+  int32_t need_dx;                 /* layer_backward: also produce dX = A^T (dZ W^T)          */
+  float eps;                       /* BatchNorm1d eps (1e-5)                                  */
+  float momentum;                  /* BatchNorm1d momentum (0.1)                              */
+  int64_t x_stride[3];             /* element strides of x  (B,N,F[0])                        */
+  int64_t adj_stride[3];           /* element strides of adj (B,N,N)                          */
+} ocgcn_desc;
+
+/* Parameter / buffer pointers, indexed by layer. Names follow the reference state_dict:
+ * graph_convolutions.{l}.weight (F[l],F[l+1]) [row-major, NOT nn.Linear layout, gcn.py:19],
+ * .bias (F[l+1]), .bn.weight, .bn.bias, .bn.running_mean, .bn.running_var, .bn.num_batches_tracked (int64 scalar),
+ * dense.weight (E,F[L]) [nn.Linear layout], dense.bias (E). */
+typedef struct ocgcn_params {
+  const float* W[OCGCN_MAX_LAYERS];
+  const float* b[OCGCN_MAX_LAYERS]; /* NULL entries when has_bias == 0 */
+  const float* gamma[OCGCN_MAX_LAYERS];
+  const float* beta[OCGCN_MAX_LAYERS];
+  float* running_mean[OCGCN_MAX_LAYERS];         /* updated in place when training */
+  float* running_var[OCGCN_MAX_LAYERS];          /* updated in place when training */
+  int64_t* num_batches_tracked[OCGCN_MAX_LAYERS]; /* += 1 when training (may be NULL) */
+  const float* Wd;
+  const float* bd;
+} ocgcn_params;
+
+typedef struct ocgcn_grads {
+  float* dW[OCGCN_MAX_LAYERS];
+  float* db[OCGCN_MAX_LAYERS]; /* NULL entries when has_bias == 0 */
+  float* dgamma[OCGCN_MAX_LAYERS];
+  float* dbeta[OCGCN_MAX_LAYERS];
+  float* dWd;
+  float* dbd;
+} ocgcn_grads;
+
+/* Bytes of the two caller-provided buffers:
+ *   saved_bytes   — written by *_forward, read by *_backward (keep it alive in the autograd ctx);
+ *   scratch_bytes — transient, needed only for the duration of one *_forward or *_backward call.
+ * Valid for both encoder_* (desc->L layers + readout) and layer_* (desc->L == 1) calls. 256-byte aligned. */
+int ocgcn_query_workspace(const ocgcn_desc* desc, size_t* saved_bytes, size_t* scratch_bytes);
+
+/* out (B,E) contiguous fp32. x (B,N,F[0]) and adj (B,N,N) fp32 with the strides in desc. */
+int ocgcn_encoder_forward(const ocgcn_desc* desc, const float* x, const float* adj, const ocgcn_params* params,
+                          void* saved, void* scratch, float* out, void* stream);
+
+/* grad_out (B,E) contiguous. Writes (does not accumulate) every gradient in `grads`. */
+int ocgcn_encoder_backward(const ocgcn_desc* desc, const float* grad_out, const float* x, const float* adj,
+                           const ocgcn_params* params, const ocgcn_grads* grads, void* saved, void* scratch,
+                           void* stream);
+
+/* Standalone GraphConvolution: y (B,N,F[1]) contiguous = BN((adj x) W + b). Uses layer index 0 of params. */
+int ocgcn_layer_forward(const ocgcn_desc* desc, const float* x, const float* adj, const ocgcn_params* params,
+                        void* saved, void* scratch, float* y, void* stream);
+
+/* grad_y (B,N,F[1]) contiguous. grad_x (B,N,F[0]) contiguous, written when desc->need_dx. Layer index 0 of grads. */
+int ocgcn_layer_backward(const ocgcn_desc* desc, const float* grad_y, const float* x, const float* adj,
+                         const ocgcn_params* params, const ocgcn_grads* grads, float* grad_x, void* saved,
+                         void* scratch, void* stream);
+
+/* Number of kernel launches the last call on this host thread enqueued (bench.py's gpu_launches claim). */
+int ocgcn_last_launch_count(void);
+/* cudaError_t of the last failing CUDA call on this host thread (0 if none). */
+int ocgcn_last_cuda_error(void);
+const char* ocgcn_status_string(int status);
+/* ABI version; bumped whenever a struct above changes. */
+int ocgcn_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCGCN_H_ */

@@ -1,0 +1,135 @@
+"""ctypes binding of libocgcn.so (the C ABI declared in include/ocgcn.h) and its in-tree build.
+
+There is deliberately no fallback: if the shared library is missing or the device is not a B200 the
+product path raises. The oracle under ``oracle/`` is test infrastructure and is never imported here.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libocgcn.so")
+SOURCES = ["ocgcn_api.cu", "ocgcn_tile.cuh", "ocgcn_aux.cuh", "ocgcn_common.cuh"]
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "ocgcn.h")
+
+MAX_LAYERS = 16
+MODES = {"fp32": 0, "tf32": 1, "bf16": 2}
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+
+
+class Desc(ctypes.Structure):
+    _fields_ = [
+        ("B", ctypes.c_int32), ("N", ctypes.c_int32), ("L", ctypes.c_int32), ("E", ctypes.c_int32),
+        ("F", ctypes.c_int32 * (MAX_LAYERS + 1)),
+        ("mode", ctypes.c_int32), ("training", ctypes.c_int32), ("has_bias", ctypes.c_int32), ("need_dx", ctypes.c_int32),
+        ("eps", ctypes.c_float), ("momentum", ctypes.c_float),
+        ("x_stride", ctypes.c_int64 * 3), ("adj_stride", ctypes.c_int64 * 3),
+    ]
+
+
+class Params(ctypes.Structure):
+    _fields_ = [
+        ("W", ctypes.c_void_p * MAX_LAYERS), ("b", ctypes.c_void_p * MAX_LAYERS),
+        ("gamma", ctypes.c_void_p * MAX_LAYERS), ("beta", ctypes.c_void_p * MAX_LAYERS),
+        ("running_mean", ctypes.c_void_p * MAX_LAYERS), ("running_var", ctypes.c_void_p * MAX_LAYERS),
+        ("num_batches_tracked", ctypes.c_void_p * MAX_LAYERS),
+        ("Wd", ctypes.c_void_p), ("bd", ctypes.c_void_p),
+    ]
+
+
+class Grads(ctypes.Structure):
+    _fields_ = [
+        ("dW", ctypes.c_void_p * MAX_LAYERS), ("db", ctypes.c_void_p * MAX_LAYERS),
+        ("dgamma", ctypes.c_void_p * MAX_LAYERS), ("dbeta", ctypes.c_void_p * MAX_LAYERS),
+        ("dWd", ctypes.c_void_p), ("dbd", ctypes.c_void_p),
+    ]
+
+
+EXPORTS = [
+    "ocgcn_query_workspace", "ocgcn_encoder_forward", "ocgcn_encoder_backward", "ocgcn_layer_forward",
+    "ocgcn_layer_backward", "ocgcn_last_launch_count", "ocgcn_last_cuda_error", "ocgcn_status_string",
+    "ocgcn_abi_version",
+]
+
+
+def nvcc_command(out=LIB_PATH, extra=()):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    return [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+            "-Xcompiler", "-fPIC", "-shared", *extra, "-o", out, os.path.join(CSRC, "ocgcn_api.cu")]
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [HEADER]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu for sm_100a into csrc/libocgcn.so (nvcc cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    cmd = nvcc_command(extra=("-Xptxas", "-v") if verbose else ())
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load():
+    """Load libocgcn.so (building it if nvcc is available and it is missing/stale). Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if _stale():
+            try:
+                build()
+            except Exception as exc:  # noqa: BLE001
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        "openchem_b200: libocgcn.so is missing and could not be built (%s). "
+                        "There is no CPU/PyTorch fallback for this path; run `python -c 'import __graft_entry__ as g; g.build()'`." % exc)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name in EXPORTS:
+            if not hasattr(lib, name):
+                raise RuntimeError("libocgcn.so does not export %s" % name)
+        vp = ctypes.c_void_p
+        lib.ocgcn_query_workspace.argtypes = [ctypes.POINTER(Desc), ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]
+        lib.ocgcn_encoder_forward.argtypes = [ctypes.POINTER(Desc), vp, vp, ctypes.POINTER(Params), vp, vp, vp, vp]
+        lib.ocgcn_encoder_backward.argtypes = [ctypes.POINTER(Desc), vp, vp, vp, ctypes.POINTER(Params), ctypes.POINTER(Grads), vp, vp, vp]
+        lib.ocgcn_layer_forward.argtypes = [ctypes.POINTER(Desc), vp, vp, ctypes.POINTER(Params), vp, vp, vp, vp]
+        lib.ocgcn_layer_backward.argtypes = [ctypes.POINTER(Desc), vp, vp, vp, ctypes.POINTER(Params), ctypes.POINTER(Grads), vp, vp, vp, vp]
+        lib.ocgcn_status_string.restype = ctypes.c_char_p
+        lib.ocgcn_status_string.argtypes = [ctypes.c_int]
+        for name in ("ocgcn_query_workspace", "ocgcn_encoder_forward", "ocgcn_encoder_backward", "ocgcn_layer_forward",
+                     "ocgcn_layer_backward", "ocgcn_last_launch_count", "ocgcn_last_cuda_error", "ocgcn_abi_version"):
+            getattr(lib, name).restype = ctypes.c_int
+        if lib.ocgcn_abi_version() != 1:
+            raise RuntimeError("libocgcn.so ABI version mismatch; rebuild it")
+        _lib = lib
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        lib = load()
+        msg = lib.ocgcn_status_string(status).decode()
+        if status == 5:
+            msg += " [cudaError %d]" % lib.ocgcn_last_cuda_error()
+        raise RuntimeError(msg)

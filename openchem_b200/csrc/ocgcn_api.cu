@@ -1,0 +1,517 @@
+// extern "C" boundary of libocgcn.so: argument validation, workspace layout, kernel sequencing.
+// No torch types, no device allocation, no synchronisation: everything is enqueued on the caller's stream.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "ocgcn_aux.cuh"
+#include "ocgcn_common.cuh"
+#include "ocgcn_tile.cuh"
+
+namespace ocgcn {
+
+static thread_local int tl_launches = 0;
+static thread_local int tl_cuda_err = 0;
+
+#define CU_TRY(expr)                                   \
+  do {                                                 \
+    cudaError_t e__ = (expr);                          \
+    if (e__ != cudaSuccess) {                          \
+      tl_cuda_err = (int)e__;                          \
+      return OCGCN_ECUDA;                              \
+    }                                                  \
+  } while (0)
+#define ST_TRY(expr)              \
+  do {                            \
+    int s__ = (expr);             \
+    if (s__ != OCGCN_OK) return s__; \
+  } while (0)
+#define LAUNCH_CHECK()       \
+  do {                       \
+    ++tl_launches;           \
+    CU_TRY(cudaGetLastError()); \
+  } while (0)
+
+static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------------------
+// workspace layout (byte offsets). "saved" lives from forward to backward, "scratch" only within one call.
+// ---------------------------------------------------------------------------------------------------------
+struct Layout {
+  int TR, MT, NW, tiles, Fmax;
+  size_t rows;
+  // saved
+  size_t rowmask, colmask, molflag;
+  size_t Z[OCGCN_MAX_LAYERS], arg[OCGCN_MAX_LAYERS], S[OCGCN_MAX_LAYERS], stats[OCGCN_MAX_LAYERS];
+  size_t HL, D, O;
+  size_t saved_total;
+  // scratch
+  size_t partials, prodpart, WT[OCGCN_MAX_LAYERS], WdT, G[3], dU, coef, gemm_partial;
+  size_t scratch_total;
+  int max_splits;
+};
+
+static void gemm_tn_config(size_t R, int M, int Nn, int* splits, int* rows_per_split) {
+  const int nblocks = ((M + 127) / 128) * ((Nn + 127) / 128);
+  int s = 296 / nblocks;
+  if (s < 1) s = 1;
+  size_t rps = (R + s - 1) / s;
+  if (rps < 4 * GK) rps = 4 * GK;
+  rps = (rps + GK - 1) / GK * GK;
+  *rows_per_split = (int)rps;
+  *splits = (int)((R + rps - 1) / rps);
+}
+
+static int make_layout(const ocgcn_desc* d, bool layer_only, Layout* lo) {
+  memset(lo, 0, sizeof(*lo));
+  if (!d) return OCGCN_EINVAL;
+  if (d->B <= 0 || d->N <= 0 || d->L <= 0 || d->L > OCGCN_MAX_LAYERS) return OCGCN_EINVAL;
+  if (d->N > OCGCN_MAX_ATOMS) return OCGCN_EUNSUPPORTED;
+  if (!layer_only && d->E <= 0) return OCGCN_EINVAL;
+  if (layer_only && d->L != 1) return OCGCN_EINVAL;
+  for (int l = 0; l <= d->L; ++l)
+    if (d->F[l] <= 0) return OCGCN_EINVAL;
+  if (d->mode != OCGCN_FP32 && d->mode != OCGCN_TF32 && d->mode != OCGCN_BF16) return OCGCN_EINVAL;
+  if ((size_t)d->B * d->N >= (size_t)1 << 31) return OCGCN_EUNSUPPORTED;
+  lo->TR = d->N <= 128 ? 128 : 256;
+  lo->MT = lo->TR / d->N;
+  lo->NW = (d->N + 63) / 64;
+  lo->tiles = (d->B + lo->MT - 1) / lo->MT;
+  lo->rows = (size_t)d->B * d->N;
+  int Fmax = d->E > 0 && !layer_only ? d->E : 1;
+  for (int l = 0; l <= d->L; ++l) Fmax = d->F[l] > Fmax ? d->F[l] : Fmax;
+  lo->Fmax = Fmax;
+  const size_t rows = lo->rows;
+  size_t off = 0;
+  auto take = [&off](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+  lo->rowmask = take(rows * lo->NW * 8);
+  lo->colmask = take(rows * lo->NW * 8);
+  lo->molflag = take((size_t)d->B * 4);
+  for (int l = 0; l < d->L; ++l) {
+    lo->Z[l] = take(rows * d->F[l + 1] * 4);
+    lo->arg[l] = layer_only ? 0 : take(rows * d->F[l + 1]);
+    lo->S[l] = take(rows * d->F[l] * 4);
+    lo->stats[l] = take((size_t)4 * d->F[l + 1] * 4);
+  }
+  if (!layer_only) {
+    lo->HL = take(rows * d->F[d->L] * 4);
+    lo->D = take(rows * d->E * 4);
+    lo->O = take((size_t)d->B * d->E * 4);
+  }
+  lo->saved_total = off;
+
+  off = 0;
+  lo->partials = take((size_t)lo->tiles * 2 * Fmax * 4);
+  lo->prodpart = take((size_t)lo->tiles * Fmax * 4);
+  int max_splits = 1;
+  size_t max_partial = 0;
+  for (int l = 0; l < d->L; ++l) {
+    lo->WT[l] = take((size_t)d->F[l] * d->F[l + 1] * 4);
+    int s, rps;
+    gemm_tn_config(rows, d->F[l], d->F[l + 1], &s, &rps);
+    size_t p = (size_t)s * d->F[l] * d->F[l + 1] * 4;
+    max_partial = p > max_partial ? p : max_partial;
+    max_splits = s > max_splits ? s : max_splits;
+  }
+  if (!layer_only) {
+    lo->WdT = take((size_t)d->F[d->L] * d->E * 4);
+    int s, rps;
+    gemm_tn_config(rows, d->E, d->F[d->L], &s, &rps);
+    size_t p = (size_t)s * d->E * d->F[d->L] * 4;
+    max_partial = p > max_partial ? p : max_partial;
+    lo->dU = take(rows * d->E * 4);
+  }
+  for (int i = 0; i < 3; ++i) lo->G[i] = take(rows * Fmax * 4);
+  lo->coef = take((size_t)3 * Fmax * 4);
+  lo->gemm_partial = take(max_partial);
+  lo->max_splits = max_splits;
+  lo->scratch_total = off;
+  return OCGCN_OK;
+}
+
+static int check_device() {
+  int dev = 0, major = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  CU_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return OCGCN_EARCH;
+  return OCGCN_OK;
+}
+
+static int check_device_ptr(const void* p) {
+  if (!p) return OCGCN_EINVAL;
+  if (((uintptr_t)p & 3) != 0) return OCGCN_EALIGN;
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return OCGCN_EINVAL;
+  }
+  if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) return OCGCN_EINVAL;  // no CPU fallback
+  return OCGCN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------------------
+template <int TR, int PROD, int EPI>
+static int launch_tile_t(const TileArgs& a, int tiles, cudaStream_t st) {
+  constexpr int TC = tile_cols<TR>();
+  auto kern = tile_kernel<TR, TC, PROD, EPI>;
+  const size_t smem = tile_smem_bytes<TR, TC>(a.NW);
+  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<tiles, kThreads, smem, st>>>(a);
+  LAUNCH_CHECK();
+  return OCGCN_OK;
+}
+template <int PROD, int EPI>
+static int launch_tile(const Layout& lo, const TileArgs& a, cudaStream_t st) {
+  if (lo.TR == 128) return launch_tile_t<128, PROD, EPI>(a, lo.tiles, st);
+  return launch_tile_t<256, PROD, EPI>(a, lo.tiles, st);
+}
+
+static int launch_bwd_dy(const Layout& lo, const BwdDyArgs& a, cudaStream_t st) {
+  if (lo.TR == 128) {
+    const size_t smem = bwd_dy_smem_bytes<128>(a.NW);
+    CU_TRY(cudaFuncSetAttribute(bwd_dy_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bwd_dy_kernel<128><<<lo.tiles, kThreads, smem, st>>>(a);
+  } else {
+    const size_t smem = bwd_dy_smem_bytes<256>(a.NW);
+    CU_TRY(cudaFuncSetAttribute(bwd_dy_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bwd_dy_kernel<256><<<lo.tiles, kThreads, smem, st>>>(a);
+  }
+  LAUNCH_CHECK();
+  return OCGCN_OK;
+}
+
+static TileArgs base_tile_args(const ocgcn_desc* d, const Layout& lo, const float* adj, char* saved) {
+  TileArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = d->B; a.N = d->N; a.NW = lo.NW; a.MT = lo.MT;
+  a.adj = adj; a.as0 = d->adj_stride[0]; a.as1 = d->adj_stride[1]; a.as2 = d->adj_stride[2];
+  a.rowmask = reinterpret_cast<const u64*>(saved + lo.rowmask);
+  a.colmask = reinterpret_cast<const u64*>(saved + lo.colmask);
+  a.molflag = reinterpret_cast<const unsigned*>(saved + lo.molflag);
+  return a;
+}
+
+static int run_adj_pack(const ocgcn_desc* d, const Layout& lo, const float* adj, char* saved, cudaStream_t st) {
+  adj_pack_kernel<<<d->B, kThreads, (size_t)d->N * lo.NW * 8, st>>>(
+      adj, d->adj_stride[0], d->adj_stride[1], d->adj_stride[2], d->N, lo.NW, reinterpret_cast<u64*>(saved + lo.rowmask),
+      reinterpret_cast<u64*>(saved + lo.colmask), reinterpret_cast<unsigned*>(saved + lo.molflag));
+  LAUNCH_CHECK();
+  return OCGCN_OK;
+}
+
+static int run_bn_finalize(const ocgcn_desc* d, const Layout& lo, const ocgcn_params* p, int l, char* saved, char* scratch,
+                           cudaStream_t st) {
+  BnFinalizeArgs f;
+  const int F = d->F[l + 1];
+  float* stats = reinterpret_cast<float*>(saved + lo.stats[l]);
+  f.partials = reinterpret_cast<const float*>(scratch + lo.partials);
+  f.T = lo.tiles; f.F = F; f.B = d->B; f.N = d->N; f.MT = lo.MT;
+  f.training = d->training; f.eps = d->eps; f.momentum = d->momentum;
+  f.gamma = p->gamma[l]; f.beta = p->beta[l];
+  f.running_mean = p->running_mean[l]; f.running_var = p->running_var[l];
+  f.nbt = reinterpret_cast<long long*>(p->num_batches_tracked[l]);
+  f.mean = stats; f.invstd = stats + F; f.scale = stats + 2 * F; f.shift = stats + 3 * F;
+  bn_finalize_kernel<<<(F + 31) / 32, kThreads, 0, st>>>(f);
+  LAUNCH_CHECK();
+  return OCGCN_OK;
+}
+
+static int run_gemm_tn(const float* A, const float* Bm, size_t R, int M, int Nn, float* partial, cudaStream_t st, int* splits_out) {
+  int splits, rps;
+  gemm_tn_config(R, M, Nn, &splits, &rps);
+  dim3 grid(splits, ((M + 127) / 128) * ((Nn + 127) / 128));
+  gemm_tn_kernel<<<grid, kThreads, 0, st>>>(A, Bm, (int)R, M, Nn, rps, partial);
+  LAUNCH_CHECK();
+  *splits_out = splits;
+  return OCGCN_OK;
+}
+
+static int run_reduce(const float* p0, float* o0, int P0, int c0, const float* p1, float* o1, int P1, int c1, cudaStream_t st) {
+  ReduceJobs j;
+  j.partial[0] = p0; j.out[0] = o0; j.P[0] = P0; j.count[0] = c0;
+  j.partial[1] = p1; j.out[1] = o1; j.P[1] = P1; j.count[1] = c1;
+  const int mx = c0 > c1 ? c0 : c1;
+  dim3 grid((mx + 255) / 256, 2);
+  reduce_partials_kernel<<<grid, 256, 0, st>>>(j);
+  LAUNCH_CHECK();
+  return OCGCN_OK;
+}
+
+static int validate_params(const ocgcn_desc* d, const ocgcn_params* p, bool layer_only) {
+  if (!p) return OCGCN_EINVAL;
+  for (int l = 0; l < d->L; ++l) {
+    if (!p->W[l] || !p->gamma[l] || !p->beta[l] || !p->running_mean[l] || !p->running_var[l]) return OCGCN_EINVAL;
+    if (d->has_bias && !p->b[l]) return OCGCN_EINVAL;
+  }
+  if (!layer_only && (!p->Wd || !p->bd)) return OCGCN_EINVAL;
+  return OCGCN_OK;
+}
+
+// The forward of one graph-conv layer's GEMM stage (producer P_X for l==0, P_MID otherwise) + BN statistics.
+static int run_layer_forward(const ocgcn_desc* d, const Layout& lo, const float* x, const float* adj, const ocgcn_params* p, int l,
+                             char* saved, char* scratch, cudaStream_t st) {
+  TileArgs a = base_tile_args(d, lo, adj, saved);
+  a.K = d->F[l]; a.NC = d->F[l + 1];
+  a.Bm = p->W[l];
+  a.bias = d->has_bias ? p->b[l] : nullptr;
+  a.out0 = reinterpret_cast<float*>(saved + lo.Z[l]);
+  a.prod_out = reinterpret_cast<float*>(saved + lo.S[l]);
+  a.partials = reinterpret_cast<float*>(scratch + lo.partials);
+  if (l == 0) {
+    a.in0 = x; a.xs0 = d->x_stride[0]; a.xs1 = d->x_stride[1]; a.xs2 = d->x_stride[2];
+    ST_TRY((launch_tile<P_X, E_ZSTATS>(lo, a, st)));
+  } else {
+    const float* stats = reinterpret_cast<const float*>(saved + lo.stats[l - 1]);
+    a.in0 = reinterpret_cast<const float*>(saved + lo.Z[l - 1]);
+    a.vec0 = stats + 2 * d->F[l]; a.vec1 = stats + 3 * d->F[l];
+    a.arg_out = reinterpret_cast<unsigned char*>(saved + lo.arg[l - 1]);
+    ST_TRY((launch_tile<P_MID, E_ZSTATS>(lo, a, st)));
+  }
+  return run_bn_finalize(d, lo, p, l, saved, scratch, st);
+}
+
+// Backward of one graph-conv layer given dY (layer API) or dH (encoder) in buffer `g_in`.
+// Produces dgamma/dbeta/dW/db, and dHprev (= dX) in `g_out` unless skip_dx.
+static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float* adj, const ocgcn_params* p, const ocgcn_grads* g,
+                              int l, bool plain, float* g_in, float* g_dz, float* g_out, bool skip_dx, char* saved, char* scratch,
+                              cudaStream_t st) {
+  const int Fin = d->F[l], Fout = d->F[l + 1];
+  const float* stats = reinterpret_cast<const float*>(saved + lo.stats[l]);
+  float* coef = reinterpret_cast<float*>(scratch + lo.coef);
+  float* partials = reinterpret_cast<float*>(scratch + lo.partials);
+  float* prodpart = reinterpret_cast<float*>(scratch + lo.prodpart);
+  const float* Z = reinterpret_cast<const float*>(saved + lo.Z[l]);
+
+  BwdDyArgs y;
+  memset(&y, 0, sizeof(y));
+  y.B = d->B; y.N = d->N; y.NW = lo.NW; y.MT = lo.MT; y.F = Fout; y.plain = plain ? 1 : 0;
+  y.adj = adj; y.as0 = d->adj_stride[0]; y.as1 = d->adj_stride[1]; y.as2 = d->adj_stride[2];
+  y.colmask = reinterpret_cast<const u64*>(saved + lo.colmask);
+  y.molflag = reinterpret_cast<const unsigned*>(saved + lo.molflag);
+  y.Z = Z;
+  y.arg = plain ? nullptr : reinterpret_cast<const unsigned char*>(saved + lo.arg[l]);
+  y.mean = stats; y.invstd = stats + Fout; y.scale = stats + 2 * Fout; y.shift = stats + 3 * Fout;
+  y.dH = g_in; y.partials = partials;
+  ST_TRY(launch_bwd_dy(lo, y, st));
+
+  BwdFinalizeArgs f;
+  f.partials = partials; f.T = lo.tiles; f.F = Fout; f.training = d->training; f.n = (double)lo.rows;
+  f.gamma = p->gamma[l]; f.invstd = stats + Fout;
+  f.dgamma = g->dgamma[l]; f.dbeta = g->dbeta[l];
+  f.g = coef; f.c1 = coef + lo.Fmax; f.c2 = coef + 2 * lo.Fmax;
+  bwd_finalize_kernel<<<(Fout + 31) / 32, kThreads, 0, st>>>(f);
+  LAUNCH_CHECK();
+
+  TileArgs a = base_tile_args(d, lo, adj, saved);
+  a.K = Fout; a.NC = Fin;
+  a.in0 = g_in; a.in1 = Z;
+  a.vec0 = coef; a.vec1 = coef + lo.Fmax; a.vec2 = coef + 2 * lo.Fmax; a.vec3 = stats; a.vec4 = stats + Fout;
+  a.prod_out = g_dz;
+  a.prod_partials = (d->has_bias && g->db[l]) ? prodpart : nullptr;
+  a.Bm = reinterpret_cast<const float*>(scratch + lo.WT[l]);
+  a.out0 = g_out;
+  a.skip_gemm = skip_dx ? 1 : 0;
+  ST_TRY((launch_tile<P_DZ, E_ATG>(lo, a, st)));
+
+  int splits = 0;
+  float* gp = reinterpret_cast<float*>(scratch + lo.gemm_partial);
+  ST_TRY(run_gemm_tn(reinterpret_cast<const float*>(saved + lo.S[l]), g_dz, lo.rows, Fin, Fout, gp, st, &splits));
+  ST_TRY(run_reduce(gp, g->dW[l], splits, Fin * Fout, prodpart, (d->has_bias ? g->db[l] : nullptr), lo.tiles, Fout, st));
+  return OCGCN_OK;
+}
+
+static int run_transposes(const TransposeJobs& jobs, int n, cudaStream_t st) {
+  if (n == 0) return OCGCN_OK;
+  dim3 grid(32, n);
+  transpose_kernel<<<grid, 256, 0, st>>>(jobs);
+  LAUNCH_CHECK();
+  return OCGCN_OK;
+}
+
+}  // namespace ocgcn
+
+using namespace ocgcn;
+
+extern "C" {
+
+int ocgcn_abi_version(void) { return 1; }
+int ocgcn_last_launch_count(void) { return tl_launches; }
+int ocgcn_last_cuda_error(void) { return tl_cuda_err; }
+
+const char* ocgcn_status_string(int s) {
+  switch (s) {
+    case OCGCN_OK: return "ok";
+    case OCGCN_EINVAL: return "ocgcn: invalid argument (shape, null/host pointer or enum)";
+    case OCGCN_EUNSUPPORTED: return "ocgcn: unsupported size or mode (N <= 256, layers <= 16, B*N < 2^31)";
+    case OCGCN_EALIGN: return "ocgcn: misaligned pointer";
+    case OCGCN_EARCH: return "ocgcn: current CUDA device is not sm_100 (B200)";
+    case OCGCN_ECUDA: return "ocgcn: CUDA error (see ocgcn_last_cuda_error)";
+    default: return "ocgcn: unknown status";
+  }
+}
+
+int ocgcn_query_workspace(const ocgcn_desc* desc, size_t* saved_bytes, size_t* scratch_bytes) {
+  Layout lo;
+  const bool layer_only = desc && desc->E <= 0;
+  ST_TRY(make_layout(desc, layer_only, &lo));
+  if (saved_bytes) *saved_bytes = lo.saved_total;
+  if (scratch_bytes) *scratch_bytes = lo.scratch_total;
+  return OCGCN_OK;
+}
+
+int ocgcn_encoder_forward(const ocgcn_desc* d, const float* x, const float* adj, const ocgcn_params* p, void* saved_v,
+                          void* scratch_v, float* out, void* stream) {
+  tl_launches = 0;
+  Layout lo;
+  ST_TRY(make_layout(d, false, &lo));
+  ST_TRY(validate_params(d, p, false));
+  if (!saved_v || !scratch_v || !out) return OCGCN_EINVAL;
+  ST_TRY(check_device());
+  ST_TRY(check_device_ptr(x));
+  ST_TRY(check_device_ptr(adj));
+  ST_TRY(check_device_ptr(out));
+  if (((uintptr_t)saved_v & 255) || ((uintptr_t)scratch_v & 255)) return OCGCN_EALIGN;
+  char* saved = static_cast<char*>(saved_v);
+  char* scratch = static_cast<char*>(scratch_v);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int L = d->L;
+
+  ST_TRY(run_adj_pack(d, lo, adj, saved, st));
+  TransposeJobs tj;
+  memset(&tj, 0, sizeof(tj));
+  tj.in[0] = p->Wd; tj.out[0] = reinterpret_cast<float*>(scratch + lo.WdT); tj.R[0] = d->E; tj.C[0] = d->F[L];
+  ST_TRY(run_transposes(tj, 1, st));
+  for (int l = 0; l < L; ++l) ST_TRY(run_layer_forward(d, lo, x, adj, p, l, saved, scratch, st));
+
+  // readout: H_L = pool(tanh(BN(Z_L))), D = tanh(H_L Wd^T + bd), O = tanh(sum_i D)
+  TileArgs a = base_tile_args(d, lo, adj, saved);
+  const float* stats = reinterpret_cast<const float*>(saved + lo.stats[L - 1]);
+  a.K = d->F[L]; a.NC = d->E;
+  a.in0 = reinterpret_cast<const float*>(saved + lo.Z[L - 1]);
+  a.vec0 = stats + 2 * d->F[L]; a.vec1 = stats + 3 * d->F[L];
+  a.arg_out = reinterpret_cast<unsigned char*>(saved + lo.arg[L - 1]);
+  a.prod_out = reinterpret_cast<float*>(saved + lo.HL);
+  a.Bm = reinterpret_cast<const float*>(scratch + lo.WdT);
+  a.bias = p->bd;
+  a.out0 = reinterpret_cast<float*>(saved + lo.D);
+  a.out1 = out;
+  ST_TRY((launch_tile<P_RO, E_READOUT>(lo, a, st)));
+  CU_TRY(cudaMemcpyAsync(saved + lo.O, out, (size_t)d->B * d->E * 4, cudaMemcpyDeviceToDevice, st));
+  return OCGCN_OK;
+}
+
+int ocgcn_encoder_backward(const ocgcn_desc* d, const float* grad_out, const float* x, const float* adj, const ocgcn_params* p,
+                           const ocgcn_grads* g, void* saved_v, void* scratch_v, void* stream) {
+  (void)x;
+  tl_launches = 0;
+  Layout lo;
+  ST_TRY(make_layout(d, false, &lo));
+  ST_TRY(validate_params(d, p, false));
+  if (!g || !saved_v || !scratch_v || !g->dWd || !g->dbd) return OCGCN_EINVAL;
+  for (int l = 0; l < d->L; ++l)
+    if (!g->dW[l] || !g->dgamma[l] || !g->dbeta[l]) return OCGCN_EINVAL;
+  ST_TRY(check_device());
+  ST_TRY(check_device_ptr(grad_out));
+  ST_TRY(check_device_ptr(adj));
+  if (((uintptr_t)saved_v & 255) || ((uintptr_t)scratch_v & 255)) return OCGCN_EALIGN;
+  char* saved = static_cast<char*>(saved_v);
+  char* scratch = static_cast<char*>(scratch_v);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int L = d->L;
+
+  TransposeJobs tj;
+  memset(&tj, 0, sizeof(tj));
+  int nj = 0;
+  for (int l = 1; l < L; ++l) {
+    tj.in[nj] = p->W[l]; tj.out[nj] = reinterpret_cast<float*>(scratch + lo.WT[l]); tj.R[nj] = d->F[l]; tj.C[nj] = d->F[l + 1];
+    ++nj;
+  }
+  ST_TRY(run_transposes(tj, nj, st));
+
+  float* G[3] = {reinterpret_cast<float*>(scratch + lo.G[0]), reinterpret_cast<float*>(scratch + lo.G[1]),
+                 reinterpret_cast<float*>(scratch + lo.G[2])};
+  float* prodpart = reinterpret_cast<float*>(scratch + lo.prodpart);
+  float* dU = reinterpret_cast<float*>(scratch + lo.dU);
+  float* gp = reinterpret_cast<float*>(scratch + lo.gemm_partial);
+
+  // readout backward: dU = dO(1-O^2)(1-D^2); dH_L = dU.Wd; dWd = dU^T.H_L; dbd = sum dU
+  TileArgs a = base_tile_args(d, lo, adj, saved);
+  a.K = d->E; a.NC = d->F[L];
+  a.in0 = reinterpret_cast<const float*>(saved + lo.D);
+  a.in1 = grad_out;
+  a.in2 = reinterpret_cast<const float*>(saved + lo.O);
+  a.prod_out = dU;
+  a.prod_partials = prodpart;
+  a.Bm = p->Wd;
+  a.out0 = G[0];
+  ST_TRY((launch_tile<P_DU, E_STORE>(lo, a, st)));
+  int splits = 0;
+  ST_TRY(run_gemm_tn(dU, reinterpret_cast<const float*>(saved + lo.HL), lo.rows, d->E, d->F[L], gp, st, &splits));
+  ST_TRY(run_reduce(gp, g->dWd, splits, d->E * d->F[L], prodpart, g->dbd, lo.tiles, d->E, st));
+
+  int cur = 0;
+  for (int l = L - 1; l >= 0; --l) {
+    const int dz = (cur + 1) % 3, nxt = (cur + 2) % 3;
+    ST_TRY(run_layer_backward(d, lo, adj, p, g, l, false, G[cur], G[dz], G[nxt], l == 0, saved, scratch, st));
+    cur = nxt;
+  }
+  return OCGCN_OK;
+}
+
+int ocgcn_layer_forward(const ocgcn_desc* d, const float* x, const float* adj, const ocgcn_params* p, void* saved_v, void* scratch_v,
+                        float* y, void* stream) {
+  tl_launches = 0;
+  Layout lo;
+  ST_TRY(make_layout(d, true, &lo));
+  ST_TRY(validate_params(d, p, true));
+  if (!saved_v || !scratch_v || !y) return OCGCN_EINVAL;
+  ST_TRY(check_device());
+  ST_TRY(check_device_ptr(x));
+  ST_TRY(check_device_ptr(adj));
+  ST_TRY(check_device_ptr(y));
+  if (((uintptr_t)saved_v & 255) || ((uintptr_t)scratch_v & 255)) return OCGCN_EALIGN;
+  char* saved = static_cast<char*>(saved_v);
+  char* scratch = static_cast<char*>(scratch_v);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ST_TRY(run_adj_pack(d, lo, adj, saved, st));
+  ST_TRY(run_layer_forward(d, lo, x, adj, p, 0, saved, scratch, st));
+  const int F = d->F[1];
+  const float* stats = reinterpret_cast<const float*>(saved + lo.stats[0]);
+  const size_t total = lo.rows * F;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  bn_apply_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(saved + lo.Z[0]), stats + 2 * F, stats + 3 * F, y, total, F);
+  LAUNCH_CHECK();
+  return OCGCN_OK;
+}
+
+int ocgcn_layer_backward(const ocgcn_desc* d, const float* grad_y, const float* x, const float* adj, const ocgcn_params* p,
+                         const ocgcn_grads* g, float* grad_x, void* saved_v, void* scratch_v, void* stream) {
+  (void)x;
+  tl_launches = 0;
+  Layout lo;
+  ST_TRY(make_layout(d, true, &lo));
+  ST_TRY(validate_params(d, p, true));
+  if (!g || !saved_v || !scratch_v || !g->dW[0] || !g->dgamma[0] || !g->dbeta[0]) return OCGCN_EINVAL;
+  if (d->need_dx && !grad_x) return OCGCN_EINVAL;
+  ST_TRY(check_device());
+  ST_TRY(check_device_ptr(grad_y));
+  ST_TRY(check_device_ptr(adj));
+  if (((uintptr_t)saved_v & 255) || ((uintptr_t)scratch_v & 255)) return OCGCN_EALIGN;
+  char* saved = static_cast<char*>(saved_v);
+  char* scratch = static_cast<char*>(scratch_v);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d->need_dx) {
+    TransposeJobs tj;
+    memset(&tj, 0, sizeof(tj));
+    tj.in[0] = p->W[0]; tj.out[0] = reinterpret_cast<float*>(scratch + lo.WT[0]); tj.R[0] = d->F[0]; tj.C[0] = d->F[1];
+    ST_TRY(run_transposes(tj, 1, st));
+  }
+  float* dz = reinterpret_cast<float*>(scratch + lo.G[0]);
+  return run_layer_backward(d, lo, adj, p, g, 0, true, const_cast<float*>(grad_y), dz, grad_x, !d->need_dx, saved, scratch, st);
+}
+
+}  // extern "C"

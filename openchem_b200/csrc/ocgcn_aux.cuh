@@ -1,0 +1,379 @@
+// Streaming / reduction kernels around the tile kernel: adjacency packing, BatchNorm finalisation,
+// pool-scatter + tanh' (backward first half), the split-K weight-gradient GEMM and fixed-order reductions.
+#pragma once
+#include "ocgcn_common.cuh"
+
+namespace ocgcn {
+
+// ---------------------------------------------------------------------------------------------------------
+// adjacency -> bit masks. One CTA per molecule. Also classifies the molecule: molflag = 1 iff every entry is
+// exactly 0 or 1 (what openchem/utils/graph.py:77-86 produces); other molecules take the dense float path.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) adj_pack_kernel(const float* __restrict__ adj, long long as0, long long as1,
+                                                            long long as2, int N, int NW, u64* __restrict__ rowmask,
+                                                            u64* __restrict__ colmask, unsigned* __restrict__ molflag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u64* sR = reinterpret_cast<u64*>(smem_raw);
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* ab = adj + (long long)b * as0;
+  int nonbin = 0;
+  for (int i = warp; i < N; i += kWarps) {
+    for (int w = 0; w < NW; ++w) {
+      u64 word = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = 64 * w + 32 * h + lane;
+        const float v = (j < N) ? __ldg(&ab[(long long)i * as1 + (long long)j * as2]) : 0.f;
+        nonbin |= (v != 0.f && v != 1.f);
+        const unsigned bal = __ballot_sync(0xffffffffu, v != 0.f);
+        word |= (u64)bal << (32 * h);
+      }
+      if (lane == 0) {
+        sR[i * NW + w] = word;
+        rowmask[((size_t)b * N + i) * NW + w] = word;
+      }
+    }
+  }
+  nonbin = __syncthreads_or(nonbin);
+  for (int idx = tid; idx < N * NW; idx += kThreads) {
+    const int j = idx / NW, w = idx - j * NW;
+    u64 word = 0;
+    for (int ii = 0; ii < 64; ++ii) {
+      const int i = 64 * w + ii;
+      if (i < N) word |= ((sR[i * NW + (j >> 6)] >> (j & 63)) & 1ull) << ii;
+    }
+    colmask[((size_t)b * N + j) * NW + w] = word;
+  }
+  if (tid == 0) molflag[b] = nonbin ? 0u : 1u;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small batched transposes of the weight matrices (W_l^T for dS = dZ.W^T, Wd^T for the readout GEMM)
+// ---------------------------------------------------------------------------------------------------------
+struct TransposeJobs {
+  const float* in[OCGCN_MAX_LAYERS + 1];
+  float* out[OCGCN_MAX_LAYERS + 1];
+  int R[OCGCN_MAX_LAYERS + 1];
+  int C[OCGCN_MAX_LAYERS + 1];
+};
+__global__ void transpose_kernel(const TransposeJobs jobs) {
+  const int jb = blockIdx.y;
+  const float* in = jobs.in[jb];
+  float* out = jobs.out[jb];
+  const int R = jobs.R[jb], C = jobs.C[jb];
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < R * C; idx += gridDim.x * blockDim.x) {
+    const int c = idx / R, r = idx - c * R;  // out is [C][R]
+    out[idx] = __ldg(&in[(size_t)r * C + c]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BatchNorm statistics: merge per-tile Welford partials (fixed order, fp64) -> mean, invstd, scale, shift;
+// running-stat update with the unbiased variance (torch.nn.BatchNorm1d semantics, gcn.py:25,40).
+// grid = ceil(F/32), block = 256: lane = channel, warp = slice of tiles.
+// ---------------------------------------------------------------------------------------------------------
+struct BnFinalizeArgs {
+  const float* partials;  // [T][2][F]
+  int T, F, B, N, MT;
+  int training;
+  float eps, momentum;
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  long long* nbt;
+  float* mean;
+  float* invstd;
+  float* scale;
+  float* shift;
+};
+__global__ void __launch_bounds__(kThreads) bn_finalize_kernel(const BnFinalizeArgs a) {
+  __shared__ double sred[kWarps][32];
+  __shared__ double smean[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const bool valid = c < a.F;
+  const double n = (double)a.B * (double)a.N;
+  double mean = 0.0, var = 1.0;
+  if (a.training) {
+    double s = 0.0;
+    if (valid)
+      for (int t = warp; t < a.T; t += kWarps) {
+        const double nt = (double)(min(a.MT, a.B - t * a.MT) * a.N);
+        s += nt * (double)a.partials[((size_t)t * 2 + 0) * a.F + c];
+      }
+    sred[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < kWarps; ++w) tot += sred[w][lane];
+      smean[lane] = tot / n;
+    }
+    __syncthreads();
+    mean = smean[lane];
+    double m2 = 0.0;
+    if (valid)
+      for (int t = warp; t < a.T; t += kWarps) {
+        const double nt = (double)(min(a.MT, a.B - t * a.MT) * a.N);
+        const double d = (double)a.partials[((size_t)t * 2 + 0) * a.F + c] - mean;
+        m2 += (double)a.partials[((size_t)t * 2 + 1) * a.F + c] + nt * d * d;
+      }
+    __syncthreads();
+    sred[warp][lane] = m2;
+    __syncthreads();
+    if (warp != 0 || !valid) return;
+    double tot = 0.0;
+    for (int w = 0; w < kWarps; ++w) tot += sred[w][lane];
+    var = tot / n;
+    const double unbiased = tot / (n > 1.0 ? n - 1.0 : 1.0);
+    a.running_mean[c] = (float)((1.0 - (double)a.momentum) * (double)a.running_mean[c] + (double)a.momentum * mean);
+    a.running_var[c] = (float)((1.0 - (double)a.momentum) * (double)a.running_var[c] + (double)a.momentum * unbiased);
+    if (c == 0 && a.nbt) *a.nbt += 1;
+  } else {
+    if (warp != 0 || !valid) return;
+    mean = (double)a.running_mean[c];
+    var = (double)a.running_var[c];
+  }
+  const float invstd = (float)(1.0 / sqrt(var + (double)a.eps));
+  const float sc = a.gamma[c] * invstd;
+  a.mean[c] = (float)mean;
+  a.invstd[c] = invstd;
+  a.scale[c] = sc;
+  a.shift[c] = a.beta[c] - (float)mean * sc;
+}
+
+// y = scale*z + shift (standalone GraphConvolution output, gcn.py:40)
+__global__ void bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                                float* __restrict__ y, size_t total, int F) {
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % F);
+    y[idx] = fmaf(z[idx], __ldg(&scale[c]), __ldg(&shift[c]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Backward, first half of a layer: dT = pool-scatter(dH) through the saved arg-max, dY = dT*(1-T^2),
+// per-tile partial sums of dY and dY*Yhat (the two global sums BatchNorm backward needs).
+// plain != 0: the incoming gradient already is dY (standalone GraphConvolution): only the sums are formed.
+// dY is written in place over dH.
+// ---------------------------------------------------------------------------------------------------------
+struct BwdDyArgs {
+  int B, N, NW, MT, F, plain;
+  const float* adj;
+  long long as0, as1, as2;
+  const u64* colmask;
+  const unsigned* molflag;
+  const float* Z;
+  const unsigned char* arg;
+  const float* mean;
+  const float* invstd;
+  const float* scale;
+  const float* shift;
+  float* dH;        // in: dH (or dY when plain), out: dY
+  float* partials;  // [tile][2][F]
+};
+template <int TR>
+__global__ void __launch_bounds__(kThreads, 2) bwd_dy_kernel(const BwdDyArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = a.N, NW = a.NW, F = a.F;
+  u64* sCol = reinterpret_cast<u64*>(smem_raw);
+  float* sDH = reinterpret_cast<float*>(sCol + (size_t)TR * NW);
+  unsigned char* sArg = reinterpret_cast<unsigned char*>(sDH + TR * KCP);
+  float* sWarp = reinterpret_cast<float*>(sArg + TR * KC);
+  unsigned* sFlag = reinterpret_cast<unsigned*>(sWarp + 2 * kWarps * 32);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x;
+  const int mol0 = tile * a.MT;
+  const int nm = min(a.MT, a.B - mol0);
+  const int rows = nm * N;
+  const size_t row0 = (size_t)mol0 * N;
+  if (!a.plain) {
+    for (int idx = tid; idx < rows * NW; idx += kThreads) sCol[idx] = a.colmask[row0 * NW + idx];
+    for (int idx = tid; idx < nm; idx += kThreads) sFlag[idx] = a.molflag[mol0 + idx];
+  }
+  __syncthreads();
+
+  for (int k0 = 0; k0 < F; k0 += KC) {
+    const int c = k0 + lane;
+    const bool cvalid = c < F;
+    float mu = 0.f, is = 0.f, sc = 0.f, sh = 0.f;
+    if (cvalid) { mu = __ldg(&a.mean[c]); is = __ldg(&a.invstd[c]); sc = __ldg(&a.scale[c]); sh = __ldg(&a.shift[c]); }
+    if (!a.plain) {
+      for (int r = warp; r < rows; r += kWarps) {
+        float v = 0.f;
+        unsigned char ag = 0;
+        if (cvalid) { v = a.dH[(row0 + r) * F + c]; ag = a.arg[(row0 + r) * F + c]; }
+        sDH[r * KCP + lane] = v;
+        sArg[r * KC + lane] = ag;
+      }
+      __syncthreads();
+    }
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = warp; r < rows; r += kWarps) {
+      if (!cvalid) continue;
+      const size_t o = (row0 + r) * F + c;
+      const float z = __ldg(&a.Z[o]);
+      const float yhat = (z - mu) * is;
+      float dy;
+      if (a.plain) {
+        dy = a.dH[o];
+      } else {
+        const int m = r / N, j = r - m * N, mb = m * N;
+        float dt = 0.f;
+        if (sFlag[m]) {
+          const u64* mk = &sCol[(size_t)r * NW];
+          for (int w = 0; w < NW; ++w) {
+            u64 bits = mk[w];
+            while (bits) {
+              int i = 64 * w + __ffsll((long long)bits) - 1;
+              bits &= bits - 1;
+              if (sArg[(mb + i) * KC + lane] == (unsigned char)j) dt += sDH[(mb + i) * KCP + lane];
+            }
+          }
+        } else {
+          const float* acol = a.adj + (long long)(mol0 + m) * a.as0 + (long long)j * a.as2;
+          for (int i = 0; i < N; ++i)
+            if (sArg[(mb + i) * KC + lane] == (unsigned char)j) dt = fmaf(__ldg(&acol[(long long)i * a.as1]), sDH[(mb + i) * KCP + lane], dt);
+        }
+        const float t = tanhf(fmaf(z, sc, sh));
+        dy = dt * (1.f - t * t);
+        a.dH[o] = dy;
+      }
+      s1 += dy;
+      s2 = fmaf(dy, yhat, s2);
+    }
+    sWarp[warp * 32 + lane] = s1;
+    sWarp[(kWarps + warp) * 32 + lane] = s2;
+    __syncthreads();
+    if (warp == 0 && cvalid) {
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) { t1 += sWarp[w * 32 + lane]; t2 += sWarp[(kWarps + w) * 32 + lane]; }
+      a.partials[((size_t)tile * 2 + 0) * F + c] = t1;
+      a.partials[((size_t)tile * 2 + 1) * F + c] = t2;
+    }
+    __syncthreads();
+  }
+}
+
+template <int TR>
+inline size_t bwd_dy_smem_bytes(int NW) {
+  return (size_t)TR * NW * sizeof(u64) + (size_t)TR * KCP * 4 + (size_t)TR * KC + (size_t)2 * kWarps * 32 * 4 + (size_t)TR * 4 + 64;
+}
+
+// merge the per-tile (sum dY, sum dY*Yhat) partials in fixed order (fp64) -> dgamma, dbeta, and the
+// coefficient vectors of dZ = g*(dY - c1 - Yhat*c2)
+struct BwdFinalizeArgs {
+  const float* partials;  // [T][2][F]
+  int T, F, training;
+  double n;
+  const float* gamma;
+  const float* invstd;
+  float* dgamma;
+  float* dbeta;
+  float* g;
+  float* c1;
+  float* c2;
+};
+__global__ void __launch_bounds__(kThreads) bwd_finalize_kernel(const BwdFinalizeArgs a) {
+  __shared__ double sred[2][kWarps][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const bool valid = c < a.F;
+  double s1 = 0.0, s2 = 0.0;
+  if (valid)
+    for (int t = warp; t < a.T; t += kWarps) {
+      s1 += (double)a.partials[((size_t)t * 2 + 0) * a.F + c];
+      s2 += (double)a.partials[((size_t)t * 2 + 1) * a.F + c];
+    }
+  sred[0][warp][lane] = s1;
+  sred[1][warp][lane] = s2;
+  __syncthreads();
+  if (warp != 0 || !valid) return;
+  double db = 0.0, dg = 0.0;
+  for (int w = 0; w < kWarps; ++w) { db += sred[0][w][lane]; dg += sred[1][w][lane]; }
+  a.dbeta[c] = (float)db;
+  a.dgamma[c] = (float)dg;
+  a.g[c] = a.gamma[c] * a.invstd[c];
+  a.c1[c] = a.training ? (float)(db / a.n) : 0.f;
+  a.c2[c] = a.training ? (float)(dg / a.n) : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// dW = A^T . B with A [R][M], B [R][Nn] row-major (R = B*N rows): split-K over CTAs, 128x128 output blocks,
+// per-split partials reduced afterwards in fixed order (bit-reproducible, no atomics).
+// grid = (splits, mblocks*nblocks)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int GK = 16;  // rows per staged chunk
+__global__ void __launch_bounds__(kThreads, 2) gemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ Bm, int R, int M,
+                                                               int Nn, int rows_per_split, float* __restrict__ partial) {
+  __shared__ __align__(16) float sA[GK][128];
+  __shared__ __align__(16) float sB[GK][128];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int nbn = (Nn + 127) / 128;
+  const int mb = (blockIdx.y / nbn) * 128, nb = (blockIdx.y % nbn) * 128;
+  const int r_begin = blockIdx.x * rows_per_split;
+  const int r_end = min(R, r_begin + rows_per_split);
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int r0 = r_begin; r0 < r_end; r0 += GK) {
+    for (int idx = tid; idx < GK * 128; idx += kThreads) {
+      const int kk = idx >> 7, cc = idx & 127;
+      const int rr = r0 + kk;
+      sA[kk][cc] = (rr < r_end && mb + cc < M) ? __ldg(&A[(size_t)rr * M + mb + cc]) : 0.f;
+      sB[kk][cc] = (rr < r_end && nb + cc < Nn) ? __ldg(&Bm[(size_t)rr * Nn + nb + cc]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&sA[kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sA[kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&sB[kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&sB[kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* out = partial + (size_t)blockIdx.x * M * Nn;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = mb + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int nn = nb + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+      if (nn < Nn) out[(size_t)m * Nn + nn] = acc[i][j];
+    }
+  }
+}
+
+// out[i] = sum_p partial[p][i], p ascending (fixed order). Two jobs per launch (e.g. dW and db).
+struct ReduceJobs {
+  const float* partial[2];
+  float* out[2];
+  int P[2];
+  int count[2];
+};
+__global__ void reduce_partials_kernel(const ReduceJobs jobs) {
+  const int jb = blockIdx.y;
+  const float* p = jobs.partial[jb];
+  float* out = jobs.out[jb];
+  if (!out) return;
+  const int P = jobs.P[jb], cnt = jobs.count[jb];
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < cnt; idx += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int q = 0; q < P; ++q) s += (double)p[(size_t)q * cnt + idx];
+    out[idx] = (float)s;
+  }
+}
+
+}  // namespace ocgcn

@@ -1,0 +1,75 @@
+// Shared definitions for the ocgcn kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ocgcn.h"
+
+namespace ocgcn {
+
+constexpr int kThreads = 256;  // every tile kernel runs 8 warps
+constexpr int kWarps = kThreads / 32;
+constexpr int KC = 32;          // channel chunk = one channel per lane
+constexpr int KCP = KC + 4;     // padded chunk row (floats): float4-aligned, conflict-free for lane==channel
+
+typedef unsigned long long u64;
+
+// ---- producer / epilogue kinds of the tile kernel ------------------------------------------------------------
+enum Prod : int {
+  P_X = 0,    // first layer: H = x (strided load);            S = A.H
+  P_MID = 1,  // H = pool(tanh(scale*Zprev+shift)) (+arg-max);  S = A.H
+  P_RO = 2,   // H = pool(tanh(scale*Zprev+shift)) (+arg-max);  GEMM operand = H   (readout)
+  P_DZ = 3,   // dZ = g*(dY - c1 - Yhat*c2)                     (BatchNorm backward, second half)
+  P_DU = 4    // dU = dO*(1-O^2)*(1-D^2)                        (readout backward)
+};
+enum Epi : int {
+  E_ZSTATS = 0,   // Z = acc + bias -> global, per-tile Welford partials (count, mean, M2) per channel
+  E_READOUT = 1,  // D = tanh(acc + bias) -> global, O = tanh(sum_i D) -> global
+  E_STORE = 2,    // out = acc
+  E_ATG = 3       // out = A^T . acc  (per molecule)
+};
+
+struct TileArgs {
+  int B, N, NW, MT;  // molecules, atoms, mask words per row, molecules per tile
+  int K, NC;         // GEMM reduction width (producer channels) and output columns
+  // adjacency: dense (general path) + packed
+  const float* adj;
+  long long as0, as1, as2;
+  const u64* rowmask;       // [B*N][NW] bit j of row i  <=> adj[b,i,j] != 0
+  const u64* colmask;       // [B*N][NW] bit i of col j  <=> adj[b,i,j] != 0
+  const unsigned* molflag;  // [B] 1 = every entry of adj[b] is exactly 0 or 1
+  // producer inputs
+  const float* in0;  // P_X: x | P_MID/P_RO: Zprev | P_DZ: dY | P_DU: D
+  long long xs0, xs1, xs2;
+  const float* in1;   // P_DZ: Z | P_DU: dO
+  const float* in2;   // P_DU: O
+  const float* vec0;  // P_MID/P_RO: scale | P_DZ: g = gamma*invstd
+  const float* vec1;  // P_MID/P_RO: shift | P_DZ: c1 = dbeta/n
+  const float* vec2;  // P_DZ: c2 = dgamma/n
+  const float* vec3;  // P_DZ: mean
+  const float* vec4;  // P_DZ: invstd
+  // producer outputs (written on the first column pass only)
+  unsigned char* arg_out;  // P_MID/P_RO  [rows][K]
+  float* prod_out;         // P_X/P_MID: S | P_RO: H_L | P_DZ: dZ | P_DU: dU   [rows][K]
+  float* prod_partials;    // P_DZ/P_DU: per-tile column sums [tile][K]
+  // GEMM right operand [K][NC] row-major
+  const float* Bm;
+  const float* bias;  // NC or null
+  // epilogue outputs
+  float* out0;      // Z | D | dH | dHprev  [rows][NC]
+  float* out1;      // E_READOUT: O [B][NC]
+  float* partials;  // E_ZSTATS: [tile][3][NC]  (count is implicit; slots: mean, M2, unused)
+  int skip_gemm;    // producers only (P_DZ of the first layer when dX is not needed)
+};
+
+__device__ __forceinline__ int first_zero_bit(const u64* m, int NW, int N) {
+  for (int w = 0; w < NW; ++w) {
+    u64 inv = ~m[w];
+    int hi = N - 64 * w;
+    if (hi < 64) inv &= (hi <= 0) ? 0ull : ((1ull << hi) - 1ull);
+    if (inv) return 64 * w + __ffsll((long long)inv) - 1;
+  }
+  return -1;
+}
+
+}  // namespace ocgcn

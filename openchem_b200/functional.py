@@ -1,0 +1,212 @@
+"""autograd.Function wrappers that marshal torch tensors into the C ABI (include/ocgcn.h).
+
+PyTorch is plumbing here: device memory (workspaces live in torch tensors owned by the autograd ctx),
+the current stream, and the autograd graph. All arithmetic happens in libocgcn.so.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+# launches enqueued by this process through the C ABI (bench.py reports it as gpu_launches)
+launch_counter = {"n": 0}
+
+
+def _require_cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("openchem_b200: %s must be a CUDA tensor (this path has no CPU fallback)" % name)
+
+
+def _f32(t):
+    return t if t.dtype == torch.float32 else t.to(torch.float32)
+
+
+class LayerSpec:
+    """Non-tensor arguments + in-place updated buffers of one call (kept out of autograd's sight)."""
+
+    def __init__(self, widths, encoder_dim, mode, training, has_bias, eps, momentum, running_mean, running_var, nbt):
+        self.widths = list(widths)          # [F0, F1, ..., FL]
+        self.encoder_dim = int(encoder_dim)  # 0 => standalone layer call
+        self.mode = mode
+        self.training = bool(training)
+        self.has_bias = bool(has_bias)
+        self.eps = float(eps)
+        self.momentum = float(momentum)
+        self.running_mean = running_mean
+        self.running_var = running_var
+        self.nbt = nbt
+
+
+def _make_desc(spec, x, adj, need_dx=False):
+    d = _lib.Desc()
+    B, N, F0 = x.shape
+    if adj.dim() != 3 or adj.shape[0] != B or adj.shape[1] != N or adj.shape[2] != N:
+        raise RuntimeError("openchem_b200: adj must be (B,N,N) matching x (B,N,F); got %s and %s" % (tuple(adj.shape), tuple(x.shape)))
+    if F0 != spec.widths[0]:
+        raise RuntimeError("openchem_b200: x has %d features, layer expects %d" % (F0, spec.widths[0]))
+    d.B, d.N, d.L, d.E = B, N, len(spec.widths) - 1, spec.encoder_dim
+    for i, f in enumerate(spec.widths):
+        d.F[i] = f
+    d.mode = _lib.MODES[spec.mode]
+    d.training = int(spec.training)
+    d.has_bias = int(spec.has_bias)
+    d.need_dx = int(need_dx)
+    d.eps, d.momentum = spec.eps, spec.momentum
+    for i in range(3):
+        d.x_stride[i] = x.stride(i)
+        d.adj_stride[i] = adj.stride(i)
+    return d
+
+
+def _make_params(spec, Ws, bs, gammas, betas, Wd=None, bd=None):
+    p = _lib.Params()
+    for l in range(len(Ws)):
+        p.W[l] = Ws[l].data_ptr()
+        p.b[l] = bs[l].data_ptr() if bs[l] is not None else None
+        p.gamma[l] = gammas[l].data_ptr()
+        p.beta[l] = betas[l].data_ptr()
+        p.running_mean[l] = spec.running_mean[l].data_ptr()
+        p.running_var[l] = spec.running_var[l].data_ptr()
+        p.num_batches_tracked[l] = spec.nbt[l].data_ptr() if spec.nbt[l] is not None else None
+    if Wd is not None:
+        p.Wd, p.bd = Wd.data_ptr(), bd.data_ptr()
+    return p
+
+
+def _workspaces(desc, device):
+    lib = _lib.load()
+    sb, cb = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    _lib.check(lib.ocgcn_query_workspace(ctypes.byref(desc), ctypes.byref(sb), ctypes.byref(cb)))
+    return sb.value, cb.value
+
+
+def _alloc(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _stream_ptr(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _count(lib):
+    launch_counter["n"] += lib.ocgcn_last_launch_count()
+
+
+class EncoderFn(torch.autograd.Function):
+    """GraphCNNEncoder.forward (gcn_encoder.py:38-53) as ONE autograd node. inputs: x, adj, spec, then per layer
+    W, b, gamma, beta (b may be None) and finally Wd, bd."""
+
+    @staticmethod
+    def forward(ctx, x, adj, spec, *tensors):
+        lib = _lib.load()
+        _require_cuda(x, "x")
+        _require_cuda(adj, "adj")
+        if x.requires_grad or adj.requires_grad:
+            raise RuntimeError("openchem_b200: the fused encoder treats x and adj as data (no gradient); "
+                               "use GraphConvolution layers if you need d/dx")
+        L = len(spec.widths) - 1
+        x, adj = _f32(x), _f32(adj)
+        tensors = [None if t is None else t.detach().contiguous() for t in tensors]
+        Ws, bs, gammas, betas = tensors[0:4 * L:4], tensors[1:4 * L:4], tensors[2:4 * L:4], tensors[3:4 * L:4]
+        Wd, bd = tensors[4 * L], tensors[4 * L + 1]
+        with torch.cuda.device(x.device):
+            desc = _make_desc(spec, x, adj)
+            params = _make_params(spec, Ws, bs, gammas, betas, Wd, bd)
+            sbytes, cbytes = _workspaces(desc, x.device)
+            saved = _alloc(sbytes, x.device)
+            scratch = _alloc(cbytes, x.device)
+            out = torch.empty((x.shape[0], spec.encoder_dim), dtype=torch.float32, device=x.device)
+            _lib.check(lib.ocgcn_encoder_forward(ctypes.byref(desc), x.data_ptr(), adj.data_ptr(), ctypes.byref(params),
+                                                 saved.data_ptr(), scratch.data_ptr(), out.data_ptr(), _stream_ptr(x.device)))
+            _count(lib)
+        ctx.spec = spec
+        ctx.cbytes = cbytes
+        ctx.save_for_backward(x, adj, saved, *[t for t in tensors if t is not None])
+        ctx.none_mask = [t is None for t in tensors]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        spec = ctx.spec
+        L = len(spec.widths) - 1
+        x, adj, saved, *rest = ctx.saved_tensors
+        it = iter(rest)
+        tensors = [None if isnone else next(it) for isnone in ctx.none_mask]
+        Ws, bs, gammas, betas = tensors[0:4 * L:4], tensors[1:4 * L:4], tensors[2:4 * L:4], tensors[3:4 * L:4]
+        Wd, bd = tensors[4 * L], tensors[4 * L + 1]
+        grad_out = _f32(grad_out).contiguous()
+        with torch.cuda.device(x.device):
+            desc = _make_desc(spec, x, adj)
+            params = _make_params(spec, Ws, bs, gammas, betas, Wd, bd)
+            grads = _lib.Grads()
+            outs = []
+            for l in range(L):
+                gW, gg, gb_ = torch.empty_like(Ws[l]), torch.empty_like(gammas[l]), torch.empty_like(betas[l])
+                gbias = torch.empty_like(bs[l]) if bs[l] is not None else None
+                grads.dW[l], grads.dgamma[l], grads.dbeta[l] = gW.data_ptr(), gg.data_ptr(), gb_.data_ptr()
+                grads.db[l] = gbias.data_ptr() if gbias is not None else None
+                outs += [gW, gbias, gg, gb_]
+            gWd, gbd = torch.empty_like(Wd), torch.empty_like(bd)
+            grads.dWd, grads.dbd = gWd.data_ptr(), gbd.data_ptr()
+            scratch = _alloc(ctx.cbytes, x.device)
+            _lib.check(lib.ocgcn_encoder_backward(ctypes.byref(desc), grad_out.data_ptr(), x.data_ptr(), adj.data_ptr(),
+                                                  ctypes.byref(params), ctypes.byref(grads), saved.data_ptr(), scratch.data_ptr(),
+                                                  _stream_ptr(x.device)))
+            _count(lib)
+        return (None, None, None, *outs, gWd, gbd)
+
+
+class LayerFn(torch.autograd.Function):
+    """GraphConvolution.forward (gcn.py:33-42) as one autograd node: inputs x, adj, spec, W, b, gamma, beta."""
+
+    @staticmethod
+    def forward(ctx, x, adj, spec, W, b, gamma, beta):
+        lib = _lib.load()
+        _require_cuda(x, "x")
+        _require_cuda(adj, "adj")
+        if adj.requires_grad:
+            raise RuntimeError("openchem_b200: gradients w.r.t. the adjacency are not supported (no reference caller needs them)")
+        need_dx = bool(x.requires_grad)
+        x, adj = _f32(x.detach()), _f32(adj)
+        W, gamma, beta = W.detach().contiguous(), gamma.detach().contiguous(), beta.detach().contiguous()
+        b = None if b is None else b.detach().contiguous()
+        with torch.cuda.device(x.device):
+            desc = _make_desc(spec, x, adj, need_dx)
+            params = _make_params(spec, [W], [b], [gamma], [beta])
+            sbytes, cbytes = _workspaces(desc, x.device)
+            saved = _alloc(sbytes, x.device)
+            scratch = _alloc(cbytes, x.device)
+            y = torch.empty((x.shape[0], x.shape[1], spec.widths[1]), dtype=torch.float32, device=x.device)
+            _lib.check(lib.ocgcn_layer_forward(ctypes.byref(desc), x.data_ptr(), adj.data_ptr(), ctypes.byref(params),
+                                               saved.data_ptr(), scratch.data_ptr(), y.data_ptr(), _stream_ptr(x.device)))
+            _count(lib)
+        ctx.spec, ctx.cbytes, ctx.need_dx, ctx.has_b = spec, cbytes, need_dx, b is not None
+        ctx.save_for_backward(x, adj, saved, W, gamma, beta, *([b] if b is not None else []))
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        lib = _lib.load()
+        spec = ctx.spec
+        x, adj, saved, W, gamma, beta, *rest = ctx.saved_tensors
+        b = rest[0] if ctx.has_b else None
+        grad_y = _f32(grad_y).contiguous()
+        with torch.cuda.device(x.device):
+            desc = _make_desc(spec, x, adj, ctx.need_dx)
+            params = _make_params(spec, [W], [b], [gamma], [beta])
+            grads = _lib.Grads()
+            gW, gg, gb_ = torch.empty_like(W), torch.empty_like(gamma), torch.empty_like(beta)
+            gbias = torch.empty_like(b) if b is not None else None
+            grads.dW[0], grads.dgamma[0], grads.dbeta[0] = gW.data_ptr(), gg.data_ptr(), gb_.data_ptr()
+            grads.db[0] = gbias.data_ptr() if gbias is not None else None
+            gx = torch.empty((x.shape[0], x.shape[1], spec.widths[0]), dtype=torch.float32, device=x.device) if ctx.need_dx else None
+            scratch = _alloc(ctx.cbytes, x.device)
+            _lib.check(lib.ocgcn_layer_backward(ctypes.byref(desc), grad_y.data_ptr(), x.data_ptr(), adj.data_ptr(),
+                                                ctypes.byref(params), ctypes.byref(grads), gx.data_ptr() if gx is not None else None,
+                                                saved.data_ptr(), scratch.data_ptr(), _stream_ptr(x.device)))
+            _count(lib)
+        return gx, None, None, gW, gbias, gg, gb_

@@ -1,0 +1,148 @@
+"""Parity of the CUDA path (through the nn.Module surface -> C ABI) against the reference.
+
+Two anchors: (1) golden fixtures produced by the unmodified reference (oracle/make_golden.py), both its fp32 run
+and its fp64-promoted run; (2) the numpy oracle evaluated in fp64 on seeded synthetic batches at sizes it
+finishes in seconds. Metric: per-tensor rel-L2; tolerance 1e-5 for the fp32 mode
+(north star), absolute 1e-5*scale for the analytically-zero GraphConvolution bias gradient.
+"""
+import numpy as np
+import pytest
+
+from _util import ENC_CASES, LAYER_CASES, build_encoder, golden_params, load_golden, random_params, rel_l2
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-5}
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _run_encoder(enc, x, adj, dO, dev):
+    enc.train()
+    enc.zero_grad()
+    tx, ta = torch.from_numpy(x).to(dev), torch.from_numpy(adj).to(dev)
+    out = enc((tx, ta))
+    out.backward(torch.from_numpy(dO).to(dev))
+    torch.cuda.synchronize()
+    res = dict(out_train=out.detach().cpu().numpy())
+    for l, gc in enumerate(enc.graph_convolutions):
+        res[f"dW{l}"] = gc.weight.grad.cpu().numpy()
+        res[f"db{l}"] = gc.bias.grad.cpu().numpy()
+        res[f"dgamma{l}"] = gc.bn.weight.grad.cpu().numpy()
+        res[f"dbeta{l}"] = gc.bn.bias.grad.cpu().numpy()
+        res[f"rm{l}"] = gc.bn.running_mean.cpu().numpy()
+        res[f"rv{l}"] = gc.bn.running_var.cpu().numpy()
+        assert int(gc.bn.num_batches_tracked) == 1
+    res["dWd"] = enc.dense.weight.grad.cpu().numpy()
+    res["dbd"] = enc.dense.bias.grad.cpu().numpy()
+    enc.eval()
+    res["out_eval"] = enc((tx, ta)).detach().cpu().numpy()
+    torch.cuda.synchronize()
+    return res
+
+
+def _compare(res, ref, L, tol, label):
+    worst, report = 0.0, []
+    for k in ["out_train", "out_eval", "dWd", "dbd"] + [f"{n}{l}" for l in range(L) for n in ("dW", "dgamma", "dbeta", "rm", "rv")]:
+        e = rel_l2(res[k], ref[k])
+        report.append(f"{k}={e:.2e}")
+        worst = max(worst, e)
+    for l in range(L):  # bias grad is analytically 0 (BN removes the mean): absolute bound scaled by the dW magnitude
+        scale = np.abs(ref[f"dW{l}"]).max() + 1e-30
+        e = np.abs(res[f"db{l}"]).max() / scale
+        report.append(f"db{l}(abs/scale)={e:.2e}")
+        assert e < 1e-4, f"{label}: bias grad not ~0: {report}"
+    assert worst < tol, f"{label}: worst rel-L2 {worst:.3e} >= {tol}: {' '.join(report)}"
+    return worst
+
+
+@pytest.mark.parametrize("case", ENC_CASES)
+def test_encoder_vs_reference_golden(case):
+    dev = _dev()
+    g = load_golden(case)
+    L = len(g["hidden"])
+    cfg = {"input_size": int(g["x"].shape[2]), "encoder_dim": int(g["Wd"].shape[0]), "n_layers": L, "hidden_size": [int(h) for h in g["hidden"]]}
+    enc = build_encoder(cfg, golden_params(g, np.float32), dev)
+    res = _run_encoder(enc, g["x"], g["adj"], g["dO"], dev)
+    ref64 = {k[6:]: v for k, v in g.items() if k.startswith("ref64_")}
+    ref32 = {k[6:]: v for k, v in g.items() if k.startswith("ref32_")}
+    _compare(res, ref64, L, TOL["fp32"], case + " vs ref64")
+    _compare(res, ref32, L, 2 * TOL["fp32"], case + " vs ref32")
+
+
+@pytest.mark.parametrize("shape", [
+    dict(B=64, N=50, F0=33, hidden=[128] * 5, E=128, occ="molecular"),   # C2 shape
+    dict(B=96, N=64, F0=64, hidden=[128] * 4, E=128, occ="full"),        # C3 shape
+    dict(B=33, N=85, F0=33, hidden=[128] * 5, E=128, occ="molecular"),   # C1 shape (ragged last tile)
+    dict(B=10, N=128, F0=64, hidden=[256] * 3, E=256, occ="molecular"),  # C5 widths
+    dict(B=7, N=132, F0=20, hidden=[48, 200], E=36, occ="molecular"),    # N > 128: 256-row tiles, 3 mask words
+])
+def test_encoder_vs_oracle(shape):
+    from oracle import gcn_oracle as orc
+    from openchem_b200.synthetic import make_graph_batch
+    dev = _dev()
+    gb = make_graph_batch(shape["B"], shape["N"], shape["F0"], occupancy=shape["occ"], seed=11)
+    widths = [shape["F0"]] + shape["hidden"]
+    p = random_params(widths, shape["E"], seed=5)
+    rng = np.random.RandomState(3)
+    dO = rng.randn(shape["B"], shape["E"]).astype(np.float32)
+    p64 = orc.cast_params(p, np.float64)
+    x64, a64 = gb["x"].astype(np.float64), gb["adj"].astype(np.float64)
+    O, cache, rms, rvs = orc.encoder_forward(x64, a64, p64, training=True)
+    gr = orc.encoder_backward(dO.astype(np.float64), cache)
+    Oe = orc.encoder_forward(x64, a64, dict(p64, running_mean=rms, running_var=rvs), training=False)[0]
+    ref = dict(out_train=O, out_eval=Oe, dWd=gr["dWd"], dbd=gr["dbd"])
+    L = len(shape["hidden"])
+    for l in range(L):
+        ref.update({f"dW{l}": gr["dW"][l], f"db{l}": gr["db"][l], f"dgamma{l}": gr["dgamma"][l], f"dbeta{l}": gr["dbeta"][l],
+                    f"rm{l}": rms[l], f"rv{l}": rvs[l]})
+    cfg = {"input_size": shape["F0"], "encoder_dim": shape["E"], "n_layers": L, "hidden_size": list(shape["hidden"])}
+    enc = build_encoder(cfg, p, dev)
+    res = _run_encoder(enc, gb["x"], gb["adj"], dO, dev)
+    _compare(res, ref, L, TOL["fp32"], str(shape))
+
+
+@pytest.mark.parametrize("case", LAYER_CASES)
+def test_layer_vs_reference_golden(case):
+    from openchem_b200.layers.gcn import GraphConvolution
+    dev = _dev()
+    g = load_golden(case)
+    has_b = "b" in g
+    gc = GraphConvolution(g["W"].shape[0], g["W"].shape[1], bias=has_b)
+    with torch.no_grad():
+        gc.weight.copy_(torch.from_numpy(g["W"]))
+        if has_b:
+            gc.bias.copy_(torch.from_numpy(g["b"]))
+        gc.bn.weight.copy_(torch.from_numpy(g["gamma"]))
+        gc.bn.bias.copy_(torch.from_numpy(g["beta"]))
+        gc.bn.running_mean.copy_(torch.from_numpy(g["running_mean"]))
+        gc.bn.running_var.copy_(torch.from_numpy(g["running_var"]))
+    gc = gc.to(dev)
+    gc.train()
+    tx = torch.from_numpy(g["x"]).to(dev).requires_grad_(True)
+    ta = torch.from_numpy(g["adj"]).to(dev)
+    y = gc(tx, ta)
+    y.backward(torch.from_numpy(g["dY"]).to(dev))
+    res = dict(y_train=y.detach().cpu().numpy(), dx=tx.grad.cpu().numpy(), dW=gc.weight.grad.cpu().numpy(),
+               dgamma=gc.bn.weight.grad.cpu().numpy(), dbeta=gc.bn.bias.grad.cpu().numpy(),
+               rm=gc.bn.running_mean.cpu().numpy(), rv=gc.bn.running_var.cpu().numpy())
+    gc.eval()
+    tx2 = torch.from_numpy(g["x"]).to(dev).requires_grad_(True)
+    ye = gc(tx2, ta)
+    ye.backward(torch.from_numpy(g["dY"]).to(dev))
+    res["y_eval"] = ye.detach().cpu().numpy()
+    res["dx_eval"] = tx2.grad.cpu().numpy()
+    report, worst = [], 0.0
+    for k, v in res.items():
+        e = rel_l2(v, g["ref64_" + k])
+        report.append(f"{k}={e:.2e}")
+        worst = max(worst, e)
+    if has_b:
+        e = np.abs(gc.bias.grad.cpu().numpy()).max() / (np.abs(g["ref64_dW"]).max() + 1e-30)
+        assert e < 1e-4, report
+    assert worst < TOL["fp32"], f"{case}: {' '.join(report)}"
