@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""GraphCNN train-step benchmark (BASELINE.json metric: "GraphCNN train molecules/sec at 1/2/4/8 B200; % of
+HBM/tensor roofline").
+
+    python bench.py --gpus 1 --steps K --warmup W                 # this repo's CUDA path (default)
+    python bench.py --impl reference --steps K --warmup W         # the reference's CPU op sequence (oracle port)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One step = Graph2Label-shaped train step on one synthetic padded-graph batch: encoder (libocgcn.so) -> MLP head
+(Linear-BN-ReLU-Linear, plain torch: SURVEY section 8(f) "next" row) -> loss -> backward -> (DDP grad
+all-reduce over NCCL when N > 1) -> Adam step. Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from openchem_b200.synthetic import WORKLOADS, make_graph_batch, make_labels, random_params  # noqa: E402
+
+METRIC = "graphcnn_train_molecules_per_sec"
+UNIT = "molecules/s"
+
+
+# --------------------------------------------------------------------------------------------------------------
+# algorithmic work per molecule (DESIGN.md "Roofline arithmetic"): dense GEMM flops, compulsory HBM bytes
+# --------------------------------------------------------------------------------------------------------------
+def algorithmic_work(w):
+    N, F, E = w["n_max"], [w["f0"]] + list(w["hidden"]), w["encoder_dim"]
+    head = 0
+    prev = E
+    for h in w["mlp_hidden"]:
+        head += 2 * prev * h
+        prev = h
+    L = len(F) - 1
+    fwd = sum(2 * N * N * F[l] + 2 * N * F[l] * F[l + 1] for l in range(L)) + 2 * N * F[L] * E + head
+    bwd = sum(2 * N * F[l] * F[l + 1] for l in range(L))                                    # dW_l = S^T dZ
+    bwd += sum(2 * N * F[l] * F[l + 1] + 2 * N * N * F[l] for l in range(1, L))              # dS = dZ W^T, dH = A^T dS (l >= 2)
+    bwd += 2 * (2 * N * F[L] * E) + 2 * head                                                # readout + head
+    bytes_ = 4 * N * N + 4 * N * F[0] + 8 * E
+    per_layer_fwd = [2 * N * N * F[l] + 2 * N * F[l] * F[l + 1] for l in range(L)]
+    return dict(flops_fwd=fwd, flops_bwd=bwd, flops=fwd + bwd, bytes=bytes_, per_layer_fwd=per_layer_fwd)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_burst=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# --------------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], threading.Event(), None
+
+    def _loop(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.1)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 7 for i in range(4) if s[3 + i].lower() == "active"})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# the model of the step
+# --------------------------------------------------------------------------------------------------------------
+def build_model(w, precision, device):
+    import torch
+    import torch.nn as nn
+    from openchem_b200.modules.encoders.gcn_encoder import GraphCNNEncoder
+
+    class Graph2LabelStep(nn.Module):
+        """Encoder -> MLP head, the shape of openchem/models/Graph2Label.py:21-37 with OpenChemMLP
+        (Linear -> BatchNorm1d -> ReLU -> Linear, example_configs/logp_gcnn_config.py:111-116)."""
+
+        def __init__(self):
+            super().__init__()
+            self.Encoder = GraphCNNEncoder({"input_size": w["f0"], "encoder_dim": w["encoder_dim"], "n_layers": len(w["hidden"]),
+                                            "hidden_size": list(w["hidden"]), "precision": precision}, True)
+            hs = w["mlp_hidden"]
+            self.MLP = nn.Sequential(nn.Linear(w["encoder_dim"], hs[0]), nn.BatchNorm1d(hs[0]), nn.ReLU(), nn.Linear(hs[0], hs[1]))
+            self.sigmoid_out = w["task"] == "multitask"
+
+        def forward(self, inp):
+            out = self.MLP(self.Encoder(inp))
+            return torch.sigmoid(out) if self.sigmoid_out else out
+
+    torch.manual_seed(0)
+    return Graph2LabelStep().to(device)
+
+
+def make_criterion(w):
+    import torch
+    import torch.nn.functional as F
+    if w["task"] != "multitask":
+        return torch.nn.MSELoss()
+
+    def masked_bce(inp, target):  # semantics of openchem/criterion/multitask_loss.py:40-49 (ignore_index = 9)
+        mask = (target != 9).to(inp.dtype)
+        loss = F.binary_cross_entropy(inp, mask * target, reduction="none") * mask
+        return (loss.sum(dim=0) / mask.sum(dim=0).clamp_min(1)).mean()
+
+    return masked_bce
+
+
+# --------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's CPU op sequence (oracle/torch_restatement.py) on host cores
+# --------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(w, steps, warmup, chunk=256, seed=1234):
+    """molecules/s of the reference's eager CPU path (fwd + loss + bwd + Adam) on a bounded sample: chunks of `chunk`
+    molecules of the same workload (the reference materialises (B,N,N,D) temporaries, ~8.6 GB each at B=4096)."""
+    import torch
+    from oracle import torch_restatement as tr
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = min(chunk, w["batch"])
+    g = make_graph_batch(B, w["n_max"], w["f0"], occupancy="full", seed=seed)
+    x, adj = torch.from_numpy(g["x"]), torch.from_numpy(g["adj"])
+    T = w["mlp_hidden"][-1]
+    y = torch.from_numpy(make_labels(B, T, "regression"))
+    p = tr.params_to_torch(random_params([w["f0"]] + list(w["hidden"]), w["encoder_dim"], seed=0))
+    H1 = w["mlp_hidden"][0]
+    hp = dict(W1=torch.randn(H1, w["encoder_dim"]) * 0.05, b1=torch.zeros(H1), g=torch.ones(H1), be=torch.zeros(H1),
+              rm=torch.zeros(H1), rv=torch.ones(H1), W2=torch.randn(T, H1) * 0.05, b2=torch.zeros(T))
+    leaves = [t for k in ("W", "b", "gamma", "beta") for t in p[k]] + [p["Wd"], p["bd"]]
+    for k in ("W1", "b1", "g", "be", "W2", "b2"):
+        hp[k].requires_grad_(True)
+        leaves.append(hp[k])
+    opt = torch.optim.Adam(leaves, lr=5e-4)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        out = tr.mlp_head(tr.encoder(x, adj, p, True), hp, True)
+        loss = torch.nn.functional.mse_loss(out, y)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return dict(value=B * len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores, chunk=B, steps=len(times))
+
+
+def run_reference_arm(args, w, wname):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_rate(w, args.steps, args.warmup)
+    sample = "%d steps of a %d-molecule chunk of %s (full occupancy), fwd+loss+bwd+Adam, torch CPU eager, %d threads" % (
+        r["steps"], r["chunk"], wname, r["cores"])
+    line = dict(impl="reference", metric=METRIC, value=r["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=wname, chunk=r["chunk"], n_max=w["n_max"], f0=w["f0"], hidden=w["hidden"], encoder_dim=w["encoder_dim"]),
+                cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=sample),
+                e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# native arm
+# --------------------------------------------------------------------------------------------------------------
+def run_native(args, w, wname):
+    import torch
+    import torch.distributed as dist
+    from openchem_b200 import _lib, functional
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group(backend="nccl", init_method="env://", device_id=dev)
+    _lib.load()
+
+    B = w["batch"]
+    g = make_graph_batch(B, w["n_max"], w["f0"], occupancy=args.occupancy, seed=1234 + rank)
+    T = w["mlp_hidden"][-1]
+    labels = make_labels(B, T, w["task"] if w["task"] == "multitask" else "regression", seed=4321 + rank)
+    hx, hadj, hy = (torch.from_numpy(a).pin_memory() for a in (g["x"], g["adj"], labels))
+    x, adj, y = hx.to(dev), hadj.to(dev), hy.to(dev)
+
+    model = build_model(w, args.precision, dev)
+    step_model = model
+    if world > 1:
+        step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], output_device=local)
+    crit = make_criterion(w)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, fused=True)
+
+    def step(xb, adjb, yb):
+        opt.zero_grad(set_to_none=True)
+        loss = crit(step_model((xb, adjb)), yb)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step(x, adj, y)
+    barrier()
+
+    # ---- device-resident timed region: exactly K steps, CUDA events, max over ranks ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    functional.launch_counter["n"] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(x, adj, y)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = functional.launch_counter["n"]
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end region: pinned host inputs copied every step, loss read back every step ----
+    h2d = hx.numel() * 4 + hadj.numel() * 4 + hy.numel() * 4
+    for _ in range(2):
+        float(step(hx.to(dev, non_blocking=True), hadj.to(dev, non_blocking=True), hy.to(dev, non_blocking=True)).item())
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(hx.to(dev, non_blocking=True), hadj.to(dev, non_blocking=True), hy.to(dev, non_blocking=True))
+        float(loss.item())
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- per-kernel timing (CUDA events around every launch, on the launching stream) ----
+    kern = {}
+    if rank == 0:
+        _lib.profile_enable(True)
+        for _ in range(args.profile_steps):
+            step(x, adj, y)
+        torch.cuda.synchronize()
+        kern = _lib.profile_collect()
+        _lib.profile_enable(False)
+    barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    work = algorithmic_work(w)
+    ms_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    tensor_peak = peaks["bf16_sustained"] * (0.5 if args.precision == "tf32" else 1.0)
+    t_roof_mol = max(work["bytes"] / (peaks["hbm_gbs"] * 1e9), work["flops"] / (tensor_peak * 1e12))
+    step_frac = (B * t_roof_mol) / (ms_step * 1e-3)
+
+    # dominant kernel: the one with the largest share of the profiled steps
+    roofline, shares = None, {}
+    tot_ms = sum(v[0] for v in kern.values()) or 1.0
+    for k, (ms, n) in sorted(kern.items(), key=lambda kv: -kv[1][0]):
+        shares[k] = dict(ms_per_step=ms / args.profile_steps, launches_per_step=n / args.profile_steps, share=ms / tot_ms)
+    if kern:
+        top = max(kern, key=lambda k: kern[k][0])
+        ms_launch = kern[top][0] / kern[top][1]
+        N, F = w["n_max"], [w["f0"]] + list(w["hidden"])
+        mid = F[1]
+        flops_launch = {
+            "fwd_mid": B * (2 * N * N * mid + 2 * N * mid * mid),
+            "fwd_first": B * (2 * N * N * F[0] + 2 * N * F[0] * F[1]),
+            "bwd_dz": B * (2 * N * mid * mid + 2 * N * N * mid),
+            "gemm_tn": B * (2 * N * mid * mid),
+            "fwd_readout": B * (2 * N * F[-1] * w["encoder_dim"]),
+            "bwd_readout": B * (2 * N * F[-1] * w["encoder_dim"]),
+        }.get(top)
+        if flops_launch is not None:
+            ach = flops_launch / (ms_launch * 1e-3) / 1e12
+            peak = peaks["bf16_burst"] * (0.5 if args.precision == "tf32" else 1.0)
+            roofline = dict(bound="tensor", kernel=top, achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
+                            ms_per_launch=ms_launch, peak_source=peaks["source"] + ", burst bf16" + (" /2 for tf32" if args.precision == "tf32" else ""),
+                            fp32_ffma_peak_tflops=74.5, frac_of_fp32_ffma_peak=(ach / 74.5) if args.precision == "fp32" else None)
+        else:  # a streaming kernel dominates: report its HBM traffic
+            by = B * N * mid * (4 + 4 + 1 + 4)
+            ach = by / (ms_launch * 1e-3) / 1e9
+            roofline = dict(bound="hbm", kernel=top, achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"], traffic=None,
+                            ms_per_launch=ms_launch, peak_source=peaks["source"])
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_reference_rate(w, steps=args.cpu_steps, warmup=1)
+        cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port",
+                   sample="%d steps of a %d-molecule chunk of %s, fwd+loss+bwd+Adam, reference op sequence on torch CPU (%d threads)" % (
+                       r["steps"], r["chunk"], wname, r["cores"]))
+
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype={"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision],
+                data="synthetic",
+                config=dict(workload=wname, per_gpu_batch=B, global_batch=B * world, n_max=w["n_max"], f0=w["f0"], hidden=w["hidden"],
+                            encoder_dim=w["encoder_dim"], occupancy=args.occupancy, precision=args.precision, parallelism="dp%d" % world,
+                            optimizer="Adam(fused)", l2_policy="inputs+saved state per step (>1 GB at c3) exceed the 126 MB L2; no explicit flush"),
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
+                gpu_launches=launches, clocks=clocks, roofline=roofline,
+                step_roofline=dict(frac=step_frac, t_roof_us=B * t_roof_mol * 1e6, flops_per_molecule=work["flops"],
+                                   bytes_per_molecule=work["bytes"], tensor_peak_tflops=tensor_peak, hbm_gbs=peaks["hbm_gbs"],
+                                   peak_source=peaks["source"] + ", sustained bf16"),
+                kernels=shares, cpu_baseline=cpu)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--occupancy", default="full", choices=["full", "molecular"])
+    ap.add_argument("--profile-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    # N=1 headline: C3 (batch 4096 on one B200). N>1: C4 = the same model at per-GPU batch 2048 (weak scaling).
+    wname = args.workload or ("c3_synth" if max(world, args.gpus) == 1 else "c4_ddp")
+    w = WORKLOADS[wname]
+    if args.impl == "reference":
+        run_reference_arm(args, w, wname)
+    else:
+        run_native(args, w, wname)
+
+
+if __name__ == "__main__":
+    main()

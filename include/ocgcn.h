@@ -111,6 +111,15 @@ int ocgcn_layer_backward(const ocgcn_desc* desc, const float* grad_y, const floa
                          const ocgcn_params* params, const ocgcn_grads* grads, float* grad_x, void* saved,
                          void* scratch, void* stream);
 
+/* Opt-in, process-wide per-kernel timing (used by bench.py's roofline leg, never by training):
+ * while enabled every kernel launch is bracketed by CUDA events recorded on the launching stream.
+ * ocgcn_profile_collect synchronises those events, sums milliseconds and launch counts per kernel kind
+ * (ocgcn_profile_kinds() kinds, names via ocgcn_profile_kind_name) and clears the record. */
+int ocgcn_profile_enable(int on);
+int ocgcn_profile_kinds(void);
+const char* ocgcn_profile_kind_name(int kind);
+int ocgcn_profile_collect(float* ms_by_kind, int* launches_by_kind, int n_kinds);
+
 /* Number of kernel launches the last call on this host thread enqueued (bench.py's gpu_launches claim). */
 int ocgcn_last_launch_count(void);
 /* cudaError_t of the last failing CUDA call on this host thread (0 if none). */

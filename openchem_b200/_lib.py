@@ -54,7 +54,7 @@ class Grads(ctypes.Structure):
 EXPORTS = [
     "ocgcn_query_workspace", "ocgcn_encoder_forward", "ocgcn_encoder_backward", "ocgcn_layer_forward",
     "ocgcn_layer_backward", "ocgcn_last_launch_count", "ocgcn_last_cuda_error", "ocgcn_status_string",
-    "ocgcn_abi_version",
+    "ocgcn_abi_version", "ocgcn_profile_enable", "ocgcn_profile_kinds", "ocgcn_profile_kind_name", "ocgcn_profile_collect",
 ]
 
 
@@ -115,6 +115,10 @@ def load():
         lib.ocgcn_encoder_backward.argtypes = [ctypes.POINTER(Desc), vp, vp, vp, ctypes.POINTER(Params), ctypes.POINTER(Grads), vp, vp, vp]
         lib.ocgcn_layer_forward.argtypes = [ctypes.POINTER(Desc), vp, vp, ctypes.POINTER(Params), vp, vp, vp, vp]
         lib.ocgcn_layer_backward.argtypes = [ctypes.POINTER(Desc), vp, vp, vp, ctypes.POINTER(Params), ctypes.POINTER(Grads), vp, vp, vp, vp]
+        lib.ocgcn_profile_kind_name.restype = ctypes.c_char_p
+        lib.ocgcn_profile_kind_name.argtypes = [ctypes.c_int]
+        lib.ocgcn_profile_enable.argtypes = [ctypes.c_int]
+        lib.ocgcn_profile_collect.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int), ctypes.c_int]
         lib.ocgcn_status_string.restype = ctypes.c_char_p
         lib.ocgcn_status_string.argtypes = [ctypes.c_int]
         for name in ("ocgcn_query_workspace", "ocgcn_encoder_forward", "ocgcn_encoder_backward", "ocgcn_layer_forward",
@@ -133,3 +137,17 @@ def check(status):
         if status == 5:
             msg += " [cudaError %d]" % lib.ocgcn_last_cuda_error()
         raise RuntimeError(msg)
+
+
+def profile_enable(on):
+    load().ocgcn_profile_enable(int(bool(on)))
+
+
+def profile_collect():
+    """-> {kind_name: (total_ms, launches)} for the launches recorded since the last collect (synchronises)."""
+    lib = load()
+    n = lib.ocgcn_profile_kinds()
+    ms = (ctypes.c_float * n)()
+    cnt = (ctypes.c_int * n)()
+    check(lib.ocgcn_profile_collect(ms, cnt, n))
+    return {lib.ocgcn_profile_kind_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}

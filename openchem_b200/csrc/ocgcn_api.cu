@@ -4,6 +4,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "ocgcn_aux.cuh"
 #include "ocgcn_common.cuh"
 #include "ocgcn_tile.cuh"
@@ -12,6 +16,32 @@ namespace ocgcn {
 
 static thread_local int tl_launches = 0;
 static thread_local int tl_cuda_err = 0;
+
+// ---- opt-in per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream ----------
+enum KernelKind : int {
+  KK_ADJ_PACK = 0, KK_TRANSPOSE, KK_FWD_FIRST, KK_FWD_MID, KK_BN_FINALIZE, KK_FWD_READOUT, KK_BWD_READOUT, KK_BWD_DY,
+  KK_BWD_FINALIZE, KK_BWD_DZ, KK_GEMM_TN, KK_REDUCE, KK_BN_APPLY, KK_COUNT
+};
+static const char* const kKindNames[KK_COUNT] = {"adj_pack", "transpose", "fwd_first", "fwd_mid", "bn_finalize", "fwd_readout",
+                                                 "bwd_readout", "bwd_dy", "bwd_finalize", "bwd_dz", "gemm_tn", "reduce", "bn_apply"};
+struct ProfRec { int kind; cudaEvent_t e0, e1; };
+// process-wide (autograd runs backward on its own thread), guarded by a mutex; off by default
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+struct ProfScope {
+  cudaStream_t st; cudaEvent_t e1; bool on;
+  ProfScope(int kind, cudaStream_t s) : st(s), e1(nullptr), on(false) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfRec r; r.kind = kind;
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, st);
+    e1 = r.e1; on = true;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(r);
+  }
+  ~ProfScope() { if (on) cudaEventRecord(e1, st); }
+};
 
 #define CU_TRY(expr)                                   \
   do {                                                 \
@@ -156,6 +186,7 @@ static int check_device_ptr(const void* p) {
 template <int TR, int PROD, int EPI>
 static int launch_tile_t(const TileArgs& a, int tiles, cudaStream_t st) {
   constexpr int TC = tile_cols<TR>();
+  ProfScope prof(PROD == P_X ? KK_FWD_FIRST : PROD == P_MID ? KK_FWD_MID : PROD == P_RO ? KK_FWD_READOUT : PROD == P_DZ ? KK_BWD_DZ : KK_BWD_READOUT, st);
   auto kern = tile_kernel<TR, TC, PROD, EPI>;
   const size_t smem = tile_smem_bytes<TR, TC>(a.NW);
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -170,6 +201,7 @@ static int launch_tile(const Layout& lo, const TileArgs& a, cudaStream_t st) {
 }
 
 static int launch_bwd_dy(const Layout& lo, const BwdDyArgs& a, cudaStream_t st) {
+  ProfScope prof(KK_BWD_DY, st);
   if (lo.TR == 128) {
     const size_t smem = bwd_dy_smem_bytes<128>(a.NW);
     CU_TRY(cudaFuncSetAttribute(bwd_dy_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -195,6 +227,7 @@ static TileArgs base_tile_args(const ocgcn_desc* d, const Layout& lo, const floa
 }
 
 static int run_adj_pack(const ocgcn_desc* d, const Layout& lo, const float* adj, char* saved, cudaStream_t st) {
+  ProfScope prof(KK_ADJ_PACK, st);
   adj_pack_kernel<<<d->B, kThreads, (size_t)d->N * lo.NW * 8, st>>>(
       adj, d->adj_stride[0], d->adj_stride[1], d->adj_stride[2], d->N, lo.NW, reinterpret_cast<u64*>(saved + lo.rowmask),
       reinterpret_cast<u64*>(saved + lo.colmask), reinterpret_cast<unsigned*>(saved + lo.molflag));
@@ -204,6 +237,7 @@ static int run_adj_pack(const ocgcn_desc* d, const Layout& lo, const float* adj,
 
 static int run_bn_finalize(const ocgcn_desc* d, const Layout& lo, const ocgcn_params* p, int l, char* saved, char* scratch,
                            cudaStream_t st) {
+  ProfScope prof(KK_BN_FINALIZE, st);
   BnFinalizeArgs f;
   const int F = d->F[l + 1];
   float* stats = reinterpret_cast<float*>(saved + lo.stats[l]);
@@ -220,6 +254,7 @@ static int run_bn_finalize(const ocgcn_desc* d, const Layout& lo, const ocgcn_pa
 }
 
 static int run_gemm_tn(const float* A, const float* Bm, size_t R, int M, int Nn, float* partial, cudaStream_t st, int* splits_out) {
+  ProfScope prof(KK_GEMM_TN, st);
   int splits, rps;
   gemm_tn_config(R, M, Nn, &splits, &rps);
   dim3 grid(splits, ((M + 127) / 128) * ((Nn + 127) / 128));
@@ -230,6 +265,7 @@ static int run_gemm_tn(const float* A, const float* Bm, size_t R, int M, int Nn,
 }
 
 static int run_reduce(const float* p0, float* o0, int P0, int c0, const float* p1, float* o1, int P1, int c1, cudaStream_t st) {
+  ProfScope prof(KK_REDUCE, st);
   ReduceJobs j;
   j.partial[0] = p0; j.out[0] = o0; j.P[0] = P0; j.count[0] = c0;
   j.partial[1] = p1; j.out[1] = o1; j.P[1] = P1; j.count[1] = c1;
@@ -302,8 +338,11 @@ static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float
   f.gamma = p->gamma[l]; f.invstd = stats + Fout;
   f.dgamma = g->dgamma[l]; f.dbeta = g->dbeta[l];
   f.g = coef; f.c1 = coef + lo.Fmax; f.c2 = coef + 2 * lo.Fmax;
-  bwd_finalize_kernel<<<(Fout + 31) / 32, kThreads, 0, st>>>(f);
-  LAUNCH_CHECK();
+  {
+    ProfScope prof(KK_BWD_FINALIZE, st);
+    bwd_finalize_kernel<<<(Fout + 31) / 32, kThreads, 0, st>>>(f);
+    LAUNCH_CHECK();
+  }
 
   TileArgs a = base_tile_args(d, lo, adj, saved);
   a.K = Fout; a.NC = Fin;
@@ -325,6 +364,7 @@ static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float
 
 static int run_transposes(const TransposeJobs& jobs, int n, cudaStream_t st) {
   if (n == 0) return OCGCN_OK;
+  ProfScope prof(KK_TRANSPOSE, st);
   dim3 grid(32, n);
   transpose_kernel<<<grid, 256, 0, st>>>(jobs);
   LAUNCH_CHECK();
@@ -338,6 +378,29 @@ using namespace ocgcn;
 extern "C" {
 
 int ocgcn_abi_version(void) { return 1; }
+
+int ocgcn_profile_enable(int on) {
+  g_prof_on.store(on != 0);
+  return OCGCN_OK;
+}
+int ocgcn_profile_kinds(void) { return KK_COUNT; }
+const char* ocgcn_profile_kind_name(int kind) { return (kind >= 0 && kind < KK_COUNT) ? kKindNames[kind] : "?"; }
+int ocgcn_profile_collect(float* ms_by_kind, int* launches_by_kind, int n_kinds) {
+  if (!ms_by_kind || !launches_by_kind || n_kinds < KK_COUNT) return OCGCN_EINVAL;
+  for (int i = 0; i < n_kinds; ++i) { ms_by_kind[i] = 0.f; launches_by_kind[i] = 0; }
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    CU_TRY(cudaEventSynchronize(r.e1));
+    CU_TRY(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    ms_by_kind[r.kind] += ms;
+    launches_by_kind[r.kind] += 1;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  return OCGCN_OK;
+}
 int ocgcn_last_launch_count(void) { return tl_launches; }
 int ocgcn_last_cuda_error(void) { return tl_cuda_err; }
 
@@ -483,8 +546,11 @@ int ocgcn_layer_forward(const ocgcn_desc* d, const float* x, const float* adj, c
   const size_t total = lo.rows * F;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  bn_apply_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(saved + lo.Z[0]), stats + 2 * F, stats + 3 * F, y, total, F);
-  LAUNCH_CHECK();
+  {
+    ProfScope prof(KK_BN_APPLY, st);
+    bn_apply_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(saved + lo.Z[0]), stats + 2 * F, stats + 3 * F, y, total, F);
+    LAUNCH_CHECK();
+  }
   return OCGCN_OK;
 }
 

@@ -92,6 +92,26 @@ def make_labels(batch, n_tasks=1, kind="regression", seed=4321, missing=0.15):
     return y
 
 
+def random_params(widths, encoder_dim, seed):
+    """Reference-style initialisation (U(+-1/sqrt(F_out)), gcn.py:27-31; nn.Linear-like dense) as numpy arrays, with the
+    BatchNorm affine parameters and running statistics randomised so parity tests exercise them."""
+    rng = np.random.RandomState(seed)
+    p = dict(W=[], b=[], gamma=[], beta=[], running_mean=[], running_var=[])
+    for l in range(len(widths) - 1):
+        fin, fout = widths[l], widths[l + 1]
+        s = 1.0 / np.sqrt(fout)
+        p["W"].append(rng.uniform(-s, s, size=(fin, fout)).astype(np.float32))
+        p["b"].append(rng.uniform(-s, s, size=(fout,)).astype(np.float32))
+        p["gamma"].append(rng.uniform(0.5, 1.5, size=(fout,)).astype(np.float32))
+        p["beta"].append(rng.uniform(-0.3, 0.3, size=(fout,)).astype(np.float32))
+        p["running_mean"].append(rng.uniform(-0.2, 0.2, size=(fout,)).astype(np.float32))
+        p["running_var"].append(rng.uniform(0.5, 1.5, size=(fout,)).astype(np.float32))
+    s = 1.0 / np.sqrt(widths[-1])
+    p["Wd"] = rng.uniform(-s, s, size=(encoder_dim, widths[-1])).astype(np.float32)
+    p["bd"] = rng.uniform(-s, s, size=(encoder_dim,)).astype(np.float32)
+    return p
+
+
 # Named workloads of BASELINE.json `configs` (SURVEY.md section 8): per-GPU batch, N, F0, hidden, E, tasks
 WORKLOADS = {
     "c1_logp":  dict(batch=256, n_max=85, f0=33, hidden=[128] * 5, encoder_dim=128, mlp_hidden=[128, 1], task="regression"),

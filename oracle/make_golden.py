@@ -211,6 +211,21 @@ def make_layer_case(name, c, seed):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **blob)
 
 
+def make_init_fixture():
+    """Initial weights of the reference encoder under a fixed seed: our module must consume the RNG identically
+    (dense first, then the layers; gcn_encoder.py:23-25, gcn.py:27-31) so --random_seed reproduces the same model."""
+    cfg = {"input_size": 33, "encoder_dim": 24, "n_layers": 3, "hidden_size": [16, 40, 8]}
+    torch.manual_seed(7)
+    enc = GraphCNNEncoder(cfg, False)
+    blob = {k: v.numpy().copy() for k, v in enc.state_dict().items()}
+    blob["after_rand"] = torch.rand(4).numpy()          # RNG position after construction
+    np.savez_compressed(os.path.join(OUT, "init_seed7.npz"), **blob)
+    torch.manual_seed(9)
+    gc = GraphConvolution(12, 20, bias=False)
+    np.savez_compressed(os.path.join(OUT, "init_layer_seed9.npz"), weight=gc.weight.detach().numpy().copy(), after_rand=torch.rand(4).numpy())
+    print("init fixtures written")
+
+
 def check_tie_rule():
     """The reference's CPU max keeps the first index on exact ties; the oracle must as well."""
     T = np.zeros((1, 3, 2), dtype=np.float64)
@@ -231,6 +246,7 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(4)
     check_tie_rule()
+    make_init_fixture()
     for i, (name, c) in enumerate(ENCODER_CASES.items()):
         make_encoder_case(name, c, seed=100 + i)
     for i, (name, c) in enumerate(LAYER_CASES.items()):

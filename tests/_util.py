@@ -53,20 +53,4 @@ def build_encoder(cfg, params, device, precision="fp32"):
     return enc.to(device)
 
 
-def random_params(widths, E, seed):
-    """Reference-style initialisation (gcn.py:27-31, nn.Linear default) + randomised BN affine/running stats."""
-    rng = np.random.RandomState(seed)
-    p = dict(W=[], b=[], gamma=[], beta=[], running_mean=[], running_var=[])
-    for l in range(len(widths) - 1):
-        fin, fout = widths[l], widths[l + 1]
-        s = 1.0 / np.sqrt(fout)
-        p["W"].append(rng.uniform(-s, s, size=(fin, fout)).astype(np.float32))
-        p["b"].append(rng.uniform(-s, s, size=(fout,)).astype(np.float32))
-        p["gamma"].append(rng.uniform(0.5, 1.5, size=(fout,)).astype(np.float32))
-        p["beta"].append(rng.uniform(-0.3, 0.3, size=(fout,)).astype(np.float32))
-        p["running_mean"].append(rng.uniform(-0.2, 0.2, size=(fout,)).astype(np.float32))
-        p["running_var"].append(rng.uniform(0.5, 1.5, size=(fout,)).astype(np.float32))
-    s = 1.0 / np.sqrt(widths[-1])
-    p["Wd"] = rng.uniform(-s, s, size=(E, widths[-1])).astype(np.float32)
-    p["bd"] = rng.uniform(-s, s, size=(E,)).astype(np.float32)
-    return p
+from openchem_b200.synthetic import random_params  # noqa: E402,F401

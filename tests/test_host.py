@@ -1,0 +1,166 @@
+"""Host-side logic without a GPU: the C-ABI library loads and exports what include/ocgcn.h declares, the
+nn.Module surface mirrors the reference (names, state_dict, RNG consumption, config validation, errors)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from _util import ROOT, load_golden
+
+torch = pytest.importorskip("torch")
+
+
+def test_library_exports_every_declared_symbol():
+    from openchem_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "ocgcn.h")).read()
+    declared = set(re.findall(r"\b(ocgcn_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ocgcn_abi_version() == 1
+    assert lib.ocgcn_status_string(0) == b"ok"
+    assert b"unsupported" in lib.ocgcn_status_string(2)
+
+
+def _desc(B=8, N=20, widths=(33, 16, 8), E=12):
+    from openchem_b200 import _lib
+    d = _lib.Desc()
+    d.B, d.N, d.L, d.E = B, N, len(widths) - 1, E
+    for i, f in enumerate(widths):
+        d.F[i] = f
+    d.training, d.has_bias, d.eps, d.momentum = 1, 1, 1e-5, 0.1
+    return d
+
+
+def test_query_workspace_and_error_codes_on_host():
+    from openchem_b200 import _lib
+    lib = _lib.load()
+    sb, cb = ctypes.c_size_t(), ctypes.c_size_t()
+    assert lib.ocgcn_query_workspace(ctypes.byref(_desc()), ctypes.byref(sb), ctypes.byref(cb)) == 0
+    assert sb.value % 256 == 0 and cb.value % 256 == 0
+    rows = 8 * 20
+    assert sb.value >= rows * (16 + 8) * 4 + rows * (16 + 8)            # Z_l fp32 + u8 arg-max per layer
+    s2 = ctypes.c_size_t()
+    assert lib.ocgcn_query_workspace(ctypes.byref(_desc(B=16)), ctypes.byref(s2), ctypes.byref(cb)) == 0
+    assert s2.value > sb.value
+    assert lib.ocgcn_query_workspace(ctypes.byref(_desc(N=300)), ctypes.byref(sb), ctypes.byref(cb)) == 2   # N > 256 unsupported
+    assert lib.ocgcn_query_workspace(ctypes.byref(_desc(B=0)), ctypes.byref(sb), ctypes.byref(cb)) == 1
+    assert lib.ocgcn_query_workspace(ctypes.byref(_desc(widths=(33, 0, 8))), ctypes.byref(sb), ctypes.byref(cb)) == 1
+    d = _desc()
+    d.mode = 7
+    assert lib.ocgcn_query_workspace(ctypes.byref(d), ctypes.byref(sb), ctypes.byref(cb)) == 1
+    assert lib.ocgcn_query_workspace(None, ctypes.byref(sb), ctypes.byref(cb)) == 1
+    # layer-only layout (E == 0, L == 1)
+    assert lib.ocgcn_query_workspace(ctypes.byref(_desc(widths=(12, 10), E=0)), ctypes.byref(sb), ctypes.byref(cb)) == 0
+
+
+def test_encoder_surface_matches_reference_contract():
+    from openchem_b200.modules.encoders.gcn_encoder import GraphCNNEncoder
+    from openchem_b200.modules.encoders.openchem_encoder import OpenChemEncoder
+    cfg = {"input_size": 12, "encoder_dim": 10, "hidden_size": [10, 10, 10], "n_layers": 3}   # module_instantiation_test.py:36-43
+    enc = GraphCNNEncoder(cfg, use_cuda=True)
+    assert isinstance(enc, OpenChemEncoder)
+    assert enc.n_layers == 3 and enc.hidden_size == [12, 10, 10, 10] and enc.dropout == 0
+    assert enc.input_size == 12 and enc.encoder_dim == 10 and enc.params is cfg and enc.use_cuda is True
+    assert isinstance(enc.dropout_layer, torch.nn.Dropout) and isinstance(enc.dense, torch.nn.Linear)
+    assert GraphCNNEncoder.get_required_params() == {"n_layers": int, "hidden_size": list}
+    assert "dropout" in GraphCNNEncoder.get_optional_params()
+    sd = enc.state_dict()
+    expect = {}
+    widths = [12, 10, 10, 10]
+    for l in range(3):
+        expect[f"graph_convolutions.{l}.weight"] = (widths[l], widths[l + 1])
+        for k in ("bias", "bn.weight", "bn.bias", "bn.running_mean", "bn.running_var"):
+            expect[f"graph_convolutions.{l}.{k}"] = (widths[l + 1],)
+        expect[f"graph_convolutions.{l}.bn.num_batches_tracked"] = ()
+    expect["dense.weight"], expect["dense.bias"] = (10, 10), (10,)
+    assert {k: tuple(v.shape) for k, v in sd.items()} == expect
+    assert sd["graph_convolutions.0.bn.num_batches_tracked"].dtype == torch.int64
+    assert repr(enc.graph_convolutions[0]).startswith("GraphConvolution (12 -> 10)")
+    for p in enc.parameters():
+        assert p.is_leaf and p.requires_grad
+
+
+def test_config_validation_like_reference():
+    from openchem_b200.modules.encoders.gcn_encoder import GraphCNNEncoder
+    with pytest.raises(ValueError, match="n_layers parameter has to be specified"):
+        GraphCNNEncoder({"input_size": 12, "encoder_dim": 10, "hidden_size": [10]}, False)
+    with pytest.raises(ValueError, match="has to be of type"):
+        GraphCNNEncoder({"input_size": 12, "encoder_dim": 10, "hidden_size": (10,), "n_layers": 1}, False)
+    # like the reference, the base-class check resolves get_required_params() on the subclass
+    # (openchem_encoder.py:11), so a missing input_size surfaces as the KeyError of openchem_encoder.py:16
+    with pytest.raises(KeyError):
+        GraphCNNEncoder({"encoder_dim": 10, "hidden_size": [10], "n_layers": 1}, False)
+    with pytest.raises(AssertionError):
+        GraphCNNEncoder({"input_size": 12, "encoder_dim": 10, "hidden_size": [10, 10], "n_layers": 1}, False)
+    with pytest.raises(ValueError, match="has to be one of"):
+        GraphCNNEncoder({"input_size": 12, "encoder_dim": 10, "hidden_size": [10], "n_layers": 1, "precision": "fp8"}, False)
+    GraphCNNEncoder({"input_size": 12, "encoder_dim": 10, "hidden_size": [10], "n_layers": 1, "unknown_key": 3}, False)  # tolerated
+
+
+def test_initialisation_consumes_rng_like_reference():
+    from openchem_b200.layers.gcn import GraphConvolution
+    from openchem_b200.modules.encoders.gcn_encoder import GraphCNNEncoder
+    g = load_golden("init_seed7")
+    torch.manual_seed(7)
+    enc = GraphCNNEncoder({"input_size": 33, "encoder_dim": 24, "n_layers": 3, "hidden_size": [16, 40, 8]}, False)
+    after = torch.rand(4).numpy()
+    for k, v in enc.state_dict().items():
+        assert np.array_equal(v.numpy(), g[k]), k
+    assert np.array_equal(after, g["after_rand"])
+    g = load_golden("init_layer_seed9")
+    torch.manual_seed(9)
+    gc = GraphConvolution(12, 20, bias=False)
+    assert gc.bias is None and np.array_equal(gc.weight.detach().numpy(), g["weight"])
+    assert np.array_equal(torch.rand(4).numpy(), g["after_rand"])
+
+
+def test_reference_checkpoint_keys_load_with_module_prefix():
+    """run.py:240-243 loads DataParallel/DDP checkpoints ('module.' prefix) with load_state_dict."""
+    from openchem_b200.modules.encoders.gcn_encoder import GraphCNNEncoder
+    g = load_golden("init_seed7")
+    enc = GraphCNNEncoder({"input_size": 33, "encoder_dim": 24, "n_layers": 3, "hidden_size": [16, 40, 8]}, False)
+    wrapped = torch.nn.Module()
+    wrapped.module = torch.nn.Module()
+    wrapped.module.Encoder = enc
+    sd = {"module.Encoder." + k: torch.from_numpy(np.asarray(v)) for k, v in g.items() if k != "after_rand"}
+    wrapped.load_state_dict(sd, strict=True)
+    assert np.array_equal(enc.dense.weight.detach().numpy(), g["dense.weight"])
+
+
+def test_cpu_tensors_raise_no_fallback():
+    from openchem_b200.layers.gcn import GraphConvolution
+    from openchem_b200.modules.encoders.gcn_encoder import GraphCNNEncoder
+    enc = GraphCNNEncoder({"input_size": 12, "encoder_dim": 10, "hidden_size": [10], "n_layers": 1}, False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        enc((torch.zeros(2, 5, 12), torch.zeros(2, 5, 5)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        GraphConvolution(12, 4)(torch.zeros(2, 5, 12), torch.zeros(2, 5, 5))
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "openchem_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_namespace_shadow_resolves_to_this_package():
+    import importlib
+    import sys
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "openchem" or k.startswith("openchem.")}
+    try:
+        sys.path.insert(0, ROOT)
+        m = importlib.import_module("openchem.layers.gcn")
+        e = importlib.import_module("openchem.modules.encoders.gcn_encoder")
+        assert m.GraphConvolution.__module__ == "openchem_b200.layers.gcn"
+        assert e.GraphCNNEncoder.__module__ == "openchem_b200.modules.encoders.gcn_encoder"
+    finally:
+        sys.path.remove(ROOT)
+        for k in [k for k in sys.modules if k == "openchem" or k.startswith("openchem.")]:
+            sys.modules.pop(k)
+        sys.modules.update(saved)
