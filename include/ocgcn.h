@@ -93,6 +93,18 @@ typedef struct ocgcn_grads {
  * Valid for both encoder_* (desc->L layers + readout) and layer_* (desc->L == 1) calls. 256-byte aligned. */
 int ocgcn_query_workspace(const ocgcn_desc* desc, size_t* saved_bytes, size_t* scratch_bytes);
 
+/* Where a tensor lives inside the `saved` buffer (for tests / debugging; the layout is otherwise private):
+ * Z = pre-BatchNorm activations (B*N, F[layer+1]) fp32; ARGMAX = pool arg-max j* (B*N, F[layer+1]) u8;
+ * S = adj@H_{layer} (B*N, F[layer]) fp32; STATS = mean, invstd, scale, shift (4, F[layer+1]) fp32;
+ * ROWMASK = adjacency bit rows (B*N, ceil(N/64)) u64; MOLFLAG = per-molecule "adjacency is exactly 0/1" (B) u32. */
+#define OCGCN_SAVED_Z 0
+#define OCGCN_SAVED_ARGMAX 1
+#define OCGCN_SAVED_S 2
+#define OCGCN_SAVED_STATS 3
+#define OCGCN_SAVED_ROWMASK 4
+#define OCGCN_SAVED_MOLFLAG 5
+int ocgcn_saved_tensor(const ocgcn_desc* desc, int what, int layer, size_t* offset, size_t* bytes);
+
 /* out (B,E) contiguous fp32. x (B,N,F[0]) and adj (B,N,N) fp32 with the strides in desc. */
 int ocgcn_encoder_forward(const ocgcn_desc* desc, const float* x, const float* adj, const ocgcn_params* params,
                           void* saved, void* scratch, float* out, void* stream);

@@ -55,6 +55,7 @@ EXPORTS = [
     "ocgcn_query_workspace", "ocgcn_encoder_forward", "ocgcn_encoder_backward", "ocgcn_layer_forward",
     "ocgcn_layer_backward", "ocgcn_last_launch_count", "ocgcn_last_cuda_error", "ocgcn_status_string",
     "ocgcn_abi_version", "ocgcn_profile_enable", "ocgcn_profile_kinds", "ocgcn_profile_kind_name", "ocgcn_profile_collect",
+    "ocgcn_saved_tensor",
 ]
 
 
@@ -115,6 +116,8 @@ def load():
         lib.ocgcn_encoder_backward.argtypes = [ctypes.POINTER(Desc), vp, vp, vp, ctypes.POINTER(Params), ctypes.POINTER(Grads), vp, vp, vp]
         lib.ocgcn_layer_forward.argtypes = [ctypes.POINTER(Desc), vp, vp, ctypes.POINTER(Params), vp, vp, vp, vp]
         lib.ocgcn_layer_backward.argtypes = [ctypes.POINTER(Desc), vp, vp, vp, ctypes.POINTER(Params), ctypes.POINTER(Grads), vp, vp, vp, vp]
+        lib.ocgcn_saved_tensor.argtypes = [ctypes.POINTER(Desc), ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]
+        lib.ocgcn_saved_tensor.restype = ctypes.c_int
         lib.ocgcn_profile_kind_name.restype = ctypes.c_char_p
         lib.ocgcn_profile_kind_name.argtypes = [ctypes.c_int]
         lib.ocgcn_profile_enable.argtypes = [ctypes.c_int]

@@ -248,7 +248,7 @@ static int run_bn_finalize(const ocgcn_desc* d, const Layout& lo, const ocgcn_pa
   f.running_mean = p->running_mean[l]; f.running_var = p->running_var[l];
   f.nbt = reinterpret_cast<long long*>(p->num_batches_tracked[l]);
   f.mean = stats; f.invstd = stats + F; f.scale = stats + 2 * F; f.shift = stats + 3 * F;
-  bn_finalize_kernel<<<(F + 31) / 32, kThreads, 0, st>>>(f);
+  bn_finalize_kernel<<<(F + 31) / 32, 1024, 0, st>>>(f);
   LAUNCH_CHECK();
   return OCGCN_OK;
 }
@@ -270,8 +270,8 @@ static int run_reduce(const float* p0, float* o0, int P0, int c0, const float* p
   j.partial[0] = p0; j.out[0] = o0; j.P[0] = P0; j.count[0] = c0;
   j.partial[1] = p1; j.out[1] = o1; j.P[1] = P1; j.count[1] = c1;
   const int mx = c0 > c1 ? c0 : c1;
-  dim3 grid((mx + 255) / 256, 2);
-  reduce_partials_kernel<<<grid, 256, 0, st>>>(j);
+  dim3 grid((mx + 31) / 32, 2);
+  reduce_partials_kernel<<<grid, 1024, 0, st>>>(j);
   LAUNCH_CHECK();
   return OCGCN_OK;
 }
@@ -340,7 +340,7 @@ static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float
   f.g = coef; f.c1 = coef + lo.Fmax; f.c2 = coef + 2 * lo.Fmax;
   {
     ProfScope prof(KK_BWD_FINALIZE, st);
-    bwd_finalize_kernel<<<(Fout + 31) / 32, kThreads, 0, st>>>(f);
+    bwd_finalize_kernel<<<(Fout + 31) / 32, 1024, 0, st>>>(f);
     LAUNCH_CHECK();
   }
 
@@ -414,6 +414,24 @@ const char* ocgcn_status_string(int s) {
     case OCGCN_ECUDA: return "ocgcn: CUDA error (see ocgcn_last_cuda_error)";
     default: return "ocgcn: unknown status";
   }
+}
+
+int ocgcn_saved_tensor(const ocgcn_desc* desc, int what, int layer, size_t* offset, size_t* bytes) {
+  Layout lo;
+  const bool layer_only = desc && desc->E <= 0;
+  ST_TRY(make_layout(desc, layer_only, &lo));
+  if (!offset || !bytes || layer < 0 || layer >= desc->L) return OCGCN_EINVAL;
+  const size_t rows = lo.rows;
+  switch (what) {
+    case OCGCN_SAVED_Z: *offset = lo.Z[layer]; *bytes = rows * desc->F[layer + 1] * 4; break;
+    case OCGCN_SAVED_ARGMAX: if (layer_only) return OCGCN_EINVAL; *offset = lo.arg[layer]; *bytes = rows * desc->F[layer + 1]; break;
+    case OCGCN_SAVED_S: *offset = lo.S[layer]; *bytes = rows * desc->F[layer] * 4; break;
+    case OCGCN_SAVED_STATS: *offset = lo.stats[layer]; *bytes = (size_t)4 * desc->F[layer + 1] * 4; break;
+    case OCGCN_SAVED_ROWMASK: *offset = lo.rowmask; *bytes = rows * lo.NW * 8; break;
+    case OCGCN_SAVED_MOLFLAG: *offset = lo.molflag; *bytes = (size_t)desc->B * 4; break;
+    default: return OCGCN_EINVAL;
+  }
+  return OCGCN_OK;
 }
 
 int ocgcn_query_workspace(const ocgcn_desc* desc, size_t* saved_bytes, size_t* scratch_bytes) {

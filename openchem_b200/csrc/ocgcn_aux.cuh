@@ -87,45 +87,54 @@ struct BnFinalizeArgs {
   float* scale;
   float* shift;
 };
-__global__ void __launch_bounds__(kThreads) bn_finalize_kernel(const BnFinalizeArgs a) {
-  __shared__ double sred[kWarps][32];
-  __shared__ double smean[32];
+constexpr int kFinWarps = 32;  // finalize / reduce kernels run 1024 threads: 32 slices x 32 channels
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const BnFinalizeArgs a) {
+  __shared__ double s_n[kFinWarps][32], s_mean[kFinWarps][32], s_m2[kFinWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   const bool valid = c < a.F;
   const double n = (double)a.B * (double)a.N;
   double mean = 0.0, var = 1.0;
   if (a.training) {
-    double s = 0.0;
-    if (valid)
-      for (int t = warp; t < a.T; t += kWarps) {
-        const double nt = (double)(min(a.MT, a.B - t * a.MT) * a.N);
-        s += nt * (double)a.partials[((size_t)t * 2 + 0) * a.F + c];
+    // Chan et al. pairwise merge of (count, mean, M2): each warp folds its slice of tiles in ascending order,
+    // then warp 0 folds the 32 slice results in ascending order -> bit-reproducible, robust to |mean| >> std
+    double cn = 0.0, cm = 0.0, cm2 = 0.0;
+    if (valid) {
+      for (int t0 = warp; t0 < a.T; t0 += kFinWarps * 4) {
+        float pm[4], pv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = t0 + u * kFinWarps;
+          pm[u] = (t < a.T) ? a.partials[((size_t)t * 2 + 0) * a.F + c] : 0.f;
+          pv[u] = (t < a.T) ? a.partials[((size_t)t * 2 + 1) * a.F + c] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = t0 + u * kFinWarps;
+          if (t >= a.T) break;
+          const double nt = (double)(min(a.MT, a.B - t * a.MT) * a.N);
+          const double tot = cn + nt, d = (double)pm[u] - cm;
+          cm += d * (nt / tot);
+          cm2 += (double)pv[u] + d * d * (cn * nt / tot);
+          cn = tot;
+        }
       }
-    sred[warp][lane] = s;
-    __syncthreads();
-    if (warp == 0) {
-      double tot = 0.0;
-      for (int w = 0; w < kWarps; ++w) tot += sred[w][lane];
-      smean[lane] = tot / n;
     }
-    __syncthreads();
-    mean = smean[lane];
-    double m2 = 0.0;
-    if (valid)
-      for (int t = warp; t < a.T; t += kWarps) {
-        const double nt = (double)(min(a.MT, a.B - t * a.MT) * a.N);
-        const double d = (double)a.partials[((size_t)t * 2 + 0) * a.F + c] - mean;
-        m2 += (double)a.partials[((size_t)t * 2 + 1) * a.F + c] + nt * d * d;
-      }
-    __syncthreads();
-    sred[warp][lane] = m2;
+    s_n[warp][lane] = cn; s_mean[warp][lane] = cm; s_m2[warp][lane] = cm2;
     __syncthreads();
     if (warp != 0 || !valid) return;
-    double tot = 0.0;
-    for (int w = 0; w < kWarps; ++w) tot += sred[w][lane];
-    var = tot / n;
-    const double unbiased = tot / (n > 1.0 ? n - 1.0 : 1.0);
+    cn = 0.0; cm = 0.0; cm2 = 0.0;
+    for (int w = 0; w < kFinWarps; ++w) {
+      const double nt = s_n[w][lane];
+      if (nt == 0.0) continue;
+      const double tot = cn + nt, d = s_mean[w][lane] - cm;
+      cm += d * (nt / tot);
+      cm2 += s_m2[w][lane] + d * d * (cn * nt / tot);
+      cn = tot;
+    }
+    mean = cm;
+    var = cm2 / n;
+    const double unbiased = cm2 / (n > 1.0 ? n - 1.0 : 1.0);
     a.running_mean[c] = (float)((1.0 - (double)a.momentum) * (double)a.running_mean[c] + (double)a.momentum * mean);
     a.running_var[c] = (float)((1.0 - (double)a.momentum) * (double)a.running_var[c] + (double)a.momentum * unbiased);
     if (c == 0 && a.nbt) *a.nbt += 1;
@@ -194,54 +203,92 @@ __global__ void __launch_bounds__(kThreads, 2) bwd_dy_kernel(const BwdDyArgs a) 
   }
   __syncthreads();
 
+  constexpr int RPW = TR / kWarps;
   for (int k0 = 0; k0 < F; k0 += KC) {
     const int c = k0 + lane;
     const bool cvalid = c < F;
     float mu = 0.f, is = 0.f, sc = 0.f, sh = 0.f;
     if (cvalid) { mu = __ldg(&a.mean[c]); is = __ldg(&a.invstd[c]); sc = __ldg(&a.scale[c]); sh = __ldg(&a.shift[c]); }
     if (!a.plain) {
-      for (int r = warp; r < rows; r += kWarps) {
-        float v = 0.f;
-        unsigned char ag = 0;
-        if (cvalid) { v = a.dH[(row0 + r) * F + c]; ag = a.arg[(row0 + r) * F + c]; }
-        sDH[r * KCP + lane] = v;
-        sArg[r * KC + lane] = ag;
+#pragma unroll
+      for (int h = 0; h < RPW / 16; ++h) {
+        float v[16];
+        unsigned char ag[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int r = warp + (h * 16 + q) * kWarps;
+          const bool ok = r < rows && cvalid;
+          v[q] = ok ? a.dH[(row0 + r) * F + c] : 0.f;
+          ag[q] = ok ? __ldg(&a.arg[(row0 + r) * F + c]) : (unsigned char)0;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int r = warp + (h * 16 + q) * kWarps;
+          if (r < rows) { sDH[r * KCP + lane] = v[q]; sArg[r * KC + lane] = ag[q]; }
+        }
       }
       __syncthreads();
     }
     float s1 = 0.f, s2 = 0.f;
-    for (int r = warp; r < rows; r += kWarps) {
-      if (!cvalid) continue;
-      const size_t o = (row0 + r) * F + c;
-      const float z = __ldg(&a.Z[o]);
-      const float yhat = (z - mu) * is;
-      float dy;
-      if (a.plain) {
-        dy = a.dH[o];
-      } else {
-        const int m = r / N, j = r - m * N, mb = m * N;
-        float dt = 0.f;
-        if (sFlag[m]) {
-          const u64* mk = &sCol[(size_t)r * NW];
-          for (int w = 0; w < NW; ++w) {
-            u64 bits = mk[w];
-            while (bits) {
-              int i = 64 * w + __ffsll((long long)bits) - 1;
-              bits &= bits - 1;
-              if (sArg[(mb + i) * KC + lane] == (unsigned char)j) dt += sDH[(mb + i) * KCP + lane];
-            }
-          }
-        } else {
-          const float* acol = a.adj + (long long)(mol0 + m) * a.as0 + (long long)j * a.as2;
-          for (int i = 0; i < N; ++i)
-            if (sArg[(mb + i) * KC + lane] == (unsigned char)j) dt = fmaf(__ldg(&acol[(long long)i * a.as1]), sDH[(mb + i) * KCP + lane], dt);
-        }
-        const float t = tanhf(fmaf(z, sc, sh));
-        dy = dt * (1.f - t * t);
-        a.dH[o] = dy;
+#pragma unroll
+    for (int h = 0; h < RPW / 16; ++h) {
+      float zv[16], gv[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int r = warp + (h * 16 + q) * kWarps;
+        const bool ok = r < rows && cvalid;
+        zv[q] = ok ? __ldg(&a.Z[(row0 + r) * F + c]) : 0.f;
+        gv[q] = (ok && a.plain) ? a.dH[(row0 + r) * F + c] : 0.f;
       }
-      s1 += dy;
-      s2 = fmaf(dy, yhat, s2);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int r = warp + (h * 16 + q) * kWarps;
+        if (r >= rows || !cvalid) continue;
+        const size_t o = (row0 + r) * F + c;
+        const float z = zv[q];
+        const float yhat = (z - mu) * is;
+        float dy;
+        if (a.plain) {
+          dy = gv[q];
+        } else {
+          const int m = r / N, j = r - m * N, mb = m * N;
+          float dt = 0.f;
+          if (sFlag[m]) {
+            // dT[j,c] = sum over rows i that list j as a neighbour and whose arg-max in channel c is j
+            const u64* mk = &sCol[(size_t)r * NW];
+            for (int w = 0; w < NW; ++w) {
+              u64 bits = mk[w];
+              while (bits) {
+                int ii[8];
+                float v[8];
+                unsigned char ag[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  ii[u] = -1;
+                  if (bits) { ii[u] = 64 * w + __ffsll((long long)bits) - 1; bits &= bits - 1; }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  v[u] = (ii[u] >= 0) ? sDH[(mb + ii[u]) * KCP + lane] : 0.f;
+                  ag[u] = (ii[u] >= 0) ? sArg[(mb + ii[u]) * KC + lane] : (unsigned char)255;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  if (ii[u] >= 0 && ag[u] == (unsigned char)j) dt += v[u];
+              }
+            }
+          } else {
+            const float* acol = a.adj + (long long)(mol0 + m) * a.as0 + (long long)j * a.as2;
+            for (int i = 0; i < N; ++i)
+              if (sArg[(mb + i) * KC + lane] == (unsigned char)j) dt = fmaf(__ldg(&acol[(long long)i * a.as1]), sDH[(mb + i) * KCP + lane], dt);
+          }
+          const float t = tanhf(fmaf(z, sc, sh));
+          dy = dt * (1.f - t * t);
+          a.dH[o] = dy;
+        }
+        s1 += dy;
+        s2 = fmaf(dy, yhat, s2);
+      }
     }
     sWarp[warp * 32 + lane] = s1;
     sWarp[(kWarps + warp) * 32 + lane] = s2;
@@ -276,23 +323,30 @@ struct BwdFinalizeArgs {
   float* c1;
   float* c2;
 };
-__global__ void __launch_bounds__(kThreads) bwd_finalize_kernel(const BwdFinalizeArgs a) {
-  __shared__ double sred[2][kWarps][32];
+__global__ void __launch_bounds__(1024) bwd_finalize_kernel(const BwdFinalizeArgs a) {
+  __shared__ double sred[2][kFinWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   const bool valid = c < a.F;
   double s1 = 0.0, s2 = 0.0;
   if (valid)
-    for (int t = warp; t < a.T; t += kWarps) {
-      s1 += (double)a.partials[((size_t)t * 2 + 0) * a.F + c];
-      s2 += (double)a.partials[((size_t)t * 2 + 1) * a.F + c];
+    for (int t0 = warp; t0 < a.T; t0 += kFinWarps * 4) {
+      float p1[4], p2[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + u * kFinWarps;
+        p1[u] = (t < a.T) ? a.partials[((size_t)t * 2 + 0) * a.F + c] : 0.f;
+        p2[u] = (t < a.T) ? a.partials[((size_t)t * 2 + 1) * a.F + c] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s1 += (double)p1[u]; s2 += (double)p2[u]; }
     }
   sred[0][warp][lane] = s1;
   sred[1][warp][lane] = s2;
   __syncthreads();
   if (warp != 0 || !valid) return;
   double db = 0.0, dg = 0.0;
-  for (int w = 0; w < kWarps; ++w) { db += sred[0][w][lane]; dg += sred[1][w][lane]; }
+  for (int w = 0; w < kFinWarps; ++w) { db += sred[0][w][lane]; dg += sred[1][w][lane]; }
   a.dbeta[c] = (float)db;
   a.dgamma[c] = (float)dg;
   a.g[c] = a.gamma[c] * a.invstd[c];
@@ -363,16 +417,34 @@ struct ReduceJobs {
   int P[2];
   int count[2];
 };
-__global__ void reduce_partials_kernel(const ReduceJobs jobs) {
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const ReduceJobs jobs) {
+  // block = 32 elements x 32 slices of P; fixed-order fp64 combine (slice-major), coalesced 128 B rows
+  __shared__ double sred[kFinWarps][32];
   const int jb = blockIdx.y;
   const float* p = jobs.partial[jb];
   float* out = jobs.out[jb];
-  if (!out) return;
   const int P = jobs.P[jb], cnt = jobs.count[jb];
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < cnt; idx += gridDim.x * blockDim.x) {
-    double s = 0.0;
-    for (int q = 0; q < P; ++q) s += (double)p[(size_t)q * cnt + idx];
-    out[idx] = (float)s;
+  if (!out || blockIdx.x * 32 >= cnt) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + lane;
+  double s = 0.0;
+  if (idx < cnt)
+    for (int q0 = warp; q0 < P; q0 += kFinWarps * 4) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int q = q0 + u * kFinWarps;
+        v[u] = (q < P) ? p[(size_t)q * cnt + idx] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s += (double)v[u];
+    }
+  sred[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && idx < cnt) {
+    double t = 0.0;
+    for (int w = 0; w < kFinWarps; ++w) t += sred[w][lane];
+    out[idx] = (float)t;
   }
 }
 

@@ -72,4 +72,54 @@ __device__ __forceinline__ int first_zero_bit(const u64* m, int NW, int N) {
   return -1;
 }
 
+// ---- bit-mask neighbour loops with batched shared-memory loads -------------------------------------------
+// `col` points at element (molecule base row, this lane's channel) of a [rows][stride] fp32 chunk buffer. The
+// mask is warp-uniform, so index extraction runs once per warp; up to 8 neighbour values are loaded back to
+// back (independent LDS) before the dependent compare / add chain consumes them in ascending-j order.
+__device__ __forceinline__ void masked_max_first(const u64* mk, int NW, const float* col, int stride, float& best, int& arg, int& cnt) {
+  best = -INFINITY;
+  arg = 0;
+  cnt = 0;
+  for (int w = 0; w < NW; ++w) {
+    u64 bits = mk[w];
+    cnt += __popcll(bits);
+    while (bits) {
+      int j[8];
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        j[q] = -1;
+        if (bits) { j[q] = 64 * w + __ffsll((long long)bits) - 1; bits &= bits - 1; }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = (j[q] >= 0) ? col[j[q] * stride] : -INFINITY;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (v[q] > best) { best = v[q]; arg = j[q]; }
+    }
+  }
+}
+
+__device__ __forceinline__ float masked_sum(const u64* mk, int NW, const float* col, int stride) {
+  float s = 0.f;
+  for (int w = 0; w < NW; ++w) {
+    u64 bits = mk[w];
+    while (bits) {
+      int j[8];
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        j[q] = -1;
+        if (bits) { j[q] = 64 * w + __ffsll((long long)bits) - 1; bits &= bits - 1; }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = (j[q] >= 0) ? col[j[q] * stride] : 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (j[q] >= 0) s += v[q];      // ascending j, like a dense dot product that skips exact zeros
+    }
+  }
+  return s;
+}
+
 }  // namespace ocgcn

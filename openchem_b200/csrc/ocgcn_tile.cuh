@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
   constexpr int TXN = TC / 8;
   static_assert(TYN * TXN == kThreads, "thread grid must cover the tile");
   constexpr int TCP = TC + 4;
+  constexpr int RPW = TR / kWarps;  // rows per warp (16 or 32), processed in batches of 16 independent loads
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = a.N, NW = a.NW, K = a.K, NC = a.NC;
@@ -90,22 +91,38 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
 
       // =========================== PRODUCER ===========================
       if (PROD == P_X) {
-        for (int r = warp; r < TR; r += kWarps) {
-          float v = 0.f;
-          if (r < rows && cvalid) {
-            int m = r / N, i = r - m * N;
-            v = __ldg(&a.in0[(long long)(mol0 + m) * a.xs0 + (long long)i * a.xs1 + (long long)c * a.xs2]);
+#pragma unroll
+        for (int h = 0; h < RPW / 16; ++h) {
+          float v[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int r = warp + (h * 16 + q) * kWarps;
+            v[q] = 0.f;
+            if (r < rows && cvalid) {
+              int m = r / N, i = r - m * N;
+              v[q] = __ldg(&a.in0[(long long)(mol0 + m) * a.xs0 + (long long)i * a.xs1 + (long long)c * a.xs2]);
+            }
           }
-          buf1[r * KCP + lane] = v;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) buf1[(warp + (h * 16 + q) * kWarps) * KCP + lane] = v[q];
         }
         __syncthreads();
       } else if (PROD == P_MID || PROD == P_RO) {
         const float sc = cvalid ? __ldg(&a.vec0[c]) : 0.f;
         const float sh = cvalid ? __ldg(&a.vec1[c]) : 0.f;
-        for (int r = warp; r < TR; r += kWarps) {
-          float t = 0.f;
-          if (r < rows && cvalid) t = tanhf(fmaf(__ldg(&a.in0[(row0 + r) * K + c]), sc, sh));
-          buf0[r * KCP + lane] = t;
+#pragma unroll
+        for (int h = 0; h < RPW / 16; ++h) {
+          float v[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {   // all loads of this warp's rows in flight before the first tanh
+            const int r = warp + (h * 16 + q) * kWarps;
+            v[q] = (r < rows && cvalid) ? __ldg(&a.in0[(row0 + r) * K + c]) : 0.f;
+          }
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int r = warp + (h * 16 + q) * kWarps;
+            buf0[r * KCP + lane] = (r < rows && cvalid) ? tanhf(fmaf(v[q], sc, sh)) : 0.f;
+          }
         }
         __syncthreads();
         // neighbour max-pool: P[i,c] = max_j A[i,j]*T[j,c], first index wins ties (gcn_encoder.py:44-50)
@@ -116,18 +133,8 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
             const int m = r / N, i = r - m * N, mb = m * N;
             if (sFlag[m]) {
               const u64* mk = &sRow[(size_t)r * NW];
-              best = -INFINITY;
-              int cnt = 0;
-              for (int w = 0; w < NW; ++w) {
-                u64 bits = mk[w];
-                cnt += __popcll(bits);
-                while (bits) {
-                  int j = 64 * w + __ffsll((long long)bits) - 1;
-                  bits &= bits - 1;
-                  float v = buf0[(mb + j) * KCP + lane];
-                  if (v > best) { best = v; arg = j; }
-                }
-              }
+              int cnt;
+              masked_max_first(mk, NW, &buf0[mb * KCP + lane], KCP, best, arg, cnt);
               if (cnt < N && !(best > 0.f)) {  // a zero entry A[i,jz]=0 contributes the candidate 0*T = 0
                 int jz = first_zero_bit(mk, NW, N);
                 if (best < 0.f || jz < arg) arg = jz;
@@ -153,15 +160,27 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
         float g = 0.f, c1 = 0.f, c2 = 0.f, mu = 0.f, is = 0.f;
         if (cvalid) { g = __ldg(&a.vec0[c]); c1 = __ldg(&a.vec1[c]); c2 = __ldg(&a.vec2[c]); mu = __ldg(&a.vec3[c]); is = __ldg(&a.vec4[c]); }
         float colsum = 0.f;
-        for (int r = warp; r < TR; r += kWarps) {
-          float dz = 0.f;
-          if (r < rows && cvalid) {
-            size_t o = (row0 + r) * K + c;
-            float yhat = (__ldg(&a.in1[o]) - mu) * is;
-            dz = g * (a.in0[o] - c1 - yhat * c2);
-            if (first_pass) { a.prod_out[o] = dz; colsum += dz; }
+#pragma unroll
+        for (int h = 0; h < RPW / 16; ++h) {
+          float zv[16], dv[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int r = warp + (h * 16 + q) * kWarps;
+            const bool ok = r < rows && cvalid;
+            zv[q] = ok ? __ldg(&a.in1[(row0 + r) * K + c]) : 0.f;
+            dv[q] = ok ? __ldg(&a.in0[(row0 + r) * K + c]) : 0.f;
           }
-          buf0[r * KCP + lane] = dz;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int r = warp + (h * 16 + q) * kWarps;
+            float dz = 0.f;
+            if (r < rows && cvalid) {
+              const float yhat = (zv[q] - mu) * is;
+              dz = g * (dv[q] - c1 - yhat * c2);
+              if (first_pass) { a.prod_out[(row0 + r) * K + c] = dz; colsum += dz; }
+            }
+            buf0[r * KCP + lane] = dz;
+          }
         }
         if (first_pass && a.prod_partials) sWarp[warp * 32 + lane] = colsum;
         __syncthreads();
@@ -173,16 +192,27 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
         }
       } else if (PROD == P_DU) {
         float colsum = 0.f;
-        for (int r = warp; r < TR; r += kWarps) {
-          float du = 0.f;
-          if (r < rows && cvalid) {
-            int m = r / N;
-            size_t ob = (size_t)(mol0 + m) * K + c, o = (row0 + r) * K + c;
-            float ov = __ldg(&a.in2[ob]), dv = __ldg(&a.in0[o]);
-            du = __ldg(&a.in1[ob]) * (1.f - ov * ov) * (1.f - dv * dv);
-            if (first_pass) { a.prod_out[o] = du; colsum += du; }
+#pragma unroll
+        for (int h = 0; h < RPW / 16; ++h) {
+          float dv[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int r = warp + (h * 16 + q) * kWarps;
+            dv[q] = (r < rows && cvalid) ? __ldg(&a.in0[(row0 + r) * K + c]) : 0.f;
           }
-          buf0[r * KCP + lane] = du;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int r = warp + (h * 16 + q) * kWarps;
+            float du = 0.f;
+            if (r < rows && cvalid) {
+              const int m = r / N;
+              const size_t ob = (size_t)(mol0 + m) * K + c;
+              const float ov = __ldg(&a.in2[ob]);
+              du = __ldg(&a.in1[ob]) * (1.f - ov * ov) * (1.f - dv[q] * dv[q]);
+              if (first_pass) { a.prod_out[(row0 + r) * K + c] = du; colsum += du; }
+            }
+            buf0[r * KCP + lane] = du;
+          }
         }
         if (first_pass && a.prod_partials) sWarp[warp * 32 + lane] = colsum;
         __syncthreads();
@@ -201,15 +231,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
           if (r < rows) {
             const int m = r / N, i = r - m * N, mb = m * N;
             if (sFlag[m]) {
-              const u64* mk = &sRow[(size_t)r * NW];
-              for (int w = 0; w < NW; ++w) {
-                u64 bits = mk[w];
-                while (bits) {
-                  int j = 64 * w + __ffsll((long long)bits) - 1;
-                  bits &= bits - 1;
-                  s += buf1[(mb + j) * KCP + lane];
-                }
-              }
+              s = masked_sum(&sRow[(size_t)r * NW], NW, &buf1[mb * KCP + lane], KCP);
             } else {
               const float* arow = a.adj + (long long)(mol0 + m) * a.as0 + (long long)i * a.as1;
               for (int j = 0; j < N; ++j) s = fmaf(__ldg(&arow[(long long)j * a.as2]), buf1[(mb + j) * KCP + lane], s);
@@ -371,15 +393,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
             if (cb + cl >= NC) break;
             float s = 0.f;
             if (sFlag[m]) {
-              const u64* mk = &sCol[(size_t)r * NW];
-              for (int w = 0; w < NW; ++w) {
-                u64 bits = mk[w];
-                while (bits) {
-                  int i = 64 * w + __ffsll((long long)bits) - 1;
-                  bits &= bits - 1;
-                  s += sC[(mb + i) * TCP + cl];
-                }
-              }
+              s = masked_sum(&sCol[(size_t)r * NW], NW, &sC[mb * TCP + cl], TCP);
             } else {
               const float* acol = a.adj + (long long)(mol0 + m) * a.as0 + (long long)j * a.as2;
               for (int i = 0; i < N; ++i) s = fmaf(__ldg(&acol[(long long)i * a.as1]), sC[(mb + i) * TCP + cl], s);

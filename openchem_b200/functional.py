@@ -95,6 +95,20 @@ def _count(lib):
     launch_counter["n"] += lib.ocgcn_last_launch_count()
 
 
+SAVED_KINDS = {"Z": (0, torch.float32), "argmax": (1, torch.uint8), "S": (2, torch.float32), "stats": (3, torch.float32),
+               "rowmask": (4, torch.int64), "molflag": (5, torch.int32)}
+debug_keep = {"on": False, "saved": None, "desc": None}     # tests only: keep the last forward's saved buffer
+
+
+def saved_tensor(kind, layer=0):
+    """(tests) view of one tensor inside the last forward's saved workspace; needs debug_keep['on'] = True."""
+    lib = _lib.load()
+    what, dtype = SAVED_KINDS[kind]
+    off, nb = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    _lib.check(lib.ocgcn_saved_tensor(ctypes.byref(debug_keep["desc"]), what, layer, ctypes.byref(off), ctypes.byref(nb)))
+    return debug_keep["saved"][off.value: off.value + nb.value].view(dtype)
+
+
 class EncoderFn(torch.autograd.Function):
     """GraphCNNEncoder.forward (gcn_encoder.py:38-53) as ONE autograd node. inputs: x, adj, spec, then per layer
     W, b, gamma, beta (b may be None) and finally Wd, bd."""
@@ -122,6 +136,8 @@ class EncoderFn(torch.autograd.Function):
             _lib.check(lib.ocgcn_encoder_forward(ctypes.byref(desc), x.data_ptr(), adj.data_ptr(), ctypes.byref(params),
                                                  saved.data_ptr(), scratch.data_ptr(), out.data_ptr(), _stream_ptr(x.device)))
             _count(lib)
+        if debug_keep["on"]:
+            debug_keep["saved"], debug_keep["desc"] = saved, desc
         ctx.spec = spec
         ctx.cbytes = cbytes
         ctx.save_for_backward(x, adj, saved, *[t for t in tensors if t is not None])

@@ -22,11 +22,11 @@ def _dev():
     return torch.device("cuda:0")
 
 
-def _run_encoder(enc, x, adj, dO, dev):
+def _run_encoder(enc, x, adj, dO, dev, fwd_out=None):
     enc.train()
     enc.zero_grad()
     tx, ta = torch.from_numpy(x).to(dev), torch.from_numpy(adj).to(dev)
-    out = enc((tx, ta))
+    out = enc((tx, ta)) if fwd_out is None else fwd_out
     out.backward(torch.from_numpy(dO).to(dev))
     torch.cuda.synchronize()
     res = dict(out_train=out.detach().cpu().numpy())
@@ -94,17 +94,41 @@ def test_encoder_vs_oracle(shape):
     p64 = orc.cast_params(p, np.float64)
     x64, a64 = gb["x"].astype(np.float64), gb["adj"].astype(np.float64)
     O, cache, rms, rvs = orc.encoder_forward(x64, a64, p64, training=True)
-    gr = orc.encoder_backward(dO.astype(np.float64), cache)
     Oe = orc.encoder_forward(x64, a64, dict(p64, running_mean=rms, running_var=rvs), training=False)[0]
-    ref = dict(out_train=O, out_eval=Oe, dWd=gr["dWd"], dbd=gr["dbd"])
     L = len(shape["hidden"])
+    cfg = {"input_size": shape["F0"], "encoder_dim": shape["E"], "n_layers": L, "hidden_size": list(shape["hidden"])}
+    enc = build_encoder(cfg, p, dev)
+    # run the train step by hand so the saved arg-max of THAT forward can be inspected
+    from openchem_b200 import functional
+    functional.debug_keep["on"] = True
+    try:
+        enc.train()
+        tx, ta = torch.from_numpy(gb["x"]).to(dev), torch.from_numpy(gb["adj"]).to(dev)
+        out = enc((tx, ta))
+        args = [functional.saved_tensor("argmax", l).cpu().numpy().reshape(shape["B"], shape["N"], -1).astype(np.int64) for l in range(L)]
+        flags = functional.saved_tensor("molflag").cpu().numpy()
+    finally:
+        functional.debug_keep.update(on=False, saved=None, desc=None)
+    assert np.all(flags == 1)                       # synthetic adjacency is exactly 0/1 -> bit-mask path
+    # Pool routing: identical to the oracle except at NEAR-TIES below fp32 resolution: there the
+    # fp32 forward cannot (and the fp32 reference does not) reproduce the fp64 choice. Every gradient-carrying
+    # mismatch must be such a near-tie; gradients are then compared with the routing the kernel actually used.
+    n_mism = 0
+    for l in range(L):
+        T, oarg = cache["layers"][l]["T"], cache["layers"][l]["arg"]
+        for b, i, c in np.argwhere(args[l] != oarg):
+            ja, jo = args[l][b, i, c], oarg[b, i, c]
+            va, vo = a64[b, i, ja] * T[b, ja, c], a64[b, i, jo] * T[b, jo, c]
+            assert abs(va - vo) < 2e-6, f"layer {l} {(b, i, c)}: arg-max {ja} vs oracle {jo} is not a near-tie ({va} vs {vo})"
+            n_mism += 1
+    assert n_mism <= 1e-5 * sum(a.size for a in args) + 2
+    gr = orc.encoder_backward(dO.astype(np.float64), cache, arg_override=args)
+    ref = dict(out_train=O, out_eval=Oe, dWd=gr["dWd"], dbd=gr["dbd"])
     for l in range(L):
         ref.update({f"dW{l}": gr["dW"][l], f"db{l}": gr["db"][l], f"dgamma{l}": gr["dgamma"][l], f"dbeta{l}": gr["dbeta"][l],
                     f"rm{l}": rms[l], f"rv{l}": rvs[l]})
-    cfg = {"input_size": shape["F0"], "encoder_dim": shape["E"], "n_layers": L, "hidden_size": list(shape["hidden"])}
-    enc = build_encoder(cfg, p, dev)
-    res = _run_encoder(enc, gb["x"], gb["adj"], dO, dev)
-    _compare(res, ref, L, TOL["fp32"], str(shape))
+    res = _run_encoder(enc, gb["x"], gb["adj"], dO, dev, fwd_out=out)
+    _compare(res, ref, L, TOL["fp32"], str(shape) + f" ({n_mism} near-tie routings)")
 
 
 @pytest.mark.parametrize("case", LAYER_CASES)
