@@ -71,7 +71,7 @@ struct Layout {
   int TR, MT, NW, tiles, Fmax;
   size_t rows;
   // saved
-  size_t rowmask, colmask, molflag;
+  size_t rowmask, colmask, molflag, nbr, cnbr;
   size_t Z[OCGCN_MAX_LAYERS], arg[OCGCN_MAX_LAYERS], S[OCGCN_MAX_LAYERS], stats[OCGCN_MAX_LAYERS];
   size_t HL, D, O;
   size_t saved_total;
@@ -117,6 +117,8 @@ static int make_layout(const ocgcn_desc* d, bool layer_only, Layout* lo) {
   lo->rowmask = take(rows * lo->NW * 8);
   lo->colmask = take(rows * lo->NW * 8);
   lo->molflag = take((size_t)d->B * 4);
+  lo->nbr = take(rows * 16);
+  lo->cnbr = take(rows * 16);
   for (int l = 0; l < d->L; ++l) {
     lo->Z[l] = take(rows * d->F[l + 1] * 4);
     lo->arg[l] = layer_only ? 0 : take(rows * d->F[l + 1]);
@@ -223,14 +225,17 @@ static TileArgs base_tile_args(const ocgcn_desc* d, const Layout& lo, const floa
   a.rowmask = reinterpret_cast<const u64*>(saved + lo.rowmask);
   a.colmask = reinterpret_cast<const u64*>(saved + lo.colmask);
   a.molflag = reinterpret_cast<const unsigned*>(saved + lo.molflag);
+  a.nbr = reinterpret_cast<const uint4*>(saved + lo.nbr);
+  a.cnbr = reinterpret_cast<const uint4*>(saved + lo.cnbr);
   return a;
 }
 
 static int run_adj_pack(const ocgcn_desc* d, const Layout& lo, const float* adj, char* saved, cudaStream_t st) {
   ProfScope prof(KK_ADJ_PACK, st);
-  adj_pack_kernel<<<d->B, kThreads, (size_t)d->N * lo.NW * 8, st>>>(
+  adj_pack_kernel<<<d->B, kThreads, (size_t)2 * d->N * lo.NW * 8, st>>>(
       adj, d->adj_stride[0], d->adj_stride[1], d->adj_stride[2], d->N, lo.NW, reinterpret_cast<u64*>(saved + lo.rowmask),
-      reinterpret_cast<u64*>(saved + lo.colmask), reinterpret_cast<unsigned*>(saved + lo.molflag));
+      reinterpret_cast<u64*>(saved + lo.colmask), reinterpret_cast<unsigned*>(saved + lo.molflag),
+      reinterpret_cast<uint4*>(saved + lo.nbr), reinterpret_cast<uint4*>(saved + lo.cnbr));
   LAUNCH_CHECK();
   return OCGCN_OK;
 }
@@ -326,7 +331,7 @@ static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float
   y.B = d->B; y.N = d->N; y.NW = lo.NW; y.MT = lo.MT; y.F = Fout; y.plain = plain ? 1 : 0;
   y.adj = adj; y.as0 = d->adj_stride[0]; y.as1 = d->adj_stride[1]; y.as2 = d->adj_stride[2];
   y.colmask = reinterpret_cast<const u64*>(saved + lo.colmask);
-  y.molflag = reinterpret_cast<const unsigned*>(saved + lo.molflag);
+  y.cnbr = reinterpret_cast<const uint4*>(saved + lo.cnbr);
   y.Z = Z;
   y.arg = plain ? nullptr : reinterpret_cast<const unsigned char*>(saved + lo.arg[l]);
   y.mean = stats; y.invstd = stats + Fout; y.scale = stats + 2 * Fout; y.shift = stats + 3 * Fout;

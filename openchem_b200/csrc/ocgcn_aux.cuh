@@ -9,11 +9,44 @@ namespace ocgcn {
 // adjacency -> bit masks. One CTA per molecule. Also classifies the molecule: molflag = 1 iff every entry is
 // exactly 0 or 1 (what openchem/utils/graph.py:77-86 produces); other molecules take the dense float path.
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 build_record(const u64* mk, int NW, int N, bool binary) {
+  unsigned char b[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) b[q] = 0;
+  int cnt = 0;
+  for (int w = 0; w < NW; ++w) {
+    u64 bits = mk[w];
+    while (bits) {
+      const int j = 64 * w + __ffsll((long long)bits) - 1;
+      bits &= bits - 1;
+      if (cnt < kMaxNbr) {
+#pragma unroll
+        for (int q = 0; q < kMaxNbr; ++q)
+          if (q == cnt) b[3 + q] = (unsigned char)j;
+      }
+      ++cnt;
+    }
+  }
+  const int jz = first_zero_bit(mk, NW, N);
+  unsigned flags = (cnt > kMaxNbr) ? 0x80u : (unsigned)cnt;
+  if (jz >= 0) { flags |= 0x40u; b[1] = (unsigned char)jz; }
+  if (binary) flags |= 0x20u;
+  b[0] = (unsigned char)flags;
+  uint4 r;
+  r.x = b[0] | (b[1] << 8) | (b[2] << 16) | ((unsigned)b[3] << 24);
+  r.y = b[4] | (b[5] << 8) | (b[6] << 16) | ((unsigned)b[7] << 24);
+  r.z = b[8] | (b[9] << 8) | (b[10] << 16) | ((unsigned)b[11] << 24);
+  r.w = b[12] | (b[13] << 8) | (b[14] << 16) | ((unsigned)b[15] << 24);
+  return r;
+}
+
 __global__ void __launch_bounds__(kThreads) adj_pack_kernel(const float* __restrict__ adj, long long as0, long long as1,
                                                             long long as2, int N, int NW, u64* __restrict__ rowmask,
-                                                            u64* __restrict__ colmask, unsigned* __restrict__ molflag) {
+                                                            u64* __restrict__ colmask, unsigned* __restrict__ molflag,
+                                                            uint4* __restrict__ nbr, uint4* __restrict__ cnbr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64* sR = reinterpret_cast<u64*>(smem_raw);
+  u64* sCm = sR + (size_t)N * NW;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* ab = adj + (long long)b * as0;
   int nonbin = 0;
@@ -42,7 +75,13 @@ __global__ void __launch_bounds__(kThreads) adj_pack_kernel(const float* __restr
       const int i = 64 * w + ii;
       if (i < N) word |= ((sR[i * NW + (j >> 6)] >> (j & 63)) & 1ull) << ii;
     }
+    sCm[idx] = word;
     colmask[((size_t)b * N + j) * NW + w] = word;
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * N; i += kThreads) {   // one 16-byte neighbour record per row and per column
+    if (i < N) nbr[(size_t)b * N + i] = build_record(&sR[i * NW], NW, N, !nonbin);
+    else cnbr[(size_t)b * N + (i - N)] = build_record(&sCm[(i - N) * NW], NW, N, !nonbin);
   }
   if (tid == 0) molflag[b] = nonbin ? 0u : 1u;
 }
@@ -171,7 +210,7 @@ struct BwdDyArgs {
   const float* adj;
   long long as0, as1, as2;
   const u64* colmask;
-  const unsigned* molflag;
+  const uint4* cnbr;
   const float* Z;
   const unsigned char* arg;
   const float* mean;
@@ -185,11 +224,11 @@ template <int TR>
 __global__ void __launch_bounds__(kThreads, 2) bwd_dy_kernel(const BwdDyArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = a.N, NW = a.NW, F = a.F;
-  u64* sCol = reinterpret_cast<u64*>(smem_raw);
+  uint4* sCRec = reinterpret_cast<uint4*>(smem_raw);
+  u64* sCol = reinterpret_cast<u64*>(sCRec + TR);
   float* sDH = reinterpret_cast<float*>(sCol + (size_t)TR * NW);
   unsigned char* sArg = reinterpret_cast<unsigned char*>(sDH + TR * KCP);
   float* sWarp = reinterpret_cast<float*>(sArg + TR * KC);
-  unsigned* sFlag = reinterpret_cast<unsigned*>(sWarp + 2 * kWarps * 32);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x;
@@ -197,108 +236,155 @@ __global__ void __launch_bounds__(kThreads, 2) bwd_dy_kernel(const BwdDyArgs a) 
   const int nm = min(a.MT, a.B - mol0);
   const int rows = nm * N;
   const size_t row0 = (size_t)mol0 * N;
+  const bool vec2 = (F % 2 == 0);
   if (!a.plain) {
+    for (int r = tid; r < rows; r += kThreads) {
+      const int m = r / N;
+      sCRec[r] = rec_stage(__ldg(&a.cnbr[row0 + r]), m, m * N);
+    }
     for (int idx = tid; idx < rows * NW; idx += kThreads) sCol[idx] = a.colmask[row0 * NW + idx];
-    for (int idx = tid; idx < nm; idx += kThreads) sFlag[idx] = a.molflag[mol0 + idx];
   }
   __syncthreads();
 
   constexpr int RPW = TR / kWarps;
   for (int k0 = 0; k0 < F; k0 += KC) {
-    const int c = k0 + lane;
-    const bool cvalid = c < F;
-    float mu = 0.f, is = 0.f, sc = 0.f, sh = 0.f;
-    if (cvalid) { mu = __ldg(&a.mean[c]); is = __ldg(&a.invstd[c]); sc = __ldg(&a.scale[c]); sh = __ldg(&a.shift[c]); }
+    const int c = k0 + 2 * lane;
+    const bool v0 = c < F, v1 = c + 1 < F;
+    float2 mu = make_float2(0.f, 0.f), is = mu, sc = mu, sh = mu;
+    if (v0) { mu.x = __ldg(&a.mean[c]); is.x = __ldg(&a.invstd[c]); sc.x = __ldg(&a.scale[c]); sh.x = __ldg(&a.shift[c]); }
+    if (v1) { mu.y = __ldg(&a.mean[c + 1]); is.y = __ldg(&a.invstd[c + 1]); sc.y = __ldg(&a.scale[c + 1]); sh.y = __ldg(&a.shift[c + 1]); }
     if (!a.plain) {
 #pragma unroll
-      for (int h = 0; h < RPW / 16; ++h) {
-        float v[16];
-        unsigned char ag[16];
+      for (int h = 0; h < RPW / 8; ++h) {
+        float2 v[8];
+        uchar2 ag[8];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int r = warp + (h * 16 + q) * kWarps;
-          const bool ok = r < rows && cvalid;
-          v[q] = ok ? a.dH[(row0 + r) * F + c] : 0.f;
-          ag[q] = ok ? __ldg(&a.arg[(row0 + r) * F + c]) : (unsigned char)0;
+        for (int q = 0; q < 8; ++q) {
+          const int r = warp + (h * 8 + q) * kWarps;
+          v[q] = make_float2(0.f, 0.f);
+          ag[q] = make_uchar2(0, 0);
+          if (r < rows && v0) {
+            const size_t o = (row0 + r) * F + c;
+            if (vec2) {
+              v[q] = *reinterpret_cast<const float2*>(&a.dH[o]);
+              ag[q] = __ldg(reinterpret_cast<const uchar2*>(&a.arg[o]));
+            } else {
+              v[q].x = a.dH[o];
+              ag[q].x = __ldg(&a.arg[o]);
+              if (v1) { v[q].y = a.dH[o + 1]; ag[q].y = __ldg(&a.arg[o + 1]); }
+            }
+          }
         }
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int r = warp + (h * 16 + q) * kWarps;
-          if (r < rows) { sDH[r * KCP + lane] = v[q]; sArg[r * KC + lane] = ag[q]; }
+        for (int q = 0; q < 8; ++q) {
+          const int r = warp + (h * 8 + q) * kWarps;
+          if (r < rows) {
+            *reinterpret_cast<float2*>(&sDH[r * KCP + 2 * lane]) = v[q];
+            *reinterpret_cast<uchar2*>(&sArg[r * KC + 2 * lane]) = ag[q];
+          }
         }
       }
       __syncthreads();
     }
-    float s1 = 0.f, s2 = 0.f;
+    float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int h = 0; h < RPW / 16; ++h) {
-      float zv[16], gv[16];
+    for (int h = 0; h < RPW / 8; ++h) {
+      float2 zv[8], gv[8];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int r = warp + (h * 16 + q) * kWarps;
-        const bool ok = r < rows && cvalid;
-        zv[q] = ok ? __ldg(&a.Z[(row0 + r) * F + c]) : 0.f;
-        gv[q] = (ok && a.plain) ? a.dH[(row0 + r) * F + c] : 0.f;
+      for (int q = 0; q < 8; ++q) {
+        const int r = warp + (h * 8 + q) * kWarps;
+        const bool ok = r < rows && v0;
+        zv[q] = make_float2(0.f, 0.f);
+        gv[q] = make_float2(0.f, 0.f);
+        if (ok) {
+          const size_t o = (row0 + r) * F + c;
+          if (vec2) {
+            zv[q] = __ldg(reinterpret_cast<const float2*>(&a.Z[o]));
+            if (a.plain) gv[q] = *reinterpret_cast<const float2*>(&a.dH[o]);
+          } else {
+            zv[q].x = __ldg(&a.Z[o]);
+            if (v1) zv[q].y = __ldg(&a.Z[o + 1]);
+            if (a.plain) { gv[q].x = a.dH[o]; if (v1) gv[q].y = a.dH[o + 1]; }
+          }
+        }
       }
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int r = warp + (h * 16 + q) * kWarps;
-        if (r >= rows || !cvalid) continue;
+      for (int q = 0; q < 8; ++q) {
+        const int r = warp + (h * 8 + q) * kWarps;
+        if (r >= rows || !v0) continue;
         const size_t o = (row0 + r) * F + c;
-        const float z = zv[q];
-        const float yhat = (z - mu) * is;
-        float dy;
+        const float2 yhat = make_float2((zv[q].x - mu.x) * is.x, (zv[q].y - mu.y) * is.y);
+        float2 dy;
         if (a.plain) {
           dy = gv[q];
         } else {
-          const int m = r / N, j = r - m * N, mb = m * N;
-          float dt = 0.f;
-          if (sFlag[m]) {
+          const uint4 crec = sCRec[r];
+          const int m = rec_m(crec), mb = m * N;
+          const unsigned char jrel = (unsigned char)(r - mb);
+          float2 dt = make_float2(0.f, 0.f);
+          if (rec_binary(crec) && !rec_fallback(crec)) {
             // dT[j,c] = sum over rows i that list j as a neighbour and whose arg-max in channel c is j
+            const int cnt = rec_cnt(crec);
+#define OCGCN_SCAT_STEP(Q)                                                                   \
+            if (cnt > Q) {                                                                   \
+              const int ir = rec_idx<Q>(crec);                                               \
+              const float2 g = *reinterpret_cast<const float2*>(&sDH[ir * KCP + 2 * lane]);  \
+              const uchar2 ag = *reinterpret_cast<const uchar2*>(&sArg[ir * KC + 2 * lane]); \
+              if (ag.x == jrel) dt.x += g.x;                                                 \
+              if (ag.y == jrel) dt.y += g.y;                                                 \
+            }
+            OCGCN_SCAT_STEP(0) OCGCN_SCAT_STEP(1) OCGCN_SCAT_STEP(2) OCGCN_SCAT_STEP(3) OCGCN_SCAT_STEP(4)
+            if (cnt > 5) {
+              OCGCN_SCAT_STEP(5) OCGCN_SCAT_STEP(6) OCGCN_SCAT_STEP(7) OCGCN_SCAT_STEP(8)
+              if (cnt > 9) { OCGCN_SCAT_STEP(9) OCGCN_SCAT_STEP(10) OCGCN_SCAT_STEP(11) OCGCN_SCAT_STEP(12) }
+            }
+#undef OCGCN_SCAT_STEP
+          } else if (rec_binary(crec)) {
             const u64* mk = &sCol[(size_t)r * NW];
             for (int w = 0; w < NW; ++w) {
               u64 bits = mk[w];
               while (bits) {
-                int ii[8];
-                float v[8];
-                unsigned char ag[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                  ii[u] = -1;
-                  if (bits) { ii[u] = 64 * w + __ffsll((long long)bits) - 1; bits &= bits - 1; }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                  v[u] = (ii[u] >= 0) ? sDH[(mb + ii[u]) * KCP + lane] : 0.f;
-                  ag[u] = (ii[u] >= 0) ? sArg[(mb + ii[u]) * KC + lane] : (unsigned char)255;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                  if (ii[u] >= 0 && ag[u] == (unsigned char)j) dt += v[u];
+                const int ir = mb + 64 * w + __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+                if (sArg[ir * KC + 2 * lane] == jrel) dt.x += sDH[ir * KCP + 2 * lane];
+                if (sArg[ir * KC + 2 * lane + 1] == jrel) dt.y += sDH[ir * KCP + 2 * lane + 1];
               }
             }
           } else {
-            const float* acol = a.adj + (long long)(mol0 + m) * a.as0 + (long long)j * a.as2;
-            for (int i = 0; i < N; ++i)
-              if (sArg[(mb + i) * KC + lane] == (unsigned char)j) dt = fmaf(__ldg(&acol[(long long)i * a.as1]), sDH[(mb + i) * KCP + lane], dt);
+            const float* acol = a.adj + (long long)(mol0 + m) * a.as0 + (long long)(r - mb) * a.as2;
+            for (int i = 0; i < N; ++i) {
+              const float ai = __ldg(&acol[(long long)i * a.as1]);
+              if (sArg[(mb + i) * KC + 2 * lane] == jrel) dt.x = fmaf(ai, sDH[(mb + i) * KCP + 2 * lane], dt.x);
+              if (sArg[(mb + i) * KC + 2 * lane + 1] == jrel) dt.y = fmaf(ai, sDH[(mb + i) * KCP + 2 * lane + 1], dt.y);
+            }
           }
-          const float t = tanhf(fmaf(z, sc, sh));
-          dy = dt * (1.f - t * t);
-          a.dH[o] = dy;
+          const float t0 = fast_tanh(fmaf(zv[q].x, sc.x, sh.x)), t1 = fast_tanh(fmaf(zv[q].y, sc.y, sh.y));
+          dy = make_float2(dt.x * (1.f - t0 * t0), v1 ? dt.y * (1.f - t1 * t1) : 0.f);
+          if (vec2) {
+            *reinterpret_cast<float2*>(&a.dH[o]) = dy;
+          } else {
+            a.dH[o] = dy.x;
+            if (v1) a.dH[o + 1] = dy.y;
+          }
         }
-        s1 += dy;
-        s2 = fmaf(dy, yhat, s2);
+        s1.x += dy.x; s1.y += dy.y;
+        s2.x = fmaf(dy.x, yhat.x, s2.x); s2.y = fmaf(dy.y, yhat.y, s2.y);
       }
     }
-    sWarp[warp * 32 + lane] = s1;
-    sWarp[(kWarps + warp) * 32 + lane] = s2;
+    *reinterpret_cast<float2*>(&sWarp[(warp * 32 + lane) * 2]) = s1;
+    *reinterpret_cast<float2*>(&sWarp[((kWarps + warp) * 32 + lane) * 2]) = s2;
     __syncthreads();
-    if (warp == 0 && cvalid) {
-      float t1 = 0.f, t2 = 0.f;
+    if (warp == 0 && v0) {
+      float2 t1 = make_float2(0.f, 0.f), t2 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) { t1 += sWarp[w * 32 + lane]; t2 += sWarp[(kWarps + w) * 32 + lane]; }
-      a.partials[((size_t)tile * 2 + 0) * F + c] = t1;
-      a.partials[((size_t)tile * 2 + 1) * F + c] = t2;
+      for (int w = 0; w < kWarps; ++w) {
+        const float2 p1 = *reinterpret_cast<const float2*>(&sWarp[(w * 32 + lane) * 2]);
+        const float2 p2 = *reinterpret_cast<const float2*>(&sWarp[((kWarps + w) * 32 + lane) * 2]);
+        t1.x += p1.x; t1.y += p1.y; t2.x += p2.x; t2.y += p2.y;
+      }
+      a.partials[((size_t)tile * 2 + 0) * F + c] = t1.x;
+      a.partials[((size_t)tile * 2 + 1) * F + c] = t2.x;
+      if (v1) { a.partials[((size_t)tile * 2 + 0) * F + c + 1] = t1.y; a.partials[((size_t)tile * 2 + 1) * F + c + 1] = t2.y; }
     }
     __syncthreads();
   }
@@ -306,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 2) bwd_dy_kernel(const BwdDyArgs a) 
 
 template <int TR>
 inline size_t bwd_dy_smem_bytes(int NW) {
-  return (size_t)TR * NW * sizeof(u64) + (size_t)TR * KCP * 4 + (size_t)TR * KC + (size_t)2 * kWarps * 32 * 4 + (size_t)TR * 4 + 64;
+  return (size_t)TR * 16 + (size_t)TR * NW * sizeof(u64) + (size_t)TR * KCP * 4 + (size_t)TR * KC + (size_t)4 * kWarps * 32 * 4 + 64;
 }
 
 // merge the per-tile (sum dY, sum dY*Yhat) partials in fixed order (fp64) -> dgamma, dbeta, and the

@@ -9,8 +9,9 @@ namespace ocgcn {
 
 constexpr int kThreads = 256;  // every tile kernel runs 8 warps
 constexpr int kWarps = kThreads / 32;
-constexpr int KC = 32;          // channel chunk = one channel per lane
-constexpr int KCP = KC + 4;     // padded chunk row (floats): float4-aligned, conflict-free for lane==channel
+constexpr int KC = 64;          // channel chunk: two adjacent channels per lane
+constexpr int KCP = KC + 4;     // padded chunk row (floats): float4-aligned rows, conflict-free float2 per lane
+constexpr int kMaxNbr = 13;     // neighbours held inline in a 16-byte row record (more -> bit-mask fallback)
 
 typedef unsigned long long u64;
 
@@ -37,6 +38,8 @@ struct TileArgs {
   long long as0, as1, as2;
   const u64* rowmask;       // [B*N][NW] bit j of row i  <=> adj[b,i,j] != 0
   const u64* colmask;       // [B*N][NW] bit i of col j  <=> adj[b,i,j] != 0
+  const uint4* nbr;         // [B*N] row records: see NbrRec
+  const uint4* cnbr;        // [B*N] column records (neighbours of j in A^T)
   const unsigned* molflag;  // [B] 1 = every entry of adj[b] is exactly 0 or 1
   // producer inputs
   const float* in0;  // P_X: x | P_MID/P_RO: Zprev | P_DZ: dY | P_DU: D
@@ -61,6 +64,33 @@ struct TileArgs {
   float* partials;  // E_ZSTATS: [tile][3][NC]  (count is implicit; slots: mean, M2, unused)
   int skip_gemm;    // producers only (P_DZ of the first layer when dX is not needed)
 };
+
+// ---- 16-byte neighbour record of one adjacency row (built once per forward by adj_pack_kernel) ----------------
+// byte 0: count (bits 0-3, <= kMaxNbr) | 0x20 if the molecule's adjacency is exactly 0/1 | 0x40 if the row has a
+//         zero entry (j < N) | 0x80 if count > kMaxNbr (walk the bit masks instead)
+// byte 1: index of the first zero entry (the "0 * T" candidate of the reference max-pool)
+// byte 2: filled when staged into shared memory: index of the molecule inside the tile (its first row is m*N)
+// bytes 3..15: neighbour indices, ascending; molecule-relative in global memory, tile-relative once staged
+__device__ __forceinline__ int rec_cnt(const uint4& r) { return r.x & 0xf; }
+__device__ __forceinline__ bool rec_has_zero(const uint4& r) { return (r.x & 0x40) != 0; }
+__device__ __forceinline__ bool rec_fallback(const uint4& r) { return (r.x & 0x80) != 0; }
+__device__ __forceinline__ int rec_jz(const uint4& r) { return (r.x >> 8) & 0xff; }
+__device__ __forceinline__ bool rec_binary(const uint4& r) { return (r.x & 0x20) != 0; }
+__device__ __forceinline__ int rec_m(const uint4& r) { return (r.x >> 16) & 0xff; }
+template <int Q>
+__device__ __forceinline__ int rec_idx(const uint4& r) {
+  constexpr int byte = 3 + Q;
+  const unsigned w = (byte >> 2) == 0 ? r.x : (byte >> 2) == 1 ? r.y : (byte >> 2) == 2 ? r.z : r.w;
+  return (w >> ((byte & 3) * 8)) & 0xff;
+}
+__device__ __forceinline__ uint4 rec_stage(uint4 r, int m, int mb) {   // molecule-relative -> tile-relative indices
+  const unsigned add = (unsigned)mb * 0x01010101u;
+  r.x = (r.x & 0x0000ffffu) | ((unsigned)m << 16) | ((((r.x >> 24) + mb) & 0xff) << 24);
+  r.y = __vadd4(r.y, add);
+  r.z = __vadd4(r.z, add);
+  r.w = __vadd4(r.w, add);
+  return r;
+}
 
 __device__ __forceinline__ int first_zero_bit(const u64* m, int NW, int N) {
   for (int w = 0; w < NW; ++w) {
@@ -120,6 +150,15 @@ __device__ __forceinline__ float masked_sum(const u64* mk, int NW, const float* 
     }
   }
   return s;
+}
+
+// tanh(x) = 1 - 2/(exp(2x)+1) on the SFU (MUFU.EX2 + MUFU.RCP): absolute error <~ 3e-7 over the whole range,
+// saturates correctly (+-1) for large |x|. Same function in forward and backward.
+__device__ __forceinline__ float fast_tanh(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return fmaf(-2.f, r, 1.f);
 }
 
 }  // namespace ocgcn

@@ -1,11 +1,15 @@
 // The molecule-tile kernel of the exact-fp32 (FFMA) mode.
 //
-// One CTA owns a tile of MT molecules (rows = MT*N <= TR). It streams the tile's channels in chunks of 32
-// (one channel per lane): a PRODUCER turns the chunk into the left GEMM operand entirely in shared memory
-// (BatchNorm apply + tanh + neighbour max-pool + A.H gather, or the backward element-wise math), the chunk is
-// multiplied with the matching 32 rows of the weight matrix into fp32 register accumulators (8x8 per thread),
-// and an EPILOGUE finishes the tile (bias + BatchNorm partial statistics, readout, or the A^T gather).
+// One CTA owns a tile of MT molecules (rows = MT*N <= TR). It streams the tile's channels in chunks of 64
+// (two adjacent channels per lane): a PRODUCER turns the chunk into the left GEMM operand entirely in shared
+// memory (BatchNorm apply + tanh + neighbour max-pool + A.H gather, or the backward element-wise math), the
+// chunk is multiplied with the matching 64 rows of the weight matrix into fp32 register accumulators (8x8 per
+// thread), and an EPILOGUE finishes the tile (bias + BatchNorm partial statistics, readout, or the A^T gather).
 // Nothing but the layer boundary tensors (Z_l, arg-max, S_l) ever goes to HBM.
+//
+// Sparsity: the adjacency the data layer produces is 0/1 with ~3 neighbours per atom. adj_pack_kernel turns it
+// once per forward into 16-byte neighbour records per row (ocgcn_common.cuh); pool and gather walk those
+// records (warp-uniform control flow, two channels per lane). Non-binary molecules take a dense float path.
 //
 // Reference semantics implemented here: openchem/layers/gcn.py:33-42 and
 // openchem/modules/encoders/gcn_encoder.py:43-53 (see include/ocgcn.h).
@@ -20,11 +24,79 @@ __host__ __device__ constexpr int tile_cols() { return TR == 128 ? 128 : 64; }
 // dynamic shared memory needed by tile_kernel<TR, TC>
 template <int TR, int TC>
 __host__ __device__ inline size_t tile_smem_bytes(int NW) {
+  size_t recs = (size_t)2 * TR * 16;
   size_t masks = (size_t)2 * TR * NW * sizeof(u64);
   size_t main_a = (size_t)2 * TR * KCP * 4 + (size_t)KC * TC * 4;  // two chunk buffers + weight chunk
   size_t main_b = (size_t)TR * (TC + 4) * 4;                      // epilogue staging tile
   size_t mainsz = main_a > main_b ? main_a : main_b;
-  return masks + mainsz + (size_t)TR * 4 /*molecule flags*/ + (size_t)kWarps * 32 * 4 /*warp partials*/ + 64;
+  return recs + masks + mainsz + (size_t)TR * 4 /*molecule flags*/ + (size_t)2 * kWarps * 32 * 4 /*warp partials*/ + 64;
+}
+
+// ---- neighbour walks over a staged record: values of two adjacent channels (float2) per lane ------------------
+// max with first-index-wins ties (ascending neighbour order), returns tile rows of the arg-max
+__device__ __forceinline__ void rec_max2(const uint4& rec, const float* colp, float& b0, float& b1, int& a0, int& a1) {
+  const int cnt = rec_cnt(rec);
+  b0 = -INFINITY; b1 = -INFINITY; a0 = 0; a1 = 0;
+#define OCGCN_MAX_STEP(Q)                                                        \
+  if (cnt > Q) {                                                                 \
+    const int jr = rec_idx<Q>(rec);                                              \
+    const float2 v = *reinterpret_cast<const float2*>(colp + jr * KCP);          \
+    if (v.x > b0) { b0 = v.x; a0 = jr; }                                         \
+    if (v.y > b1) { b1 = v.y; a1 = jr; }                                         \
+  }
+  OCGCN_MAX_STEP(0) OCGCN_MAX_STEP(1) OCGCN_MAX_STEP(2) OCGCN_MAX_STEP(3) OCGCN_MAX_STEP(4)
+  if (cnt > 5) {
+    OCGCN_MAX_STEP(5) OCGCN_MAX_STEP(6) OCGCN_MAX_STEP(7) OCGCN_MAX_STEP(8)
+    if (cnt > 9) { OCGCN_MAX_STEP(9) OCGCN_MAX_STEP(10) OCGCN_MAX_STEP(11) OCGCN_MAX_STEP(12) }
+  }
+#undef OCGCN_MAX_STEP
+}
+
+template <int STRIDE>
+__device__ __forceinline__ float2 rec_sum2(const uint4& rec, const float* colp) {
+  const int cnt = rec_cnt(rec);
+  float s0 = 0.f, s1 = 0.f;
+#define OCGCN_SUM_STEP(Q)                                                                       \
+  if (cnt > Q) {                                                                                \
+    const float2 v = *reinterpret_cast<const float2*>(colp + rec_idx<Q>(rec) * STRIDE);         \
+    s0 += v.x; s1 += v.y;                                                                       \
+  }
+  OCGCN_SUM_STEP(0) OCGCN_SUM_STEP(1) OCGCN_SUM_STEP(2) OCGCN_SUM_STEP(3) OCGCN_SUM_STEP(4)
+  if (cnt > 5) {
+    OCGCN_SUM_STEP(5) OCGCN_SUM_STEP(6) OCGCN_SUM_STEP(7) OCGCN_SUM_STEP(8)
+    if (cnt > 9) { OCGCN_SUM_STEP(9) OCGCN_SUM_STEP(10) OCGCN_SUM_STEP(11) OCGCN_SUM_STEP(12) }
+  }
+#undef OCGCN_SUM_STEP
+  return make_float2(s0, s1);
+}
+
+template <int STRIDE>
+__device__ __forceinline__ float4 rec_sum4(const uint4& rec, const float* colp) {
+  const int cnt = rec_cnt(rec);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#define OCGCN_SUM_STEP(Q)                                                                       \
+  if (cnt > Q) {                                                                                \
+    const float4 v = *reinterpret_cast<const float4*>(colp + rec_idx<Q>(rec) * STRIDE);         \
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;                                             \
+  }
+  OCGCN_SUM_STEP(0) OCGCN_SUM_STEP(1) OCGCN_SUM_STEP(2) OCGCN_SUM_STEP(3) OCGCN_SUM_STEP(4)
+  if (cnt > 5) {
+    OCGCN_SUM_STEP(5) OCGCN_SUM_STEP(6) OCGCN_SUM_STEP(7) OCGCN_SUM_STEP(8)
+    if (cnt > 9) { OCGCN_SUM_STEP(9) OCGCN_SUM_STEP(10) OCGCN_SUM_STEP(11) OCGCN_SUM_STEP(12) }
+  }
+#undef OCGCN_SUM_STEP
+  return s;
+}
+
+// two adjacent channels of one row from global memory (8-byte access when the row pitch allows it)
+__device__ __forceinline__ float2 ldg2(const float* p, bool v0, bool v1, bool vec) {
+  if (vec && v1) return __ldg(reinterpret_cast<const float2*>(p));
+  return make_float2(v0 ? __ldg(p) : 0.f, v1 ? __ldg(p + 1) : 0.f);
+}
+__device__ __forceinline__ void stg2(float* p, float2 v, bool v0, bool v1, bool vec) {
+  if (vec && v1) { *reinterpret_cast<float2*>(p) = v; return; }
+  if (v0) p[0] = v.x;
+  if (v1) p[1] = v.y;
 }
 
 template <int TR, int TC, int PROD, int EPI>
@@ -33,11 +105,13 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
   constexpr int TXN = TC / 8;
   static_assert(TYN * TXN == kThreads, "thread grid must cover the tile");
   constexpr int TCP = TC + 4;
-  constexpr int RPW = TR / kWarps;  // rows per warp (16 or 32), processed in batches of 16 independent loads
+  constexpr int RPW = TR / kWarps;  // rows per warp (16 or 32), processed in batches of 8 independent loads
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = a.N, NW = a.NW, K = a.K, NC = a.NC;
-  u64* sRow = reinterpret_cast<u64*>(smem_raw);
+  uint4* sRec = reinterpret_cast<uint4*>(smem_raw);
+  uint4* sCRec = sRec + TR;
+  u64* sRow = reinterpret_cast<u64*>(sCRec + TR);
   u64* sCol = sRow + (size_t)TR * NW;
   float* mainp = reinterpret_cast<float*>(sCol + (size_t)TR * NW);
   float* buf0 = mainp;
@@ -57,13 +131,23 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
   const int nm = min(a.MT, a.B - mol0);
   const int rows = nm * N;
   const size_t row0 = (size_t)mol0 * N;
+  const bool kvec2 = (K % 2 == 0);
 
-  // ---- stage masks and per-molecule flags ---------------------------------------------------------------
+  // ---- stage neighbour records (made tile-relative), masks and per-molecule flags ---------------------------
+  for (int r = tid; r < TR; r += kThreads) {
+    uint4 rec = make_uint4(0u, 0u, 0u, 0u), crec = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows) {
+      const int m = r / N, mb = m * N;
+      rec = rec_stage(__ldg(&a.nbr[row0 + r]), m, mb);
+      crec = rec_stage(__ldg(&a.cnbr[row0 + r]), m, mb);
+    }
+    sRec[r] = rec;
+    sCRec[r] = crec;
+  }
   for (int idx = tid; idx < rows * NW; idx += kThreads) {
     sRow[idx] = a.rowmask[row0 * NW + idx];
-    if (EPI == E_ATG) sCol[idx] = a.colmask[row0 * NW + idx];
+    sCol[idx] = a.colmask[row0 * NW + idx];
   }
-  for (int idx = tid; idx < nm; idx += kThreads) sFlag[idx] = a.molflag[mol0 + idx];
   __syncthreads();
 
   float acc[8][8];
@@ -76,169 +160,232 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
       for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
 
     for (int k0 = 0; k0 < K; k0 += KC) {
-      const int c = k0 + lane;
-      const bool cvalid = c < K;
+      const int c = k0 + 2 * lane;  // this lane's first channel
+      const bool v0 = c < K, v1 = c + 1 < K;
       const float* opnd = buf0;
 
       // weight chunk [KC][TC] (independent of the producer; sW is free after the previous trailing sync)
       if (!a.skip_gemm) {
-        for (int idx = tid; idx < KC * TC; idx += kThreads) {
-          int kk = idx / TC, cc = idx - kk * TC;
-          int gk = k0 + kk, gc = cb + cc;
-          sW[idx] = (gk < K && gc < NC) ? __ldg(&a.Bm[(size_t)gk * NC + gc]) : 0.f;
+        if (NC % 4 == 0) {
+          for (int idx = tid; idx < KC * TC / 4; idx += kThreads) {
+            const int kk = idx / (TC / 4), cc = (idx - kk * (TC / 4)) * 4;
+            const int gk = k0 + kk, gc = cb + cc;
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gk < K && gc < NC) w = __ldg(reinterpret_cast<const float4*>(&a.Bm[(size_t)gk * NC + gc]));
+            *reinterpret_cast<float4*>(&sW[kk * TC + cc]) = w;
+          }
+        } else {
+          for (int idx = tid; idx < KC * TC; idx += kThreads) {
+            const int kk = idx / TC, cc = idx - kk * TC;
+            const int gk = k0 + kk, gc = cb + cc;
+            sW[idx] = (gk < K && gc < NC) ? __ldg(&a.Bm[(size_t)gk * NC + gc]) : 0.f;
+          }
         }
       }
 
       // =========================== PRODUCER ===========================
       if (PROD == P_X) {
 #pragma unroll
-        for (int h = 0; h < RPW / 16; ++h) {
-          float v[16];
+        for (int h = 0; h < RPW / 8; ++h) {
+          float2 v[8];
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const int r = warp + (h * 16 + q) * kWarps;
-            v[q] = 0.f;
-            if (r < rows && cvalid) {
-              int m = r / N, i = r - m * N;
-              v[q] = __ldg(&a.in0[(long long)(mol0 + m) * a.xs0 + (long long)i * a.xs1 + (long long)c * a.xs2]);
+          for (int q = 0; q < 8; ++q) {
+            const int r = warp + (h * 8 + q) * kWarps;
+            v[q] = make_float2(0.f, 0.f);
+            if (r < rows && v0) {
+              const int m = rec_m(sRec[r]), i = r - m * N;
+              const float* px = a.in0 + (long long)(mol0 + m) * a.xs0 + (long long)i * a.xs1 + (long long)c * a.xs2;
+              v[q].x = __ldg(px);
+              if (v1) v[q].y = __ldg(px + a.xs2);
             }
           }
 #pragma unroll
-          for (int q = 0; q < 16; ++q) buf1[(warp + (h * 16 + q) * kWarps) * KCP + lane] = v[q];
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float2*>(&buf1[(warp + (h * 8 + q) * kWarps) * KCP + 2 * lane]) = v[q];
         }
         __syncthreads();
       } else if (PROD == P_MID || PROD == P_RO) {
-        const float sc = cvalid ? __ldg(&a.vec0[c]) : 0.f;
-        const float sh = cvalid ? __ldg(&a.vec1[c]) : 0.f;
+        float2 sc = make_float2(0.f, 0.f), sh = make_float2(0.f, 0.f);
+        if (v0) { sc.x = __ldg(&a.vec0[c]); sh.x = __ldg(&a.vec1[c]); }
+        if (v1) { sc.y = __ldg(&a.vec0[c + 1]); sh.y = __ldg(&a.vec1[c + 1]); }
 #pragma unroll
-        for (int h = 0; h < RPW / 16; ++h) {
-          float v[16];
+        for (int h = 0; h < RPW / 8; ++h) {
+          float2 v[8];
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {   // all loads of this warp's rows in flight before the first tanh
-            const int r = warp + (h * 16 + q) * kWarps;
-            v[q] = (r < rows && cvalid) ? __ldg(&a.in0[(row0 + r) * K + c]) : 0.f;
+          for (int q = 0; q < 8; ++q) {  // all loads of the batch in flight before the first tanh
+            const int r = warp + (h * 8 + q) * kWarps;
+            v[q] = (r < rows && v0) ? ldg2(&a.in0[(row0 + r) * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
           }
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const int r = warp + (h * 16 + q) * kWarps;
-            buf0[r * KCP + lane] = (r < rows && cvalid) ? tanhf(fmaf(v[q], sc, sh)) : 0.f;
+          for (int q = 0; q < 8; ++q) {
+            const int r = warp + (h * 8 + q) * kWarps;
+            float2 t = make_float2(0.f, 0.f);
+            if (r < rows) {
+              if (v0) t.x = fast_tanh(fmaf(v[q].x, sc.x, sh.x));
+              if (v1) t.y = fast_tanh(fmaf(v[q].y, sc.y, sh.y));
+            }
+            *reinterpret_cast<float2*>(&buf0[r * KCP + 2 * lane]) = t;
           }
         }
         __syncthreads();
         // neighbour max-pool: P[i,c] = max_j A[i,j]*T[j,c], first index wins ties (gcn_encoder.py:44-50)
         for (int r = warp; r < TR; r += kWarps) {
-          float best = 0.f;
-          int arg = 0;
+          float b0 = 0.f, b1 = 0.f;
           if (r < rows) {
-            const int m = r / N, i = r - m * N, mb = m * N;
-            if (sFlag[m]) {
-              const u64* mk = &sRow[(size_t)r * NW];
-              int cnt;
-              masked_max_first(mk, NW, &buf0[mb * KCP + lane], KCP, best, arg, cnt);
-              if (cnt < N && !(best > 0.f)) {  // a zero entry A[i,jz]=0 contributes the candidate 0*T = 0
-                int jz = first_zero_bit(mk, NW, N);
-                if (best < 0.f || jz < arg) arg = jz;
-                best = 0.f;
+            const uint4 rec = sRec[r];
+            const int m = rec_m(rec), mb = m * N;
+            int a0 = mb, a1 = mb;  // tile rows of the arg-max
+            const bool flag = rec_binary(rec);
+            if (flag && !rec_fallback(rec)) {
+              rec_max2(rec, &buf0[2 * lane], b0, b1, a0, a1);
+              if (rec_has_zero(rec)) {  // a zero entry A[i,jz] contributes the candidate 0*T = 0
+                const int jz = mb + rec_jz(rec);
+                if (!(b0 > 0.f)) { if (b0 < 0.f || jz < a0) a0 = jz; b0 = 0.f; }
+                if (!(b1 > 0.f)) { if (b1 < 0.f || jz < a1) a1 = jz; b1 = 0.f; }
               }
-            } else {
+            } else if (flag) {  // binary row with more than kMaxNbr neighbours: walk the bit mask
+              const u64* mk = &sRow[(size_t)r * NW];
+              int cnt, ar;
+              masked_max_first(mk, NW, &buf0[mb * KCP + 2 * lane], KCP, b0, ar, cnt);
+              a0 = mb + ar;
+              masked_max_first(mk, NW, &buf0[mb * KCP + 2 * lane + 1], KCP, b1, ar, cnt);
+              a1 = mb + ar;
+              if (cnt < N) {
+                const int jz = mb + first_zero_bit(mk, NW, N);
+                if (!(b0 > 0.f)) { if (b0 < 0.f || jz < a0) a0 = jz; b0 = 0.f; }
+                if (!(b1 > 0.f)) { if (b1 < 0.f || jz < a1) a1 = jz; b1 = 0.f; }
+              }
+            } else {  // general float adjacency (e.g. edge-attention weights): dense scan, exactly the reference order
+              const int i = r - mb;
               const float* arow = a.adj + (long long)(mol0 + m) * a.as0 + (long long)i * a.as1;
-              best = __ldg(&arow[0]) * buf0[mb * KCP + lane];
+              const float a00 = __ldg(&arow[0]);
+              b0 = a00 * buf0[mb * KCP + 2 * lane];
+              b1 = a00 * buf0[mb * KCP + 2 * lane + 1];
               for (int j = 1; j < N; ++j) {
-                float v = __ldg(&arow[(long long)j * a.as2]) * buf0[(mb + j) * KCP + lane];
-                if (v > best) { best = v; arg = j; }
+                const float aj = __ldg(&arow[(long long)j * a.as2]);
+                const float2 t = *reinterpret_cast<const float2*>(&buf0[(mb + j) * KCP + 2 * lane]);
+                const float c0 = aj * t.x, c1 = aj * t.y;
+                if (c0 > b0) { b0 = c0; a0 = mb + j; }
+                if (c1 > b1) { b1 = c1; a1 = mb + j; }
               }
             }
-            if (first_pass && cvalid) {
-              a.arg_out[(row0 + r) * K + c] = (unsigned char)arg;
-              if (PROD == P_RO) a.prod_out[(row0 + r) * K + c] = best;
+            if (first_pass && v0) {
+              unsigned char* ap = a.arg_out + (row0 + r) * K + c;
+              if (kvec2) {
+                *reinterpret_cast<uchar2*>(ap) = make_uchar2((unsigned char)(a0 - mb), (unsigned char)(a1 - mb));
+              } else {
+                ap[0] = (unsigned char)(a0 - mb);
+                if (v1) ap[1] = (unsigned char)(a1 - mb);
+              }
+              if (PROD == P_RO) stg2(a.prod_out + (row0 + r) * K + c, make_float2(b0, b1), v0, v1, kvec2);
             }
           }
-          buf1[r * KCP + lane] = best;
+          *reinterpret_cast<float2*>(&buf1[r * KCP + 2 * lane]) = make_float2(b0, b1);
         }
         __syncthreads();
       } else if (PROD == P_DZ) {
-        float g = 0.f, c1 = 0.f, c2 = 0.f, mu = 0.f, is = 0.f;
-        if (cvalid) { g = __ldg(&a.vec0[c]); c1 = __ldg(&a.vec1[c]); c2 = __ldg(&a.vec2[c]); mu = __ldg(&a.vec3[c]); is = __ldg(&a.vec4[c]); }
-        float colsum = 0.f;
+        float2 g = make_float2(0.f, 0.f), c1 = g, c2 = g, mu = g, is = g;
+        if (v0) { g.x = __ldg(&a.vec0[c]); c1.x = __ldg(&a.vec1[c]); c2.x = __ldg(&a.vec2[c]); mu.x = __ldg(&a.vec3[c]); is.x = __ldg(&a.vec4[c]); }
+        if (v1) { g.y = __ldg(&a.vec0[c + 1]); c1.y = __ldg(&a.vec1[c + 1]); c2.y = __ldg(&a.vec2[c + 1]); mu.y = __ldg(&a.vec3[c + 1]); is.y = __ldg(&a.vec4[c + 1]); }
+        float2 colsum = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int h = 0; h < RPW / 16; ++h) {
-          float zv[16], dv[16];
+        for (int h = 0; h < RPW / 8; ++h) {
+          float2 zv[8], dv[8];
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const int r = warp + (h * 16 + q) * kWarps;
-            const bool ok = r < rows && cvalid;
-            zv[q] = ok ? __ldg(&a.in1[(row0 + r) * K + c]) : 0.f;
-            dv[q] = ok ? __ldg(&a.in0[(row0 + r) * K + c]) : 0.f;
+          for (int q = 0; q < 8; ++q) {
+            const int r = warp + (h * 8 + q) * kWarps;
+            const bool ok = r < rows && v0;
+            zv[q] = ok ? ldg2(&a.in1[(row0 + r) * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
+            dv[q] = ok ? ldg2(&a.in0[(row0 + r) * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
           }
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const int r = warp + (h * 16 + q) * kWarps;
-            float dz = 0.f;
-            if (r < rows && cvalid) {
-              const float yhat = (zv[q] - mu) * is;
-              dz = g * (dv[q] - c1 - yhat * c2);
-              if (first_pass) { a.prod_out[(row0 + r) * K + c] = dz; colsum += dz; }
+          for (int q = 0; q < 8; ++q) {
+            const int r = warp + (h * 8 + q) * kWarps;
+            float2 dz = make_float2(0.f, 0.f);
+            if (r < rows && v0) {
+              dz.x = g.x * (dv[q].x - c1.x - (zv[q].x - mu.x) * is.x * c2.x);
+              if (v1) dz.y = g.y * (dv[q].y - c1.y - (zv[q].y - mu.y) * is.y * c2.y);
+              if (first_pass) {
+                stg2(a.prod_out + (row0 + r) * K + c, dz, v0, v1, kvec2);
+                colsum.x += dz.x; colsum.y += dz.y;
+              }
             }
-            buf0[r * KCP + lane] = dz;
+            *reinterpret_cast<float2*>(&buf0[r * KCP + 2 * lane]) = dz;
           }
         }
-        if (first_pass && a.prod_partials) sWarp[warp * 32 + lane] = colsum;
+        if (first_pass && a.prod_partials) *reinterpret_cast<float2*>(&sWarp[(warp * 32 + lane) * 2]) = colsum;
         __syncthreads();
-        if (first_pass && a.prod_partials && warp == 0 && cvalid) {
-          float s = 0.f;
+        if (first_pass && a.prod_partials && warp == 0 && v0) {
+          float2 s = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int w = 0; w < kWarps; ++w) s += sWarp[w * 32 + lane];
-          a.prod_partials[(size_t)tile * K + c] = s;
+          for (int w = 0; w < kWarps; ++w) { const float2 t = *reinterpret_cast<const float2*>(&sWarp[(w * 32 + lane) * 2]); s.x += t.x; s.y += t.y; }
+          a.prod_partials[(size_t)tile * K + c] = s.x;
+          if (v1) a.prod_partials[(size_t)tile * K + c + 1] = s.y;
         }
       } else if (PROD == P_DU) {
-        float colsum = 0.f;
+        float2 colsum = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int h = 0; h < RPW / 16; ++h) {
-          float dv[16];
+        for (int h = 0; h < RPW / 8; ++h) {
+          float2 dv[8];
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const int r = warp + (h * 16 + q) * kWarps;
-            dv[q] = (r < rows && cvalid) ? __ldg(&a.in0[(row0 + r) * K + c]) : 0.f;
+          for (int q = 0; q < 8; ++q) {
+            const int r = warp + (h * 8 + q) * kWarps;
+            dv[q] = (r < rows && v0) ? ldg2(&a.in0[(row0 + r) * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
           }
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const int r = warp + (h * 16 + q) * kWarps;
-            float du = 0.f;
-            if (r < rows && cvalid) {
-              const int m = r / N;
+          for (int q = 0; q < 8; ++q) {
+            const int r = warp + (h * 8 + q) * kWarps;
+            float2 du = make_float2(0.f, 0.f);
+            if (r < rows && v0) {
+              const int m = rec_m(sRec[r]);
               const size_t ob = (size_t)(mol0 + m) * K + c;
-              const float ov = __ldg(&a.in2[ob]);
-              du = __ldg(&a.in1[ob]) * (1.f - ov * ov) * (1.f - dv[q] * dv[q]);
-              if (first_pass) { a.prod_out[(row0 + r) * K + c] = du; colsum += du; }
+              const float2 ov = ldg2(&a.in2[ob], v0, v1, kvec2), go = ldg2(&a.in1[ob], v0, v1, kvec2);
+              du.x = go.x * (1.f - ov.x * ov.x) * (1.f - dv[q].x * dv[q].x);
+              if (v1) du.y = go.y * (1.f - ov.y * ov.y) * (1.f - dv[q].y * dv[q].y);
+              if (first_pass) {
+                stg2(a.prod_out + (row0 + r) * K + c, du, v0, v1, kvec2);
+                colsum.x += du.x; colsum.y += du.y;
+              }
             }
-            buf0[r * KCP + lane] = du;
+            *reinterpret_cast<float2*>(&buf0[r * KCP + 2 * lane]) = du;
           }
         }
-        if (first_pass && a.prod_partials) sWarp[warp * 32 + lane] = colsum;
+        if (first_pass && a.prod_partials) *reinterpret_cast<float2*>(&sWarp[(warp * 32 + lane) * 2]) = colsum;
         __syncthreads();
-        if (first_pass && a.prod_partials && warp == 0 && cvalid) {
-          float s = 0.f;
+        if (first_pass && a.prod_partials && warp == 0 && v0) {
+          float2 s = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int w = 0; w < kWarps; ++w) s += sWarp[w * 32 + lane];
-          a.prod_partials[(size_t)tile * K + c] = s;
+          for (int w = 0; w < kWarps; ++w) { const float2 t = *reinterpret_cast<const float2*>(&sWarp[(w * 32 + lane) * 2]); s.x += t.x; s.y += t.y; }
+          a.prod_partials[(size_t)tile * K + c] = s.x;
+          if (v1) a.prod_partials[(size_t)tile * K + c + 1] = s.y;
         }
       }
 
       if (PROD == P_X || PROD == P_MID) {
         // S = A.H for this chunk (gcn.py:34), written over the dead T buffer
         for (int r = warp; r < TR; r += kWarps) {
-          float s = 0.f;
+          float2 s = make_float2(0.f, 0.f);
           if (r < rows) {
-            const int m = r / N, i = r - m * N, mb = m * N;
-            if (sFlag[m]) {
-              s = masked_sum(&sRow[(size_t)r * NW], NW, &buf1[mb * KCP + lane], KCP);
+            const uint4 rec = sRec[r];
+            const int m = rec_m(rec), mb = m * N;
+            const bool flag = rec_binary(rec);
+            if (flag && !rec_fallback(rec)) {
+              s = rec_sum2<KCP>(rec, &buf1[2 * lane]);
+            } else if (flag) {
+              s.x = masked_sum(&sRow[(size_t)r * NW], NW, &buf1[mb * KCP + 2 * lane], KCP);
+              s.y = masked_sum(&sRow[(size_t)r * NW], NW, &buf1[mb * KCP + 2 * lane + 1], KCP);
             } else {
-              const float* arow = a.adj + (long long)(mol0 + m) * a.as0 + (long long)i * a.as1;
-              for (int j = 0; j < N; ++j) s = fmaf(__ldg(&arow[(long long)j * a.as2]), buf1[(mb + j) * KCP + lane], s);
+              const float* arow = a.adj + (long long)(mol0 + m) * a.as0 + (long long)(r - mb) * a.as1;
+              for (int j = 0; j < N; ++j) {
+                const float aj = __ldg(&arow[(long long)j * a.as2]);
+                const float2 hv = *reinterpret_cast<const float2*>(&buf1[(mb + j) * KCP + 2 * lane]);
+                s.x = fmaf(aj, hv.x, s.x);
+                s.y = fmaf(aj, hv.y, s.y);
+              }
             }
-            if (first_pass && cvalid && a.prod_out) a.prod_out[(row0 + r) * K + c] = s;
+            if (first_pass && v0 && a.prod_out) stg2(a.prod_out + (row0 + r) * K + c, s, v0, v1, kvec2);
           }
-          buf0[r * KCP + lane] = s;
+          *reinterpret_cast<float2*>(&buf0[r * KCP + 2 * lane]) = s;
         }
         __syncthreads();
       }
@@ -311,34 +458,35 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
         // per-tile Welford partials (mean, M2) per channel: robust against |mean| >> std, merged in fp64 later
 #pragma unroll
         for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) sRed[ty * TC + h * (TC / 2) + tx * 4 + q] = colv[h * 4 + q];
+          *reinterpret_cast<float4*>(&sRed[ty * TC + h * (TC / 2) + tx * 4]) = make_float4(colv[h * 4], colv[h * 4 + 1], colv[h * 4 + 2], colv[h * 4 + 3]);
         __syncthreads();
         if (tid < TC) {
           float s = 0.f;
+#pragma unroll 8
           for (int y = 0; y < TYN; ++y) s += sRed[y * TC + tid];
           sMean[tid] = s / (float)rows;
         }
         __syncthreads();
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < 2; ++h) {
+          const float4 mu4 = *reinterpret_cast<const float4*>(&sMean[h * (TC / 2) + tx * 4]);
+          const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float mu = sMean[h * (TC / 2) + tx * 4 + q];
             float m2 = 0.f;
 #pragma unroll
             for (int r = 0; r < 8; ++r)
-              if (r * TYN + ty < rows) { float d = acc[r][h * 4 + q] - mu; m2 = fmaf(d, d, m2); }
+              if (r * TYN + ty < rows) { const float d = acc[r][h * 4 + q] - mu[q]; m2 = fmaf(d, d, m2); }
             colv[h * 4 + q] = m2;
           }
-        __syncthreads();  // everyone has read sRed's first use (sMean is separate)
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) sRed[ty * TC + h * (TC / 2) + tx * 4 + q] = colv[h * 4 + q];
+          *reinterpret_cast<float4*>(&sRed[ty * TC + h * (TC / 2) + tx * 4]) = make_float4(colv[h * 4], colv[h * 4 + 1], colv[h * 4 + 2], colv[h * 4 + 3]);
         __syncthreads();
         if (tid < TC && cb + tid < NC) {
           float s = 0.f;
+#pragma unroll 8
           for (int y = 0; y < TYN; ++y) s += sRed[y * TC + tid];
           a.partials[((size_t)tile * 2 + 0) * NC + cb + tid] = sMean[tid];
           a.partials[((size_t)tile * 2 + 1) * NC + cb + tid] = s;
@@ -363,13 +511,17 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             v[q] = acc[r][h * 4 + q];
-            if (EPI == E_READOUT) v[q] = (row < rows && gc + q < NC) ? tanhf(v[q] + bb[q]) : 0.f;   // gcn_encoder.py:51
+            if (EPI == E_READOUT) v[q] = (row < rows && gc + q < NC) ? fast_tanh(v[q] + bb[q]) : 0.f;   // gcn_encoder.py:51
           }
           if (EPI == E_READOUT && row < rows) {
             float* dst = a.out0 + (row0 + row) * NC + gc;
+            if (NC % 4 == 0 && gc + 3 < NC) {
+              *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (gc + q < NC) dst[q] = v[q];
+              for (int q = 0; q < 4; ++q)
+                if (gc + q < NC) dst[q] = v[q];
+            }
           }
           *reinterpret_cast<float4*>(&sC[row * TCP + cl]) = make_float4(v[0], v[1], v[2], v[3]);
         }
@@ -382,23 +534,43 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
           if (cb + cl < NC) {
             float s = 0.f;
             for (int i = 0; i < N; ++i) s += sC[(m * N + i) * TCP + cl];
-            a.out1[(size_t)(mol0 + m) * NC + cb + cl] = tanhf(s);
+            a.out1[(size_t)(mol0 + m) * NC + cb + cl] = fast_tanh(s);
           }
         }
       } else {
-        // dHprev[j,:] = sum_i A[i,j] * dS[i,:]
+        // dHprev[j,:] = sum_i A[i,j] * dS[i,:]   (column records; 4 channels per lane)
         for (int r = warp; r < rows; r += kWarps) {
-          const int m = r / N, j = r - m * N, mb = m * N;
-          for (int cl = lane; cl < TC; cl += 32) {
+          const uint4 crec = sCRec[r];
+          const int m = rec_m(crec), mb = m * N;
+          const bool flag = rec_binary(crec);
+          for (int cl = lane * 4; cl < TC; cl += 128) {
             if (cb + cl >= NC) break;
-            float s = 0.f;
-            if (sFlag[m]) {
-              s = masked_sum(&sCol[(size_t)r * NW], NW, &sC[mb * TCP + cl], TCP);
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (flag && !rec_fallback(crec)) {
+              s = rec_sum4<TCP>(crec, &sC[cl]);
+            } else if (flag) {
+              const u64* mk = &sCol[(size_t)r * NW];
+              s.x = masked_sum(mk, NW, &sC[mb * TCP + cl], TCP);
+              s.y = masked_sum(mk, NW, &sC[mb * TCP + cl + 1], TCP);
+              s.z = masked_sum(mk, NW, &sC[mb * TCP + cl + 2], TCP);
+              s.w = masked_sum(mk, NW, &sC[mb * TCP + cl + 3], TCP);
             } else {
-              const float* acol = a.adj + (long long)(mol0 + m) * a.as0 + (long long)j * a.as2;
-              for (int i = 0; i < N; ++i) s = fmaf(__ldg(&acol[(long long)i * a.as1]), sC[(mb + i) * TCP + cl], s);
+              const float* acol = a.adj + (long long)(mol0 + m) * a.as0 + (long long)(r - mb) * a.as2;
+              for (int i = 0; i < N; ++i) {
+                const float ai = __ldg(&acol[(long long)i * a.as1]);
+                const float4 dv = *reinterpret_cast<const float4*>(&sC[(mb + i) * TCP + cl]);
+                s.x = fmaf(ai, dv.x, s.x); s.y = fmaf(ai, dv.y, s.y); s.z = fmaf(ai, dv.z, s.z); s.w = fmaf(ai, dv.w, s.w);
+              }
             }
-            a.out0[(row0 + r) * NC + cb + cl] = s;
+            float* dst = a.out0 + (row0 + r) * NC + cb + cl;
+            if (NC % 4 == 0 && cb + cl + 3 < NC) {
+              *reinterpret_cast<float4*>(dst) = s;
+            } else {
+              const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (cb + cl + q < NC) dst[q] = sv[q];
+            }
           }
         }
       }

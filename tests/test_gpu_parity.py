@@ -61,18 +61,67 @@ def _compare(res, ref, L, tol, label):
     return worst
 
 
+def _check_against_oracle(x, adj, p, dO, cfg, label, fixture_ref64=None):
+    """Train step + eval forward on the GPU vs the fp64 oracle (and, when given, the reference's own fp64 results).
+
+    Pool routing must equal the oracle's except at NEAR-TIES below fp32 resolution: there an fp32
+    forward cannot (and the fp32 reference does not) reproduce the fp64 choice. Every gradient-carrying mismatch must
+    be such a near-tie; gradients are then compared with the routing the kernel actually used."""
+    from oracle import gcn_oracle as orc
+    from openchem_b200 import functional
+    dev = _dev()
+    B, N = x.shape[0], x.shape[1]
+    L = cfg["n_layers"]
+    p64 = orc.cast_params(p, np.float64)
+    x64, a64 = x.astype(np.float64), adj.astype(np.float64)
+    O, cache, rms, rvs = orc.encoder_forward(x64, a64, p64, training=True)
+    Oe = orc.encoder_forward(x64, a64, dict(p64, running_mean=rms, running_var=rvs), training=False)[0]
+    if fixture_ref64 is not None:   # the oracle itself is pinned to the reference's fp64 run of this very case
+        assert rel_l2(O, fixture_ref64["out_train"]) < 1e-10 and rel_l2(Oe, fixture_ref64["out_eval"]) < 1e-10
+    enc = build_encoder(cfg, p, dev)
+    functional.debug_keep["on"] = True
+    try:
+        enc.train()
+        tx, ta = torch.from_numpy(x).to(dev), torch.from_numpy(adj).to(dev)
+        out = enc((tx, ta))
+        args = [functional.saved_tensor("argmax", l).cpu().numpy().reshape(B, N, -1).astype(np.int64) for l in range(L)]
+        flags = functional.saved_tensor("molflag").cpu().numpy()
+    finally:
+        functional.debug_keep.update(on=False, saved=None, desc=None)
+    binary = np.all((adj == 0) | (adj == 1), axis=(1, 2))
+    assert np.array_equal(flags.astype(bool), binary)            # 0/1 molecules take the neighbour-record path
+    n_mism = 0
+    for l in range(L):
+        T, oarg = cache["layers"][l]["T"], cache["layers"][l]["arg"]
+        for b, i, c in np.argwhere(args[l] != oarg):
+            ja, jo = args[l][b, i, c], oarg[b, i, c]
+            va, vo = a64[b, i, ja] * T[b, ja, c], a64[b, i, jo] * T[b, jo, c]
+            assert abs(va - vo) < 2e-6, f"{label} layer {l} {(b, i, c)}: arg-max {ja} vs oracle {jo} is not a near-tie ({va} vs {vo})"
+            n_mism += 1
+    assert n_mism <= 1e-5 * sum(a.size for a in args) + 2, n_mism
+    gr = orc.encoder_backward(dO.astype(np.float64), cache, arg_override=args)
+    if fixture_ref64 is not None and n_mism == 0:
+        for l in range(L):
+            assert rel_l2(gr["dW"][l], fixture_ref64[f"dW{l}"]) < 1e-10
+    ref = dict(out_train=O, out_eval=Oe, dWd=gr["dWd"], dbd=gr["dbd"])
+    for l in range(L):
+        ref.update({f"dW{l}": gr["dW"][l], f"db{l}": gr["db"][l], f"dgamma{l}": gr["dgamma"][l], f"dbeta{l}": gr["dbeta"][l],
+                    f"rm{l}": rms[l], f"rv{l}": rvs[l]})
+    res = _run_encoder(enc, x, adj, dO, dev, fwd_out=out)
+    _compare(res, ref, L, TOL["fp32"], f"{label} ({n_mism} near-tie routings)")
+    return res
+
+
 @pytest.mark.parametrize("case", ENC_CASES)
 def test_encoder_vs_reference_golden(case):
-    dev = _dev()
     g = load_golden(case)
     L = len(g["hidden"])
     cfg = {"input_size": int(g["x"].shape[2]), "encoder_dim": int(g["Wd"].shape[0]), "n_layers": L, "hidden_size": [int(h) for h in g["hidden"]]}
-    enc = build_encoder(cfg, golden_params(g, np.float32), dev)
-    res = _run_encoder(enc, g["x"], g["adj"], g["dO"], dev)
     ref64 = {k[6:]: v for k, v in g.items() if k.startswith("ref64_")}
-    ref32 = {k[6:]: v for k, v in g.items() if k.startswith("ref32_")}
-    _compare(res, ref64, L, TOL["fp32"], case + " vs ref64")
-    _compare(res, ref32, L, 2 * TOL["fp32"], case + " vs ref32")
+    res = _check_against_oracle(g["x"], g["adj"], golden_params(g, np.float32), g["dO"], cfg, case, fixture_ref64=ref64)
+    # and directly against the reference's own fp32 run (outputs; gradients are covered above)
+    assert rel_l2(res["out_train"], g["ref32_out_train"]) < 2 * TOL["fp32"]
+    assert rel_l2(res["out_eval"], g["ref32_out_eval"]) < 2 * TOL["fp32"]
 
 
 @pytest.mark.parametrize("shape", [
@@ -81,54 +130,30 @@ def test_encoder_vs_reference_golden(case):
     dict(B=33, N=85, F0=33, hidden=[128] * 5, E=128, occ="molecular"),   # C1 shape (ragged last tile)
     dict(B=10, N=128, F0=64, hidden=[256] * 3, E=256, occ="molecular"),  # C5 widths
     dict(B=7, N=132, F0=20, hidden=[48, 200], E=36, occ="molecular"),    # N > 128: 256-row tiles, 3 mask words
+    dict(B=5, N=40, F0=9, hidden=[7, 13], E=5, occ="molecular"),         # odd widths: scalar (non-vector) paths
 ])
 def test_encoder_vs_oracle(shape):
-    from oracle import gcn_oracle as orc
     from openchem_b200.synthetic import make_graph_batch
-    dev = _dev()
     gb = make_graph_batch(shape["B"], shape["N"], shape["F0"], occupancy=shape["occ"], seed=11)
     widths = [shape["F0"]] + shape["hidden"]
     p = random_params(widths, shape["E"], seed=5)
-    rng = np.random.RandomState(3)
-    dO = rng.randn(shape["B"], shape["E"]).astype(np.float32)
-    p64 = orc.cast_params(p, np.float64)
-    x64, a64 = gb["x"].astype(np.float64), gb["adj"].astype(np.float64)
-    O, cache, rms, rvs = orc.encoder_forward(x64, a64, p64, training=True)
-    Oe = orc.encoder_forward(x64, a64, dict(p64, running_mean=rms, running_var=rvs), training=False)[0]
-    L = len(shape["hidden"])
-    cfg = {"input_size": shape["F0"], "encoder_dim": shape["E"], "n_layers": L, "hidden_size": list(shape["hidden"])}
-    enc = build_encoder(cfg, p, dev)
-    # run the train step by hand so the saved arg-max of THAT forward can be inspected
-    from openchem_b200 import functional
-    functional.debug_keep["on"] = True
-    try:
-        enc.train()
-        tx, ta = torch.from_numpy(gb["x"]).to(dev), torch.from_numpy(gb["adj"]).to(dev)
-        out = enc((tx, ta))
-        args = [functional.saved_tensor("argmax", l).cpu().numpy().reshape(shape["B"], shape["N"], -1).astype(np.int64) for l in range(L)]
-        flags = functional.saved_tensor("molflag").cpu().numpy()
-    finally:
-        functional.debug_keep.update(on=False, saved=None, desc=None)
-    assert np.all(flags == 1)                       # synthetic adjacency is exactly 0/1 -> bit-mask path
-    # Pool routing: identical to the oracle except at NEAR-TIES below fp32 resolution: there the
-    # fp32 forward cannot (and the fp32 reference does not) reproduce the fp64 choice. Every gradient-carrying
-    # mismatch must be such a near-tie; gradients are then compared with the routing the kernel actually used.
-    n_mism = 0
-    for l in range(L):
-        T, oarg = cache["layers"][l]["T"], cache["layers"][l]["arg"]
-        for b, i, c in np.argwhere(args[l] != oarg):
-            ja, jo = args[l][b, i, c], oarg[b, i, c]
-            va, vo = a64[b, i, ja] * T[b, ja, c], a64[b, i, jo] * T[b, jo, c]
-            assert abs(va - vo) < 2e-6, f"layer {l} {(b, i, c)}: arg-max {ja} vs oracle {jo} is not a near-tie ({va} vs {vo})"
-            n_mism += 1
-    assert n_mism <= 1e-5 * sum(a.size for a in args) + 2
-    gr = orc.encoder_backward(dO.astype(np.float64), cache, arg_override=args)
-    ref = dict(out_train=O, out_eval=Oe, dWd=gr["dWd"], dbd=gr["dbd"])
-    for l in range(L):
-        ref.update({f"dW{l}": gr["dW"][l], f"db{l}": gr["db"][l], f"dgamma{l}": gr["dgamma"][l], f"dbeta{l}": gr["dbeta"][l],
-                    f"rm{l}": rms[l], f"rv{l}": rvs[l]})
-    res = _run_encoder(enc, gb["x"], gb["adj"], dO, dev, fwd_out=out)
-    _compare(res, ref, L, TOL["fp32"], str(shape) + f" ({n_mism} near-tie routings)")
+    dO = np.random.RandomState(3).randn(shape["B"], shape["E"]).astype(np.float32)
+    cfg = {"input_size": shape["F0"], "encoder_dim": shape["E"], "n_layers": len(shape["hidden"]), "hidden_size": list(shape["hidden"])}
+    _check_against_oracle(gb["x"], gb["adj"], p, dO, cfg, str(shape))
+
+
+def test_dense_hub_atom_uses_mask_fallback():
+    """A row with more than 13 neighbours does not fit a neighbour record: the bit-mask walk must give the same answer."""
+    from openchem_b200.synthetic import make_graph_batch
+    gb = make_graph_batch(6, 24, 12, occupancy="full", seed=4)
+    adj = gb["adj"].copy()
+    adj[:, 3, :20] = 1.0          # atom 3 bonded to 20 atoms
+    adj[:, :20, 3] = 1.0
+    adj[1] = 1.0                  # one fully connected molecule: no zero entry anywhere (no implicit 0 candidate)
+    p = random_params([12, 16, 8], 6, seed=2)
+    dO = np.random.RandomState(1).randn(6, 6).astype(np.float32)
+    cfg = {"input_size": 12, "encoder_dim": 6, "n_layers": 2, "hidden_size": [16, 8]}
+    _check_against_oracle(gb["x"], adj, p, dO, cfg, "hub")
 
 
 @pytest.mark.parametrize("case", LAYER_CASES)
