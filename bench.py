@@ -278,14 +278,17 @@ def run_native(args, w, wname):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
 
     # ---- per-kernel timing (CUDA events around every launch, on the launching stream) ----
+    # (every rank runs the steps - they contain the DDP all-reduce - but only rank 0 records events)
     kern = {}
-    if rank == 0:
-        _lib.profile_enable(True)
+    if args.profile_steps > 0:
+        if rank == 0:
+            _lib.profile_enable(True)
         for _ in range(args.profile_steps):
             step(x, adj, y)
         torch.cuda.synchronize()
-        kern = _lib.profile_collect()
-        _lib.profile_enable(False)
+        if rank == 0:
+            kern = _lib.profile_collect()
+            _lib.profile_enable(False)
     barrier()
 
     if rank != 0:
@@ -306,7 +309,7 @@ def run_native(args, w, wname):
     roofline, shares = None, {}
     tot_ms = sum(v[0] for v in kern.values()) or 1.0
     for k, (ms, n) in sorted(kern.items(), key=lambda kv: -kv[1][0]):
-        shares[k] = dict(ms_per_step=ms / args.profile_steps, launches_per_step=n / args.profile_steps, share=ms / tot_ms)
+        shares[k] = dict(ms_per_step=ms / max(args.profile_steps, 1), launches_per_step=n / max(args.profile_steps, 1), share=ms / tot_ms)
     if kern:
         top = max(kern, key=lambda k: kern[k][0])
         ms_launch = kern[top][0] / kern[top][1]
