@@ -14,7 +14,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libocgcn.so")
-SOURCES = ["ocgcn_api.cu", "ocgcn_tile.cuh", "ocgcn_aux.cuh", "ocgcn_common.cuh"]
+SOURCES = ["ocgcn_api.cu", "ocgcn_tile.cuh", "ocgcn_aux.cuh", "ocgcn_common.cuh", "ocgcn_tc.cuh", "ocgcn_dw.cuh"]
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "ocgcn.h")
 
 MAX_LAYERS = 16

@@ -10,6 +10,7 @@
 
 #include "ocgcn_aux.cuh"
 #include "ocgcn_common.cuh"
+#include "ocgcn_dw.cuh"
 #include "ocgcn_tile.cuh"
 
 namespace ocgcn {
@@ -20,10 +21,11 @@ static thread_local int tl_cuda_err = 0;
 // ---- opt-in per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream ----------
 enum KernelKind : int {
   KK_ADJ_PACK = 0, KK_TRANSPOSE, KK_FWD_FIRST, KK_FWD_MID, KK_BN_FINALIZE, KK_FWD_READOUT, KK_BWD_READOUT, KK_BWD_DY,
-  KK_BWD_FINALIZE, KK_BWD_DZ, KK_GEMM_TN, KK_REDUCE, KK_BN_APPLY, KK_COUNT
+  KK_BWD_FINALIZE, KK_BWD_DZ, KK_GEMM_TN, KK_REDUCE, KK_BN_APPLY, KK_WPREP, KK_DW_MMA, KK_COUNT
 };
 static const char* const kKindNames[KK_COUNT] = {"adj_pack", "transpose", "fwd_first", "fwd_mid", "bn_finalize", "fwd_readout",
-                                                 "bwd_readout", "bwd_dy", "bwd_finalize", "bwd_dz", "gemm_tn", "reduce", "bn_apply"};
+                                                 "bwd_readout", "bwd_dy", "bwd_finalize", "bwd_dz", "gemm_tn", "reduce", "bn_apply",
+                                                 "wprep", "dw_mma"};
 struct ProfRec { int kind; cudaEvent_t e0, e1; };
 // process-wide (autograd runs backward on its own thread), guarded by a mutex; off by default
 static std::atomic<bool> g_prof_on{false};
@@ -69,6 +71,8 @@ static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a
 // ---------------------------------------------------------------------------------------------------------
 struct Layout {
   int TR, MT, NW, tiles, Fmax;
+  int mm;                            // 1: tensor-core engine (bf16 operand images), 0: exact-fp32 FFMA engine
+  int KP[OCGCN_MAX_LAYERS + 1], KPE;  // channel counts padded to multiples of 64 (operand image extents)
   size_t rows;
   // saved
   size_t rowmask, colmask, molflag, nbr, cnbr;
@@ -77,6 +81,7 @@ struct Layout {
   size_t saved_total;
   // scratch
   size_t partials, prodpart, WT[OCGCN_MAX_LAYERS], WdT, G[3], dU, coef, gemm_partial;
+  size_t Wf[OCGCN_MAX_LAYERS], Wro, Wb[OCGCN_MAX_LAYERS], Wrob, dZimg, dUimg;   // mm: weight operand images, dZ / dU tile images
   size_t scratch_total;
   int max_splits;
 };
@@ -111,6 +116,11 @@ static int make_layout(const ocgcn_desc* d, bool layer_only, Layout* lo) {
   int Fmax = d->E > 0 && !layer_only ? d->E : 1;
   for (int l = 0; l <= d->L; ++l) Fmax = d->F[l] > Fmax ? d->F[l] : Fmax;
   lo->Fmax = Fmax;
+  // the tensor-core engine covers 128-row tiles and widths up to 256; anything else runs the exact-fp32 engine
+  lo->mm = (d->mode != OCGCN_FP32 && d->N <= 128 && Fmax <= 256) ? 1 : 0;
+  int KPmax = 64;
+  for (int l = 0; l <= d->L; ++l) { lo->KP[l] = (d->F[l] + 63) / 64 * 64; KPmax = lo->KP[l] > KPmax ? lo->KP[l] : KPmax; }
+  lo->KPE = layer_only ? 64 : (d->E + 63) / 64 * 64;
   const size_t rows = lo->rows;
   size_t off = 0;
   auto take = [&off](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
@@ -122,11 +132,11 @@ static int make_layout(const ocgcn_desc* d, bool layer_only, Layout* lo) {
   for (int l = 0; l < d->L; ++l) {
     lo->Z[l] = take(rows * d->F[l + 1] * 4);
     lo->arg[l] = layer_only ? 0 : take(rows * d->F[l + 1]);
-    lo->S[l] = take(rows * d->F[l] * 4);
+    lo->S[l] = lo->mm ? take((size_t)lo->tiles * lo->KP[l] * 256) : take(rows * d->F[l] * 4);
     lo->stats[l] = take((size_t)4 * d->F[l + 1] * 4);
   }
   if (!layer_only) {
-    lo->HL = take(rows * d->F[d->L] * 4);
+    lo->HL = lo->mm ? take((size_t)lo->tiles * lo->KP[d->L] * 256) : take(rows * d->F[d->L] * 4);
     lo->D = take(rows * d->E * 4);
     lo->O = take((size_t)d->B * d->E * 4);
   }
@@ -155,6 +165,20 @@ static int make_layout(const ocgcn_desc* d, bool layer_only, Layout* lo) {
   }
   for (int i = 0; i < 3; ++i) lo->G[i] = take(rows * Fmax * 4);
   lo->coef = take((size_t)3 * Fmax * 4);
+  if (lo->mm) {
+    for (int l = 0; l < d->L; ++l) {
+      lo->Wf[l] = take(wimg_bytes(d->F[l], d->F[l + 1], 2));
+      lo->Wb[l] = take(wimg_bytes(d->F[l + 1], d->F[l], 2));
+    }
+    if (!layer_only) {
+      lo->Wro = take(wimg_bytes(d->F[d->L], d->E, 2));
+      lo->Wrob = take(wimg_bytes(d->E, d->F[d->L], 2));
+      lo->dUimg = take((size_t)lo->tiles * lo->KPE * 256);
+    }
+    lo->dZimg = take((size_t)lo->tiles * KPmax * 256);
+    const size_t p = (size_t)148 * KPmax * (lo->KPE > KPmax ? lo->KPE : KPmax) * 4;   // per-CTA dW partials of dw_mma_kernel
+    max_partial = p > max_partial ? p : max_partial;
+  }
   lo->gemm_partial = take(max_partial);
   lo->max_splits = max_splits;
   lo->scratch_total = off;
@@ -185,12 +209,12 @@ static int check_device_ptr(const void* p) {
 // ---------------------------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------------------------
-template <int TR, int PROD, int EPI>
+template <int TR, int PROD, int EPI, int MM>
 static int launch_tile_t(const TileArgs& a, int tiles, cudaStream_t st) {
   constexpr int TC = tile_cols<TR>();
   ProfScope prof(PROD == P_X ? KK_FWD_FIRST : PROD == P_MID ? KK_FWD_MID : PROD == P_RO ? KK_FWD_READOUT : PROD == P_DZ ? KK_BWD_DZ : KK_BWD_READOUT, st);
-  auto kern = tile_kernel<TR, TC, PROD, EPI>;
-  const size_t smem = tile_smem_bytes<TR, TC>(a.NW);
+  auto kern = tile_kernel<TR, TC, PROD, EPI, MM>;
+  const size_t smem = tile_smem_bytes<TR, TC, MM>(a.NW);
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<tiles, kThreads, smem, st>>>(a);
   LAUNCH_CHECK();
@@ -198,8 +222,47 @@ static int launch_tile_t(const TileArgs& a, int tiles, cudaStream_t st) {
 }
 template <int PROD, int EPI>
 static int launch_tile(const Layout& lo, const TileArgs& a, cudaStream_t st) {
-  if (lo.TR == 128) return launch_tile_t<128, PROD, EPI>(a, lo.tiles, st);
-  return launch_tile_t<256, PROD, EPI>(a, lo.tiles, st);
+  if (lo.mm) return launch_tile_t<128, PROD, EPI, 1>(a, lo.tiles, st);
+  if (lo.TR == 128) return launch_tile_t<128, PROD, EPI, 0>(a, lo.tiles, st);
+  return launch_tile_t<256, PROD, EPI, 0>(a, lo.tiles, st);
+}
+
+// dW (M x Nn) = sum over tiles of Aimg^T . Bimg on tcgen05 (per-CTA partials in `partial`, merged by run_reduce)
+static int run_dw_mma(const Layout& lo, const void* Aimg, const void* Bimg, int KPa, int KPb, int M, int Nn, float* partial,
+                      cudaStream_t st, int* splits_out) {
+  ProfScope prof(KK_DW_MMA, st);
+  DwArgs g;
+  g.Aimg = Aimg; g.Bimg = Bimg; g.tiles = lo.tiles; g.chA = KPa / 8; g.chB = KPb / 8; g.M = M; g.Nn = Nn; g.partial = partial;
+  int splits = lo.tiles < 148 ? lo.tiles : 148;
+  g.tiles_per_cta = (lo.tiles + splits - 1) / splits;
+  splits = (lo.tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
+  const size_t stage = dw_stage_bytes(g.chA, g.chB);
+  int stages = (int)((size_t)(200 * 1024) / stage);
+  stages = stages < 1 ? 1 : stages > 4 ? 4 : stages;
+  g.stages = stages;
+  const size_t smem = stage * stages + (size_t)(2 * stages + 1) * 8 + 16;
+  CU_TRY(cudaFuncSetAttribute(dw_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dw_mma_kernel<<<splits, 128, smem, st>>>(g);
+  LAUNCH_CHECK();
+  *splits_out = splits;
+  return OCGCN_OK;
+}
+
+static int run_wprep(const WPrepJobs& jobs, int n, cudaStream_t st) {
+  if (n == 0) return OCGCN_OK;
+  ProfScope prof(KK_WPREP, st);
+  int pieces = 1;
+  for (int j = 0; j < n; ++j) {
+    const int p = ((jobs.K[j] + 63) / 64) * ((jobs.Nn[j] + 127) / 128);
+    pieces = p > pieces ? p : pieces;
+  }
+  wprep_kernel<<<dim3(pieces, n), 256, 0, st>>>(jobs);
+  LAUNCH_CHECK();
+  return OCGCN_OK;
+}
+static void add_wprep(WPrepJobs& jobs, int& n, const float* src, void* dst, int K, int Nn, int form, int parts) {
+  jobs.src[n] = src; jobs.dst[n] = dst; jobs.K[n] = K; jobs.Nn[n] = Nn; jobs.form[n] = form; jobs.parts[n] = parts;
+  ++n;
 }
 
 static int launch_bwd_dy(const Layout& lo, const BwdDyArgs& a, cudaStream_t st) {
@@ -301,6 +364,11 @@ static int run_layer_forward(const ocgcn_desc* d, const Layout& lo, const float*
   a.out0 = reinterpret_cast<float*>(saved + lo.Z[l]);
   a.prod_out = reinterpret_cast<float*>(saved + lo.S[l]);
   a.partials = reinterpret_cast<float*>(scratch + lo.partials);
+  if (lo.mm) {
+    a.prod_out = nullptr;
+    a.prod_img = saved + lo.S[l]; a.img_chunks = lo.KP[l] / 8;
+    a.wimg = scratch + lo.Wf[l]; a.ncb = (d->F[l + 1] + 127) / 128;
+  }
   if (l == 0) {
     a.in0 = x; a.xs0 = d->x_stride[0]; a.xs1 = d->x_stride[1]; a.xs2 = d->x_stride[2];
     ST_TRY((launch_tile<P_X, E_ZSTATS>(lo, a, st)));
@@ -358,11 +426,17 @@ static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float
   a.Bm = reinterpret_cast<const float*>(scratch + lo.WT[l]);
   a.out0 = g_out;
   a.skip_gemm = skip_dx ? 1 : 0;
+  if (lo.mm) {
+    a.prod_out = nullptr;
+    a.prod_img = scratch + lo.dZimg; a.img_chunks = lo.KP[l + 1] / 8;
+    a.wimg = scratch + lo.Wb[l]; a.ncb = (Fin + 127) / 128;
+  }
   ST_TRY((launch_tile<P_DZ, E_ATG>(lo, a, st)));
 
   int splits = 0;
   float* gp = reinterpret_cast<float*>(scratch + lo.gemm_partial);
-  ST_TRY(run_gemm_tn(reinterpret_cast<const float*>(saved + lo.S[l]), g_dz, lo.rows, Fin, Fout, gp, st, &splits));
+  if (lo.mm) ST_TRY(run_dw_mma(lo, saved + lo.S[l], scratch + lo.dZimg, lo.KP[l], lo.KP[l + 1], Fin, Fout, gp, st, &splits));
+  else ST_TRY(run_gemm_tn(reinterpret_cast<const float*>(saved + lo.S[l]), g_dz, lo.rows, Fin, Fout, gp, st, &splits));
   ST_TRY(run_reduce(gp, g->dW[l], splits, Fin * Fout, prodpart, (d->has_bias ? g->db[l] : nullptr), lo.tiles, Fout, st));
   return OCGCN_OK;
 }
@@ -430,7 +504,7 @@ int ocgcn_saved_tensor(const ocgcn_desc* desc, int what, int layer, size_t* offs
   switch (what) {
     case OCGCN_SAVED_Z: *offset = lo.Z[layer]; *bytes = rows * desc->F[layer + 1] * 4; break;
     case OCGCN_SAVED_ARGMAX: if (layer_only) return OCGCN_EINVAL; *offset = lo.arg[layer]; *bytes = rows * desc->F[layer + 1]; break;
-    case OCGCN_SAVED_S: *offset = lo.S[layer]; *bytes = rows * desc->F[layer] * 4; break;
+    case OCGCN_SAVED_S: *offset = lo.S[layer]; *bytes = lo.mm ? (size_t)lo.tiles * lo.KP[layer] * 256 : rows * desc->F[layer] * 4; break;
     case OCGCN_SAVED_STATS: *offset = lo.stats[layer]; *bytes = (size_t)4 * desc->F[layer + 1] * 4; break;
     case OCGCN_SAVED_ROWMASK: *offset = lo.rowmask; *bytes = rows * lo.NW * 8; break;
     case OCGCN_SAVED_MOLFLAG: *offset = lo.molflag; *bytes = (size_t)desc->B * 4; break;
@@ -466,10 +540,19 @@ int ocgcn_encoder_forward(const ocgcn_desc* d, const float* x, const float* adj,
   const int L = d->L;
 
   ST_TRY(run_adj_pack(d, lo, adj, saved, st));
-  TransposeJobs tj;
-  memset(&tj, 0, sizeof(tj));
-  tj.in[0] = p->Wd; tj.out[0] = reinterpret_cast<float*>(scratch + lo.WdT); tj.R[0] = d->E; tj.C[0] = d->F[L];
-  ST_TRY(run_transposes(tj, 1, st));
+  if (lo.mm) {
+    WPrepJobs wj;
+    memset(&wj, 0, sizeof(wj));
+    int nj = 0;
+    for (int l = 0; l < L; ++l) add_wprep(wj, nj, p->W[l], scratch + lo.Wf[l], d->F[l], d->F[l + 1], 0, 2);
+    add_wprep(wj, nj, p->Wd, scratch + lo.Wro, d->F[L], d->E, 1, 2);
+    ST_TRY(run_wprep(wj, nj, st));
+  } else {
+    TransposeJobs tj;
+    memset(&tj, 0, sizeof(tj));
+    tj.in[0] = p->Wd; tj.out[0] = reinterpret_cast<float*>(scratch + lo.WdT); tj.R[0] = d->E; tj.C[0] = d->F[L];
+    ST_TRY(run_transposes(tj, 1, st));
+  }
   for (int l = 0; l < L; ++l) ST_TRY(run_layer_forward(d, lo, x, adj, p, l, saved, scratch, st));
 
   // readout: H_L = pool(tanh(BN(Z_L))), D = tanh(H_L Wd^T + bd), O = tanh(sum_i D)
@@ -484,6 +567,11 @@ int ocgcn_encoder_forward(const ocgcn_desc* d, const float* x, const float* adj,
   a.bias = p->bd;
   a.out0 = reinterpret_cast<float*>(saved + lo.D);
   a.out1 = out;
+  if (lo.mm) {
+    a.prod_out = nullptr;
+    a.prod_img = saved + lo.HL; a.img_chunks = lo.KP[L] / 8;
+    a.wimg = scratch + lo.Wro; a.ncb = (d->E + 127) / 128;
+  }
   ST_TRY((launch_tile<P_RO, E_READOUT>(lo, a, st)));
   CU_TRY(cudaMemcpyAsync(saved + lo.O, out, (size_t)d->B * d->E * 4, cudaMemcpyDeviceToDevice, st));
   return OCGCN_OK;
@@ -508,14 +596,23 @@ int ocgcn_encoder_backward(const ocgcn_desc* d, const float* grad_out, const flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int L = d->L;
 
-  TransposeJobs tj;
-  memset(&tj, 0, sizeof(tj));
-  int nj = 0;
-  for (int l = 1; l < L; ++l) {
-    tj.in[nj] = p->W[l]; tj.out[nj] = reinterpret_cast<float*>(scratch + lo.WT[l]); tj.R[nj] = d->F[l]; tj.C[nj] = d->F[l + 1];
-    ++nj;
+  if (lo.mm) {
+    WPrepJobs wj;
+    memset(&wj, 0, sizeof(wj));
+    int nj = 0;
+    for (int l = 1; l < L; ++l) add_wprep(wj, nj, p->W[l], scratch + lo.Wb[l], d->F[l + 1], d->F[l], 1, 2);
+    add_wprep(wj, nj, p->Wd, scratch + lo.Wrob, d->E, d->F[L], 0, 2);
+    ST_TRY(run_wprep(wj, nj, st));
+  } else {
+    TransposeJobs tj;
+    memset(&tj, 0, sizeof(tj));
+    int nj = 0;
+    for (int l = 1; l < L; ++l) {
+      tj.in[nj] = p->W[l]; tj.out[nj] = reinterpret_cast<float*>(scratch + lo.WT[l]); tj.R[nj] = d->F[l]; tj.C[nj] = d->F[l + 1];
+      ++nj;
+    }
+    ST_TRY(run_transposes(tj, nj, st));
   }
-  ST_TRY(run_transposes(tj, nj, st));
 
   float* G[3] = {reinterpret_cast<float*>(scratch + lo.G[0]), reinterpret_cast<float*>(scratch + lo.G[1]),
                  reinterpret_cast<float*>(scratch + lo.G[2])};
@@ -533,9 +630,15 @@ int ocgcn_encoder_backward(const ocgcn_desc* d, const float* grad_out, const flo
   a.prod_partials = prodpart;
   a.Bm = p->Wd;
   a.out0 = G[0];
+  if (lo.mm) {
+    a.prod_out = nullptr;
+    a.prod_img = scratch + lo.dUimg; a.img_chunks = lo.KPE / 8;
+    a.wimg = scratch + lo.Wrob; a.ncb = (d->F[L] + 127) / 128;
+  }
   ST_TRY((launch_tile<P_DU, E_STORE>(lo, a, st)));
   int splits = 0;
-  ST_TRY(run_gemm_tn(dU, reinterpret_cast<const float*>(saved + lo.HL), lo.rows, d->E, d->F[L], gp, st, &splits));
+  if (lo.mm) ST_TRY(run_dw_mma(lo, scratch + lo.dUimg, saved + lo.HL, lo.KPE, lo.KP[L], d->E, d->F[L], gp, st, &splits));
+  else ST_TRY(run_gemm_tn(dU, reinterpret_cast<const float*>(saved + lo.HL), lo.rows, d->E, d->F[L], gp, st, &splits));
   ST_TRY(run_reduce(gp, g->dWd, splits, d->E * d->F[L], prodpart, g->dbd, lo.tiles, d->E, st));
 
   int cur = 0;
@@ -563,6 +666,13 @@ int ocgcn_layer_forward(const ocgcn_desc* d, const float* x, const float* adj, c
   char* scratch = static_cast<char*>(scratch_v);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ST_TRY(run_adj_pack(d, lo, adj, saved, st));
+  if (lo.mm) {
+    WPrepJobs wj;
+    memset(&wj, 0, sizeof(wj));
+    int nj = 0;
+    add_wprep(wj, nj, p->W[0], scratch + lo.Wf[0], d->F[0], d->F[1], 0, 2);
+    ST_TRY(run_wprep(wj, nj, st));
+  }
   ST_TRY(run_layer_forward(d, lo, x, adj, p, 0, saved, scratch, st));
   const int F = d->F[1];
   const float* stats = reinterpret_cast<const float*>(saved + lo.stats[0]);
@@ -593,7 +703,13 @@ int ocgcn_layer_backward(const ocgcn_desc* d, const float* grad_y, const float* 
   char* saved = static_cast<char*>(saved_v);
   char* scratch = static_cast<char*>(scratch_v);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (d->need_dx) {
+  if (d->need_dx && lo.mm) {
+    WPrepJobs wj;
+    memset(&wj, 0, sizeof(wj));
+    int nj = 0;
+    add_wprep(wj, nj, p->W[0], scratch + lo.Wb[0], d->F[1], d->F[0], 1, 2);
+    ST_TRY(run_wprep(wj, nj, st));
+  } else if (d->need_dx) {
     TransposeJobs tj;
     memset(&tj, 0, sizeof(tj));
     tj.in[0] = p->W[0]; tj.out[0] = reinterpret_cast<float*>(scratch + lo.WT[0]); tj.R[0] = d->F[0]; tj.C[0] = d->F[1];

@@ -63,6 +63,11 @@ struct TileArgs {
   float* out1;      // E_READOUT: O [B][NC]
   float* partials;  // E_ZSTATS: [tile][3][NC]  (count is implicit; slots: mean, M2, unused)
   int skip_gemm;    // producers only (P_DZ of the first layer when dX is not needed)
+  // tensor-core engine (tile_kernel<.., MM = 1>) only
+  const void* wimg;  // weight operand images: pieces [K/64][ceil(NC/128)][hi(,lo)] of [8 k-chunks][128 n][8] bf16 (ocgcn_dw.cuh)
+  int ncb;           // ceil(NC/128)
+  void* prod_img;    // producer output as bf16 tile images [tile][img_chunks][128 rows][8] (operand of the dW GEMM) or null
+  int img_chunks;    // 16-byte channel chunks per tile image = 8 * ceil(K/64)
 };
 
 // ---- 16-byte neighbour record of one adjacency row (built once per forward by adj_pack_kernel) ----------------

@@ -1,11 +1,20 @@
-// The molecule-tile kernel of the exact-fp32 (FFMA) mode.
+// The molecule-tile kernel.
 //
 // One CTA owns a tile of MT molecules (rows = MT*N <= TR). It streams the tile's channels in chunks of 64
 // (two adjacent channels per lane): a PRODUCER turns the chunk into the left GEMM operand entirely in shared
 // memory (BatchNorm apply + tanh + neighbour max-pool + A.H gather, or the backward element-wise math), the
-// chunk is multiplied with the matching 64 rows of the weight matrix into fp32 register accumulators (8x8 per
-// thread), and an EPILOGUE finishes the tile (bias + BatchNorm partial statistics, readout, or the A^T gather).
-// Nothing but the layer boundary tensors (Z_l, arg-max, S_l) ever goes to HBM.
+// chunk is multiplied with the matching 64 rows of the weight matrix, and an EPILOGUE finishes the tile (bias +
+// BatchNorm partial statistics, readout, or the A^T gather). Nothing but the layer boundary tensors ever goes
+// to HBM.
+//
+// Two GEMM engines, selected by the template parameter MM:
+//   MM == 0  exact-fp32 mode: FFMA into fp32 register accumulators (8x8 per thread).
+//   MM == 1  bf16 tensor-core mode (sm_100a): the producer writes the operand as bf16 hi/lo images in the
+//            no-swizzle core-matrix layout (ocgcn_tc.cuh), the weight images arrive by 1-D bulk copies (TMA
+//            engine), one thread issues tcgen05.mma (4 passes hi.hi + lo.hi + hi.lo + lo.lo in the forward, 3 in the
+//            backward), the fp32 accumulator tile lives in TMEM and is read back with tcgen05.ld for the
+//            epilogue. The hi image of the operand is also bulk-stored to HBM: it is the (already formatted)
+//            operand of the weight-gradient GEMM (ocgcn_dw.cuh).
 //
 // Sparsity: the adjacency the data layer produces is 0/1 with ~3 neighbours per atom. adj_pack_kernel turns it
 // once per forward into 16-byte neighbour records per row (ocgcn_common.cuh); pool and gather walk those
@@ -15,32 +24,39 @@
 // openchem/modules/encoders/gcn_encoder.py:43-53 (see include/ocgcn.h).
 #pragma once
 #include "ocgcn_common.cuh"
+#include "ocgcn_tc.cuh"
 
 namespace ocgcn {
 
 template <int TR>
 __host__ __device__ constexpr int tile_cols() { return TR == 128 ? 128 : 64; }
 
-// dynamic shared memory needed by tile_kernel<TR, TC>
-template <int TR, int TC>
+constexpr int kImgPitch = 128 * 16 + 16;   // MM: bytes between 16-byte channel chunks of the operand image (padded: conflict-free stores)
+constexpr int kWPiece = 8 * 128 * 16;      // MM: bytes of one weight image piece: [8 k-chunks][128 n][16 B]
+constexpr int kTmemCols = 128;
+
+// dynamic shared memory needed by tile_kernel<TR, TC, ., ., MM>
+template <int TR, int TC, int MM>
 __host__ __device__ inline size_t tile_smem_bytes(int NW) {
   size_t recs = (size_t)2 * TR * 16;
   size_t masks = (size_t)2 * TR * NW * sizeof(u64);
-  size_t main_a = (size_t)2 * TR * KCP * 4 + (size_t)KC * TC * 4;  // two chunk buffers + weight chunk
-  size_t main_b = (size_t)TR * (TC + 4) * 4;                      // epilogue staging tile
+  size_t main_a = MM ? (size_t)2 * TR * KC * 4 + (size_t)2 * 8 * kImgPitch
+                     : (size_t)2 * TR * KCP * 4 + (size_t)KC * TC * 4;  // two chunk buffers + weight chunk / operand images
+  size_t main_b = (size_t)TR * (TC + 4) * 4;                            // epilogue staging tile
   size_t mainsz = main_a > main_b ? main_a : main_b;
   return recs + masks + mainsz + (size_t)TR * 4 /*molecule flags*/ + (size_t)2 * kWarps * 32 * 4 /*warp partials*/ + 64;
 }
 
 // ---- neighbour walks over a staged record: values of two adjacent channels (float2) per lane ------------------
 // max with first-index-wins ties (ascending neighbour order), returns tile rows of the arg-max
+template <int STRIDE>
 __device__ __forceinline__ void rec_max2(const uint4& rec, const float* colp, float& b0, float& b1, int& a0, int& a1) {
   const int cnt = rec_cnt(rec);
   b0 = -INFINITY; b1 = -INFINITY; a0 = 0; a1 = 0;
 #define OCGCN_MAX_STEP(Q)                                                        \
   if (cnt > Q) {                                                                 \
     const int jr = rec_idx<Q>(rec);                                              \
-    const float2 v = *reinterpret_cast<const float2*>(colp + jr * KCP);          \
+    const float2 v = *reinterpret_cast<const float2*>(colp + jr * STRIDE);       \
     if (v.x > b0) { b0 = v.x; a0 = jr; }                                         \
     if (v.y > b1) { b1 = v.y; a1 = jr; }                                         \
   }
@@ -99,13 +115,18 @@ __device__ __forceinline__ void stg2(float* p, float2 v, bool v0, bool v1, bool 
   if (v1) p[1] = v.y;
 }
 
-template <int TR, int TC, int PROD, int EPI>
+template <int TR, int TC, int PROD, int EPI, int MM>
 __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(const TileArgs a) {
   constexpr int TYN = TR / 8;
   constexpr int TXN = TC / 8;
   static_assert(TYN * TXN == kThreads, "thread grid must cover the tile");
+  static_assert(MM == 0 || (TR == 128 && TC == 128), "the tensor-core path works on 128x128 tiles");
   constexpr int TCP = TC + 4;
-  constexpr int RPW = TR / kWarps;  // rows per warp (16 or 32), processed in batches of 8 independent loads
+  constexpr int RPW = TR / kWarps;      // rows per warp (16 or 32), processed in batches of 8 independent loads
+  constexpr int BS = MM ? KC : KCP;     // chunk buffer row stride (floats); the FFMA fragment loads want the padding
+  // MM: every operand is split x = hi + lo (bf16 each). Forward products take 4 passes (hi.hi + lo.hi + hi.lo + lo.lo:
+  // fp32-class values, so the pool arg-max decisions match an fp32 forward), backward products 3 (no lo.lo).
+  constexpr int NPASS = (PROD == P_X || PROD == P_MID || PROD == P_RO) ? 4 : 3;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = a.N, NW = a.NW, K = a.K, NC = a.NC;
@@ -115,14 +136,19 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
   u64* sCol = sRow + (size_t)TR * NW;
   float* mainp = reinterpret_cast<float*>(sCol + (size_t)TR * NW);
   float* buf0 = mainp;
-  float* buf1 = buf0 + TR * KCP;
-  float* sW = buf1 + TR * KCP;
+  float* buf1 = buf0 + TR * BS;
+  float* sW = buf1 + TR * BS;                                          // MM == 0: weight chunk
+  unsigned char* imgHi = reinterpret_cast<unsigned char*>(buf1 + TR * BS);   // MM == 1: operand images [8][kImgPitch]
+  unsigned char* imgLo = imgHi + 8 * kImgPitch;
+  unsigned char* wHi = reinterpret_cast<unsigned char*>(buf0);                 // MM == 1: weight image pieces (hi, lo) alias buf0
   float* sC = mainp;  // epilogue staging, aliases buf0/buf1/sW
-  constexpr size_t main_a = (size_t)2 * TR * KCP + (size_t)KC * TC;
+  constexpr size_t main_a = MM ? ((size_t)2 * TR * KC * 4 + (size_t)2 * 8 * kImgPitch) / 4 : (size_t)2 * TR * KCP + (size_t)KC * TC;
   constexpr size_t main_b = (size_t)TR * TCP;
   constexpr size_t mainsz = main_a > main_b ? main_a : main_b;
   unsigned* sFlag = reinterpret_cast<unsigned*>(mainp + mainsz);
   float* sWarp = reinterpret_cast<float*>(sFlag + TR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sWarp + 2 * kWarps * 32);   // MM: [0] weight image landed, [1] MMAs complete
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 2);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid % TXN, ty = tid / TXN;
@@ -132,6 +158,14 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
   const int rows = nm * N;
   const size_t row0 = (size_t)mol0 * N;
   const bool kvec2 = (K % 2 == 0);
+  // T goes to the buffer the weight image does NOT alias while the pool still reads it
+  float* const bufT = (MM && PROD == P_RO) ? buf1 : buf0;
+  float* const bufH = (MM && PROD == P_RO) ? buf0 : buf1;
+  // this lane's slot inside a 64-channel operand image row: 16-byte chunk lane/4, word lane%4
+  const uint32_t img_lane_off = (uint32_t)(lane >> 2) * kImgPitch + (uint32_t)(lane & 3) * 4;
+  const bool use_mma = MM && !a.skip_gemm;
+  uint32_t tmem = 0, ph_w = 0, ph_mma = 0;
+  bool mma_pending = false;
 
   // ---- stage neighbour records (made tile-relative), masks and per-molecule flags ---------------------------
   for (int r = tid; r < TR; r += kThreads) {
@@ -148,24 +182,56 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
     sRow[idx] = a.rowmask[row0 * NW + idx];
     sCol[idx] = a.colmask[row0 * NW + idx];
   }
+  if (use_mma) {
+    if (tid == 0) {
+      tc::mbar_init(&bars[0], 1);
+      tc::mbar_init(&bars[1], 1);
+      tc::mbar_init_fence();
+    }
+    if (warp == 0) {
+      __syncwarp();
+      tc::tmem_alloc(tslot, kTmemCols);
+    }
+    tc::fence_before_sync();
+  }
   __syncthreads();
+  if (use_mma) {
+    tc::fence_after_sync();
+    tmem = *tslot;
+  }
 
-  float acc[8][8];
+  float acc[MM ? 1 : 8][MM ? 1 : 8];
 
   for (int cb = 0; cb < NC || (a.skip_gemm && cb == 0); cb += TC) {
     const bool first_pass = (cb == 0);
+    if (!MM) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
+      for (int r = 0; r < (MM ? 1 : 8); ++r)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+        for (int c = 0; c < (MM ? 1 : 8); ++c) acc[r][c] = 0.f;
+    }
 
     for (int k0 = 0; k0 < K; k0 += KC) {
       const int c = k0 + 2 * lane;  // this lane's first channel
       const bool v0 = c < K, v1 = c + 1 < K;
       const float* opnd = buf0;
 
-      // weight chunk [KC][TC] (independent of the producer; sW is free after the previous trailing sync)
-      if (!a.skip_gemm) {
+      if (MM) {
+        // the previous chunk's MMAs read the weight image (buf0) and the operand images: wait before touching them
+        if (mma_pending) {
+          tc::mbar_wait(&bars[1], ph_mma);
+          ph_mma ^= 1;
+          mma_pending = false;
+        }
+        if (use_mma && tid == 0 && !(PROD == P_MID)) {   // buf0 is free for the whole chunk: fetch the weight pieces now
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(a.wimg) +
+                                     ((size_t)(k0 / KC) * a.ncb + (cb / TC)) * 2 * kWPiece;
+          tc::mbar_expect_tx(&bars[0], 2 * kWPiece);
+          tc::bulk_g2s(wHi, src, kWPiece, &bars[0]);
+          tc::bulk_g2s(wHi + kWPiece, src + kWPiece, kWPiece, &bars[0]);
+        }
+      } else if (!a.skip_gemm) {
+        // weight chunk [KC][TC] (independent of the producer; sW is free after the previous trailing sync)
         if (NC % 4 == 0) {
           for (int idx = tid; idx < KC * TC / 4; idx += kThreads) {
             const int kk = idx / (TC / 4), cc = (idx - kk * (TC / 4)) * 4;
@@ -182,6 +248,19 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
           }
         }
       }
+
+      // the producer's result for (row r, channels c, c+1): fp32 chunk buffer (FFMA) or bf16 hi/lo operand images (MMA)
+      auto put_operand = [&](float* dst, int r, float2 val) {
+        if (MM) {
+          uint32_t hi, lo;
+          tc::split2_bf16(val.x, val.y, hi, lo);
+          const uint32_t off = img_lane_off + (uint32_t)r * 16;
+          *reinterpret_cast<uint32_t*>(imgHi + off) = hi;
+          *reinterpret_cast<uint32_t*>(imgLo + off) = lo;
+        } else {
+          *reinterpret_cast<float2*>(&dst[r * BS + 2 * lane]) = val;
+        }
+      };
 
       // =========================== PRODUCER ===========================
       if (PROD == P_X) {
@@ -201,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
           }
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float2*>(&buf1[(warp + (h * 8 + q) * kWarps) * KCP + 2 * lane]) = v[q];
+            *reinterpret_cast<float2*>(&buf1[(warp + (h * 8 + q) * kWarps) * BS + 2 * lane]) = v[q];
         }
         __syncthreads();
       } else if (PROD == P_MID || PROD == P_RO) {
@@ -224,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
               if (v0) t.x = fast_tanh(fmaf(v[q].x, sc.x, sh.x));
               if (v1) t.y = fast_tanh(fmaf(v[q].y, sc.y, sh.y));
             }
-            *reinterpret_cast<float2*>(&buf0[r * KCP + 2 * lane]) = t;
+            *reinterpret_cast<float2*>(&bufT[r * BS + 2 * lane]) = t;
           }
         }
         __syncthreads();
@@ -237,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
             int a0 = mb, a1 = mb;  // tile rows of the arg-max
             const bool flag = rec_binary(rec);
             if (flag && !rec_fallback(rec)) {
-              rec_max2(rec, &buf0[2 * lane], b0, b1, a0, a1);
+              rec_max2<BS>(rec, &bufT[2 * lane], b0, b1, a0, a1);
               if (rec_has_zero(rec)) {  // a zero entry A[i,jz] contributes the candidate 0*T = 0
                 const int jz = mb + rec_jz(rec);
                 if (!(b0 > 0.f)) { if (b0 < 0.f || jz < a0) a0 = jz; b0 = 0.f; }
@@ -246,9 +325,9 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
             } else if (flag) {  // binary row with more than kMaxNbr neighbours: walk the bit mask
               const u64* mk = &sRow[(size_t)r * NW];
               int cnt, ar;
-              masked_max_first(mk, NW, &buf0[mb * KCP + 2 * lane], KCP, b0, ar, cnt);
+              masked_max_first(mk, NW, &bufT[mb * BS + 2 * lane], BS, b0, ar, cnt);
               a0 = mb + ar;
-              masked_max_first(mk, NW, &buf0[mb * KCP + 2 * lane + 1], KCP, b1, ar, cnt);
+              masked_max_first(mk, NW, &bufT[mb * BS + 2 * lane + 1], BS, b1, ar, cnt);
               a1 = mb + ar;
               if (cnt < N) {
                 const int jz = mb + first_zero_bit(mk, NW, N);
@@ -259,11 +338,11 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
               const int i = r - mb;
               const float* arow = a.adj + (long long)(mol0 + m) * a.as0 + (long long)i * a.as1;
               const float a00 = __ldg(&arow[0]);
-              b0 = a00 * buf0[mb * KCP + 2 * lane];
-              b1 = a00 * buf0[mb * KCP + 2 * lane + 1];
+              b0 = a00 * bufT[mb * BS + 2 * lane];
+              b1 = a00 * bufT[mb * BS + 2 * lane + 1];
               for (int j = 1; j < N; ++j) {
                 const float aj = __ldg(&arow[(long long)j * a.as2]);
-                const float2 t = *reinterpret_cast<const float2*>(&buf0[(mb + j) * KCP + 2 * lane]);
+                const float2 t = *reinterpret_cast<const float2*>(&bufT[(mb + j) * BS + 2 * lane]);
                 const float c0 = aj * t.x, c1 = aj * t.y;
                 if (c0 > b0) { b0 = c0; a0 = mb + j; }
                 if (c1 > b1) { b1 = c1; a1 = mb + j; }
@@ -277,12 +356,20 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
                 ap[0] = (unsigned char)(a0 - mb);
                 if (v1) ap[1] = (unsigned char)(a1 - mb);
               }
-              if (PROD == P_RO) stg2(a.prod_out + (row0 + r) * K + c, make_float2(b0, b1), v0, v1, kvec2);
+              if (!MM && PROD == P_RO) stg2(a.prod_out + (row0 + r) * K + c, make_float2(b0, b1), v0, v1, kvec2);
             }
           }
-          *reinterpret_cast<float2*>(&buf1[r * KCP + 2 * lane]) = make_float2(b0, b1);
+          if (PROD == P_RO) put_operand(bufH, r, make_float2(b0, b1));   // readout: the pooled H is the GEMM operand
+          else *reinterpret_cast<float2*>(&bufH[r * BS + 2 * lane]) = make_float2(b0, b1);
         }
+        if (MM && PROD == P_RO) tc::fence_async_smem();
         __syncthreads();
+        if (MM && PROD == P_MID && use_mma && tid == 0) {   // T (buf0) is dead now: fetch the weight pieces over it
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(a.wimg) + ((size_t)(k0 / KC) * a.ncb + (cb / TC)) * 2 * kWPiece;
+          tc::mbar_expect_tx(&bars[0], 2 * kWPiece);
+          tc::bulk_g2s(wHi, src, kWPiece, &bars[0]);
+          tc::bulk_g2s(wHi + kWPiece, src + kWPiece, kWPiece, &bars[0]);
+        }
       } else if (PROD == P_DZ) {
         float2 g = make_float2(0.f, 0.f), c1 = g, c2 = g, mu = g, is = g;
         if (v0) { g.x = __ldg(&a.vec0[c]); c1.x = __ldg(&a.vec1[c]); c2.x = __ldg(&a.vec2[c]); mu.x = __ldg(&a.vec3[c]); is.x = __ldg(&a.vec4[c]); }
@@ -306,14 +393,15 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
               dz.x = g.x * (dv[q].x - c1.x - (zv[q].x - mu.x) * is.x * c2.x);
               if (v1) dz.y = g.y * (dv[q].y - c1.y - (zv[q].y - mu.y) * is.y * c2.y);
               if (first_pass) {
-                stg2(a.prod_out + (row0 + r) * K + c, dz, v0, v1, kvec2);
+                if (!MM) stg2(a.prod_out + (row0 + r) * K + c, dz, v0, v1, kvec2);
                 colsum.x += dz.x; colsum.y += dz.y;
               }
             }
-            *reinterpret_cast<float2*>(&buf0[r * KCP + 2 * lane]) = dz;
+            put_operand(buf0, r, dz);
           }
         }
         if (first_pass && a.prod_partials) *reinterpret_cast<float2*>(&sWarp[(warp * 32 + lane) * 2]) = colsum;
+        if (MM) tc::fence_async_smem();
         __syncthreads();
         if (first_pass && a.prod_partials && warp == 0 && v0) {
           float2 s = make_float2(0.f, 0.f);
@@ -343,14 +431,15 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
               du.x = go.x * (1.f - ov.x * ov.x) * (1.f - dv[q].x * dv[q].x);
               if (v1) du.y = go.y * (1.f - ov.y * ov.y) * (1.f - dv[q].y * dv[q].y);
               if (first_pass) {
-                stg2(a.prod_out + (row0 + r) * K + c, du, v0, v1, kvec2);
+                if (!MM) stg2(a.prod_out + (row0 + r) * K + c, du, v0, v1, kvec2);
                 colsum.x += du.x; colsum.y += du.y;
               }
             }
-            *reinterpret_cast<float2*>(&buf0[r * KCP + 2 * lane]) = du;
+            put_operand(buf0, r, du);
           }
         }
         if (first_pass && a.prod_partials) *reinterpret_cast<float2*>(&sWarp[(warp * 32 + lane) * 2]) = colsum;
+        if (MM) tc::fence_async_smem();
         __syncthreads();
         if (first_pass && a.prod_partials && warp == 0 && v0) {
           float2 s = make_float2(0.f, 0.f);
@@ -362,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
       }
 
       if (PROD == P_X || PROD == P_MID) {
-        // S = A.H for this chunk (gcn.py:34), written over the dead T buffer
+        // S = A.H for this chunk (gcn.py:34): over the dead T buffer (FFMA) or into the operand images (MMA)
         for (int r = warp; r < TR; r += kWarps) {
           float2 s = make_float2(0.f, 0.f);
           if (r < rows) {
@@ -370,55 +459,150 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
             const int m = rec_m(rec), mb = m * N;
             const bool flag = rec_binary(rec);
             if (flag && !rec_fallback(rec)) {
-              s = rec_sum2<KCP>(rec, &buf1[2 * lane]);
+              s = rec_sum2<BS>(rec, &buf1[2 * lane]);
             } else if (flag) {
-              s.x = masked_sum(&sRow[(size_t)r * NW], NW, &buf1[mb * KCP + 2 * lane], KCP);
-              s.y = masked_sum(&sRow[(size_t)r * NW], NW, &buf1[mb * KCP + 2 * lane + 1], KCP);
+              s.x = masked_sum(&sRow[(size_t)r * NW], NW, &buf1[mb * BS + 2 * lane], BS);
+              s.y = masked_sum(&sRow[(size_t)r * NW], NW, &buf1[mb * BS + 2 * lane + 1], BS);
             } else {
               const float* arow = a.adj + (long long)(mol0 + m) * a.as0 + (long long)(r - mb) * a.as1;
               for (int j = 0; j < N; ++j) {
                 const float aj = __ldg(&arow[(long long)j * a.as2]);
-                const float2 hv = *reinterpret_cast<const float2*>(&buf1[(mb + j) * KCP + 2 * lane]);
+                const float2 hv = *reinterpret_cast<const float2*>(&buf1[(mb + j) * BS + 2 * lane]);
                 s.x = fmaf(aj, hv.x, s.x);
                 s.y = fmaf(aj, hv.y, s.y);
               }
             }
-            if (first_pass && v0 && a.prod_out) stg2(a.prod_out + (row0 + r) * K + c, s, v0, v1, kvec2);
+            if (!MM && first_pass && v0 && a.prod_out) stg2(a.prod_out + (row0 + r) * K + c, s, v0, v1, kvec2);
           }
-          *reinterpret_cast<float2*>(&buf0[r * KCP + 2 * lane]) = s;
+          put_operand(buf0, r, s);
         }
+        if (MM) tc::fence_async_smem();
         __syncthreads();
       }
-      if (PROD == P_RO) opnd = buf1;
+      if (!MM && PROD == P_RO) opnd = buf1;
 
       // =========================== GEMM chunk ===========================
-      if (!a.skip_gemm) {
+      if (MM) {
+        if (tid == 0) {
+          if (use_mma) {
+            const int kleft = K - k0;
+            const int nks = (kleft >= KC) ? KC / 16 : (kleft + 15) / 16;
+            tc::mbar_wait(&bars[0], ph_w);
+            tc::fence_after_sync();
+            constexpr uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, 128, false, false);
+            const uint32_t aHi = tc::smem_u32(imgHi), aLo = tc::smem_u32(imgLo), bHi = tc::smem_u32(wHi), bLo = bHi + kWPiece;
+#pragma unroll
+            for (int p = 0; p < NPASS; ++p) {
+              const uint32_t ab = (p & 1) ? aLo : aHi, bb = (p & 2) ? bLo : bHi;
+              for (int ks = 0; ks < nks; ++ks) {
+                const uint64_t da = tc::make_desc(ab + ks * 2 * kImgPitch, kImgPitch, 128);
+                const uint64_t db = tc::make_desc(bb + ks * 2 * (128 * 16), 128 * 16, 128);
+                tc::mma_ss<false>(tmem, da, db, idesc, (k0 > 0 || p > 0 || ks > 0) ? 1u : 0u);
+              }
+            }
+            tc::mma_commit(&bars[1]);
+          }
+          if (first_pass && a.prod_img) {
+            // the hi image of this chunk is the formatted operand of the weight-gradient GEMM: tile image [K/8][128][8] bf16
+            unsigned char* dst = reinterpret_cast<unsigned char*>(a.prod_img) + ((size_t)tile * a.img_chunks + (k0 / 8)) * 2048;
+            const int nch = min(8, a.img_chunks - k0 / 8);
+            for (int q = 0; q < nch; ++q) tc::bulk_s2g(dst + (size_t)q * 2048, imgHi + q * kImgPitch, 2048);
+            tc::bulk_commit();
+            tc::bulk_wait_read0();
+          }
+        }
+        if (use_mma) { ph_w ^= 1; mma_pending = true; }
+      } else if (!a.skip_gemm) {
 #pragma unroll 2
         for (int kk = 0; kk < KC; kk += 4) {
           float4 av[8];
 #pragma unroll
-          for (int r = 0; r < 8; ++r) av[r] = *reinterpret_cast<const float4*>(&opnd[(r * TYN + ty) * KCP + kk]);
+          for (int r = 0; r < 8; ++r) av[r] = *reinterpret_cast<const float4*>(&opnd[(r * TYN + ty) * BS + kk]);
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
             const float4 b0 = *reinterpret_cast<const float4*>(&sW[(kk + k4) * TC + tx * 4]);
             const float4 b1 = *reinterpret_cast<const float4*>(&sW[(kk + k4) * TC + TC / 2 + tx * 4]);
             const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
+            for (int r = 0; r < (MM ? 1 : 8); ++r) {
               const float ar = (k4 == 0) ? av[r].x : (k4 == 1) ? av[r].y : (k4 == 2) ? av[r].z : av[r].w;
 #pragma unroll
-              for (int cc = 0; cc < 8; ++cc) acc[r][cc] = fmaf(ar, bv[cc], acc[r][cc]);
+              for (int cc = 0; cc < (MM ? 1 : 8); ++cc) acc[r][cc] = fmaf(ar, bv[cc], acc[r][cc]);
             }
           }
         }
       }
-      __syncthreads();  // chunk buffers and sW are free again
+      __syncthreads();  // chunk buffers (and, for the FFMA path, sW) are free again
     }
     if (a.skip_gemm) break;
 
     // =========================== EPILOGUE ===========================
-    // thread's output coordinates: rows r*TYN+ty, local cols {tx*4..+3, TC/2+tx*4..+3}
-    if (EPI == E_ZSTATS || EPI == E_STORE) {
+    if (MM) {
+      // accumulator tile: TMEM -> registers (thread = row) -> bias / activation -> staging tile in shared memory
+      tc::mbar_wait(&bars[1], ph_mma);
+      ph_mma ^= 1;
+      mma_pending = false;
+      tc::fence_after_sync();
+      const int q = warp & 3, hsel = warp >> 2;
+      const int row = q * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        const int cl = hsel * 64 + c0;
+        float v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cl, v);
+        if (EPI == E_ZSTATS || EPI == E_READOUT) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int gc = cb + cl + i;
+            const float bv = (a.bias && gc < NC) ? __ldg(&a.bias[gc]) : 0.f;
+            v[i] += bv;
+            if (EPI == E_READOUT) v[i] = (row < rows && gc < NC) ? fast_tanh(v[i]) : 0.f;   // gcn_encoder.py:51
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(&sC[row * TCP + cl + i]) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+      tc::fence_before_sync();
+      __syncthreads();
+      if (EPI == E_ZSTATS || EPI == E_STORE || EPI == E_READOUT) {
+        // coalesced store of the finished tile
+        const bool vec_ok = (NC % 4 == 0);
+        for (int idx = tid; idx < rows * (TC / 4); idx += kThreads) {
+          const int r = idx / (TC / 4), cl = (idx - r * (TC / 4)) * 4;
+          const int gc = cb + cl;
+          if (gc >= NC) continue;
+          const float4 v = *reinterpret_cast<const float4*>(&sC[r * TCP + cl]);
+          float* dst = a.out0 + (row0 + r) * NC + gc;
+          if (vec_ok && gc + 3 < NC) {
+            *reinterpret_cast<float4*>(dst) = v;
+          } else {
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (gc + i < NC) dst[i] = vv[i];
+          }
+        }
+      }
+      if (EPI == E_ZSTATS) {
+        // per-tile Welford partials (mean, M2) per channel; thread = (row half, column)
+        const int cl = tid & (TC - 1), half = tid >> 7;
+        const int r_lo = half * (TR / 2), r_hi = min(rows, r_lo + TR / 2);
+        float s = 0.f;
+        for (int r = r_lo; r < r_hi; ++r) s += sC[r * TCP + cl];
+        sWarp[half * TC + cl] = s;
+        __syncthreads();
+        const float mean = (sWarp[cl] + sWarp[TC + cl]) / (float)rows;
+        float m2 = 0.f;
+        for (int r = r_lo; r < r_hi; ++r) { const float d = sC[r * TCP + cl] - mean; m2 = fmaf(d, d, m2); }
+        sWarp[2 * TC + half * TC + cl] = m2;
+        __syncthreads();
+        if (tid < TC && cb + tid < NC) {
+          a.partials[((size_t)tile * 2 + 0) * NC + cb + tid] = mean;
+          a.partials[((size_t)tile * 2 + 1) * NC + cb + tid] = sWarp[2 * TC + tid] + sWarp[3 * TC + tid];
+        }
+      }
+    } else if (EPI == E_ZSTATS || EPI == E_STORE) {
+      // thread's output coordinates: rows r*TYN+ty, local cols {tx*4..+3, TC/2+tx*4..+3}
       float* sRed = mainp;             // [TYN][TC]
       float* sMean = mainp + TYN * TC;  // [TC]
       float colv[8];
@@ -436,21 +620,21 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
             if (gc + q < NC) bb[q] = __ldg(&a.bias[gc + q]);
         }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < (MM ? 1 : 8); ++r) {
           const int row = r * TYN + ty;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) acc[r][h * 4 + q] += bb[q];
+          for (int q = 0; q < 4; ++q) acc[r][(MM ? 0 : h * 4 + q)] += bb[q];
           if (row < rows) {
             float* dst = a.out0 + (row0 + row) * NC + gc;
             if (vec_ok && gc + 3 < NC) {
-              *reinterpret_cast<float4*>(dst) = make_float4(acc[r][h * 4 + 0], acc[r][h * 4 + 1], acc[r][h * 4 + 2], acc[r][h * 4 + 3]);
+              *reinterpret_cast<float4*>(dst) = make_float4(acc[r][(MM ? 0 : h * 4 + 0)], acc[r][(MM ? 0 : h * 4 + 1)], acc[r][(MM ? 0 : h * 4 + 2)], acc[r][(MM ? 0 : h * 4 + 3)]);
             } else {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
-                if (gc + q < NC) dst[q] = acc[r][h * 4 + q];
+                if (gc + q < NC) dst[q] = acc[r][(MM ? 0 : h * 4 + q)];
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) colv[h * 4 + q] += acc[r][h * 4 + q];
+            for (int q = 0; q < 4; ++q) colv[h * 4 + q] += acc[r][(MM ? 0 : h * 4 + q)];
           }
         }
       }
@@ -475,8 +659,8 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
           for (int q = 0; q < 4; ++q) {
             float m2 = 0.f;
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
-              if (r * TYN + ty < rows) { const float d = acc[r][h * 4 + q] - mu[q]; m2 = fmaf(d, d, m2); }
+            for (int r = 0; r < (MM ? 1 : 8); ++r)
+              if (r * TYN + ty < rows) { const float d = acc[r][(MM ? 0 : h * 4 + q)] - mu[q]; m2 = fmaf(d, d, m2); }
             colv[h * 4 + q] = m2;
           }
         }
@@ -493,7 +677,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
         }
         __syncthreads();
       }
-    } else {  // E_READOUT / E_ATG: stage the finished tile in shared memory
+    } else {  // FFMA, E_READOUT / E_ATG: stage the finished tile in shared memory
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int cl = h * (TC / 2) + tx * 4;
@@ -505,12 +689,12 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
             if (gc + q < NC) bb[q] = __ldg(&a.bias[gc + q]);
         }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < (MM ? 1 : 8); ++r) {
           const int row = r * TYN + ty;
           float v[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            v[q] = acc[r][h * 4 + q];
+            v[q] = acc[r][(MM ? 0 : h * 4 + q)];
             if (EPI == E_READOUT) v[q] = (row < rows && gc + q < NC) ? fast_tanh(v[q] + bb[q]) : 0.f;   // gcn_encoder.py:51
           }
           if (EPI == E_READOUT && row < rows) {
@@ -527,55 +711,66 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
         }
       }
       __syncthreads();
-      if (EPI == E_READOUT) {
-        // O[b,:] = tanh(sum over ALL N rows of D[b,i,:])  (unmasked, gcn_encoder.py:52-53)
-        for (int idx = tid; idx < nm * TC; idx += kThreads) {
-          const int m = idx / TC, cl = idx - m * TC;
-          if (cb + cl < NC) {
-            float s = 0.f;
-            for (int i = 0; i < N; ++i) s += sC[(m * N + i) * TCP + cl];
-            a.out1[(size_t)(mol0 + m) * NC + cb + cl] = fast_tanh(s);
-          }
+    }
+
+    // ---- epilogue work on the staged tile (both engines) ----
+    if (EPI == E_READOUT) {
+      // O[b,:] = tanh(sum over ALL N rows of D[b,i,:])  (unmasked, gcn_encoder.py:52-53)
+      for (int idx = tid; idx < nm * TC; idx += kThreads) {
+        const int m = idx / TC, cl = idx - m * TC;
+        if (cb + cl < NC) {
+          float s = 0.f;
+          for (int i = 0; i < N; ++i) s += sC[(m * N + i) * TCP + cl];
+          a.out1[(size_t)(mol0 + m) * NC + cb + cl] = fast_tanh(s);
         }
-      } else {
-        // dHprev[j,:] = sum_i A[i,j] * dS[i,:]   (column records; 4 channels per lane)
-        for (int r = warp; r < rows; r += kWarps) {
-          const uint4 crec = sCRec[r];
-          const int m = rec_m(crec), mb = m * N;
-          const bool flag = rec_binary(crec);
-          for (int cl = lane * 4; cl < TC; cl += 128) {
-            if (cb + cl >= NC) break;
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (flag && !rec_fallback(crec)) {
-              s = rec_sum4<TCP>(crec, &sC[cl]);
-            } else if (flag) {
-              const u64* mk = &sCol[(size_t)r * NW];
-              s.x = masked_sum(mk, NW, &sC[mb * TCP + cl], TCP);
-              s.y = masked_sum(mk, NW, &sC[mb * TCP + cl + 1], TCP);
-              s.z = masked_sum(mk, NW, &sC[mb * TCP + cl + 2], TCP);
-              s.w = masked_sum(mk, NW, &sC[mb * TCP + cl + 3], TCP);
-            } else {
-              const float* acol = a.adj + (long long)(mol0 + m) * a.as0 + (long long)(r - mb) * a.as2;
-              for (int i = 0; i < N; ++i) {
-                const float ai = __ldg(&acol[(long long)i * a.as1]);
-                const float4 dv = *reinterpret_cast<const float4*>(&sC[(mb + i) * TCP + cl]);
-                s.x = fmaf(ai, dv.x, s.x); s.y = fmaf(ai, dv.y, s.y); s.z = fmaf(ai, dv.z, s.z); s.w = fmaf(ai, dv.w, s.w);
-              }
+      }
+      __syncthreads();
+    } else if (EPI == E_ATG) {
+      // dHprev[j,:] = sum_i A[i,j] * dS[i,:]   (column records; 4 channels per lane)
+      for (int r = warp; r < rows; r += kWarps) {
+        const uint4 crec = sCRec[r];
+        const int m = rec_m(crec), mb = m * N;
+        const bool flag = rec_binary(crec);
+        for (int cl = lane * 4; cl < TC; cl += 128) {
+          if (cb + cl >= NC) break;
+          float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (flag && !rec_fallback(crec)) {
+            s = rec_sum4<TCP>(crec, &sC[cl]);
+          } else if (flag) {
+            const u64* mk = &sCol[(size_t)r * NW];
+            s.x = masked_sum(mk, NW, &sC[mb * TCP + cl], TCP);
+            s.y = masked_sum(mk, NW, &sC[mb * TCP + cl + 1], TCP);
+            s.z = masked_sum(mk, NW, &sC[mb * TCP + cl + 2], TCP);
+            s.w = masked_sum(mk, NW, &sC[mb * TCP + cl + 3], TCP);
+          } else {
+            const float* acol = a.adj + (long long)(mol0 + m) * a.as0 + (long long)(r - mb) * a.as2;
+            for (int i = 0; i < N; ++i) {
+              const float ai = __ldg(&acol[(long long)i * a.as1]);
+              const float4 dv = *reinterpret_cast<const float4*>(&sC[(mb + i) * TCP + cl]);
+              s.x = fmaf(ai, dv.x, s.x); s.y = fmaf(ai, dv.y, s.y); s.z = fmaf(ai, dv.z, s.z); s.w = fmaf(ai, dv.w, s.w);
             }
-            float* dst = a.out0 + (row0 + r) * NC + cb + cl;
-            if (NC % 4 == 0 && cb + cl + 3 < NC) {
-              *reinterpret_cast<float4*>(dst) = s;
-            } else {
-              const float sv[4] = {s.x, s.y, s.z, s.w};
+          }
+          float* dst = a.out0 + (row0 + r) * NC + cb + cl;
+          if (NC % 4 == 0 && cb + cl + 3 < NC) {
+            *reinterpret_cast<float4*>(dst) = s;
+          } else {
+            const float sv[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (cb + cl + q < NC) dst[q] = sv[q];
-            }
+            for (int q = 0; q < 4; ++q)
+              if (cb + cl + q < NC) dst[q] = sv[q];
           }
         }
       }
       __syncthreads();
+    } else if (MM) {
+      __syncthreads();   // the staging tile aliases the chunk buffers of the next column pass
     }
+  }
+
+  if (MM && use_mma) {
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, kTmemCols);
   }
 }
 

@@ -196,3 +196,90 @@ def test_layer_vs_reference_golden(case):
         e = np.abs(db_train).max() / (np.abs(g["ref64_dW"]).max() + 1e-30)      # analytically zero in train mode
         assert e < 1e-4, report
     assert worst < TOL["fp32"], f"{case}: {' '.join(report)}"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tensor-core precision classes (encoder_params['precision'] = 'bf16' / 'tf32'): tcgen05 products with split operands
+# in the forward, single-pass products in the backward. Tolerance (north star): 1e-2 relative on outputs and
+# gradients, measured as per-tensor rel-L2 against the fp64 oracle WITHOUT any arg-max override.
+# ---------------------------------------------------------------------------------------------------------------
+TC_TOL = 1e-2
+TC_SHAPES = [
+    dict(B=64, N=50, F0=33, hidden=[128] * 5, E=128, occ="molecular"),   # C2 shape (100-row tiles)
+    dict(B=96, N=64, F0=64, hidden=[128] * 4, E=128, occ="full"),        # C3 shape
+    dict(B=33, N=85, F0=33, hidden=[128] * 5, E=128, occ="molecular"),   # C1 shape (one molecule per tile, ragged)
+    dict(B=10, N=128, F0=64, hidden=[256] * 3, E=256, occ="molecular"),  # C5 widths: two column blocks, two M blocks in dW
+    dict(B=5, N=40, F0=9, hidden=[7, 13], E=5, occ="molecular"),         # odd widths: zero-padded operand images
+    dict(B=7, N=132, F0=20, hidden=[48, 200], E=36, occ="molecular"),    # N > 128: falls back to the fp32 engine
+]
+
+
+def _tc_check(x, adj, p, dO, cfg, precision, label):
+    from oracle import gcn_oracle as orc
+    dev = _dev()
+    L = cfg["n_layers"]
+    p64 = orc.cast_params(p, np.float64)
+    x64, a64 = x.astype(np.float64), adj.astype(np.float64)
+    O, cache, rms, rvs = orc.encoder_forward(x64, a64, p64, training=True)
+    Oe = orc.encoder_forward(x64, a64, dict(p64, running_mean=rms, running_var=rvs), training=False)[0]
+    gr = orc.encoder_backward(dO.astype(np.float64), cache)
+    ref = dict(out_train=O, out_eval=Oe, dWd=gr["dWd"], dbd=gr["dbd"])
+    for l in range(L):
+        ref.update({f"dW{l}": gr["dW"][l], f"db{l}": gr["db"][l], f"dgamma{l}": gr["dgamma"][l], f"dbeta{l}": gr["dbeta"][l],
+                    f"rm{l}": rms[l], f"rv{l}": rvs[l]})
+    enc = build_encoder(cfg, p, dev, precision=precision)
+    res = _run_encoder(enc, x, adj, dO, dev)
+    return _compare(res, ref, L, TC_TOL, f"{label} [{precision}]")
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_encoder_tensor_core_vs_oracle(shape, precision):
+    from openchem_b200.synthetic import make_graph_batch
+    gb = make_graph_batch(shape["B"], shape["N"], shape["F0"], occupancy=shape["occ"], seed=21)
+    widths = [shape["F0"]] + shape["hidden"]
+    p = random_params(widths, shape["E"], seed=6)
+    dO = np.random.RandomState(4).randn(shape["B"], shape["E"]).astype(np.float32)
+    cfg = {"input_size": shape["F0"], "encoder_dim": shape["E"], "n_layers": len(shape["hidden"]), "hidden_size": list(shape["hidden"])}
+    worst = _tc_check(gb["x"], gb["adj"], p, dO, cfg, precision, str(shape))
+    print(f"tc {precision} {shape}: worst rel-L2 {worst:.2e}")
+
+
+@pytest.mark.parametrize("case", ENC_CASES)
+def test_encoder_tensor_core_vs_reference_golden(case):
+    g = load_golden(case)
+    L = len(g["hidden"])
+    cfg = {"input_size": int(g["x"].shape[2]), "encoder_dim": int(g["Wd"].shape[0]), "n_layers": L, "hidden_size": [int(h) for h in g["hidden"]]}
+    _tc_check(g["x"], g["adj"], golden_params(g, np.float32), g["dO"], cfg, "bf16", case)
+
+
+@pytest.mark.parametrize("case", LAYER_CASES)
+def test_layer_tensor_core_vs_reference_golden(case):
+    from openchem_b200.layers.gcn import GraphConvolution
+    dev = _dev()
+    g = load_golden(case)
+    has_b = "b" in g
+    gc = GraphConvolution(g["W"].shape[0], g["W"].shape[1], bias=has_b, precision="bf16")
+    with torch.no_grad():
+        gc.weight.copy_(torch.from_numpy(g["W"]))
+        if has_b:
+            gc.bias.copy_(torch.from_numpy(g["b"]))
+        gc.bn.weight.copy_(torch.from_numpy(g["gamma"]))
+        gc.bn.bias.copy_(torch.from_numpy(g["beta"]))
+        gc.bn.running_mean.copy_(torch.from_numpy(g["running_mean"]))
+        gc.bn.running_var.copy_(torch.from_numpy(g["running_var"]))
+    gc = gc.to(dev)
+    gc.train()
+    tx = torch.from_numpy(g["x"]).to(dev).requires_grad_(True)
+    ta = torch.from_numpy(g["adj"]).to(dev)
+    y = gc(tx, ta)
+    y.backward(torch.from_numpy(g["dY"]).to(dev))
+    res = dict(y_train=y.detach().cpu().numpy(), dx=tx.grad.cpu().numpy(), dW=gc.weight.grad.cpu().numpy(),
+               dgamma=gc.bn.weight.grad.cpu().numpy(), dbeta=gc.bn.bias.grad.cpu().numpy(),
+               rm=gc.bn.running_mean.cpu().numpy(), rv=gc.bn.running_var.cpu().numpy())
+    report, worst = [], 0.0
+    for k, v in res.items():
+        e = rel_l2(v, g["ref64_" + k])
+        report.append(f"{k}={e:.2e}")
+        worst = max(worst, e)
+    assert worst < TC_TOL, f"{case}: {' '.join(report)}"
