@@ -82,6 +82,8 @@ struct Layout {
   // scratch
   size_t partials, prodpart, WT[OCGCN_MAX_LAYERS], WdT, G[3], dU, coef, gemm_partial;
   size_t Wf[OCGCN_MAX_LAYERS], Wro, Wb[OCGCN_MAX_LAYERS], Wrob, dZimg, dUimg;   // mm: weight operand images, dZ / dU tile images
+  size_t slice0, slice1, counters;   // sliced_reduce: fp64 slice results (matrix / per-channel jobs), ticket counters
+  int counter_words;
   size_t scratch_total;
   int max_splits;
 };
@@ -180,6 +182,13 @@ static int make_layout(const ocgcn_desc* d, bool layer_only, Layout* lo) {
     max_partial = p > max_partial ? p : max_partial;
   }
   lo->gemm_partial = take(max_partial);
+  {
+    size_t maxMN = (size_t)Fmax * Fmax;
+    lo->slice0 = take((size_t)4 * maxMN * 8);                 // <= 4 slices of an (Fmax x Fmax) matrix job, fp64
+    lo->slice1 = take((size_t)32 * 2 * Fmax * 8);             // 32 slices x 2 values x Fmax channels
+    lo->counter_words = (int)(maxMN / 32 + 2 * ((Fmax + 31) / 32) + 64);
+    lo->counters = take((size_t)lo->counter_words * 4);
+  }
   lo->max_splits = max_splits;
   lo->scratch_total = off;
   return OCGCN_OK;
@@ -316,7 +325,10 @@ static int run_bn_finalize(const ocgcn_desc* d, const Layout& lo, const ocgcn_pa
   f.running_mean = p->running_mean[l]; f.running_var = p->running_var[l];
   f.nbt = reinterpret_cast<long long*>(p->num_batches_tracked[l]);
   f.mean = stats; f.invstd = stats + F; f.scale = stats + 2 * F; f.shift = stats + 3 * F;
-  bn_finalize_kernel<<<(F + 31) / 32, 1024, 0, st>>>(f);
+  f.SL = d->training ? reduce_slices(lo.tiles) : 1;
+  f.slicebuf = reinterpret_cast<double*>(scratch + lo.slice1);
+  f.counters = reinterpret_cast<unsigned*>(scratch + lo.counters);
+  bn_finalize_kernel<<<dim3((F + 31) / 32, f.SL), 256, 0, st>>>(f);
   LAUNCH_CHECK();
   return OCGCN_OK;
 }
@@ -332,15 +344,26 @@ static int run_gemm_tn(const float* A, const float* Bm, size_t R, int M, int Nn,
   return OCGCN_OK;
 }
 
-static int run_reduce(const float* p0, float* o0, int P0, int c0, const float* p1, float* o1, int P1, int c1, cudaStream_t st) {
+static int run_reduce(const Layout& lo, char* scratch, const float* p0, float* o0, int P0, int c0, const float* p1, float* o1, int P1,
+                      int c1, cudaStream_t st) {
   ProfScope prof(KK_REDUCE, st);
   ReduceJobs j;
   j.partial[0] = p0; j.out[0] = o0; j.P[0] = P0; j.count[0] = c0;
   j.partial[1] = p1; j.out[1] = o1; j.P[1] = P1; j.count[1] = c1;
-  const int mx = c0 > c1 ? c0 : c1;
-  dim3 grid((mx + 31) / 32, 2);
-  reduce_partials_kernel<<<grid, 1024, 0, st>>>(j);
+  j.SL[0] = reduce_slices(P0) > 4 ? 4 : reduce_slices(P0);
+  j.SL[1] = reduce_slices(P1);
+  j.slicebuf[0] = reinterpret_cast<double*>(scratch + lo.slice0);
+  j.slicebuf[1] = reinterpret_cast<double*>(scratch + lo.slice1);
+  unsigned* cnt = reinterpret_cast<unsigned*>(scratch + lo.counters);
+  j.counters[0] = cnt + 2 * ((lo.Fmax + 31) / 32);          // matrix job: one ticket per 32 outputs
+  j.counters[1] = cnt + (lo.Fmax + 31) / 32;                // per-channel job
+  const int nblk = ((c0 + 31) / 32) * j.SL[0] + (o1 ? ((c1 + 31) / 32) * j.SL[1] : 0);
+  reduce_partials_kernel<<<nblk, 256, 0, st>>>(j);
   LAUNCH_CHECK();
+  return OCGCN_OK;
+}
+static int zero_counters(const Layout& lo, char* scratch, cudaStream_t st) {
+  CU_TRY(cudaMemsetAsync(scratch + lo.counters, 0, (size_t)lo.counter_words * 4, st));
   return OCGCN_OK;
 }
 
@@ -382,7 +405,18 @@ static int run_layer_forward(const ocgcn_desc* d, const Layout& lo, const float*
   return run_bn_finalize(d, lo, p, l, saved, scratch, st);
 }
 
-// Backward of one graph-conv layer given dY (layer API) or dH (encoder) in buffer `g_in`.
+// E_DY / E_ATG_DY epilogues: saved state of layer `lp`, whose dY the tile kernel produces
+static void set_prev_layer(TileArgs& a, const ocgcn_desc* d, const Layout& lo, int lp, char* saved, float* partials) {
+  const int F = d->F[lp + 1];
+  const float* stats = reinterpret_cast<const float*>(saved + lo.stats[lp]);
+  a.arg_in = reinterpret_cast<const unsigned char*>(saved + lo.arg[lp]);
+  a.zprev = reinterpret_cast<const float*>(saved + lo.Z[lp]);
+  a.pv_mean = stats; a.pv_invstd = stats + F; a.pv_scale = stats + 2 * F; a.pv_shift = stats + 3 * F;
+  a.partials = partials;
+}
+
+// Backward of one graph-conv layer given dY in buffer `g_in` (layer API: plain; encoder: produced by the fused epilogue of
+// the layer above, together with its partial sums).
 // Produces dgamma/dbeta/dW/db, and dHprev (= dX) in `g_out` unless skip_dx.
 static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float* adj, const ocgcn_params* p, const ocgcn_grads* g,
                               int l, bool plain, float* g_in, float* g_dz, float* g_out, bool skip_dx, char* saved, char* scratch,
@@ -404,16 +438,19 @@ static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float
   y.arg = plain ? nullptr : reinterpret_cast<const unsigned char*>(saved + lo.arg[l]);
   y.mean = stats; y.invstd = stats + Fout; y.scale = stats + 2 * Fout; y.shift = stats + 3 * Fout;
   y.dH = g_in; y.partials = partials;
-  ST_TRY(launch_bwd_dy(lo, y, st));
+  if (plain) ST_TRY(launch_bwd_dy(lo, y, st));   // encoder: dY and its partial sums come from the previous fused epilogue
 
   BwdFinalizeArgs f;
   f.partials = partials; f.T = lo.tiles; f.F = Fout; f.training = d->training; f.n = (double)lo.rows;
   f.gamma = p->gamma[l]; f.invstd = stats + Fout;
   f.dgamma = g->dgamma[l]; f.dbeta = g->dbeta[l];
   f.g = coef; f.c1 = coef + lo.Fmax; f.c2 = coef + 2 * lo.Fmax;
+  f.SL = reduce_slices(lo.tiles);
+  f.slicebuf = reinterpret_cast<double*>(scratch + lo.slice1);
+  f.counters = reinterpret_cast<unsigned*>(scratch + lo.counters);
   {
     ProfScope prof(KK_BWD_FINALIZE, st);
-    bwd_finalize_kernel<<<(Fout + 31) / 32, 1024, 0, st>>>(f);
+    bwd_finalize_kernel<<<dim3((Fout + 31) / 32, f.SL), 256, 0, st>>>(f);
     LAUNCH_CHECK();
   }
 
@@ -431,13 +468,18 @@ static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float
     a.prod_img = scratch + lo.dZimg; a.img_chunks = lo.KP[l + 1] / 8;
     a.wimg = scratch + lo.Wb[l]; a.ncb = (Fin + 127) / 128;
   }
-  ST_TRY((launch_tile<P_DZ, E_ATG>(lo, a, st)));
+  if (plain) {
+    ST_TRY((launch_tile<P_DZ, E_ATG>(lo, a, st)));
+  } else {
+    if (l > 0) set_prev_layer(a, d, lo, l - 1, saved, partials);
+    ST_TRY((launch_tile<P_DZ, E_ATG_DY>(lo, a, st)));
+  }
 
   int splits = 0;
   float* gp = reinterpret_cast<float*>(scratch + lo.gemm_partial);
   if (lo.mm) ST_TRY(run_dw_mma(lo, saved + lo.S[l], scratch + lo.dZimg, lo.KP[l], lo.KP[l + 1], Fin, Fout, gp, st, &splits));
   else ST_TRY(run_gemm_tn(reinterpret_cast<const float*>(saved + lo.S[l]), g_dz, lo.rows, Fin, Fout, gp, st, &splits));
-  ST_TRY(run_reduce(gp, g->dW[l], splits, Fin * Fout, prodpart, (d->has_bias ? g->db[l] : nullptr), lo.tiles, Fout, st));
+  ST_TRY(run_reduce(lo, scratch, gp, g->dW[l], splits, Fin * Fout, prodpart, (d->has_bias ? g->db[l] : nullptr), lo.tiles, Fout, st));
   return OCGCN_OK;
 }
 
@@ -539,6 +581,7 @@ int ocgcn_encoder_forward(const ocgcn_desc* d, const float* x, const float* adj,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int L = d->L;
 
+  ST_TRY(zero_counters(lo, scratch, st));
   ST_TRY(run_adj_pack(d, lo, adj, saved, st));
   if (lo.mm) {
     WPrepJobs wj;
@@ -596,6 +639,7 @@ int ocgcn_encoder_backward(const ocgcn_desc* d, const float* grad_out, const flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int L = d->L;
 
+  ST_TRY(zero_counters(lo, scratch, st));
   if (lo.mm) {
     WPrepJobs wj;
     memset(&wj, 0, sizeof(wj));
@@ -635,11 +679,12 @@ int ocgcn_encoder_backward(const ocgcn_desc* d, const float* grad_out, const flo
     a.prod_img = scratch + lo.dUimg; a.img_chunks = lo.KPE / 8;
     a.wimg = scratch + lo.Wrob; a.ncb = (d->F[L] + 127) / 128;
   }
-  ST_TRY((launch_tile<P_DU, E_STORE>(lo, a, st)));
+  set_prev_layer(a, d, lo, L - 1, saved, reinterpret_cast<float*>(scratch + lo.partials));
+  ST_TRY((launch_tile<P_DU, E_DY>(lo, a, st)));
   int splits = 0;
   if (lo.mm) ST_TRY(run_dw_mma(lo, scratch + lo.dUimg, saved + lo.HL, lo.KPE, lo.KP[L], d->E, d->F[L], gp, st, &splits));
   else ST_TRY(run_gemm_tn(dU, reinterpret_cast<const float*>(saved + lo.HL), lo.rows, d->E, d->F[L], gp, st, &splits));
-  ST_TRY(run_reduce(gp, g->dWd, splits, d->E * d->F[L], prodpart, g->dbd, lo.tiles, d->E, st));
+  ST_TRY(run_reduce(lo, scratch, gp, g->dWd, splits, d->E * d->F[L], prodpart, g->dbd, lo.tiles, d->E, st));
 
   int cur = 0;
   for (int l = L - 1; l >= 0; --l) {
@@ -665,6 +710,7 @@ int ocgcn_layer_forward(const ocgcn_desc* d, const float* x, const float* adj, c
   char* saved = static_cast<char*>(saved_v);
   char* scratch = static_cast<char*>(scratch_v);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ST_TRY(zero_counters(lo, scratch, st));
   ST_TRY(run_adj_pack(d, lo, adj, saved, st));
   if (lo.mm) {
     WPrepJobs wj;
@@ -703,6 +749,7 @@ int ocgcn_layer_backward(const ocgcn_desc* d, const float* grad_y, const float* 
   char* saved = static_cast<char*>(saved_v);
   char* scratch = static_cast<char*>(scratch_v);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ST_TRY(zero_counters(lo, scratch, st));
   if (d->need_dx && lo.mm) {
     WPrepJobs wj;
     memset(&wj, 0, sizeof(wj));

@@ -107,9 +107,74 @@ __global__ void transpose_kernel(const TransposeJobs jobs) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// BatchNorm statistics: merge per-tile Welford partials (fixed order, fp64) -> mean, invstd, scale, shift;
-// running-stat update with the unbiased variance (torch.nn.BatchNorm1d semantics, gcn.py:25,40).
-// grid = ceil(F/32), block = 256: lane = channel, warp = slice of tiles.
+// Deterministic two-level column reductions over per-tile / per-split partial rows.
+// grid = (ceil(cnt/32), SL slices[, jobs]); block = 256: lane = column, warp = row phase inside the slice.
+// Every CTA folds its slice of rows in a fixed order (fp64), writes the slice result, and the LAST CTA of a column
+// group to finish (atomic ticket) folds the SL slice results in ascending slice order and runs the finaliser:
+// bit-reproducible whatever the arrival order. The ticket counters live in caller scratch, are zeroed once per
+// API call and reset themselves.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kRedWarps = 8;
+template <int NV, typename Job>
+__device__ __forceinline__ void sliced_reduce(const Job& job, int P, int cnt, int SL, double* slicebuf, unsigned* counters, int cgroup,
+                                              int slice) {
+  __shared__ double sred[kRedWarps][NV][32];
+  __shared__ unsigned s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = cgroup * 32 + lane;
+  const bool valid = c < cnt;
+  const int per = (P + SL - 1) / SL;
+  const int p0 = slice * per, p1 = min(P, p0 + per);
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+  if (valid) {
+    for (int p = p0 + warp; p < p1; p += kRedWarps * 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (p + u * kRedWarps < p1) job.add(p + u * kRedWarps, c, acc);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) sred[warp][v][lane] = acc[v];
+  __syncthreads();
+  if (warp == 0 && valid) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      double t = 0.0;
+      for (int w = 0; w < kRedWarps; ++w) t += sred[w][v][lane];
+      acc[v] = t;
+    }
+    if (SL == 1) job.finish(c, acc);
+    else {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) slicebuf[((size_t)slice * NV + v) * cnt + c] = acc[v];
+    }
+  }
+  if (SL == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&counters[cgroup], 1u) == (unsigned)(SL - 1)) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (warp == 0 && valid) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      double t = 0.0;
+      for (int sl = 0; sl < SL; ++sl) t += __ldcg(&slicebuf[((size_t)sl * NV + v) * cnt + c]);
+      acc[v] = t;
+    }
+    job.finish(c, acc);
+  }
+  if (threadIdx.x == 0) counters[cgroup] = 0u;
+}
+static inline int reduce_slices(int P) { int s = (P + 63) / 64; return s < 1 ? 1 : s > 32 ? 32 : s; }
+
+// ---------------------------------------------------------------------------------------------------------
+// BatchNorm statistics: merge per-tile (mean, M2) partials -> mean, invstd, scale, shift; running-stat update with
+// the unbiased variance (torch.nn.BatchNorm1d semantics, gcn.py:25,40). Sums n_t*mean_t and M2_t + n_t*mean_t^2 in
+// fp64 (the tile partials themselves are centred, so the fp64 recombination loses nothing that fp32 inputs hold).
 // ---------------------------------------------------------------------------------------------------------
 struct BnFinalizeArgs {
   const float* partials;  // [T][2][F]
@@ -125,69 +190,52 @@ struct BnFinalizeArgs {
   float* invstd;
   float* scale;
   float* shift;
+  int SL;
+  double* slicebuf;
+  unsigned* counters;
 };
-constexpr int kFinWarps = 32;  // finalize / reduce kernels run 1024 threads: 32 slices x 32 channels
-__global__ void __launch_bounds__(1024) bn_finalize_kernel(const BnFinalizeArgs a) {
-  __shared__ double s_n[kFinWarps][32], s_mean[kFinWarps][32], s_m2[kFinWarps][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
-  const bool valid = c < a.F;
-  const double n = (double)a.B * (double)a.N;
-  double mean = 0.0, var = 1.0;
-  if (a.training) {
-    // Chan et al. pairwise merge of (count, mean, M2): each warp folds its slice of tiles in ascending order,
-    // then warp 0 folds the 32 slice results in ascending order -> bit-reproducible, robust to |mean| >> std
-    double cn = 0.0, cm = 0.0, cm2 = 0.0;
-    if (valid) {
-      for (int t0 = warp; t0 < a.T; t0 += kFinWarps * 4) {
-        float pm[4], pv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int t = t0 + u * kFinWarps;
-          pm[u] = (t < a.T) ? a.partials[((size_t)t * 2 + 0) * a.F + c] : 0.f;
-          pv[u] = (t < a.T) ? a.partials[((size_t)t * 2 + 1) * a.F + c] : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int t = t0 + u * kFinWarps;
-          if (t >= a.T) break;
-          const double nt = (double)(min(a.MT, a.B - t * a.MT) * a.N);
-          const double tot = cn + nt, d = (double)pm[u] - cm;
-          cm += d * (nt / tot);
-          cm2 += (double)pv[u] + d * d * (cn * nt / tot);
-          cn = tot;
-        }
-      }
-    }
-    s_n[warp][lane] = cn; s_mean[warp][lane] = cm; s_m2[warp][lane] = cm2;
-    __syncthreads();
-    if (warp != 0 || !valid) return;
-    cn = 0.0; cm = 0.0; cm2 = 0.0;
-    for (int w = 0; w < kFinWarps; ++w) {
-      const double nt = s_n[w][lane];
-      if (nt == 0.0) continue;
-      const double tot = cn + nt, d = s_mean[w][lane] - cm;
-      cm += d * (nt / tot);
-      cm2 += s_m2[w][lane] + d * d * (cn * nt / tot);
-      cn = tot;
-    }
-    mean = cm;
-    var = cm2 / n;
-    const double unbiased = cm2 / (n > 1.0 ? n - 1.0 : 1.0);
+struct BnJob {
+  const BnFinalizeArgs& a;
+  __device__ __forceinline__ void add(int t, int c, double* acc) const {
+    const double m = (double)__ldg(&a.partials[((size_t)t * 2 + 0) * a.F + c]);
+    const double m2 = (double)__ldg(&a.partials[((size_t)t * 2 + 1) * a.F + c]);
+    const double nt = (double)(min(a.MT, a.B - t * a.MT) * a.N);
+    acc[0] += nt * m;
+    acc[1] += m2 + nt * m * m;
+  }
+  __device__ __forceinline__ void finish(int c, const double* acc) const {
+    const double n = (double)a.B * (double)a.N;
+    const double mean = acc[0] / n;
+    double m2 = acc[1] - n * mean * mean;
+    m2 = m2 > 0.0 ? m2 : 0.0;
+    const double var = m2 / n;
+    const double unbiased = m2 / (n > 1.0 ? n - 1.0 : 1.0);
     a.running_mean[c] = (float)((1.0 - (double)a.momentum) * (double)a.running_mean[c] + (double)a.momentum * mean);
     a.running_var[c] = (float)((1.0 - (double)a.momentum) * (double)a.running_var[c] + (double)a.momentum * unbiased);
     if (c == 0 && a.nbt) *a.nbt += 1;
-  } else {
-    if (warp != 0 || !valid) return;
-    mean = (double)a.running_mean[c];
-    var = (double)a.running_var[c];
+    const float invstd = (float)(1.0 / sqrt(var + (double)a.eps));
+    const float sc = a.gamma[c] * invstd;
+    a.mean[c] = (float)mean;
+    a.invstd[c] = invstd;
+    a.scale[c] = sc;
+    a.shift[c] = a.beta[c] - (float)mean * sc;
   }
-  const float invstd = (float)(1.0 / sqrt(var + (double)a.eps));
-  const float sc = a.gamma[c] * invstd;
-  a.mean[c] = (float)mean;
-  a.invstd[c] = invstd;
-  a.scale[c] = sc;
-  a.shift[c] = a.beta[c] - (float)mean * sc;
+};
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const BnFinalizeArgs a) {
+  if (!a.training) {   // eval: running statistics (grid.y == 1)
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    if ((threadIdx.x >> 5) != 0 || c >= a.F) return;
+    const double mean = (double)a.running_mean[c], var = (double)a.running_var[c];
+    const float invstd = (float)(1.0 / sqrt(var + (double)a.eps));
+    const float sc = a.gamma[c] * invstd;
+    a.mean[c] = (float)mean;
+    a.invstd[c] = invstd;
+    a.scale[c] = sc;
+    a.shift[c] = a.beta[c] - (float)mean * sc;
+    return;
+  }
+  BnJob job{a};
+  sliced_reduce<2>(job, a.T, a.F, a.SL, a.slicebuf, a.counters, blockIdx.x, blockIdx.y);
 }
 
 // y = scale*z + shift (standalone GraphConvolution output, gcn.py:40)
@@ -408,36 +456,27 @@ struct BwdFinalizeArgs {
   float* g;
   float* c1;
   float* c2;
+  int SL;
+  double* slicebuf;
+  unsigned* counters;
 };
-__global__ void __launch_bounds__(1024) bwd_finalize_kernel(const BwdFinalizeArgs a) {
-  __shared__ double sred[2][kFinWarps][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
-  const bool valid = c < a.F;
-  double s1 = 0.0, s2 = 0.0;
-  if (valid)
-    for (int t0 = warp; t0 < a.T; t0 += kFinWarps * 4) {
-      float p1[4], p2[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int t = t0 + u * kFinWarps;
-        p1[u] = (t < a.T) ? a.partials[((size_t)t * 2 + 0) * a.F + c] : 0.f;
-        p2[u] = (t < a.T) ? a.partials[((size_t)t * 2 + 1) * a.F + c] : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { s1 += (double)p1[u]; s2 += (double)p2[u]; }
-    }
-  sred[0][warp][lane] = s1;
-  sred[1][warp][lane] = s2;
-  __syncthreads();
-  if (warp != 0 || !valid) return;
-  double db = 0.0, dg = 0.0;
-  for (int w = 0; w < kFinWarps; ++w) { db += sred[0][w][lane]; dg += sred[1][w][lane]; }
-  a.dbeta[c] = (float)db;
-  a.dgamma[c] = (float)dg;
-  a.g[c] = a.gamma[c] * a.invstd[c];
-  a.c1[c] = a.training ? (float)(db / a.n) : 0.f;
-  a.c2[c] = a.training ? (float)(dg / a.n) : 0.f;
+struct BwdFinJob {
+  const BwdFinalizeArgs& a;
+  __device__ __forceinline__ void add(int t, int c, double* acc) const {
+    acc[0] += (double)__ldg(&a.partials[((size_t)t * 2 + 0) * a.F + c]);
+    acc[1] += (double)__ldg(&a.partials[((size_t)t * 2 + 1) * a.F + c]);
+  }
+  __device__ __forceinline__ void finish(int c, const double* acc) const {
+    a.dbeta[c] = (float)acc[0];
+    a.dgamma[c] = (float)acc[1];
+    a.g[c] = a.gamma[c] * a.invstd[c];
+    a.c1[c] = a.training ? (float)(acc[0] / a.n) : 0.f;
+    a.c2[c] = a.training ? (float)(acc[1] / a.n) : 0.f;
+  }
+};
+__global__ void __launch_bounds__(256) bwd_finalize_kernel(const BwdFinalizeArgs a) {
+  BwdFinJob job{a};
+  sliced_reduce<2>(job, a.T, a.F, a.SL, a.slicebuf, a.counters, blockIdx.x, blockIdx.y);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -496,42 +535,32 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tn_kernel(const float* __res
   }
 }
 
-// out[i] = sum_p partial[p][i], p ascending (fixed order). Two jobs per launch (e.g. dW and db).
+// out[i] = sum_p partial[p][i] (fixed order). Two jobs per launch (e.g. dW and db).
 struct ReduceJobs {
   const float* partial[2];
   float* out[2];
   int P[2];
   int count[2];
+  int SL[2];
+  double* slicebuf[2];
+  unsigned* counters[2];
 };
-__global__ void __launch_bounds__(1024) reduce_partials_kernel(const ReduceJobs jobs) {
-  // block = 32 elements x 32 slices of P; fixed-order fp64 combine (slice-major), coalesced 128 B rows
-  __shared__ double sred[kFinWarps][32];
-  const int jb = blockIdx.y;
-  const float* p = jobs.partial[jb];
-  float* out = jobs.out[jb];
-  const int P = jobs.P[jb], cnt = jobs.count[jb];
-  if (!out || blockIdx.x * 32 >= cnt) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int idx = blockIdx.x * 32 + lane;
-  double s = 0.0;
-  if (idx < cnt)
-    for (int q0 = warp; q0 < P; q0 += kFinWarps * 4) {
-      float v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int q = q0 + u * kFinWarps;
-        v[u] = (q < P) ? p[(size_t)q * cnt + idx] : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) s += (double)v[u];
-    }
-  sred[warp][lane] = s;
-  __syncthreads();
-  if (warp == 0 && idx < cnt) {
-    double t = 0.0;
-    for (int w = 0; w < kFinWarps; ++w) t += sred[w][lane];
-    out[idx] = (float)t;
-  }
+struct SumJob {
+  const float* p;
+  float* out;
+  int cnt;
+  __device__ __forceinline__ void add(int q, int c, double* acc) const { acc[0] += (double)__ldg(&p[(size_t)q * cnt + c]); }
+  __device__ __forceinline__ void finish(int c, const double* acc) const { out[c] = (float)acc[0]; }
+};
+// 1-D grid: the first ceil(count[0]/32)*SL[0] CTAs serve job 0 (slice-major), the rest job 1
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceJobs jobs) {
+  const int n0 = ((jobs.count[0] + 31) / 32) * jobs.SL[0];
+  const int jb = (int)blockIdx.x < n0 ? 0 : 1;
+  const int rel = (int)blockIdx.x - (jb ? n0 : 0);
+  const int ng = (jobs.count[jb] + 31) / 32;
+  if (!jobs.out[jb]) return;
+  SumJob job{jobs.partial[jb], jobs.out[jb], jobs.count[jb]};
+  sliced_reduce<1>(job, jobs.P[jb], jobs.count[jb], jobs.SL[jb], jobs.slicebuf[jb], jobs.counters[jb], rel % ng, rel / ng);
 }
 
 }  // namespace ocgcn

@@ -27,7 +27,9 @@ enum Epi : int {
   E_ZSTATS = 0,   // Z = acc + bias -> global, per-tile Welford partials (count, mean, M2) per channel
   E_READOUT = 1,  // D = tanh(acc + bias) -> global, O = tanh(sum_i D) -> global
   E_STORE = 2,    // out = acc
-  E_ATG = 3       // out = A^T . acc  (per molecule)
+  E_ATG = 3,      // out = A^T . acc  (per molecule)
+  E_DY = 4,       // acc is dH of the previous layer: pool scatter through its arg-max + tanh' -> out = dY_prev, partial sums
+  E_ATG_DY = 5    // dH = A^T . acc, then as E_DY  (fuses the first half of the previous layer's backward)
 };
 
 struct TileArgs {
@@ -61,8 +63,15 @@ struct TileArgs {
   // epilogue outputs
   float* out0;      // Z | D | dH | dHprev  [rows][NC]
   float* out1;      // E_READOUT: O [B][NC]
-  float* partials;  // E_ZSTATS: [tile][3][NC]  (count is implicit; slots: mean, M2, unused)
+  float* partials;  // E_ZSTATS: [tile][2][NC] (mean, M2) | E_DY / E_ATG_DY: [tile][2][NC] (sum dY, sum dY*Yhat)
   int skip_gemm;    // producers only (P_DZ of the first layer when dX is not needed)
+  // E_DY / E_ATG_DY: saved state of the PREVIOUS layer (the one whose pooled output this tile's dH is the gradient of)
+  const unsigned char* arg_in;  // [rows][NC] pool arg-max
+  const float* zprev;           // [rows][NC] pre-BatchNorm activations
+  const float* pv_scale;        // [NC] gamma*invstd
+  const float* pv_shift;        // [NC] beta - mean*scale
+  const float* pv_mean;         // [NC]
+  const float* pv_invstd;       // [NC]
   // tensor-core engine (tile_kernel<.., MM = 1>) only
   const void* wimg;  // weight operand images: pieces [K/64][ceil(NC/128)][hi(,lo)] of [8 k-chunks][128 n][8] bf16 (ocgcn_dw.cuh)
   int ncb;           // ceil(NC/128)

@@ -42,7 +42,7 @@ __host__ __device__ inline size_t tile_smem_bytes(int NW) {
   size_t masks = (size_t)2 * TR * NW * sizeof(u64);
   size_t main_a = MM ? (size_t)2 * TR * KC * 4 + (size_t)2 * 8 * kImgPitch
                      : (size_t)2 * TR * KCP * 4 + (size_t)KC * TC * 4;  // two chunk buffers + weight chunk / operand images
-  size_t main_b = (size_t)TR * (TC + 4) * 4;                            // epilogue staging tile
+  size_t main_b = (size_t)TR * (TC + 4) * 4 + (size_t)TR * TC;          // epilogue staging tile + arg-max tile (E_DY / E_ATG_DY)
   size_t mainsz = main_a > main_b ? main_a : main_b;
   return recs + masks + mainsz + (size_t)TR * 4 /*molecule flags*/ + (size_t)2 * kWarps * 32 * 4 /*warp partials*/ + 64;
 }
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
   unsigned char* wHi = reinterpret_cast<unsigned char*>(buf0);                 // MM == 1: weight image pieces (hi, lo) alias buf0
   float* sC = mainp;  // epilogue staging, aliases buf0/buf1/sW
   constexpr size_t main_a = MM ? ((size_t)2 * TR * KC * 4 + (size_t)2 * 8 * kImgPitch) / 4 : (size_t)2 * TR * KCP + (size_t)KC * TC;
-  constexpr size_t main_b = (size_t)TR * TCP;
+  constexpr size_t main_b = (size_t)TR * TCP + (size_t)TR * TC / 4;
   constexpr size_t mainsz = main_a > main_b ? main_a : main_b;
   unsigned* sFlag = reinterpret_cast<unsigned*>(mainp + mainsz);
   float* sWarp = reinterpret_cast<float*>(sFlag + TR);
@@ -762,6 +762,176 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
         }
       }
       __syncthreads();
+    } else if (EPI == E_DY || EPI == E_ATG_DY) {
+      // ---- fused first half of the previous layer's backward (gcn_encoder.py:43-50 differentiated) ----
+      // staged tile -> dH (A^T gather, in place) -> dT = pool scatter through the saved arg-max -> dY = dT*(1-T^2)
+      unsigned char* sArg = reinterpret_cast<unsigned char*>(sC + TR * TCP);   // [TR][TC] arg-max of the previous layer
+      {
+        const bool vec = (NC % 16 == 0);
+        for (int idx = tid; idx < rows * (TC / 16); idx += kThreads) {
+          const int r = idx / (TC / 16), c16 = (idx - r * (TC / 16)) * 16;
+          const int gc = cb + c16;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (gc < NC) {
+            const unsigned char* src = a.arg_in + (row0 + r) * NC + gc;
+            if (vec) {
+              v = __ldg(reinterpret_cast<const uint4*>(src));
+            } else {
+              unsigned w[4] = {0u, 0u, 0u, 0u};
+              for (int b = 0; b < 16; ++b)
+                if (gc + b < NC) w[b >> 2] |= (unsigned)__ldg(&src[b]) << ((b & 3) * 8);
+              v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+          *reinterpret_cast<uint4*>(&sArg[r * TC + c16]) = v;
+        }
+      }
+      if (EPI == E_ATG_DY) {
+        // dH[j,:] = sum_i A[i,j] * dS[i,:]: 64 columns at a time through registers, written back over dS
+#pragma unroll 1
+        for (int cs = 0; cs < TC; cs += 64) {
+          float2 hv[RPW];
+#pragma unroll
+          for (int q = 0; q < RPW; ++q) {
+            const int r = warp + q * kWarps;
+            float2 sv = make_float2(0.f, 0.f);
+            if (r < rows) {
+              const uint4 crec = sCRec[r];
+              const int m = rec_m(crec), mb = m * N;
+              if (rec_binary(crec) && !rec_fallback(crec)) {
+                sv = rec_sum2<TCP>(crec, &sC[cs + 2 * lane]);
+              } else if (rec_binary(crec)) {
+                const u64* mk = &sCol[(size_t)r * NW];
+                sv.x = masked_sum(mk, NW, &sC[mb * TCP + cs + 2 * lane], TCP);
+                sv.y = masked_sum(mk, NW, &sC[mb * TCP + cs + 2 * lane + 1], TCP);
+              } else {
+                const float* acol = a.adj + (long long)(mol0 + m) * a.as0 + (long long)(r - mb) * a.as2;
+                for (int i = 0; i < N; ++i) {
+                  const float ai = __ldg(&acol[(long long)i * a.as1]);
+                  const float2 dv = *reinterpret_cast<const float2*>(&sC[(mb + i) * TCP + cs + 2 * lane]);
+                  sv.x = fmaf(ai, dv.x, sv.x);
+                  sv.y = fmaf(ai, dv.y, sv.y);
+                }
+              }
+            }
+            hv[q] = sv;
+          }
+          __syncthreads();
+#pragma unroll
+          for (int q = 0; q < RPW; ++q) {
+            const int r = warp + q * kWarps;
+            if (r < rows) *reinterpret_cast<float2*>(&sC[r * TCP + cs + 2 * lane]) = hv[q];
+          }
+        }
+      }
+      __syncthreads();
+      {
+        const int cl = lane * 4, gc = cb + cl;
+        const bool act = cl < TC && gc < NC;
+        const bool vec4 = (NC % 4 == 0);
+        float sc[4], sh[4], mu[4], is[4], s1[4], s2[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const bool ok = act && gc + e < NC;
+          sc[e] = ok ? __ldg(&a.pv_scale[gc + e]) : 0.f;
+          sh[e] = ok ? __ldg(&a.pv_shift[gc + e]) : 0.f;
+          mu[e] = ok ? __ldg(&a.pv_mean[gc + e]) : 0.f;
+          is[e] = ok ? __ldg(&a.pv_invstd[gc + e]) : 0.f;
+          s1[e] = 0.f;
+          s2[e] = 0.f;
+        }
+        auto load_z = [&](int r) -> float4 {
+          float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (act && r < rows) {
+            const float* zp = a.zprev + (row0 + r) * NC + gc;
+            if (vec4) z = __ldg(reinterpret_cast<const float4*>(zp));
+            else { z.x = __ldg(zp); if (gc + 1 < NC) z.y = __ldg(zp + 1); if (gc + 2 < NC) z.z = __ldg(zp + 2); if (gc + 3 < NC) z.w = __ldg(zp + 3); }
+          }
+          return z;
+        };
+        float4 znext = load_z(warp);
+        for (int r = warp; r < rows; r += kWarps) {
+          const float4 z4 = znext;
+          znext = load_z(r + kWarps);
+          if (!act) continue;
+          const uint4 crec = sCRec[r];
+          const int m = rec_m(crec), mb = m * N;
+          const unsigned jrel = (unsigned)(r - mb);
+          float dt[4] = {0.f, 0.f, 0.f, 0.f};
+          if (rec_binary(crec) && !rec_fallback(crec)) {
+            // dT[j,c] = sum over rows i that list j as a neighbour and whose arg-max in channel c is j
+            const int cnt = rec_cnt(crec);
+#define OCGCN_SCAT_STEP(Q)                                                                    \
+            if (cnt > Q) {                                                                    \
+              const int ir = rec_idx<Q>(crec);                                                \
+              const float4 g = *reinterpret_cast<const float4*>(&sC[ir * TCP + cl]);          \
+              const unsigned ag = *reinterpret_cast<const unsigned*>(&sArg[ir * TC + cl]);    \
+              if ((ag & 0xffu) == jrel) dt[0] += g.x;                                         \
+              if (((ag >> 8) & 0xffu) == jrel) dt[1] += g.y;                                  \
+              if (((ag >> 16) & 0xffu) == jrel) dt[2] += g.z;                                 \
+              if ((ag >> 24) == jrel) dt[3] += g.w;                                           \
+            }
+            OCGCN_SCAT_STEP(0) OCGCN_SCAT_STEP(1) OCGCN_SCAT_STEP(2) OCGCN_SCAT_STEP(3) OCGCN_SCAT_STEP(4)
+            if (cnt > 5) {
+              OCGCN_SCAT_STEP(5) OCGCN_SCAT_STEP(6) OCGCN_SCAT_STEP(7) OCGCN_SCAT_STEP(8)
+              if (cnt > 9) { OCGCN_SCAT_STEP(9) OCGCN_SCAT_STEP(10) OCGCN_SCAT_STEP(11) OCGCN_SCAT_STEP(12) }
+            }
+#undef OCGCN_SCAT_STEP
+          } else if (rec_binary(crec)) {
+            const u64* mk = &sCol[(size_t)r * NW];
+            for (int w = 0; w < NW; ++w) {
+              u64 bits = mk[w];
+              while (bits) {
+                const int ir = mb + 64 * w + __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (sArg[ir * TC + cl + e] == jrel) dt[e] += sC[ir * TCP + cl + e];
+              }
+            }
+          } else {
+            const float* acol = a.adj + (long long)(mol0 + m) * a.as0 + (long long)(r - mb) * a.as2;
+            for (int i = 0; i < N; ++i) {
+              const float ai = __ldg(&acol[(long long)i * a.as1]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (sArg[(mb + i) * TC + cl + e] == jrel) dt[e] = fmaf(ai, sC[(mb + i) * TCP + cl + e], dt[e]);
+            }
+          }
+          const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+          float dy[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float t = fast_tanh(fmaf(zz[e], sc[e], sh[e]));
+            dy[e] = (gc + e < NC) ? dt[e] * (1.f - t * t) : 0.f;
+            s1[e] += dy[e];
+            s2[e] = fmaf(dy[e], (zz[e] - mu[e]) * is[e], s2[e]);
+          }
+          float* dst = a.out0 + (row0 + r) * NC + gc;
+          if (vec4) {
+            *reinterpret_cast<float4*>(dst) = make_float4(dy[0], dy[1], dy[2], dy[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (gc + e < NC) dst[e] = dy[e];
+          }
+        }
+        __syncthreads();   // every warp is done with the dH tile: reuse it for the cross-warp sums
+        float* sRed = sC;    // [kWarps][2][TC]
+        if (cl < TC) {
+          *reinterpret_cast<float4*>(&sRed[(warp * 2 + 0) * TC + cl]) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+          *reinterpret_cast<float4*>(&sRed[(warp * 2 + 1) * TC + cl]) = make_float4(s2[0], s2[1], s2[2], s2[3]);
+        }
+        __syncthreads();
+        if (tid < TC && cb + tid < NC) {
+          float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+          for (int w = 0; w < kWarps; ++w) { t1 += sRed[(w * 2 + 0) * TC + tid]; t2 += sRed[(w * 2 + 1) * TC + tid]; }
+          a.partials[((size_t)tile * 2 + 0) * NC + cb + tid] = t1;
+          a.partials[((size_t)tile * 2 + 1) * NC + cb + tid] = t2;
+        }
+        __syncthreads();
+      }
     } else if (MM) {
       __syncthreads();   // the staging tile aliases the chunk buffers of the next column pass
     }
