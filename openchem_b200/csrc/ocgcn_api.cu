@@ -221,11 +221,12 @@ static int check_device_ptr(const void* p) {
 template <int TR, int PROD, int EPI, int MM>
 static int launch_tile_t(const TileArgs& a, int tiles, cudaStream_t st) {
   constexpr int TC = tile_cols<TR>();
+  constexpr int NT = MM ? kThreadsMM : kThreads;
   ProfScope prof(PROD == P_X ? KK_FWD_FIRST : PROD == P_MID ? KK_FWD_MID : PROD == P_RO ? KK_FWD_READOUT : PROD == P_DZ ? KK_BWD_DZ : KK_BWD_READOUT, st);
-  auto kern = tile_kernel<TR, TC, PROD, EPI, MM>;
-  const size_t smem = tile_smem_bytes<TR, TC, MM>(a.NW);
+  auto kern = tile_kernel<TR, TC, PROD, EPI, MM, NT>;
+  const size_t smem = tile_smem_bytes<TR, TC, MM, NT>(a.NW);
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<tiles, kThreads, smem, st>>>(a);
+  kern<<<tiles, NT, smem, st>>>(a);
   LAUNCH_CHECK();
   return OCGCN_OK;
 }

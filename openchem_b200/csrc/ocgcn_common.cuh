@@ -7,7 +7,8 @@
 
 namespace ocgcn {
 
-constexpr int kThreads = 256;  // every tile kernel runs 8 warps
+constexpr int kThreads = 256;    // the exact-fp32 tile kernels and the streaming kernels run 8 warps
+constexpr int kThreadsMM = 512;  // tensor-core tile kernels: 16 warps (accumulators live in TMEM, <= 64 registers per thread)
 constexpr int kWarps = kThreads / 32;
 constexpr int KC = 64;          // channel chunk: two adjacent channels per lane
 constexpr int KCP = KC + 4;     // padded chunk row (floats): float4-aligned rows, conflict-free float2 per lane

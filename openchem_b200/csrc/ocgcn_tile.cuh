@@ -36,23 +36,41 @@ constexpr int kWPiece = 8 * 128 * 16;      // MM: bytes of one weight image piec
 constexpr int kTmemCols = 128;
 
 // dynamic shared memory needed by tile_kernel<TR, TC, ., ., MM>
-template <int TR, int TC, int MM>
+template <int TR, int TC, int MM, int NT>
 __host__ __device__ inline size_t tile_smem_bytes(int NW) {
   size_t recs = (size_t)2 * TR * 16;
   size_t masks = (size_t)2 * TR * NW * sizeof(u64);
-  size_t main_a = MM ? (size_t)2 * TR * KC * 4 + (size_t)2 * 8 * kImgPitch
-                     : (size_t)2 * TR * KCP * 4 + (size_t)KC * TC * 4;  // two chunk buffers + weight chunk / operand images
+  size_t main_a = MM ? (size_t)TR * (TC + 4) * 4 + (size_t)2 * 8 * kImgPitch   // [chunk buffers | pad] = staging tile, then operand images
+                     : (size_t)2 * TR * KCP * 4 + (size_t)KC * TC * 4;          // two chunk buffers + weight chunk
   size_t main_b = (size_t)TR * (TC + 4) * 4 + (size_t)TR * TC;          // epilogue staging tile + arg-max tile (E_DY / E_ATG_DY)
   size_t mainsz = main_a > main_b ? main_a : main_b;
-  return recs + masks + mainsz + (size_t)TR * 4 /*molecule flags*/ + (size_t)2 * kWarps * 32 * 4 /*warp partials*/ + 64;
+  return recs + masks + mainsz + (size_t)TR * 4 /*molecule flags*/ + (size_t)2 * (NT / 32) * 32 * 4 /*warp partials*/ + 64;
 }
 
 // ---- neighbour walks over a staged record: values of two adjacent channels (float2) per lane ------------------
 // max with first-index-wins ties (ascending neighbour order), returns tile rows of the arg-max
+// The first four neighbours are handled WITHOUT branches so that their shared-memory loads are all in flight at
+// once (the walk is latency-bound): a missing neighbour q >= cnt re-reads neighbour 0, which can never win a strict '>'
+// comparison (max) or is masked out of the sum. `self` is any valid row of the buffer (used when cnt == 0).
 template <int STRIDE>
-__device__ __forceinline__ void rec_max2(const uint4& rec, const float* colp, float& b0, float& b1, int& a0, int& a1) {
+__device__ __forceinline__ void rec_max2(const uint4& rec, const float* colp, int self, float& b0, float& b1, int& a0, int& a1) {
   const int cnt = rec_cnt(rec);
-  b0 = -INFINITY; b1 = -INFINITY; a0 = 0; a1 = 0;
+  const int j0 = cnt > 0 ? rec_idx<0>(rec) : self;
+  const int j1 = cnt > 1 ? rec_idx<1>(rec) : j0;
+  const int j2 = cnt > 2 ? rec_idx<2>(rec) : j0;
+  const int j3 = cnt > 3 ? rec_idx<3>(rec) : j0;
+  const float2 v0 = *reinterpret_cast<const float2*>(colp + j0 * STRIDE);
+  const float2 v1 = *reinterpret_cast<const float2*>(colp + j1 * STRIDE);
+  const float2 v2 = *reinterpret_cast<const float2*>(colp + j2 * STRIDE);
+  const float2 v3 = *reinterpret_cast<const float2*>(colp + j3 * STRIDE);
+  b0 = cnt > 0 ? v0.x : -INFINITY; b1 = cnt > 0 ? v0.y : -INFINITY; a0 = j0; a1 = j0;
+  if (v1.x > b0) { b0 = v1.x; a0 = j1; }
+  if (v1.y > b1) { b1 = v1.y; a1 = j1; }
+  if (v2.x > b0) { b0 = v2.x; a0 = j2; }
+  if (v2.y > b1) { b1 = v2.y; a1 = j2; }
+  if (v3.x > b0) { b0 = v3.x; a0 = j3; }
+  if (v3.y > b1) { b1 = v3.y; a1 = j3; }
+  if (cnt == 0) { b0 = -INFINITY; b1 = -INFINITY; }   // (the re-read row would otherwise beat the -inf start value)
 #define OCGCN_MAX_STEP(Q)                                                        \
   if (cnt > Q) {                                                                 \
     const int jr = rec_idx<Q>(rec);                                              \
@@ -60,26 +78,36 @@ __device__ __forceinline__ void rec_max2(const uint4& rec, const float* colp, fl
     if (v.x > b0) { b0 = v.x; a0 = jr; }                                         \
     if (v.y > b1) { b1 = v.y; a1 = jr; }                                         \
   }
-  OCGCN_MAX_STEP(0) OCGCN_MAX_STEP(1) OCGCN_MAX_STEP(2) OCGCN_MAX_STEP(3) OCGCN_MAX_STEP(4)
-  if (cnt > 5) {
-    OCGCN_MAX_STEP(5) OCGCN_MAX_STEP(6) OCGCN_MAX_STEP(7) OCGCN_MAX_STEP(8)
+  if (cnt > 4) {
+    OCGCN_MAX_STEP(4) OCGCN_MAX_STEP(5) OCGCN_MAX_STEP(6) OCGCN_MAX_STEP(7) OCGCN_MAX_STEP(8)
     if (cnt > 9) { OCGCN_MAX_STEP(9) OCGCN_MAX_STEP(10) OCGCN_MAX_STEP(11) OCGCN_MAX_STEP(12) }
   }
 #undef OCGCN_MAX_STEP
 }
 
 template <int STRIDE>
-__device__ __forceinline__ float2 rec_sum2(const uint4& rec, const float* colp) {
+__device__ __forceinline__ float2 rec_sum2(const uint4& rec, const float* colp, int self) {
   const int cnt = rec_cnt(rec);
-  float s0 = 0.f, s1 = 0.f;
+  const int j0 = cnt > 0 ? rec_idx<0>(rec) : self;
+  const int j1 = cnt > 1 ? rec_idx<1>(rec) : j0;
+  const int j2 = cnt > 2 ? rec_idx<2>(rec) : j0;
+  const int j3 = cnt > 3 ? rec_idx<3>(rec) : j0;
+  const float2 v0 = *reinterpret_cast<const float2*>(colp + j0 * STRIDE);
+  const float2 v1 = *reinterpret_cast<const float2*>(colp + j1 * STRIDE);
+  const float2 v2 = *reinterpret_cast<const float2*>(colp + j2 * STRIDE);
+  const float2 v3 = *reinterpret_cast<const float2*>(colp + j3 * STRIDE);
+  // ascending neighbour order, exactly the additions the branchy walk performs
+  float s0 = cnt > 0 ? v0.x : 0.f, s1 = cnt > 0 ? v0.y : 0.f;
+  s0 += cnt > 1 ? v1.x : 0.f; s1 += cnt > 1 ? v1.y : 0.f;
+  s0 += cnt > 2 ? v2.x : 0.f; s1 += cnt > 2 ? v2.y : 0.f;
+  s0 += cnt > 3 ? v3.x : 0.f; s1 += cnt > 3 ? v3.y : 0.f;
 #define OCGCN_SUM_STEP(Q)                                                                       \
   if (cnt > Q) {                                                                                \
     const float2 v = *reinterpret_cast<const float2*>(colp + rec_idx<Q>(rec) * STRIDE);         \
     s0 += v.x; s1 += v.y;                                                                       \
   }
-  OCGCN_SUM_STEP(0) OCGCN_SUM_STEP(1) OCGCN_SUM_STEP(2) OCGCN_SUM_STEP(3) OCGCN_SUM_STEP(4)
-  if (cnt > 5) {
-    OCGCN_SUM_STEP(5) OCGCN_SUM_STEP(6) OCGCN_SUM_STEP(7) OCGCN_SUM_STEP(8)
+  if (cnt > 4) {
+    OCGCN_SUM_STEP(4) OCGCN_SUM_STEP(5) OCGCN_SUM_STEP(6) OCGCN_SUM_STEP(7) OCGCN_SUM_STEP(8)
     if (cnt > 9) { OCGCN_SUM_STEP(9) OCGCN_SUM_STEP(10) OCGCN_SUM_STEP(11) OCGCN_SUM_STEP(12) }
   }
 #undef OCGCN_SUM_STEP
@@ -115,14 +143,15 @@ __device__ __forceinline__ void stg2(float* p, float2 v, bool v0, bool v1, bool 
   if (v1) p[1] = v.y;
 }
 
-template <int TR, int TC, int PROD, int EPI, int MM>
-__global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(const TileArgs a) {
+template <int TR, int TC, int PROD, int EPI, int MM, int NT>
+__global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const TileArgs a) {
+  constexpr int NWARP = NT / 32;
   constexpr int TYN = TR / 8;
   constexpr int TXN = TC / 8;
-  static_assert(TYN * TXN == kThreads, "thread grid must cover the tile");
+  static_assert(MM == 1 || TYN * TXN == NT, "thread grid must cover the tile");
   static_assert(MM == 0 || (TR == 128 && TC == 128), "the tensor-core path works on 128x128 tiles");
   constexpr int TCP = TC + 4;
-  constexpr int RPW = TR / kWarps;      // rows per warp (16 or 32), processed in batches of 8 independent loads
+  constexpr int RPW = TR / NWARP;      // rows per warp (16 or 32), processed in batches of 8 independent loads
   constexpr int BS = MM ? KC : KCP;     // chunk buffer row stride (floats); the FFMA fragment loads want the padding
   // MM: every operand is split x = hi + lo (bf16 each). Forward products take 4 passes (hi.hi + lo.hi + hi.lo + lo.lo:
   // fp32-class values, so the pool arg-max decisions match an fp32 forward), backward products 3 (no lo.lo).
@@ -138,16 +167,16 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
   float* buf0 = mainp;
   float* buf1 = buf0 + TR * BS;
   float* sW = buf1 + TR * BS;                                          // MM == 0: weight chunk
-  unsigned char* imgHi = reinterpret_cast<unsigned char*>(buf1 + TR * BS);   // MM == 1: operand images [8][kImgPitch]
+  unsigned char* imgHi = reinterpret_cast<unsigned char*>(mainp + TR * TCP);  // MM == 1: operand images [8][kImgPitch], after the staging tile
   unsigned char* imgLo = imgHi + 8 * kImgPitch;
   unsigned char* wHi = reinterpret_cast<unsigned char*>(buf0);                 // MM == 1: weight image pieces (hi, lo) alias buf0
   float* sC = mainp;  // epilogue staging, aliases buf0/buf1/sW
-  constexpr size_t main_a = MM ? ((size_t)2 * TR * KC * 4 + (size_t)2 * 8 * kImgPitch) / 4 : (size_t)2 * TR * KCP + (size_t)KC * TC;
+  constexpr size_t main_a = MM ? (size_t)TR * TCP + (size_t)2 * 8 * kImgPitch / 4 : (size_t)2 * TR * KCP + (size_t)KC * TC;
   constexpr size_t main_b = (size_t)TR * TCP + (size_t)TR * TC / 4;
   constexpr size_t mainsz = main_a > main_b ? main_a : main_b;
   unsigned* sFlag = reinterpret_cast<unsigned*>(mainp + mainsz);
   float* sWarp = reinterpret_cast<float*>(sFlag + TR);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sWarp + 2 * kWarps * 32);   // MM: [0] weight image landed, [1] MMAs complete
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sWarp + 2 * NWARP * 32);   // MM: [0] weight image landed, [1] MMAs complete
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 2);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -165,10 +194,10 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
   const uint32_t img_lane_off = (uint32_t)(lane >> 2) * kImgPitch + (uint32_t)(lane & 3) * 4;
   const bool use_mma = MM && !a.skip_gemm;
   uint32_t tmem = 0, ph_w = 0, ph_mma = 0;
-  bool mma_pending = false;
+  bool mma_pending = false, store_pending = false;
 
   // ---- stage neighbour records (made tile-relative), masks and per-molecule flags ---------------------------
-  for (int r = tid; r < TR; r += kThreads) {
+  for (int r = tid; r < TR; r += NT) {
     uint4 rec = make_uint4(0u, 0u, 0u, 0u), crec = make_uint4(0u, 0u, 0u, 0u);
     if (r < rows) {
       const int m = r / N, mb = m * N;
@@ -178,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
     sRec[r] = rec;
     sCRec[r] = crec;
   }
-  for (int idx = tid; idx < rows * NW; idx += kThreads) {
+  for (int idx = tid; idx < rows * NW; idx += NT) {
     sRow[idx] = a.rowmask[row0 * NW + idx];
     sCol[idx] = a.colmask[row0 * NW + idx];
   }
@@ -223,6 +252,9 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
           ph_mma ^= 1;
           mma_pending = false;
         }
+        if (tid == 0 && store_pending) tc::bulk_wait_read0();   // the previous chunk's image has been read by the bulk store
+        if ((PROD == P_DZ || PROD == P_DU) && store_pending) __syncthreads();   // these producers write the image in their first stage
+        store_pending = false;
         if (use_mma && tid == 0 && !(PROD == P_MID)) {   // buf0 is free for the whole chunk: fetch the weight pieces now
           const unsigned char* src = reinterpret_cast<const unsigned char*>(a.wimg) +
                                      ((size_t)(k0 / KC) * a.ncb + (cb / TC)) * 2 * kWPiece;
@@ -233,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
       } else if (!a.skip_gemm) {
         // weight chunk [KC][TC] (independent of the producer; sW is free after the previous trailing sync)
         if (NC % 4 == 0) {
-          for (int idx = tid; idx < KC * TC / 4; idx += kThreads) {
+          for (int idx = tid; idx < KC * TC / 4; idx += NT) {
             const int kk = idx / (TC / 4), cc = (idx - kk * (TC / 4)) * 4;
             const int gk = k0 + kk, gc = cb + cc;
             float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -241,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
             *reinterpret_cast<float4*>(&sW[kk * TC + cc]) = w;
           }
         } else {
-          for (int idx = tid; idx < KC * TC; idx += kThreads) {
+          for (int idx = tid; idx < KC * TC; idx += NT) {
             const int kk = idx / TC, cc = idx - kk * TC;
             const int gk = k0 + kk, gc = cb + cc;
             sW[idx] = (gk < K && gc < NC) ? __ldg(&a.Bm[(size_t)gk * NC + gc]) : 0.f;
@@ -269,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
           float2 v[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const int r = warp + (h * 8 + q) * kWarps;
+            const int r = warp + (h * 8 + q) * NWARP;
             v[q] = make_float2(0.f, 0.f);
             if (r < rows && v0) {
               const int m = rec_m(sRec[r]), i = r - m * N;
@@ -280,35 +312,38 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
           }
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float2*>(&buf1[(warp + (h * 8 + q) * kWarps) * BS + 2 * lane]) = v[q];
+            *reinterpret_cast<float2*>(&buf1[(warp + (h * 8 + q) * NWARP) * BS + 2 * lane]) = v[q];
         }
         __syncthreads();
       } else if (PROD == P_MID || PROD == P_RO) {
         float2 sc = make_float2(0.f, 0.f), sh = make_float2(0.f, 0.f);
         if (v0) { sc.x = __ldg(&a.vec0[c]); sh.x = __ldg(&a.vec1[c]); }
         if (v1) { sc.y = __ldg(&a.vec0[c + 1]); sh.y = __ldg(&a.vec1[c + 1]); }
+        {
+          constexpr int TB = (RPW > 16) ? 16 : RPW;   // rows per batch: all their loads are in flight before the first tanh
 #pragma unroll
-        for (int h = 0; h < RPW / 8; ++h) {
-          float2 v[8];
+          for (int h = 0; h < RPW / TB; ++h) {
+            float2 v[TB];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {  // all loads of the batch in flight before the first tanh
-            const int r = warp + (h * 8 + q) * kWarps;
-            v[q] = (r < rows && v0) ? ldg2(&a.in0[(row0 + r) * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
-          }
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int r = warp + (h * 8 + q) * kWarps;
-            float2 t = make_float2(0.f, 0.f);
-            if (r < rows) {
-              if (v0) t.x = fast_tanh(fmaf(v[q].x, sc.x, sh.x));
-              if (v1) t.y = fast_tanh(fmaf(v[q].y, sc.y, sh.y));
+            for (int q = 0; q < TB; ++q) {
+              const int r = warp + (h * TB + q) * NWARP;
+              v[q] = (r < rows && v0) ? ldg2(&a.in0[(row0 + r) * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
             }
-            *reinterpret_cast<float2*>(&bufT[r * BS + 2 * lane]) = t;
+#pragma unroll
+            for (int q = 0; q < TB; ++q) {
+              const int r = warp + (h * TB + q) * NWARP;
+              float2 t = make_float2(0.f, 0.f);
+              if (r < rows) {
+                if (v0) t.x = fast_tanh(fmaf(v[q].x, sc.x, sh.x));
+                if (v1) t.y = fast_tanh(fmaf(v[q].y, sc.y, sh.y));
+              }
+              *reinterpret_cast<float2*>(&bufT[r * BS + 2 * lane]) = t;
+            }
           }
         }
         __syncthreads();
         // neighbour max-pool: P[i,c] = max_j A[i,j]*T[j,c], first index wins ties (gcn_encoder.py:44-50)
-        for (int r = warp; r < TR; r += kWarps) {
+        for (int r = warp; r < TR; r += NWARP) {
           float b0 = 0.f, b1 = 0.f;
           if (r < rows) {
             const uint4 rec = sRec[r];
@@ -316,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
             int a0 = mb, a1 = mb;  // tile rows of the arg-max
             const bool flag = rec_binary(rec);
             if (flag && !rec_fallback(rec)) {
-              rec_max2<BS>(rec, &bufT[2 * lane], b0, b1, a0, a1);
+              rec_max2<BS>(rec, &bufT[2 * lane], r, b0, b1, a0, a1);
               if (rec_has_zero(rec)) {  // a zero entry A[i,jz] contributes the candidate 0*T = 0
                 const int jz = mb + rec_jz(rec);
                 if (!(b0 > 0.f)) { if (b0 < 0.f || jz < a0) a0 = jz; b0 = 0.f; }
@@ -380,14 +415,14 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
           float2 zv[8], dv[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const int r = warp + (h * 8 + q) * kWarps;
+            const int r = warp + (h * 8 + q) * NWARP;
             const bool ok = r < rows && v0;
             zv[q] = ok ? ldg2(&a.in1[(row0 + r) * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
             dv[q] = ok ? ldg2(&a.in0[(row0 + r) * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
           }
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const int r = warp + (h * 8 + q) * kWarps;
+            const int r = warp + (h * 8 + q) * NWARP;
             float2 dz = make_float2(0.f, 0.f);
             if (r < rows && v0) {
               dz.x = g.x * (dv[q].x - c1.x - (zv[q].x - mu.x) * is.x * c2.x);
@@ -406,7 +441,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
         if (first_pass && a.prod_partials && warp == 0 && v0) {
           float2 s = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int w = 0; w < kWarps; ++w) { const float2 t = *reinterpret_cast<const float2*>(&sWarp[(w * 32 + lane) * 2]); s.x += t.x; s.y += t.y; }
+          for (int w = 0; w < NWARP; ++w) { const float2 t = *reinterpret_cast<const float2*>(&sWarp[(w * 32 + lane) * 2]); s.x += t.x; s.y += t.y; }
           a.prod_partials[(size_t)tile * K + c] = s.x;
           if (v1) a.prod_partials[(size_t)tile * K + c + 1] = s.y;
         }
@@ -417,12 +452,12 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
           float2 dv[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const int r = warp + (h * 8 + q) * kWarps;
+            const int r = warp + (h * 8 + q) * NWARP;
             dv[q] = (r < rows && v0) ? ldg2(&a.in0[(row0 + r) * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
           }
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const int r = warp + (h * 8 + q) * kWarps;
+            const int r = warp + (h * 8 + q) * NWARP;
             float2 du = make_float2(0.f, 0.f);
             if (r < rows && v0) {
               const int m = rec_m(sRec[r]);
@@ -444,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
         if (first_pass && a.prod_partials && warp == 0 && v0) {
           float2 s = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int w = 0; w < kWarps; ++w) { const float2 t = *reinterpret_cast<const float2*>(&sWarp[(w * 32 + lane) * 2]); s.x += t.x; s.y += t.y; }
+          for (int w = 0; w < NWARP; ++w) { const float2 t = *reinterpret_cast<const float2*>(&sWarp[(w * 32 + lane) * 2]); s.x += t.x; s.y += t.y; }
           a.prod_partials[(size_t)tile * K + c] = s.x;
           if (v1) a.prod_partials[(size_t)tile * K + c + 1] = s.y;
         }
@@ -452,14 +487,14 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
 
       if (PROD == P_X || PROD == P_MID) {
         // S = A.H for this chunk (gcn.py:34): over the dead T buffer (FFMA) or into the operand images (MMA)
-        for (int r = warp; r < TR; r += kWarps) {
+        for (int r = warp; r < TR; r += NWARP) {
           float2 s = make_float2(0.f, 0.f);
           if (r < rows) {
             const uint4 rec = sRec[r];
             const int m = rec_m(rec), mb = m * N;
             const bool flag = rec_binary(rec);
             if (flag && !rec_fallback(rec)) {
-              s = rec_sum2<BS>(rec, &buf1[2 * lane]);
+              s = rec_sum2<BS>(rec, &buf1[2 * lane], r);
             } else if (flag) {
               s.x = masked_sum(&sRow[(size_t)r * NW], NW, &buf1[mb * BS + 2 * lane], BS);
               s.y = masked_sum(&sRow[(size_t)r * NW], NW, &buf1[mb * BS + 2 * lane + 1], BS);
@@ -508,10 +543,10 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
             const int nch = min(8, a.img_chunks - k0 / 8);
             for (int q = 0; q < nch; ++q) tc::bulk_s2g(dst + (size_t)q * 2048, imgHi + q * kImgPitch, 2048);
             tc::bulk_commit();
-            tc::bulk_wait_read0();
           }
         }
         if (use_mma) { ph_w ^= 1; mma_pending = true; }
+        if (first_pass && a.prod_img) store_pending = true;
       } else if (!a.skip_gemm) {
 #pragma unroll 2
         for (int kk = 0; kk < KC; kk += 4) {
@@ -532,8 +567,10 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
           }
         }
       }
-      __syncthreads();  // chunk buffers (and, for the FFMA path, sW) are free again
+      if (!MM) __syncthreads();  // chunk buffers and sW are free again (MM: the mbarrier / bulk-group waits at the next chunk start cover it)
     }
+    if (MM && tid == 0 && store_pending) tc::bulk_wait_read0();
+    if (MM) store_pending = false;
     if (a.skip_gemm) break;
 
     // =========================== EPILOGUE ===========================
@@ -543,11 +580,12 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
       ph_mma ^= 1;
       mma_pending = false;
       tc::fence_after_sync();
+      constexpr int CPG = TC / (NWARP / 4);   // columns per warp group (the four warps of a group cover the 128 TMEM lanes)
       const int q = warp & 3, hsel = warp >> 2;
       const int row = q * 32 + lane;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        const int cl = hsel * 64 + c0;
+      for (int c0 = 0; c0 < CPG; c0 += 32) {
+        const int cl = hsel * CPG + c0;
         float v[32];
         tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cl, v);
         if (EPI == E_ZSTATS || EPI == E_READOUT) {
@@ -567,7 +605,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
       if (EPI == E_ZSTATS || EPI == E_STORE || EPI == E_READOUT) {
         // coalesced store of the finished tile
         const bool vec_ok = (NC % 4 == 0);
-        for (int idx = tid; idx < rows * (TC / 4); idx += kThreads) {
+        for (int idx = tid; idx < rows * (TC / 4); idx += NT) {
           const int r = idx / (TC / 4), cl = (idx - r * (TC / 4)) * 4;
           const int gc = cb + cl;
           if (gc >= NC) continue;
@@ -585,20 +623,28 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
       }
       if (EPI == E_ZSTATS) {
         // per-tile Welford partials (mean, M2) per channel; thread = (row half, column)
-        const int cl = tid & (TC - 1), half = tid >> 7;
-        const int r_lo = half * (TR / 2), r_hi = min(rows, r_lo + TR / 2);
+        constexpr int PARTS = NT / TC;   // row slices (2 or 4)
+        const int cl = tid & (TC - 1), part = tid / TC;
+        const int r_lo = part * (TR / PARTS), r_hi = min(rows, r_lo + TR / PARTS);
         float s = 0.f;
         for (int r = r_lo; r < r_hi; ++r) s += sC[r * TCP + cl];
-        sWarp[half * TC + cl] = s;
+        sWarp[part * TC + cl] = s;
         __syncthreads();
-        const float mean = (sWarp[cl] + sWarp[TC + cl]) / (float)rows;
+        float tot = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < PARTS; ++pp) tot += sWarp[pp * TC + cl];
+        const float mean = tot / (float)rows;
         float m2 = 0.f;
         for (int r = r_lo; r < r_hi; ++r) { const float d = sC[r * TCP + cl] - mean; m2 = fmaf(d, d, m2); }
-        sWarp[2 * TC + half * TC + cl] = m2;
+        __syncthreads();
+        sWarp[part * TC + cl] = m2;
         __syncthreads();
         if (tid < TC && cb + tid < NC) {
+          float m2t = 0.f;
+#pragma unroll
+          for (int pp = 0; pp < PARTS; ++pp) m2t += sWarp[pp * TC + tid];
           a.partials[((size_t)tile * 2 + 0) * NC + cb + tid] = mean;
-          a.partials[((size_t)tile * 2 + 1) * NC + cb + tid] = sWarp[2 * TC + tid] + sWarp[3 * TC + tid];
+          a.partials[((size_t)tile * 2 + 1) * NC + cb + tid] = m2t;
         }
       }
     } else if (EPI == E_ZSTATS || EPI == E_STORE) {
@@ -716,7 +762,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
     // ---- epilogue work on the staged tile (both engines) ----
     if (EPI == E_READOUT) {
       // O[b,:] = tanh(sum over ALL N rows of D[b,i,:])  (unmasked, gcn_encoder.py:52-53)
-      for (int idx = tid; idx < nm * TC; idx += kThreads) {
+      for (int idx = tid; idx < nm * TC; idx += NT) {
         const int m = idx / TC, cl = idx - m * TC;
         if (cb + cl < NC) {
           float s = 0.f;
@@ -727,7 +773,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
       __syncthreads();
     } else if (EPI == E_ATG) {
       // dHprev[j,:] = sum_i A[i,j] * dS[i,:]   (column records; 4 channels per lane)
-      for (int r = warp; r < rows; r += kWarps) {
+      for (int r = warp; r < rows; r += NWARP) {
         const uint4 crec = sCRec[r];
         const int m = rec_m(crec), mb = m * N;
         const bool flag = rec_binary(crec);
@@ -767,23 +813,34 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
       // staged tile -> dH (A^T gather, in place) -> dT = pool scatter through the saved arg-max -> dY = dT*(1-T^2)
       unsigned char* sArg = reinterpret_cast<unsigned char*>(sC + TR * TCP);   // [TR][TC] arg-max of the previous layer
       {
+        // TR * (TC / 16) / NT sixteen-byte pieces per thread: all loads first, then the stores
+        constexpr int PPT = TR * (TC / 16) / NT;
+        static_assert(PPT * NT == TR * (TC / 16), "arg-max staging: whole pieces per thread");
         const bool vec = (NC % 16 == 0);
-        for (int idx = tid; idx < rows * (TC / 16); idx += kThreads) {
+        uint4 pv[PPT];
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+          const int idx = tid + u * NT;
           const int r = idx / (TC / 16), c16 = (idx - r * (TC / 16)) * 16;
           const int gc = cb + c16;
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (gc < NC) {
+          pv[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (r < rows && gc < NC) {
             const unsigned char* src = a.arg_in + (row0 + r) * NC + gc;
             if (vec) {
-              v = __ldg(reinterpret_cast<const uint4*>(src));
+              pv[u] = __ldg(reinterpret_cast<const uint4*>(src));
             } else {
               unsigned w[4] = {0u, 0u, 0u, 0u};
               for (int b = 0; b < 16; ++b)
                 if (gc + b < NC) w[b >> 2] |= (unsigned)__ldg(&src[b]) << ((b & 3) * 8);
-              v = make_uint4(w[0], w[1], w[2], w[3]);
+              pv[u] = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
-          *reinterpret_cast<uint4*>(&sArg[r * TC + c16]) = v;
+        }
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+          const int idx = tid + u * NT;
+          const int r = idx / (TC / 16), c16 = (idx - r * (TC / 16)) * 16;
+          *reinterpret_cast<uint4*>(&sArg[r * TC + c16]) = pv[u];
         }
       }
       if (EPI == E_ATG_DY) {
@@ -793,13 +850,13 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
           float2 hv[RPW];
 #pragma unroll
           for (int q = 0; q < RPW; ++q) {
-            const int r = warp + q * kWarps;
+            const int r = warp + q * NWARP;
             float2 sv = make_float2(0.f, 0.f);
             if (r < rows) {
               const uint4 crec = sCRec[r];
               const int m = rec_m(crec), mb = m * N;
               if (rec_binary(crec) && !rec_fallback(crec)) {
-                sv = rec_sum2<TCP>(crec, &sC[cs + 2 * lane]);
+                sv = rec_sum2<TCP>(crec, &sC[cs + 2 * lane], r);
               } else if (rec_binary(crec)) {
                 const u64* mk = &sCol[(size_t)r * NW];
                 sv.x = masked_sum(mk, NW, &sC[mb * TCP + cs + 2 * lane], TCP);
@@ -819,7 +876,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
           __syncthreads();
 #pragma unroll
           for (int q = 0; q < RPW; ++q) {
-            const int r = warp + q * kWarps;
+            const int r = warp + q * NWARP;
             if (r < rows) *reinterpret_cast<float2*>(&sC[r * TCP + cs + 2 * lane]) = hv[q];
           }
         }
@@ -849,11 +906,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
           }
           return z;
         };
-        float4 znext = load_z(warp);
-        for (int r = warp; r < rows; r += kWarps) {
-          const float4 z4 = znext;
-          znext = load_z(r + kWarps);
-          if (!act) continue;
+        auto dy_row = [&](int r, const float4 z4) {
           const uint4 crec = sCRec[r];
           const int m = rec_m(crec), mb = m * N;
           const unsigned jrel = (unsigned)(r - mb);
@@ -861,22 +914,38 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
           if (rec_binary(crec) && !rec_fallback(crec)) {
             // dT[j,c] = sum over rows i that list j as a neighbour and whose arg-max in channel c is j
             const int cnt = rec_cnt(crec);
+#define OCGCN_SCAT_ADD(G, AG, OK)                                                             \
+            if (OK && (AG & 0xffu) == jrel) dt[0] += G.x;                                     \
+            if (OK && ((AG >> 8) & 0xffu) == jrel) dt[1] += G.y;                              \
+            if (OK && ((AG >> 16) & 0xffu) == jrel) dt[2] += G.z;                             \
+            if (OK && (AG >> 24) == jrel) dt[3] += G.w;
+            {   // first four neighbours without branches: all eight shared-memory loads in flight at once
+              const int i0 = cnt > 0 ? rec_idx<0>(crec) : r, i1 = cnt > 1 ? rec_idx<1>(crec) : i0;
+              const int i2 = cnt > 2 ? rec_idx<2>(crec) : i0, i3 = cnt > 3 ? rec_idx<3>(crec) : i0;
+              const float4 g0 = *reinterpret_cast<const float4*>(&sC[i0 * TCP + cl]);
+              const float4 g1 = *reinterpret_cast<const float4*>(&sC[i1 * TCP + cl]);
+              const float4 g2 = *reinterpret_cast<const float4*>(&sC[i2 * TCP + cl]);
+              const float4 g3 = *reinterpret_cast<const float4*>(&sC[i3 * TCP + cl]);
+              const unsigned q0 = *reinterpret_cast<const unsigned*>(&sArg[i0 * TC + cl]);
+              const unsigned q1 = *reinterpret_cast<const unsigned*>(&sArg[i1 * TC + cl]);
+              const unsigned q2 = *reinterpret_cast<const unsigned*>(&sArg[i2 * TC + cl]);
+              const unsigned q3 = *reinterpret_cast<const unsigned*>(&sArg[i3 * TC + cl]);
+              const bool k0 = cnt > 0, k1 = cnt > 1, k2 = cnt > 2, k3 = cnt > 3;
+              OCGCN_SCAT_ADD(g0, q0, k0) OCGCN_SCAT_ADD(g1, q1, k1) OCGCN_SCAT_ADD(g2, q2, k2) OCGCN_SCAT_ADD(g3, q3, k3)
+            }
 #define OCGCN_SCAT_STEP(Q)                                                                    \
             if (cnt > Q) {                                                                    \
               const int ir = rec_idx<Q>(crec);                                                \
               const float4 g = *reinterpret_cast<const float4*>(&sC[ir * TCP + cl]);          \
               const unsigned ag = *reinterpret_cast<const unsigned*>(&sArg[ir * TC + cl]);    \
-              if ((ag & 0xffu) == jrel) dt[0] += g.x;                                         \
-              if (((ag >> 8) & 0xffu) == jrel) dt[1] += g.y;                                  \
-              if (((ag >> 16) & 0xffu) == jrel) dt[2] += g.z;                                 \
-              if ((ag >> 24) == jrel) dt[3] += g.w;                                           \
+              OCGCN_SCAT_ADD(g, ag, true)                                                     \
             }
-            OCGCN_SCAT_STEP(0) OCGCN_SCAT_STEP(1) OCGCN_SCAT_STEP(2) OCGCN_SCAT_STEP(3) OCGCN_SCAT_STEP(4)
-            if (cnt > 5) {
-              OCGCN_SCAT_STEP(5) OCGCN_SCAT_STEP(6) OCGCN_SCAT_STEP(7) OCGCN_SCAT_STEP(8)
+            if (cnt > 4) {
+              OCGCN_SCAT_STEP(4) OCGCN_SCAT_STEP(5) OCGCN_SCAT_STEP(6) OCGCN_SCAT_STEP(7) OCGCN_SCAT_STEP(8)
               if (cnt > 9) { OCGCN_SCAT_STEP(9) OCGCN_SCAT_STEP(10) OCGCN_SCAT_STEP(11) OCGCN_SCAT_STEP(12) }
             }
 #undef OCGCN_SCAT_STEP
+#undef OCGCN_SCAT_ADD
           } else if (rec_binary(crec)) {
             const u64* mk = &sCol[(size_t)r * NW];
             for (int w = 0; w < NW; ++w) {
@@ -915,9 +984,18 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
             for (int e = 0; e < 4; ++e)
               if (gc + e < NC) dst[e] = dy[e];
           }
+        };
+        // Z rows are fetched four rows (of this warp) ahead of their use through a rotating register queue
+        float4 zq0 = load_z(warp), zq1 = load_z(warp + NWARP), zq2 = load_z(warp + 2 * NWARP), zq3 = load_z(warp + 3 * NWARP);
+#pragma unroll 1
+        for (int r = warp; r < rows; r += NWARP) {
+          const float4 zc = zq0;
+          zq0 = zq1; zq1 = zq2; zq2 = zq3;
+          zq3 = load_z(r + 4 * NWARP);
+          if (act) dy_row(r, zc);
         }
         __syncthreads();   // every warp is done with the dH tile: reuse it for the cross-warp sums
-        float* sRed = sC;    // [kWarps][2][TC]
+        float* sRed = sC;    // [NWARP][2][TC]
         if (cl < TC) {
           *reinterpret_cast<float4*>(&sRed[(warp * 2 + 0) * TC + cl]) = make_float4(s1[0], s1[1], s1[2], s1[3]);
           *reinterpret_cast<float4*>(&sRed[(warp * 2 + 1) * TC + cl]) = make_float4(s2[0], s2[1], s2[2], s2[3]);
@@ -926,7 +1004,7 @@ __global__ void __launch_bounds__(kThreads, (TR == 128 ? 2 : 1)) tile_kernel(con
         if (tid < TC && cb + tid < NC) {
           float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-          for (int w = 0; w < kWarps; ++w) { t1 += sRed[(w * 2 + 0) * TC + tid]; t2 += sRed[(w * 2 + 1) * TC + tid]; }
+          for (int w = 0; w < NWARP; ++w) { t1 += sRed[(w * 2 + 0) * TC + tid]; t2 += sRed[(w * 2 + 1) * TC + tid]; }
           a.partials[((size_t)tile * 2 + 0) * NC + cb + tid] = t1;
           a.partials[((size_t)tile * 2 + 1) * NC + cb + tid] = t2;
         }
