@@ -212,16 +212,17 @@ def run_native(args, w, wname):
     _lib.load()
 
     B = w["batch"]
-    g = make_graph_batch(B, w["n_max"], w["f0"], occupancy=args.occupancy, seed=1234 + rank)
+    from openchem_b200 import dist as ocd
+    g = make_graph_batch(B, w["n_max"], w["f0"], occupancy=args.occupancy, seed=ocd.shard_seed(1234, rank))
     T = w["mlp_hidden"][-1]
-    labels = make_labels(B, T, w["task"] if w["task"] == "multitask" else "regression", seed=4321 + rank)
+    labels = make_labels(B, T, w["task"] if w["task"] == "multitask" else "regression", seed=ocd.shard_seed(4321, rank))
     hx, hadj, hy = (torch.from_numpy(a).pin_memory() for a in (g["x"], g["adj"], labels))
     x, adj, y = hx.to(dev), hadj.to(dev), hy.to(dev)
 
     model = build_model(w, args.precision, dev)
     step_model = model
     if world > 1:
-        step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], output_device=local)
+        step_model = ocd.wrap_ddp(model, local)
     crit = make_criterion(w)
     opt = torch.optim.Adam(model.parameters(), lr=5e-4, fused=True)
 
@@ -238,11 +239,7 @@ def run_native(args, w, wname):
         torch.cuda.synchronize()
 
     def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return ocd.max_over_ranks(ms, dev)
 
     for _ in range(args.warmup):
         step(x, adj, y)
@@ -264,14 +261,21 @@ def run_native(args, w, wname):
     launches = functional.launch_counter["n"]
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end-to-end region: pinned host inputs copied every step, loss read back every step ----
+    # ---- end-to-end region: every step's inputs come from pinned HOST memory (reference layout: dense fp32 adj / features /
+    # labels) through the package's feeder (openchem_b200.loader.DevicePrefetcher: upload of batch t+1 overlaps step t), and
+    # the loss is read back to the host every step ----
+    from openchem_b200.loader import DevicePrefetcher
     h2d = hx.numel() * 4 + hadj.numel() * 4 + hy.numel() * 4
+    host_batches = [(hx, hadj, hy)] * (2 + args.steps)
+    feed = DevicePrefetcher(host_batches, dev)
     for _ in range(2):
-        float(step(hx.to(dev, non_blocking=True), hadj.to(dev, non_blocking=True), hy.to(dev, non_blocking=True)).item())
+        xb, adjb, yb = next(feed)
+        float(step(xb, adjb, yb).item())
     barrier()
     e0.record()
     for _ in range(args.steps):
-        loss = step(hx.to(dev, non_blocking=True), hadj.to(dev, non_blocking=True), hy.to(dev, non_blocking=True))
+        xb, adjb, yb = next(feed)
+        loss = step(xb, adjb, yb)
         float(loss.item())
     e1.record()
     barrier()
@@ -305,7 +309,9 @@ def run_native(args, w, wname):
     t_roof_mol = max(work["bytes"] / (peaks["hbm_gbs"] * 1e9), work["flops"] / (tensor_peak * 1e12))
     step_frac = (B * t_roof_mol) / (ms_step * 1e-3)
 
-    # dominant kernel: the one with the largest share of the profiled steps
+    # dominant kernel: the one with the largest share of the profiled steps. Its roofline is the slower of
+    # (algorithmic bytes / measured HBM bandwidth) and (algorithmic flops / measured tensor peak) for ONE launch
+    # (DESIGN.md section 5 states the per-launch figures: boundary tensors only, dense GEMM flops only).
     roofline, shares = None, {}
     tot_ms = sum(v[0] for v in kern.values()) or 1.0
     for k, (ms, n) in sorted(kern.items(), key=lambda kv: -kv[1][0]):
@@ -313,27 +319,38 @@ def run_native(args, w, wname):
     if kern:
         top = max(kern, key=lambda k: kern[k][0])
         ms_launch = kern[top][0] / kern[top][1]
-        N, F = w["n_max"], [w["f0"]] + list(w["hidden"])
-        mid = F[1]
-        flops_launch = {
-            "fwd_mid": B * (2 * N * N * mid + 2 * N * mid * mid),
-            "fwd_first": B * (2 * N * N * F[0] + 2 * N * F[0] * F[1]),
-            "bwd_dz": B * (2 * N * mid * mid + 2 * N * N * mid),
-            "gemm_tn": B * (2 * N * mid * mid),
-            "fwd_readout": B * (2 * N * F[-1] * w["encoder_dim"]),
-            "bwd_readout": B * (2 * N * F[-1] * w["encoder_dim"]),
+        N, F, E = w["n_max"], [w["f0"]] + list(w["hidden"]), w["encoder_dim"]
+        mid, R = F[1], B * w["n_max"]
+        tc = args.precision != "fp32"
+        simg = 2 if tc else 4                      # bytes/element of the saved S / dZ operand (bf16 image vs fp32)
+        alg = {   # kernel -> (flops, bytes) per launch, mid layers (F_in = F_out = mid)
+            "fwd_mid": (B * (2 * N * N * mid + 2 * N * mid * mid), R * mid * (4 + 4 + 1 + simg)),            # Z in; Z, arg, S out
+            "fwd_first": (B * (2 * N * N * F[0] + 2 * N * F[0] * F[1]), R * (F[0] * (4 + simg) + F[1] * 4)),
+            "bwd_dz": (B * (2 * N * mid * mid + 2 * N * N * mid), R * mid * (4 + 4 + 4 + 1 + 4 + simg)),    # dY, Z, Z_prev, arg in; dY_prev, dZ out
+            "gemm_tn": (B * (2 * N * mid * mid), R * mid * 8),
+            "dw_mma": (B * (2 * N * mid * mid), R * mid * 4),
+            "fwd_readout": (B * (2 * N * F[-1] * E), R * (F[-1] * (4 + 1 + simg) + E * 4)),
+            "bwd_readout": (B * (2 * N * F[-1] * E), R * (E * (4 + simg) + F[-1] * (4 + 1 + 4))),
+            "bwd_dy": (0, R * mid * (4 + 4 + 1 + 4)),
         }.get(top)
-        if flops_launch is not None:
-            ach = flops_launch / (ms_launch * 1e-3) / 1e12
-            peak = peaks["bf16_burst"] * (0.5 if args.precision == "tf32" else 1.0)
-            roofline = dict(bound="tensor", kernel=top, achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
-                            ms_per_launch=ms_launch, peak_source=peaks["source"] + ", burst bf16" + (" /2 for tf32" if args.precision == "tf32" else ""),
-                            fp32_ffma_peak_tflops=74.5, frac_of_fp32_ffma_peak=(ach / 74.5) if args.precision == "fp32" else None)
-        else:  # a streaming kernel dominates: report its HBM traffic
-            by = B * N * mid * (4 + 4 + 1 + 4)
-            ach = by / (ms_launch * 1e-3) / 1e9
-            roofline = dict(bound="hbm", kernel=top, achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"], traffic=None,
-                            ms_per_launch=ms_launch, peak_source=peaks["source"])
+        if alg is not None:
+            flops_launch, bytes_launch = alg
+            t_hbm = bytes_launch / (peaks["hbm_gbs"] * 1e9)
+            t_tensor = flops_launch / (peaks["bf16_burst"] * 1e12)
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get("%s/%s/%s" % (wname, args.precision, top))
+            if t_hbm >= t_tensor:
+                ach = bytes_launch / (ms_launch * 1e-3) / 1e9
+                roofline = dict(bound="hbm", kernel=top, achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"],
+                                traffic=traffic, ms_per_launch=ms_launch, algorithmic_bytes_per_launch=bytes_launch,
+                                algorithmic_flops_per_launch=flops_launch, peak_source=peaks["source"] + ", STREAM-style copy")
+            else:
+                ach = flops_launch / (ms_launch * 1e-3) / 1e12
+                roofline = dict(bound="tensor", kernel=top, achieved=ach, peak=peaks["bf16_burst"], unit="TFLOP/s", frac=ach / peaks["bf16_burst"],
+                                traffic=traffic, ms_per_launch=ms_launch, algorithmic_bytes_per_launch=bytes_launch,
+                                algorithmic_flops_per_launch=flops_launch, peak_source=peaks["source"] + ", burst bf16")
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -348,7 +365,8 @@ def run_native(args, w, wname):
                 config=dict(workload=wname, per_gpu_batch=B, global_batch=B * world, n_max=w["n_max"], f0=w["f0"], hidden=w["hidden"],
                             encoder_dim=w["encoder_dim"], occupancy=args.occupancy, precision=args.precision, parallelism="dp%d" % world,
                             optimizer="Adam(fused)", l2_policy="inputs+saved state per step (>1 GB at c3) exceed the 126 MB L2; no explicit flush"),
-                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps,
+                         feeder="openchem_b200.loader.DevicePrefetcher (pinned host -> device on a copy stream, one batch ahead)"),
                 gpu_launches=launches, clocks=clocks, roofline=roofline,
                 step_roofline=dict(frac=step_frac, t_roof_us=B * t_roof_mol * 1e6, flops_per_molecule=work["flops"],
                                    bytes_per_molecule=work["bytes"], tensor_peak_tflops=tensor_peak, hbm_gbs=peaks["hbm_gbs"],
@@ -366,7 +384,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--occupancy", default="full", choices=["full", "molecular"])
     ap.add_argument("--profile-steps", type=int, default=3)
     ap.add_argument("--cpu-steps", type=int, default=4)
