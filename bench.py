@@ -203,6 +203,8 @@ def run_native(args, w, wname):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner out of stdout: rank 0 prints exactly one JSON line
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
@@ -220,18 +222,30 @@ def run_native(args, w, wname):
     x, adj, y = hx.to(dev), hadj.to(dev), hy.to(dev)
 
     model = build_model(w, args.precision, dev)
-    step_model = model
-    if world > 1:
-        step_model = ocd.wrap_ddp(model, local)
     crit = make_criterion(w)
-    opt = torch.optim.Adam(model.parameters(), lr=5e-4, fused=True)
+    stepper, runtime = None, "eager (torch autograd + DistributedDataParallel, as run.py drives it)"
+    if args.runtime == "graph":
+        # the package's step runtime: fwd + loss + bwd + NCCL grad all-reduce + Adam captured in one CUDA graph
+        from openchem_b200.step import TrainStep
+        stepper = TrainStep(model, crit, lambda ps: torch.optim.Adam(ps, lr=5e-4, fused=True, capturable=True), (x, adj, y))
+        runtime = "openchem_b200.step.TrainStep: one CUDA graph per step (flat-gradient NCCL all-reduce inside)" if stepper.graph is not None \
+            else "openchem_b200.step.TrainStep eager (graph capture failed: %s)" % stepper.graph_error
+        opt = stepper.opt
 
-    def step(xb, adjb, yb):
-        opt.zero_grad(set_to_none=True)
-        loss = crit(step_model((xb, adjb)), yb)
-        loss.backward()
-        opt.step()
-        return loss
+        def step(xb, adjb, yb):
+            return stepper(xb, adjb, yb)
+    else:
+        step_model = model
+        if world > 1:
+            step_model = ocd.wrap_ddp(model, local)
+        opt = torch.optim.Adam(model.parameters(), lr=5e-4, fused=True)
+
+        def step(xb, adjb, yb):
+            opt.zero_grad(set_to_none=True)
+            loss = crit(step_model((xb, adjb)), yb)
+            loss.backward()
+            opt.step()
+            return loss
 
     def barrier():
         if world > 1:
@@ -240,6 +254,13 @@ def run_native(args, w, wname):
 
     def max_over_ranks(ms):
         return ocd.max_over_ranks(ms, dev)
+
+    launches_per_body = 0
+    if stepper is not None:
+        x, adj, y = stepper.inputs          # device-resident static inputs: a step is one graph replay
+        functional.launch_counter["n"] = 0
+        stepper._body()                      # one eager body: counts the library launches a replay re-issues
+        launches_per_body = functional.launch_counter["n"]
 
     for _ in range(args.warmup):
         step(x, adj, y)
@@ -259,6 +280,8 @@ def run_native(args, w, wname):
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = functional.launch_counter["n"]
+    if stepper is not None and stepper.graph is not None:
+        launches = launches_per_body * args.steps     # replays re-issue the captured launches; count them from one eager body
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end region: every step's inputs come from pinned HOST memory (reference layout: dense fp32 adj / features /
@@ -288,7 +311,10 @@ def run_native(args, w, wname):
         if rank == 0:
             _lib.profile_enable(True)
         for _ in range(args.profile_steps):
-            step(x, adj, y)
+            if stepper is not None:
+                stepper._body()
+            else:
+                step(x, adj, y)
         torch.cuda.synchronize()
         if rank == 0:
             kern = _lib.profile_collect()
@@ -364,7 +390,7 @@ def run_native(args, w, wname):
                 data="synthetic",
                 config=dict(workload=wname, per_gpu_batch=B, global_batch=B * world, n_max=w["n_max"], f0=w["f0"], hidden=w["hidden"],
                             encoder_dim=w["encoder_dim"], occupancy=args.occupancy, precision=args.precision, parallelism="dp%d" % world,
-                            optimizer="Adam(fused)", l2_policy="inputs+saved state per step (>1 GB at c3) exceed the 126 MB L2; no explicit flush"),
+                            optimizer="Adam(fused)", runtime=runtime, l2_policy="inputs+saved state per step (>1 GB at c3) exceed the 126 MB L2; no explicit flush"),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps,
                          feeder="openchem_b200.loader.DevicePrefetcher (pinned host -> device on a copy stream, one batch ahead)"),
                 gpu_launches=launches, clocks=clocks, roofline=roofline,
@@ -386,6 +412,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--occupancy", default="full", choices=["full", "molecular"])
+    ap.add_argument("--runtime", default="graph", choices=["graph", "eager"])
     ap.add_argument("--profile-steps", type=int, default=3)
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")

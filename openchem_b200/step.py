@@ -1,0 +1,86 @@
+"""Step-level runtime for the data-parallel GraphCNN train step.
+
+One train step = zero grads -> model forward -> criterion -> backward -> gradient all-reduce (NCCL, average) ->
+optimizer step. The reference drives these from Python every iteration (openchem/models/openchem_model.py:102-121, under
+torch DDP, run.py:235-236); at the 1-3 ms steps of the B200 path that host work and DDP's per-iteration bookkeeping
+show up on the critical path. `TrainStep` captures the whole step — including the all-reduce — in ONE CUDA graph:
+
+* gradients live in one flat fp32 buffer (every `p.grad` is a view), so the exchange is a single NCCL all-reduce of
+  0.4 MB issued inside the graph right after backward;
+* BatchNorm statistics stay per rank (plain BatchNorm1d semantics, as under the reference's DDP); running buffers are not
+  re-broadcast every step — rank 0's are the ones a checkpoint written by rank 0 holds, as in the reference;
+* inputs are read from static device buffers (`.inputs`); copy a new batch into them (any stream-ordered copy) and replay.
+
+Nothing here is needed to use the layer/encoder modules; the reference's own `fit` loop keeps working unchanged.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class TrainStep:
+    def __init__(self, model, criterion, make_optimizer, example_batch, use_graph=True, warmup=3):
+        """model((x, adj)) -> predictions; criterion(pred, y) -> scalar; make_optimizer(params) -> torch optimizer that is
+        CUDA-graph capturable (e.g. Adam(fused=True, capturable=True)); example_batch = (x, adj, y) device tensors."""
+        self.model, self.criterion = model, criterion
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        dev = example_batch[0].device
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.flat_grad = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat_grad[off:off + n].view_as(p)
+            off += n
+        self.opt = make_optimizer(self.params)
+        self.inputs = tuple(torch.empty_like(t) for t in example_batch)
+        for dst, src in zip(self.inputs, example_batch):
+            dst.copy_(src)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.graph, self.graph_error = None, None
+        if self.world > 1:   # identical initial weights on every rank (DDP does this at construction)
+            for t in list(model.parameters()) + list(model.buffers()):
+                dist.broadcast(t.data, src=0)
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(int(warmup), 1)):
+                self._body()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        if use_graph:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._body()
+                self.graph = g
+            except Exception as exc:  # noqa: BLE001 - capture is an optimisation; the eager body is the same work
+                self.graph, self.graph_error = None, repr(exc)[:300]
+                torch.cuda.synchronize(dev)
+
+    def _body(self):
+        self.flat_grad.zero_()
+        x, adj, y = self.inputs
+        loss = self.criterion(self.model((x, adj)), y)
+        loss.backward()
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
+        self.opt.step()
+        self.loss.copy_(loss.detach())
+
+    def load(self, x, adj, y):
+        """Stream-ordered copy of a batch into the static input buffers."""
+        for dst, src in zip(self.inputs, (x, adj, y)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+
+    def __call__(self, x=None, adj=None, y=None):
+        if x is not None:
+            self.load(x, adj, y)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._body()
+        return self.loss
