@@ -195,6 +195,17 @@ def run_reference_arm(args, w, wname):
 # --------------------------------------------------------------------------------------------------------------
 # native arm
 # --------------------------------------------------------------------------------------------------------------
+def finish(world):
+    """Multi-rank runs end with a hard exit after a final device sync: tearing down an NCCL communicator that captured CUDA
+    graphs still reference was observed to hang in destroy_process_group (r1, 2 GPUs) after the result had been printed."""
+    import torch
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        os._exit(0)
+
+
 def run_native(args, w, wname):
     import torch
     import torch.distributed as dist
@@ -203,8 +214,11 @@ def run_native(args, w, wname):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner out of stdout: rank 0 prints exactly one JSON line
+    # rank 0 must print exactly ONE JSON line on stdout: keep library banners (NCCL prints its version there) off it by
+    # pointing fd 1 at stderr for the run and writing the JSON line to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
@@ -322,8 +336,7 @@ def run_native(args, w, wname):
     barrier()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
 
     peaks = measured_peaks()
@@ -398,9 +411,8 @@ def run_native(args, w, wname):
                                    bytes_per_molecule=work["bytes"], tensor_peak_tflops=tensor_peak, hbm_gbs=peaks["hbm_gbs"],
                                    peak_source=peaks["source"] + ", sustained bf16"),
                 kernels=shares, cpu_baseline=cpu)
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
+    finish(world)
 
 
 def main():
