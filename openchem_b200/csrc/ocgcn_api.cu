@@ -82,8 +82,6 @@ struct Layout {
   // scratch
   size_t partials, prodpart, WT[OCGCN_MAX_LAYERS], WdT, G[3], dU, coef, gemm_partial;
   size_t Wf[OCGCN_MAX_LAYERS], Wro, Wb[OCGCN_MAX_LAYERS], Wrob, dZimg, dUimg;   // mm: weight operand images, dZ / dU tile images
-  size_t slice0, slice1, counters;   // sliced_reduce: fp64 slice results (matrix / per-channel jobs), ticket counters
-  int counter_words;
   size_t scratch_total;
   int max_splits;
 };
@@ -137,6 +135,10 @@ static int make_layout(const ocgcn_desc* d, bool layer_only, Layout* lo) {
     lo->S[l] = lo->mm ? take((size_t)lo->tiles * lo->KP[l] * 256) : take(rows * d->F[l] * 4);
     lo->stats[l] = take((size_t)4 * d->F[l + 1] * 4);
   }
+  if (lo->mm) {   // backward weight operand images: written by the forward call (same weights), read by the backward call
+    for (int l = 0; l < d->L; ++l) lo->Wb[l] = take(wimg_bytes(d->F[l + 1], d->F[l], 2));
+    if (!layer_only) lo->Wrob = take(wimg_bytes(d->E, d->F[d->L], 2));
+  }
   if (!layer_only) {
     lo->HL = lo->mm ? take((size_t)lo->tiles * lo->KP[d->L] * 256) : take(rows * d->F[d->L] * 4);
     lo->D = take(rows * d->E * 4);
@@ -170,11 +172,9 @@ static int make_layout(const ocgcn_desc* d, bool layer_only, Layout* lo) {
   if (lo->mm) {
     for (int l = 0; l < d->L; ++l) {
       lo->Wf[l] = take(wimg_bytes(d->F[l], d->F[l + 1], 2));
-      lo->Wb[l] = take(wimg_bytes(d->F[l + 1], d->F[l], 2));
     }
     if (!layer_only) {
       lo->Wro = take(wimg_bytes(d->F[d->L], d->E, 2));
-      lo->Wrob = take(wimg_bytes(d->E, d->F[d->L], 2));
       lo->dUimg = take((size_t)lo->tiles * lo->KPE * 256);
     }
     lo->dZimg = take((size_t)lo->tiles * KPmax * 256);
@@ -182,13 +182,6 @@ static int make_layout(const ocgcn_desc* d, bool layer_only, Layout* lo) {
     max_partial = p > max_partial ? p : max_partial;
   }
   lo->gemm_partial = take(max_partial);
-  {
-    size_t maxMN = (size_t)Fmax * Fmax;
-    lo->slice0 = take((size_t)4 * maxMN * 8);                 // <= 4 slices of an (Fmax x Fmax) matrix job, fp64
-    lo->slice1 = take((size_t)32 * 2 * Fmax * 8);             // 32 slices x 2 values x Fmax channels
-    lo->counter_words = (int)(maxMN / 32 + 2 * ((Fmax + 31) / 32) + 64);
-    lo->counters = take((size_t)lo->counter_words * 4);
-  }
   lo->max_splits = max_splits;
   lo->scratch_total = off;
   return OCGCN_OK;
@@ -326,10 +319,7 @@ static int run_bn_finalize(const ocgcn_desc* d, const Layout& lo, const ocgcn_pa
   f.running_mean = p->running_mean[l]; f.running_var = p->running_var[l];
   f.nbt = reinterpret_cast<long long*>(p->num_batches_tracked[l]);
   f.mean = stats; f.invstd = stats + F; f.scale = stats + 2 * F; f.shift = stats + 3 * F;
-  f.SL = d->training ? reduce_slices(lo.tiles) : 1;
-  f.slicebuf = reinterpret_cast<double*>(scratch + lo.slice1);
-  f.counters = reinterpret_cast<unsigned*>(scratch + lo.counters);
-  bn_finalize_kernel<<<dim3((F + 31) / 32, f.SL), 256, 0, st>>>(f);
+  bn_finalize_kernel<<<(F + kChanCols - 1) / kChanCols, kRedThreads, 0, st>>>(f);
   LAUNCH_CHECK();
   return OCGCN_OK;
 }
@@ -347,24 +337,14 @@ static int run_gemm_tn(const float* A, const float* Bm, size_t R, int M, int Nn,
 
 static int run_reduce(const Layout& lo, char* scratch, const float* p0, float* o0, int P0, int c0, const float* p1, float* o1, int P1,
                       int c1, cudaStream_t st) {
+  (void)lo; (void)scratch;
   ProfScope prof(KK_REDUCE, st);
   ReduceJobs j;
   j.partial[0] = p0; j.out[0] = o0; j.P[0] = P0; j.count[0] = c0;
-  j.partial[1] = p1; j.out[1] = o1; j.P[1] = P1; j.count[1] = c1;
-  j.SL[0] = reduce_slices(P0) > 4 ? 4 : reduce_slices(P0);
-  j.SL[1] = reduce_slices(P1);
-  j.slicebuf[0] = reinterpret_cast<double*>(scratch + lo.slice0);
-  j.slicebuf[1] = reinterpret_cast<double*>(scratch + lo.slice1);
-  unsigned* cnt = reinterpret_cast<unsigned*>(scratch + lo.counters);
-  j.counters[0] = cnt + 2 * ((lo.Fmax + 31) / 32);          // matrix job: one ticket per 32 outputs
-  j.counters[1] = cnt + (lo.Fmax + 31) / 32;                // per-channel job
-  const int nblk = ((c0 + 31) / 32) * j.SL[0] + (o1 ? ((c1 + 31) / 32) * j.SL[1] : 0);
-  reduce_partials_kernel<<<nblk, 256, 0, st>>>(j);
+  j.partial[1] = p1; j.out[1] = o1; j.P[1] = P1; j.count[1] = o1 ? c1 : 0;
+  const int nblk = (c0 + 31) / 32 + (o1 ? (c1 + kChanCols - 1) / kChanCols : 0);
+  reduce_partials_kernel<<<nblk, kRedThreads, 0, st>>>(j);
   LAUNCH_CHECK();
-  return OCGCN_OK;
-}
-static int zero_counters(const Layout& lo, char* scratch, cudaStream_t st) {
-  CU_TRY(cudaMemsetAsync(scratch + lo.counters, 0, (size_t)lo.counter_words * 4, st));
   return OCGCN_OK;
 }
 
@@ -446,12 +426,9 @@ static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float
   f.gamma = p->gamma[l]; f.invstd = stats + Fout;
   f.dgamma = g->dgamma[l]; f.dbeta = g->dbeta[l];
   f.g = coef; f.c1 = coef + lo.Fmax; f.c2 = coef + 2 * lo.Fmax;
-  f.SL = reduce_slices(lo.tiles);
-  f.slicebuf = reinterpret_cast<double*>(scratch + lo.slice1);
-  f.counters = reinterpret_cast<unsigned*>(scratch + lo.counters);
   {
     ProfScope prof(KK_BWD_FINALIZE, st);
-    bwd_finalize_kernel<<<dim3((Fout + 31) / 32, f.SL), 256, 0, st>>>(f);
+    bwd_finalize_kernel<<<(Fout + kChanCols - 1) / kChanCols, kRedThreads, 0, st>>>(f);
     LAUNCH_CHECK();
   }
 
@@ -467,7 +444,7 @@ static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float
   if (lo.mm) {
     a.prod_out = nullptr;
     a.prod_img = scratch + lo.dZimg; a.img_chunks = lo.KP[l + 1] / 8;
-    a.wimg = scratch + lo.Wb[l]; a.ncb = (Fin + 127) / 128;
+    a.wimg = saved + lo.Wb[l]; a.ncb = (Fin + 127) / 128;
   }
   if (plain) {
     ST_TRY((launch_tile<P_DZ, E_ATG>(lo, a, st)));
@@ -582,7 +559,6 @@ int ocgcn_encoder_forward(const ocgcn_desc* d, const float* x, const float* adj,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int L = d->L;
 
-  ST_TRY(zero_counters(lo, scratch, st));
   ST_TRY(run_adj_pack(d, lo, adj, saved, st));
   if (lo.mm) {
     WPrepJobs wj;
@@ -590,6 +566,8 @@ int ocgcn_encoder_forward(const ocgcn_desc* d, const float* x, const float* adj,
     int nj = 0;
     for (int l = 0; l < L; ++l) add_wprep(wj, nj, p->W[l], scratch + lo.Wf[l], d->F[l], d->F[l + 1], 0, 2);
     add_wprep(wj, nj, p->Wd, scratch + lo.Wro, d->F[L], d->E, 1, 2);
+    for (int l = 1; l < L; ++l) add_wprep(wj, nj, p->W[l], saved + lo.Wb[l], d->F[l + 1], d->F[l], 1, 2);   // for the backward call
+    add_wprep(wj, nj, p->Wd, saved + lo.Wrob, d->E, d->F[L], 0, 2);
     ST_TRY(run_wprep(wj, nj, st));
   } else {
     TransposeJobs tj;
@@ -640,14 +618,8 @@ int ocgcn_encoder_backward(const ocgcn_desc* d, const float* grad_out, const flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int L = d->L;
 
-  ST_TRY(zero_counters(lo, scratch, st));
   if (lo.mm) {
-    WPrepJobs wj;
-    memset(&wj, 0, sizeof(wj));
-    int nj = 0;
-    for (int l = 1; l < L; ++l) add_wprep(wj, nj, p->W[l], scratch + lo.Wb[l], d->F[l + 1], d->F[l], 1, 2);
-    add_wprep(wj, nj, p->Wd, scratch + lo.Wrob, d->E, d->F[L], 0, 2);
-    ST_TRY(run_wprep(wj, nj, st));
+    // (weight operand images for the backward products were written into `saved` by the forward call)
   } else {
     TransposeJobs tj;
     memset(&tj, 0, sizeof(tj));
@@ -678,7 +650,7 @@ int ocgcn_encoder_backward(const ocgcn_desc* d, const float* grad_out, const flo
   if (lo.mm) {
     a.prod_out = nullptr;
     a.prod_img = scratch + lo.dUimg; a.img_chunks = lo.KPE / 8;
-    a.wimg = scratch + lo.Wrob; a.ncb = (d->F[L] + 127) / 128;
+    a.wimg = saved + lo.Wrob; a.ncb = (d->F[L] + 127) / 128;
   }
   set_prev_layer(a, d, lo, L - 1, saved, reinterpret_cast<float*>(scratch + lo.partials));
   ST_TRY((launch_tile<P_DU, E_DY>(lo, a, st)));
@@ -711,13 +683,13 @@ int ocgcn_layer_forward(const ocgcn_desc* d, const float* x, const float* adj, c
   char* saved = static_cast<char*>(saved_v);
   char* scratch = static_cast<char*>(scratch_v);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  ST_TRY(zero_counters(lo, scratch, st));
   ST_TRY(run_adj_pack(d, lo, adj, saved, st));
   if (lo.mm) {
     WPrepJobs wj;
     memset(&wj, 0, sizeof(wj));
     int nj = 0;
     add_wprep(wj, nj, p->W[0], scratch + lo.Wf[0], d->F[0], d->F[1], 0, 2);
+    if (d->need_dx) add_wprep(wj, nj, p->W[0], saved + lo.Wb[0], d->F[1], d->F[0], 1, 2);
     ST_TRY(run_wprep(wj, nj, st));
   }
   ST_TRY(run_layer_forward(d, lo, x, adj, p, 0, saved, scratch, st));
@@ -750,13 +722,8 @@ int ocgcn_layer_backward(const ocgcn_desc* d, const float* grad_y, const float* 
   char* saved = static_cast<char*>(saved_v);
   char* scratch = static_cast<char*>(scratch_v);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  ST_TRY(zero_counters(lo, scratch, st));
   if (d->need_dx && lo.mm) {
-    WPrepJobs wj;
-    memset(&wj, 0, sizeof(wj));
-    int nj = 0;
-    add_wprep(wj, nj, p->W[0], scratch + lo.Wb[0], d->F[1], d->F[0], 1, 2);
-    ST_TRY(run_wprep(wj, nj, st));
+    // (W^T operand image written by the forward call)
   } else if (d->need_dx) {
     TransposeJobs tj;
     memset(&tj, 0, sizeof(tj));

@@ -10,34 +10,27 @@ namespace ocgcn {
 // exactly 0 or 1 (what openchem/utils/graph.py:77-86 produces); other molecules take the dense float path.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 build_record(const u64* mk, int NW, int N, bool binary) {
-  unsigned char b[16];
-#pragma unroll
-  for (int q = 0; q < 16; ++q) b[q] = 0;
+  u64 lo = 0, hi = 0;   // bytes 0-7, 8-15 of the record
   int cnt = 0;
   for (int w = 0; w < NW; ++w) {
     u64 bits = mk[w];
     while (bits) {
-      const int j = 64 * w + __ffsll((long long)bits) - 1;
+      const u64 j = (u64)(64 * w + __ffsll((long long)bits) - 1);
       bits &= bits - 1;
       if (cnt < kMaxNbr) {
-#pragma unroll
-        for (int q = 0; q < kMaxNbr; ++q)
-          if (q == cnt) b[3 + q] = (unsigned char)j;
+        const int k = 3 + cnt;
+        if (k < 8) lo |= j << (8 * k);
+        else hi |= j << (8 * (k - 8));
       }
       ++cnt;
     }
   }
   const int jz = first_zero_bit(mk, NW, N);
-  unsigned flags = (cnt > kMaxNbr) ? 0x80u : (unsigned)cnt;
-  if (jz >= 0) { flags |= 0x40u; b[1] = (unsigned char)jz; }
-  if (binary) flags |= 0x20u;
-  b[0] = (unsigned char)flags;
-  uint4 r;
-  r.x = b[0] | (b[1] << 8) | (b[2] << 16) | ((unsigned)b[3] << 24);
-  r.y = b[4] | (b[5] << 8) | (b[6] << 16) | ((unsigned)b[7] << 24);
-  r.z = b[8] | (b[9] << 8) | (b[10] << 16) | ((unsigned)b[11] << 24);
-  r.w = b[12] | (b[13] << 8) | (b[14] << 16) | ((unsigned)b[15] << 24);
-  return r;
+  u64 flags = (cnt > kMaxNbr) ? 0x80ull : (u64)cnt;
+  if (jz >= 0) { flags |= 0x40ull; lo |= (u64)jz << 8; }
+  if (binary) flags |= 0x20ull;
+  lo |= flags;
+  return make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
 }
 
 __global__ void __launch_bounds__(kThreads) adj_pack_kernel(const float* __restrict__ adj, long long as0, long long as1,
@@ -50,35 +43,36 @@ __global__ void __launch_bounds__(kThreads) adj_pack_kernel(const float* __restr
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* ab = adj + (long long)b * as0;
   int nonbin = 0;
+  for (int idx = tid; idx < N * NW; idx += kThreads) sCm[idx] = 0ull;
   for (int i = warp; i < N; i += kWarps) {
     for (int w = 0; w < NW; ++w) {
-      u64 word = 0;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int j = 64 * w + 32 * h + lane;
-        const float v = (j < N) ? __ldg(&ab[(long long)i * as1 + (long long)j * as2]) : 0.f;
-        nonbin |= (v != 0.f && v != 1.f);
-        const unsigned bal = __ballot_sync(0xffffffffu, v != 0.f);
-        word |= (u64)bal << (32 * h);
-      }
+      const int j0 = 64 * w + lane, j1 = j0 + 32;
+      const float v0 = (j0 < N) ? __ldg(&ab[(long long)i * as1 + (long long)j0 * as2]) : 0.f;
+      const float v1 = (j1 < N) ? __ldg(&ab[(long long)i * as1 + (long long)j1 * as2]) : 0.f;
+      nonbin |= (v0 != 0.f && v0 != 1.f) | (v1 != 0.f && v1 != 1.f);
+      const unsigned b0 = __ballot_sync(0xffffffffu, v0 != 0.f), b1 = __ballot_sync(0xffffffffu, v1 != 0.f);
       if (lane == 0) {
+        const u64 word = (u64)b0 | ((u64)b1 << 32);
         sR[i * NW + w] = word;
         rowmask[((size_t)b * N + i) * NW + w] = word;
       }
     }
   }
   nonbin = __syncthreads_or(nonbin);
-  for (int idx = tid; idx < N * NW; idx += kThreads) {
-    const int j = idx / NW, w = idx - j * NW;
-    u64 word = 0;
-    for (int ii = 0; ii < 64; ++ii) {
+  // column masks = bit transpose of the row masks: every thread gathers 16 bits of one word, OR-merged in shared memory
+  for (int idx = tid; idx < N * NW * 4; idx += kThreads) {
+    const int word = idx >> 2, part = idx & 3;
+    const int j = word / NW, w = word - j * NW;
+    u64 bitsv = 0;
+#pragma unroll 4
+    for (int ii = 16 * part; ii < 16 * part + 16; ++ii) {
       const int i = 64 * w + ii;
-      if (i < N) word |= ((sR[i * NW + (j >> 6)] >> (j & 63)) & 1ull) << ii;
+      if (i < N) bitsv |= ((sR[i * NW + (j >> 6)] >> (j & 63)) & 1ull) << ii;
     }
-    sCm[idx] = word;
-    colmask[((size_t)b * N + j) * NW + w] = word;
+    if (bitsv) atomicOr(reinterpret_cast<unsigned long long*>(&sCm[word]), bitsv);
   }
   __syncthreads();
+  for (int idx = tid; idx < N * NW; idx += kThreads) colmask[(size_t)b * N * NW + idx] = sCm[idx];
   for (int i = tid; i < 2 * N; i += kThreads) {   // one 16-byte neighbour record per row and per column
     if (i < N) nbr[(size_t)b * N + i] = build_record(&sR[i * NW], NW, N, !nonbin);
     else cnbr[(size_t)b * N + (i - N)] = build_record(&sCm[(i - N) * NW], NW, N, !nonbin);
@@ -107,69 +101,56 @@ __global__ void transpose_kernel(const TransposeJobs jobs) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Deterministic two-level column reductions over per-tile / per-split partial rows.
-// grid = (ceil(cnt/32), SL slices[, jobs]); block = 256: lane = column, warp = row phase inside the slice.
-// Every CTA folds its slice of rows in a fixed order (fp64), writes the slice result, and the LAST CTA of a column
-// group to finish (atomic ticket) folds the SL slice results in ascending slice order and runs the finaliser:
-// bit-reproducible whatever the arrival order. The ticket counters live in caller scratch, are zeroed once per
-// API call and reset themselves.
+// Deterministic column reductions over per-tile / per-split partial rows, one level, no atomics, no fences:
+// a CTA of 1024 threads owns COLS columns; thread = (column, row lane), RL = 1024 / COLS row lanes. Every thread folds
+// rows lane, lane + RL, ... in ascending order in fp64 with the loads of four rows in flight, the RL lane results are
+// then folded in lane order (two fixed-shape steps through shared memory) and one thread per column runs the
+// finaliser. The summation order depends only on the shape -> bit-reproducible.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kRedWarps = 8;
-template <int NV, typename Job>
-__device__ __forceinline__ void sliced_reduce(const Job& job, int P, int cnt, int SL, double* slicebuf, unsigned* counters, int cgroup,
-                                              int slice) {
-  __shared__ double sred[kRedWarps][NV][32];
-  __shared__ unsigned s_last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = cgroup * 32 + lane;
+constexpr int kRedThreads = 1024;
+template <int NV, int COLS, typename Job>
+__device__ __forceinline__ void wide_reduce(const Job& job, int P, int cnt, int cgroup) {
+  constexpr int RL = kRedThreads / COLS;
+  static_assert(RL >= 16 && RL % 16 == 0, "row lanes are folded 16 groups at a time");
+  __shared__ double sred[NV][RL][COLS];
+  __shared__ double sred2[NV][16][COLS];
+  const int col = threadIdx.x % COLS, rl = threadIdx.x / COLS;
+  const int c = cgroup * COLS + col;
   const bool valid = c < cnt;
-  const int per = (P + SL - 1) / SL;
-  const int p0 = slice * per, p1 = min(P, p0 + per);
   double acc[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) acc[v] = 0.0;
   if (valid) {
-    for (int p = p0 + warp; p < p1; p += kRedWarps * 4) {
+    for (int p = rl; p < P; p += RL * 4) {
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (p + u * kRedWarps < p1) job.add(p + u * kRedWarps, c, acc);
+        if (p + u * RL < P) job.add(p + u * RL, c, acc);
     }
   }
 #pragma unroll
-  for (int v = 0; v < NV; ++v) sred[warp][v][lane] = acc[v];
+  for (int v = 0; v < NV; ++v) sred[v][rl][col] = acc[v];
   __syncthreads();
-  if (warp == 0 && valid) {
+  if (rl < 16) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       double t = 0.0;
-      for (int w = 0; w < kRedWarps; ++w) t += sred[w][v][lane];
-      acc[v] = t;
-    }
-    if (SL == 1) job.finish(c, acc);
-    else {
 #pragma unroll
-      for (int v = 0; v < NV; ++v) slicebuf[((size_t)slice * NV + v) * cnt + c] = acc[v];
+      for (int k = 0; k < RL / 16; ++k) t += sred[v][rl * (RL / 16) + k][col];
+      sred2[v][rl][col] = t;
     }
   }
-  if (SL == 1) return;
-  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&counters[cgroup], 1u) == (unsigned)(SL - 1)) ? 1u : 0u;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (warp == 0 && valid) {
+  if (rl == 0 && valid) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       double t = 0.0;
-      for (int sl = 0; sl < SL; ++sl) t += __ldcg(&slicebuf[((size_t)sl * NV + v) * cnt + c]);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) t += sred2[v][k][col];
       acc[v] = t;
     }
     job.finish(c, acc);
   }
-  if (threadIdx.x == 0) counters[cgroup] = 0u;
 }
-static inline int reduce_slices(int P) { int s = (P + 63) / 64; return s < 1 ? 1 : s > 32 ? 32 : s; }
 
 // ---------------------------------------------------------------------------------------------------------
 // BatchNorm statistics: merge per-tile (mean, M2) partials -> mean, invstd, scale, shift; running-stat update with
@@ -190,9 +171,6 @@ struct BnFinalizeArgs {
   float* invstd;
   float* scale;
   float* shift;
-  int SL;
-  double* slicebuf;
-  unsigned* counters;
 };
 struct BnJob {
   const BnFinalizeArgs& a;
@@ -221,10 +199,11 @@ struct BnJob {
     a.shift[c] = a.beta[c] - (float)mean * sc;
   }
 };
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const BnFinalizeArgs a) {
-  if (!a.training) {   // eval: running statistics (grid.y == 1)
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-    if ((threadIdx.x >> 5) != 0 || c >= a.F) return;
+constexpr int kChanCols = 8;   // per-channel jobs: 8 channels x 128 row lanes per CTA
+__global__ void __launch_bounds__(kRedThreads) bn_finalize_kernel(const BnFinalizeArgs a) {
+  if (!a.training) {   // eval: running statistics
+    const int c = blockIdx.x * kChanCols + (threadIdx.x % kChanCols);
+    if (threadIdx.x >= kChanCols || c >= a.F) return;
     const double mean = (double)a.running_mean[c], var = (double)a.running_var[c];
     const float invstd = (float)(1.0 / sqrt(var + (double)a.eps));
     const float sc = a.gamma[c] * invstd;
@@ -235,7 +214,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const BnFinalizeArgs a
     return;
   }
   BnJob job{a};
-  sliced_reduce<2>(job, a.T, a.F, a.SL, a.slicebuf, a.counters, blockIdx.x, blockIdx.y);
+  wide_reduce<2, kChanCols>(job, a.T, a.F, blockIdx.x);
 }
 
 // y = scale*z + shift (standalone GraphConvolution output, gcn.py:40)
@@ -456,9 +435,6 @@ struct BwdFinalizeArgs {
   float* g;
   float* c1;
   float* c2;
-  int SL;
-  double* slicebuf;
-  unsigned* counters;
 };
 struct BwdFinJob {
   const BwdFinalizeArgs& a;
@@ -474,9 +450,9 @@ struct BwdFinJob {
     a.c2[c] = a.training ? (float)(acc[1] / a.n) : 0.f;
   }
 };
-__global__ void __launch_bounds__(256) bwd_finalize_kernel(const BwdFinalizeArgs a) {
+__global__ void __launch_bounds__(kRedThreads) bwd_finalize_kernel(const BwdFinalizeArgs a) {
   BwdFinJob job{a};
-  sliced_reduce<2>(job, a.T, a.F, a.SL, a.slicebuf, a.counters, blockIdx.x, blockIdx.y);
+  wide_reduce<2, kChanCols>(job, a.T, a.F, blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -535,15 +511,13 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tn_kernel(const float* __res
   }
 }
 
-// out[i] = sum_p partial[p][i] (fixed order). Two jobs per launch (e.g. dW and db).
+// out[i] = sum_p partial[p][i] (fixed order). Two jobs per launch: job 0 = a matrix of split-K partials (few rows, many
+// outputs: 32 columns x 32 row lanes per CTA), job 1 = a per-channel vector of per-tile partials (many rows, few outputs).
 struct ReduceJobs {
   const float* partial[2];
   float* out[2];
   int P[2];
   int count[2];
-  int SL[2];
-  double* slicebuf[2];
-  unsigned* counters[2];
 };
 struct SumJob {
   const float* p;
@@ -552,15 +526,16 @@ struct SumJob {
   __device__ __forceinline__ void add(int q, int c, double* acc) const { acc[0] += (double)__ldg(&p[(size_t)q * cnt + c]); }
   __device__ __forceinline__ void finish(int c, const double* acc) const { out[c] = (float)acc[0]; }
 };
-// 1-D grid: the first ceil(count[0]/32)*SL[0] CTAs serve job 0 (slice-major), the rest job 1
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceJobs jobs) {
-  const int n0 = ((jobs.count[0] + 31) / 32) * jobs.SL[0];
-  const int jb = (int)blockIdx.x < n0 ? 0 : 1;
-  const int rel = (int)blockIdx.x - (jb ? n0 : 0);
-  const int ng = (jobs.count[jb] + 31) / 32;
-  if (!jobs.out[jb]) return;
-  SumJob job{jobs.partial[jb], jobs.out[jb], jobs.count[jb]};
-  sliced_reduce<1>(job, jobs.P[jb], jobs.count[jb], jobs.SL[jb], jobs.slicebuf[jb], jobs.counters[jb], rel % ng, rel / ng);
+// 1-D grid: the first ceil(count[0]/32) CTAs serve job 0, the following ceil(count[1]/8) CTAs job 1
+__global__ void __launch_bounds__(kRedThreads) reduce_partials_kernel(const ReduceJobs jobs) {
+  const int n0 = (jobs.count[0] + 31) / 32;
+  if ((int)blockIdx.x < n0) {
+    SumJob job{jobs.partial[0], jobs.out[0], jobs.count[0]};
+    wide_reduce<1, 32>(job, jobs.P[0], jobs.count[0], blockIdx.x);
+  } else {
+    SumJob job{jobs.partial[1], jobs.out[1], jobs.count[1]};
+    wide_reduce<1, kChanCols>(job, jobs.P[1], jobs.count[1], blockIdx.x - n0);
+  }
 }
 
 }  // namespace ocgcn

@@ -588,13 +588,12 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
         const int cl = hsel * CPG + c0;
         float v[32];
         tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cl, v);
-        if (EPI == E_ZSTATS || EPI == E_READOUT) {
+        if (EPI == E_READOUT) {   // (E_ZSTATS adds its bias in the store pass, where a thread owns four fixed columns)
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int gc = cb + cl + i;
             const float bv = (a.bias && gc < NC) ? __ldg(&a.bias[gc]) : 0.f;
-            v[i] += bv;
-            if (EPI == E_READOUT) v[i] = (row < rows && gc < NC) ? fast_tanh(v[i]) : 0.f;   // gcn_encoder.py:51
+            v[i] = (row < rows && gc < NC) ? fast_tanh(v[i] + bv) : 0.f;   // gcn_encoder.py:51
           }
         }
 #pragma unroll
@@ -605,11 +604,20 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
       if (EPI == E_ZSTATS || EPI == E_STORE || EPI == E_READOUT) {
         // coalesced store of the finished tile
         const bool vec_ok = (NC % 4 == 0);
+        static_assert(NT % (TC / 4) == 0, "a thread keeps its four columns across the store pass");
+        float bb[4] = {0.f, 0.f, 0.f, 0.f};
+        if (EPI == E_ZSTATS && a.bias) {
+          const int gc0 = cb + (tid % (TC / 4)) * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (gc0 + i < NC) bb[i] = __ldg(&a.bias[gc0 + i]);
+        }
         for (int idx = tid; idx < rows * (TC / 4); idx += NT) {
           const int r = idx / (TC / 4), cl = (idx - r * (TC / 4)) * 4;
           const int gc = cb + cl;
           if (gc >= NC) continue;
-          const float4 v = *reinterpret_cast<const float4*>(&sC[r * TCP + cl]);
+          float4 v = *reinterpret_cast<const float4*>(&sC[r * TCP + cl]);
+          v.x += bb[0]; v.y += bb[1]; v.z += bb[2]; v.w += bb[3];
           float* dst = a.out0 + (row0 + r) * NC + gc;
           if (vec_ok && gc + 3 < NC) {
             *reinterpret_cast<float4*>(dst) = v;
@@ -622,29 +630,37 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
         }
       }
       if (EPI == E_ZSTATS) {
-        // per-tile Welford partials (mean, M2) per channel; thread = (row half, column)
+        // per-tile (mean, M2) per channel from the staged accumulators (bias-free: the bias shifts the mean only).
+        // thread = (row slice, column): ONE pass with the slice's first row as pivot, then a fixed-order Chan merge.
         constexpr int PARTS = NT / TC;   // row slices (2 or 4)
         const int cl = tid & (TC - 1), part = tid / TC;
         const int r_lo = part * (TR / PARTS), r_hi = min(rows, r_lo + TR / PARTS);
-        float s = 0.f;
-        for (int r = r_lo; r < r_hi; ++r) s += sC[r * TCP + cl];
-        sWarp[part * TC + cl] = s;
-        __syncthreads();
-        float tot = 0.f;
-#pragma unroll
-        for (int pp = 0; pp < PARTS; ++pp) tot += sWarp[pp * TC + cl];
-        const float mean = tot / (float)rows;
-        float m2 = 0.f;
-        for (int r = r_lo; r < r_hi; ++r) { const float d = sC[r * TCP + cl] - mean; m2 = fmaf(d, d, m2); }
-        __syncthreads();
-        sWarp[part * TC + cl] = m2;
+        float s = 0.f, q2 = 0.f, pv = 0.f;
+        if (r_lo < r_hi) {
+          pv = sC[r_lo * TCP + cl];
+          for (int r = r_lo + 1; r < r_hi; ++r) { const float d = sC[r * TCP + cl] - pv; s += d; q2 = fmaf(d, d, q2); }
+        }
+        const float np = (float)max(r_hi - r_lo, 0);
+        const float mp = (np > 0.f) ? pv + s / np : 0.f;              // slice mean
+        const float m2p = (np > 0.f) ? fmaxf(q2 - s * s / np, 0.f) : 0.f;   // slice M2
+        sWarp[part * TC + cl] = mp;
+        sWarp[(PARTS + part) * TC + cl] = m2p;
         __syncthreads();
         if (tid < TC && cb + tid < NC) {
-          float m2t = 0.f;
+          float cn = 0.f, cm = 0.f, cm2 = 0.f;
 #pragma unroll
-          for (int pp = 0; pp < PARTS; ++pp) m2t += sWarp[pp * TC + tid];
-          a.partials[((size_t)tile * 2 + 0) * NC + cb + tid] = mean;
-          a.partials[((size_t)tile * 2 + 1) * NC + cb + tid] = m2t;
+          for (int pp = 0; pp < PARTS; ++pp) {
+            const float nt = (float)max(min(rows, (pp + 1) * (TR / PARTS)) - pp * (TR / PARTS), 0);
+            if (nt > 0.f) {
+              const float totn = cn + nt, dlt = sWarp[pp * TC + tid] - cm;
+              cm += dlt * (nt / totn);
+              cm2 += sWarp[(PARTS + pp) * TC + tid] + dlt * dlt * (cn * nt / totn);
+              cn = totn;
+            }
+          }
+          const float bias_c = a.bias ? __ldg(&a.bias[cb + tid]) : 0.f;
+          a.partials[((size_t)tile * 2 + 0) * NC + cb + tid] = cm + bias_c;
+          a.partials[((size_t)tile * 2 + 1) * NC + cb + tid] = cm2;
         }
       }
     } else if (EPI == E_ZSTATS || EPI == E_STORE) {
