@@ -252,9 +252,14 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
           ph_mma ^= 1;
           mma_pending = false;
         }
-        if (tid == 0 && store_pending) tc::bulk_wait_read0();   // the previous chunk's image has been read by the bulk store
-        if ((PROD == P_DZ || PROD == P_DU) && store_pending) __syncthreads();   // these producers write the image in their first stage
-        store_pending = false;
+        // producer-only launches (skip_gemm) need no lo image: odd chunks use its space as a second hi image, so the
+        // bulk store of one chunk overlaps the production of the next and the wait is only needed every other chunk
+        const bool reuse = !a.skip_gemm || (k0 / KC) >= 2;
+        if (store_pending && reuse) {
+          if (tid == 0) tc::bulk_wait_read0();   // the previous chunks' images have been read by the bulk stores
+          if (PROD == P_DZ || PROD == P_DU) __syncthreads();   // these producers write the image in their first stage
+          store_pending = false;
+        }
         if (use_mma && tid == 0 && !(PROD == P_MID)) {   // buf0 is free for the whole chunk: fetch the weight pieces now
           const unsigned char* src = reinterpret_cast<const unsigned char*>(a.wimg) +
                                      ((size_t)(k0 / KC) * a.ncb + (cb / TC)) * 2 * kWPiece;
@@ -287,8 +292,12 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
           uint32_t hi, lo;
           tc::split2_bf16(val.x, val.y, hi, lo);
           const uint32_t off = img_lane_off + (uint32_t)r * 16;
-          *reinterpret_cast<uint32_t*>(imgHi + off) = hi;
-          *reinterpret_cast<uint32_t*>(imgLo + off) = lo;
+          if (a.skip_gemm) {
+            *reinterpret_cast<uint32_t*>(((k0 / KC) & 1 ? imgLo : imgHi) + off) = hi;
+          } else {
+            *reinterpret_cast<uint32_t*>(imgHi + off) = hi;
+            *reinterpret_cast<uint32_t*>(imgLo + off) = lo;
+          }
         } else {
           *reinterpret_cast<float2*>(&dst[r * BS + 2 * lane]) = val;
         }
@@ -541,7 +550,8 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
             // the hi image of this chunk is the formatted operand of the weight-gradient GEMM: tile image [K/8][128][8] bf16
             unsigned char* dst = reinterpret_cast<unsigned char*>(a.prod_img) + ((size_t)tile * a.img_chunks + (k0 / 8)) * 2048;
             const int nch = min(8, a.img_chunks - k0 / 8);
-            for (int q = 0; q < nch; ++q) tc::bulk_s2g(dst + (size_t)q * 2048, imgHi + q * kImgPitch, 2048);
+            const unsigned char* simg = (a.skip_gemm && ((k0 / KC) & 1)) ? imgLo : imgHi;
+            for (int q = 0; q < nch; ++q) tc::bulk_s2g(dst + (size_t)q * 2048, simg + q * kImgPitch, 2048);
             tc::bulk_commit();
           }
         }

@@ -1,0 +1,164 @@
+"""Behaviour around the kernels on a B200: strided inputs, anomaly mode, threads, determinism, varying batch sizes, the
+CUDA-graph step runtime and the prefetching feeder. Numerical parity proper lives in test_gpu_parity.py."""
+import threading
+
+import numpy as np
+import pytest
+
+from _util import build_encoder, random_params, rel_l2
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _case(B=24, N=30, F0=16, hidden=(32, 24), E=12, seed=2, occ="molecular"):
+    from openchem_b200.synthetic import make_graph_batch
+    g = make_graph_batch(B, N, F0, occupancy=occ, seed=seed)
+    p = random_params([F0] + list(hidden), E, seed=seed + 1)
+    cfg = {"input_size": F0, "encoder_dim": E, "n_layers": len(hidden), "hidden_size": list(hidden)}
+    return g, p, cfg
+
+
+def _grads(enc):
+    return [q.grad.detach().clone() for q in enc.parameters()]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_strided_inputs_equal_contiguous(precision):
+    dev = _dev()
+    g, p, cfg = _case()
+    enc = build_encoder(cfg, p, dev, precision=precision).train()
+    x, adj = torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["adj"]).to(dev)
+    out_c = enc((x, adj))
+    out_c.sum().backward()
+    gc = _grads(enc)
+    enc2 = build_encoder(cfg, p, dev, precision=precision).train()
+    big = torch.zeros(x.shape[0], x.shape[1], x.shape[2] + 5, device=dev)
+    big[:, :, 2:2 + x.shape[2]] = x
+    xs = big[:, :, 2:2 + x.shape[2]]                       # inner stride 1, row pitch != F0
+    adjs = adj.transpose(1, 2).contiguous().transpose(1, 2)   # same values, swapped strides
+    assert not xs.is_contiguous() and not adjs.is_contiguous()
+    out_s = enc2((xs, adjs))
+    out_s.sum().backward()
+    assert torch.equal(out_c, out_s)
+    for a, b in zip(gc, _grads(enc2)):
+        assert torch.equal(a, b)
+
+
+def test_bitwise_reproducible_and_varying_batch():
+    dev = _dev()
+    g, p, cfg = _case(B=40)
+    x, adj = torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["adj"]).to(dev)
+    runs = []
+    for _ in range(2):
+        enc = build_encoder(cfg, p, dev, precision="bf16").train()
+        o = enc((x, adj))
+        o.square().sum().backward()
+        runs.append((o.detach().clone(), _grads(enc)))
+    assert torch.equal(runs[0][0], runs[1][0])
+    for a, b in zip(runs[0][1], runs[1][1]):
+        assert torch.equal(a, b)                            # fixed-order reductions: no floating-point atomics anywhere
+    # the last batch of an epoch is smaller (data/utils.py:101-109 has no drop_last): B changes call to call
+    enc = build_encoder(cfg, p, dev, precision="bf16").train()
+    for b in (40, 7, 1, 33):
+        o = enc((x[:b], adj[:b]))
+        assert o.shape == (b, cfg["encoder_dim"]) and torch.isfinite(o).all()
+        o.sum().backward()
+    assert int(enc.graph_convolutions[0].bn.num_batches_tracked) == 4
+
+
+def test_anomaly_mode_and_eval_without_no_grad():
+    dev = _dev()
+    g, p, cfg = _case()
+    enc = build_encoder(cfg, p, dev, precision="bf16")
+    x, adj = torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["adj"]).to(dev)
+    with torch.autograd.set_detect_anomaly(True):          # openchem_model.py:103 wraps every train step in it
+        enc.train()
+        enc((x, adj)).sum().backward()
+    enc.eval()                                             # evaluate()/predict() run without no_grad (openchem_model.py:218-348)
+    rm = enc.graph_convolutions[0].bn.running_mean.clone()
+    o = enc((x, adj))
+    assert o.requires_grad and torch.equal(rm, enc.graph_convolutions[0].bn.running_mean)
+    o.sum().backward()                                     # eval-mode backward (running statistics) is defined too
+
+
+def test_two_host_threads_two_streams():
+    """DataParallel drives replicas from Python threads (run.py:238): the library must be re-entrant."""
+    dev = _dev()
+    g, p, cfg = _case(B=48, N=50, F0=33, hidden=(128, 128), E=64)
+    x, adj = torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["adj"]).to(dev)
+    ref_enc = build_encoder(cfg, p, dev, precision="bf16").train()
+    ref = ref_enc((x, adj)).detach().clone()
+    outs, errs = [None, None], []
+
+    def work(k):
+        try:
+            s = torch.cuda.Stream(device=dev)
+            enc = build_encoder(cfg, p, dev, precision="bf16").train()
+            with torch.cuda.stream(s):
+                for _ in range(5):
+                    o = enc((x, adj))
+                    o.sum().backward()
+                s.synchronize()
+            outs[k] = o.detach().clone()
+        except Exception as exc:  # noqa: BLE001
+            errs.append(exc)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    assert torch.equal(outs[0], ref) and torch.equal(outs[1], ref)
+
+
+def test_graph_step_matches_eager_steps():
+    from openchem_b200.step import TrainStep
+    dev = _dev()
+    g, p, cfg = _case(B=64, N=50, F0=33, hidden=(128, 128), E=64)
+    x, adj = torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["adj"]).to(dev)
+    y = torch.randn(64, 1, generator=torch.Generator().manual_seed(0)).to(dev)
+
+    def make():
+        torch.manual_seed(0)
+        enc = build_encoder(cfg, p, dev, precision="bf16")
+        head = torch.nn.Linear(64, 1).to(dev)
+        return torch.nn.Sequential(enc, head).train()
+
+    class Wrap(torch.nn.Module):
+        def __init__(self, seq):
+            super().__init__()
+            self.seq = seq
+
+        def forward(self, inp):
+            return self.seq[1](self.seq[0](inp))
+
+    crit = torch.nn.MSELoss()
+    mk = lambda ps: torch.optim.Adam(ps, lr=1e-3, fused=True, capturable=True)  # noqa: E731
+    m_graph, m_eager = Wrap(make()), Wrap(make())
+    st_g = TrainStep(m_graph, crit, mk, (x, adj, y), use_graph=True, warmup=2)
+    st_e = TrainStep(m_eager, crit, mk, (x, adj, y), use_graph=False, warmup=2)
+    assert st_g.graph is not None, st_g.graph_error
+    for _ in range(3):
+        lg, le = float(st_g(x, adj, y)), float(st_e(x, adj, y))
+        assert lg == le
+    for a, b in zip(m_graph.parameters(), m_eager.parameters()):
+        assert torch.equal(a, b)
+
+
+def test_prefetcher_feeds_batches_in_order():
+    from openchem_b200.loader import DevicePrefetcher
+    dev = _dev()
+    host = []
+    for k in range(5):
+        host.append(tuple(torch.full(s, float(k)).pin_memory() for s in ((4, 6, 3), (4, 6, 6), (4, 1))))
+    seen = []
+    for xb, adjb, yb in DevicePrefetcher(host, dev):
+        assert xb.is_cuda and xb.shape == (4, 6, 3)
+        seen.append((float(xb[0, 0, 0]), float(adjb[-1, -1, -1]), float(yb[0, 0])))
+    assert seen == [(float(k),) * 3 for k in range(5)]
