@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
   constexpr size_t mainsz = main_a > main_b ? main_a : main_b;
   unsigned* sFlag = reinterpret_cast<unsigned*>(mainp + mainsz);
   float* sWarp = reinterpret_cast<float*>(sFlag + TR);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sWarp + 2 * NWARP * 32);   // MM: [0] weight image landed, [1] MMAs complete
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sWarp + 2 * NWARP * 32);   // MM: [0] weight image landed, [1] MMAs complete, [2] second column block's weight image landed
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 3);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid % TXN, ty = tid / TXN;
@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
   // this lane's slot inside a 64-channel operand image row: 16-byte chunk lane/4, word lane%4
   const uint32_t img_lane_off = (uint32_t)(lane >> 2) * kImgPitch + (uint32_t)(lane & 3) * 4;
   const bool use_mma = MM && !a.skip_gemm;
-  uint32_t tmem = 0, ph_w = 0, ph_mma = 0;
+  uint32_t tmem = 0, ph_w = 0, ph_w1 = 0, ph_mma = 0;
+  const uint32_t tcols = (MM && a.ncb > 1) ? 2 * kTmemCols : kTmemCols;   // one 128-column accumulator per output column block (<= 2)
   bool mma_pending = false, store_pending = false;
 
   // ---- stage neighbour records (made tile-relative), masks and per-molecule flags ---------------------------
@@ -215,11 +216,12 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
     if (tid == 0) {
       tc::mbar_init(&bars[0], 1);
       tc::mbar_init(&bars[1], 1);
+      tc::mbar_init(&bars[2], 1);
       tc::mbar_init_fence();
     }
     if (warp == 0) {
       __syncwarp();
-      tc::tmem_alloc(tslot, kTmemCols);
+      tc::tmem_alloc(tslot, tcols);
     }
     tc::fence_before_sync();
   }
@@ -240,7 +242,9 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
         for (int c = 0; c < (MM ? 1 : 8); ++c) acc[r][c] = 0.f;
     }
 
-    for (int k0 = 0; k0 < K; k0 += KC) {
+    // MM: the operand images are produced ONCE; the MMAs of every output column block are issued from them into separate
+    // TMEM accumulators, and the later column passes only run their epilogue
+    for (int k0 = 0; k0 < K && (!MM || cb == 0); k0 += KC) {
       const int c = k0 + 2 * lane;  // this lane's first channel
       const bool v0 = c < K, v1 = c + 1 < K;
       const float* opnd = buf0;
@@ -531,17 +535,28 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
           if (use_mma) {
             const int kleft = K - k0;
             const int nks = (kleft >= KC) ? KC / 16 : (kleft + 15) / 16;
-            tc::mbar_wait(&bars[0], ph_w);
-            tc::fence_after_sync();
+            const bool two = a.ncb > 1;
+            if (two) {   // second column block's weight pieces -> buf1 (dead since the barrier above), overlapping the first block's MMAs
+              const unsigned char* src1 = reinterpret_cast<const unsigned char*>(a.wimg) + ((size_t)(k0 / KC) * a.ncb + 1) * 2 * kWPiece;
+              tc::mbar_expect_tx(&bars[2], 2 * kWPiece);
+              tc::bulk_g2s(buf1, src1, kWPiece, &bars[2]);
+              tc::bulk_g2s(reinterpret_cast<unsigned char*>(buf1) + kWPiece, src1 + kWPiece, kWPiece, &bars[2]);
+            }
             constexpr uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, 128, false, false);
-            const uint32_t aHi = tc::smem_u32(imgHi), aLo = tc::smem_u32(imgLo), bHi = tc::smem_u32(wHi), bLo = bHi + kWPiece;
+            const uint32_t aHi = tc::smem_u32(imgHi), aLo = tc::smem_u32(imgLo);
+            for (int cbi = 0; cbi < (two ? 2 : 1); ++cbi) {
+              if (cbi == 0) tc::mbar_wait(&bars[0], ph_w);
+              else tc::mbar_wait(&bars[2], ph_w1);
+              tc::fence_after_sync();
+              const uint32_t bHi = cbi ? tc::smem_u32(buf1) : tc::smem_u32(wHi), bLo = bHi + kWPiece;
 #pragma unroll
-            for (int p = 0; p < NPASS; ++p) {
-              const uint32_t ab = (p & 1) ? aLo : aHi, bb = (p & 2) ? bLo : bHi;
-              for (int ks = 0; ks < nks; ++ks) {
-                const uint64_t da = tc::make_desc(ab + ks * 2 * kImgPitch, kImgPitch, 128);
-                const uint64_t db = tc::make_desc(bb + ks * 2 * (128 * 16), 128 * 16, 128);
-                tc::mma_ss<false>(tmem, da, db, idesc, (k0 > 0 || p > 0 || ks > 0) ? 1u : 0u);
+              for (int p = 0; p < NPASS; ++p) {
+                const uint32_t ab = (p & 1) ? aLo : aHi, bb = (p & 2) ? bLo : bHi;
+                for (int ks = 0; ks < nks; ++ks) {
+                  const uint64_t da = tc::make_desc(ab + ks * 2 * kImgPitch, kImgPitch, 128);
+                  const uint64_t db = tc::make_desc(bb + ks * 2 * (128 * 16), 128 * 16, 128);
+                  tc::mma_ss<false>(tmem + (uint32_t)(cbi * kTmemCols), da, db, idesc, (k0 > 0 || p > 0 || ks > 0) ? 1u : 0u);
+                }
               }
             }
             tc::mma_commit(&bars[1]);
@@ -555,7 +570,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
             tc::bulk_commit();
           }
         }
-        if (use_mma) { ph_w ^= 1; mma_pending = true; }
+        if (use_mma) { ph_w ^= 1; mma_pending = true; if (a.ncb > 1) ph_w1 ^= 1; }
         if (first_pass && a.prod_img) store_pending = true;
       } else if (!a.skip_gemm) {
 #pragma unroll 2
@@ -586,9 +601,11 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
     // =========================== EPILOGUE ===========================
     if (MM) {
       // accumulator tile: TMEM -> registers (thread = row) -> bias / activation -> staging tile in shared memory
-      tc::mbar_wait(&bars[1], ph_mma);
-      ph_mma ^= 1;
-      mma_pending = false;
+      if (mma_pending) {
+        tc::mbar_wait(&bars[1], ph_mma);
+        ph_mma ^= 1;
+        mma_pending = false;
+      }
       tc::fence_after_sync();
       constexpr int CPG = TC / (NWARP / 4);   // columns per warp group (the four warps of a group cover the 128 TMEM lanes)
       const int q = warp & 3, hsel = warp >> 2;
@@ -597,7 +614,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
       for (int c0 = 0; c0 < CPG; c0 += 32) {
         const int cl = hsel * CPG + c0;
         float v[32];
-        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cl, v);
+        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((cb / TC) * kTmemCols + cl), v);
         if (EPI == E_READOUT) {   // (E_ZSTATS adds its bias in the store pass, where a thread owns four fixed columns)
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -1044,7 +1061,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
   if (MM && use_mma) {
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, kTmemCols);
+    if (warp == 0) tc::tmem_dealloc(tmem, tcols);
   }
 }
 
