@@ -65,6 +65,7 @@ struct ProfScope {
   } while (0)
 
 static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+constexpr int kMaxPersistent = 2 * 148;   // tensor-core tile kernels: two resident CTAs per SM loop over the tiles
 
 // ---------------------------------------------------------------------------------------------------------
 // workspace layout (byte offsets). "saved" lives from forward to backward, "scratch" only within one call.
@@ -72,6 +73,7 @@ static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a
 struct Layout {
   int TR, MT, NW, tiles, Fmax;
   int mm;                            // 1: tensor-core engine (bf16 operand images), 0: exact-fp32 FFMA engine
+  int fuse_dw;                       // mm and every width <= 128: weight gradients are accumulated inside the backward tile kernels
   int KP[OCGCN_MAX_LAYERS + 1], KPE;  // channel counts padded to multiples of 64 (operand image extents)
   size_t rows;
   // saved
@@ -121,6 +123,7 @@ static int make_layout(const ocgcn_desc* d, bool layer_only, Layout* lo) {
   int KPmax = 64;
   for (int l = 0; l <= d->L; ++l) { lo->KP[l] = (d->F[l] + 63) / 64 * 64; KPmax = lo->KP[l] > KPmax ? lo->KP[l] : KPmax; }
   lo->KPE = layer_only ? 64 : (d->E + 63) / 64 * 64;
+  lo->fuse_dw = (lo->mm && Fmax <= 128) ? 1 : 0;
   const size_t rows = lo->rows;
   size_t off = 0;
   auto take = [&off](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
@@ -178,7 +181,7 @@ static int make_layout(const ocgcn_desc* d, bool layer_only, Layout* lo) {
       lo->dUimg = take((size_t)lo->tiles * lo->KPE * 256);
     }
     lo->dZimg = take((size_t)lo->tiles * KPmax * 256);
-    const size_t p = (size_t)148 * KPmax * (lo->KPE > KPmax ? lo->KPE : KPmax) * 4;   // per-CTA dW partials of dw_mma_kernel
+    const size_t p = (size_t)kMaxPersistent * KPmax * (lo->KPE > KPmax ? lo->KPE : KPmax) * 4;   // per-CTA dW partials (dw_mma_kernel / fused)
     max_partial = p > max_partial ? p : max_partial;
   }
   lo->gemm_partial = take(max_partial);
@@ -211,6 +214,7 @@ static int check_device_ptr(const void* p) {
 // ---------------------------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------------------------
+static int mm_grid(int tiles) { return tiles < kMaxPersistent ? tiles : kMaxPersistent; }
 template <int TR, int PROD, int EPI, int MM>
 static int launch_tile_t(const TileArgs& a, int tiles, cudaStream_t st) {
   constexpr int TC = tile_cols<TR>();
@@ -219,7 +223,9 @@ static int launch_tile_t(const TileArgs& a, int tiles, cudaStream_t st) {
   auto kern = tile_kernel<TR, TC, PROD, EPI, MM, NT>;
   const size_t smem = tile_smem_bytes<TR, TC, MM, NT>(a.NW);
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<tiles, NT, smem, st>>>(a);
+  // persistent (two CTAs per SM looping over tiles) only where the CTA accumulates the weight gradient across its tiles;
+  // everything else launches one CTA per tile (dynamic scheduling balances and de-phases the co-resident CTAs better)
+  kern<<<((MM && a.dw_img) ? mm_grid(tiles) : tiles), NT, smem, st>>>(a);
   LAUNCH_CHECK();
   return OCGCN_OK;
 }
@@ -286,7 +292,7 @@ static int launch_bwd_dy(const Layout& lo, const BwdDyArgs& a, cudaStream_t st) 
 static TileArgs base_tile_args(const ocgcn_desc* d, const Layout& lo, const float* adj, char* saved) {
   TileArgs a;
   memset(&a, 0, sizeof(a));
-  a.B = d->B; a.N = d->N; a.NW = lo.NW; a.MT = lo.MT;
+  a.B = d->B; a.N = d->N; a.NW = lo.NW; a.MT = lo.MT; a.ntiles = lo.tiles;
   a.adj = adj; a.as0 = d->adj_stride[0]; a.as1 = d->adj_stride[1]; a.as2 = d->adj_stride[2];
   a.rowmask = reinterpret_cast<const u64*>(saved + lo.rowmask);
   a.colmask = reinterpret_cast<const u64*>(saved + lo.colmask);
@@ -336,10 +342,11 @@ static int run_gemm_tn(const float* A, const float* Bm, size_t R, int M, int Nn,
 }
 
 static int run_reduce(const Layout& lo, char* scratch, const float* p0, float* o0, int P0, int c0, const float* p1, float* o1, int P1,
-                      int c1, cudaStream_t st) {
+                      int c1, cudaStream_t st, int tr_cols = 0) {
   (void)lo; (void)scratch;
   ProfScope prof(KK_REDUCE, st);
   ReduceJobs j;
+  j.tr_cols = tr_cols;
   j.partial[0] = p0; j.out[0] = o0; j.P[0] = P0; j.count[0] = c0;
   j.partial[1] = p1; j.out[1] = o1; j.P[1] = P1; j.count[1] = o1 ? c1 : 0;
   const int nblk = (c0 + 31) / 32 + (o1 ? (c1 + kChanCols - 1) / kChanCols : 0);
@@ -441,10 +448,15 @@ static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float
   a.Bm = reinterpret_cast<const float*>(scratch + lo.WT[l]);
   a.out0 = g_out;
   a.skip_gemm = skip_dx ? 1 : 0;
+  float* gp = reinterpret_cast<float*>(scratch + lo.gemm_partial);
   if (lo.mm) {
     a.prod_out = nullptr;
     a.prod_img = scratch + lo.dZimg; a.img_chunks = lo.KP[l + 1] / 8;
     a.wimg = saved + lo.Wb[l]; a.ncb = (Fin + 127) / 128;
+    if (lo.fuse_dw) {   // dW_l = S_l^T . dZ accumulated in TMEM inside this kernel: no dZ image, no separate GEMM
+      a.prod_img = nullptr;
+      a.dw_img = saved + lo.S[l]; a.dw_chunks = lo.KP[l] / 8; a.dw_M = Fin; a.dw_partial = gp;
+    }
   }
   if (plain) {
     ST_TRY((launch_tile<P_DZ, E_ATG>(lo, a, st)));
@@ -454,8 +466,8 @@ static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float
   }
 
   int splits = 0;
-  float* gp = reinterpret_cast<float*>(scratch + lo.gemm_partial);
-  if (lo.mm) ST_TRY(run_dw_mma(lo, saved + lo.S[l], scratch + lo.dZimg, lo.KP[l], lo.KP[l + 1], Fin, Fout, gp, st, &splits));
+  if (lo.fuse_dw) splits = mm_grid(lo.tiles);
+  else if (lo.mm) ST_TRY(run_dw_mma(lo, saved + lo.S[l], scratch + lo.dZimg, lo.KP[l], lo.KP[l + 1], Fin, Fout, gp, st, &splits));
   else ST_TRY(run_gemm_tn(reinterpret_cast<const float*>(saved + lo.S[l]), g_dz, lo.rows, Fin, Fout, gp, st, &splits));
   ST_TRY(run_reduce(lo, scratch, gp, g->dW[l], splits, Fin * Fout, prodpart, (d->has_bias ? g->db[l] : nullptr), lo.tiles, Fout, st));
   return OCGCN_OK;
@@ -651,13 +663,18 @@ int ocgcn_encoder_backward(const ocgcn_desc* d, const float* grad_out, const flo
     a.prod_out = nullptr;
     a.prod_img = scratch + lo.dUimg; a.img_chunks = lo.KPE / 8;
     a.wimg = saved + lo.Wrob; a.ncb = (d->F[L] + 127) / 128;
+    if (lo.fuse_dw) {   // dWd^T = H_L^T . dU accumulated inside this kernel (transposed back by the reduction)
+      a.prod_img = nullptr;
+      a.dw_img = saved + lo.HL; a.dw_chunks = lo.KP[L] / 8; a.dw_M = d->F[L]; a.dw_partial = gp;
+    }
   }
   set_prev_layer(a, d, lo, L - 1, saved, reinterpret_cast<float*>(scratch + lo.partials));
   ST_TRY((launch_tile<P_DU, E_DY>(lo, a, st)));
   int splits = 0;
-  if (lo.mm) ST_TRY(run_dw_mma(lo, scratch + lo.dUimg, saved + lo.HL, lo.KPE, lo.KP[L], d->E, d->F[L], gp, st, &splits));
+  if (lo.fuse_dw) splits = mm_grid(lo.tiles);
+  else if (lo.mm) ST_TRY(run_dw_mma(lo, scratch + lo.dUimg, saved + lo.HL, lo.KPE, lo.KP[L], d->E, d->F[L], gp, st, &splits));
   else ST_TRY(run_gemm_tn(dU, reinterpret_cast<const float*>(saved + lo.HL), lo.rows, d->E, d->F[L], gp, st, &splits));
-  ST_TRY(run_reduce(lo, scratch, gp, g->dWd, splits, d->E * d->F[L], prodpart, g->dbd, lo.tiles, d->E, st));
+  ST_TRY(run_reduce(lo, scratch, gp, g->dWd, splits, d->E * d->F[L], prodpart, g->dbd, lo.tiles, d->E, st, lo.fuse_dw ? d->F[L] : 0));
 
   int cur = 0;
   for (int l = L - 1; l >= 0; --l) {

@@ -518,22 +518,27 @@ struct ReduceJobs {
   float* out[2];
   int P[2];
   int count[2];
+  int tr_cols;   // job 0 only: > 0 = the partials hold the TRANSPOSE ([tr_cols][count/tr_cols]... see SumJob) of the output matrix
 };
 struct SumJob {
   const float* p;
   float* out;
   int cnt;
-  __device__ __forceinline__ void add(int q, int c, double* acc) const { acc[0] += (double)__ldg(&p[(size_t)q * cnt + c]); }
+  int tr_cols;   // output is [R][tr_cols] row-major while each partial is [tr_cols][R] (fused readout gradient dWd^T); 0 = same layout
+  __device__ __forceinline__ void add(int q, int c, double* acc) const {
+    const int src = tr_cols ? (c % tr_cols) * (cnt / tr_cols) + c / tr_cols : c;
+    acc[0] += (double)__ldg(&p[(size_t)q * cnt + src]);
+  }
   __device__ __forceinline__ void finish(int c, const double* acc) const { out[c] = (float)acc[0]; }
 };
 // 1-D grid: the first ceil(count[0]/32) CTAs serve job 0, the following ceil(count[1]/8) CTAs job 1
 __global__ void __launch_bounds__(kRedThreads) reduce_partials_kernel(const ReduceJobs jobs) {
   const int n0 = (jobs.count[0] + 31) / 32;
   if ((int)blockIdx.x < n0) {
-    SumJob job{jobs.partial[0], jobs.out[0], jobs.count[0]};
+    SumJob job{jobs.partial[0], jobs.out[0], jobs.count[0], jobs.tr_cols};
     wide_reduce<1, 32>(job, jobs.P[0], jobs.count[0], blockIdx.x);
   } else {
-    SumJob job{jobs.partial[1], jobs.out[1], jobs.count[1]};
+    SumJob job{jobs.partial[1], jobs.out[1], jobs.count[1], 0};
     wide_reduce<1, kChanCols>(job, jobs.P[1], jobs.count[1], blockIdx.x - n0);
   }
 }

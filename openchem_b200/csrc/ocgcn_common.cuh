@@ -78,6 +78,12 @@ struct TileArgs {
   int ncb;           // ceil(NC/128)
   void* prod_img;    // producer output as bf16 tile images [tile][img_chunks][128 rows][8] (operand of the dW GEMM) or null
   int img_chunks;    // 16-byte channel chunks per tile image = 8 * ceil(K/64)
+  int ntiles;        // tiles of the batch (the MM kernels are persistent: a CTA loops over tiles blockIdx.x, + gridDim.x, ...)
+  // fused weight gradient (P_DZ / P_DU of the tensor-core engine, widths <= 128): dW[m][k] = sum_rows saved[row][m] * produced[row][k]
+  const void* dw_img;   // saved operand tile images [tile][dw_chunks][128][8] bf16 (S_l, or H_L for the readout), or null
+  int dw_chunks;        // 16-byte channel chunks of that image per tile (<= 16)
+  int dw_M;             // true row extent of the gradient (F_in, or F_L for the readout)
+  float* dw_partial;    // [gridDim.x][dw_M][K] per-CTA partial gradients
 };
 
 // ---- 16-byte neighbour record of one adjacency row (built once per forward by adj_pack_kernel) ----------------

@@ -123,15 +123,22 @@ __global__ void __launch_bounds__(128) dw_mma_kernel(const DwArgs a) {
   __syncwarp();
   tc::mbar_wait(done, 0);
   tc::fence_after_sync();
+  const bool vec4 = (a.Nn % 4 == 0);
   for (int mb = 0; mb < mblocks; ++mb) {
     const int m = mb * 128 + warp * 32 + lane;
     for (int c0 = 0; c0 < ncols; c0 += 32) {
       float v[32];
       tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mb * ncols + c0), v);
-      if (m < a.M) {
+      if (m < a.M && c0 < a.Nn) {
+        float* dst = out + (size_t)m * a.Nn + c0;
+        if (vec4 && c0 + 32 <= a.Nn) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c0 + i < a.Nn) out[(size_t)m * a.Nn + c0 + i] = v[i];
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < a.Nn) dst[i] = v[i];
+        }
       }
     }
   }

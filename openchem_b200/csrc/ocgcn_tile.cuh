@@ -176,26 +176,52 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
   constexpr size_t mainsz = main_a > main_b ? main_a : main_b;
   unsigned* sFlag = reinterpret_cast<unsigned*>(mainp + mainsz);
   float* sWarp = reinterpret_cast<float*>(sFlag + TR);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sWarp + 2 * NWARP * 32);   // MM: [0] weight image landed, [1] MMAs complete, [2] second column block's weight image landed
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sWarp + 2 * NWARP * 32);   // MM: [0] weight image landed, [1] MMAs complete, [2] second column block's weight image landed, [3] see tslot
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4);   // ([3]: saved operand image of the fused dW GEMM landed)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid % TXN, ty = tid / TXN;
-  const int tile = blockIdx.x;
-  const int mol0 = tile * a.MT;
-  const int nm = min(a.MT, a.B - mol0);
-  const int rows = nm * N;
-  const size_t row0 = (size_t)mol0 * N;
   const bool kvec2 = (K % 2 == 0);
   // T goes to the buffer the weight image does NOT alias while the pool still reads it
   float* const bufT = (MM && PROD == P_RO) ? buf1 : buf0;
   float* const bufH = (MM && PROD == P_RO) ? buf0 : buf1;
   // this lane's slot inside a 64-channel operand image row: 16-byte chunk lane/4, word lane%4
   const uint32_t img_lane_off = (uint32_t)(lane >> 2) * kImgPitch + (uint32_t)(lane & 3) * 4;
-  const bool use_mma = MM && !a.skip_gemm;
-  uint32_t tmem = 0, ph_w = 0, ph_w1 = 0, ph_mma = 0;
-  const uint32_t tcols = (MM && a.ncb > 1) ? 2 * kTmemCols : kTmemCols;   // one 128-column accumulator per output column block (<= 2)
+  // fused weight gradient (backward producers of the tensor-core engine, widths <= 128): dW (+)= saved_image^T . produced_image
+  // accumulated in TMEM columns [128, 256) across all tiles of this persistent CTA (ocgcn_api.cu decides via a.dw_img)
+  const bool do_dw = MM && (PROD == P_DZ || PROD == P_DU) && a.dw_img != nullptr;
+  const bool use_mma = MM && (!a.skip_gemm || do_dw);
+  uint32_t tmem = 0, ph_w = 0, ph_w1 = 0, ph_mma = 0, ph_s = 0;
+  const uint32_t tcols = (MM && (a.ncb > 1 || do_dw)) ? 2 * kTmemCols : kTmemCols;   // <= 2 accumulators of 128 columns
   bool mma_pending = false, store_pending = false;
+
+  if (use_mma) {
+    if (tid == 0) {
+      tc::mbar_init(&bars[0], 1);
+      tc::mbar_init(&bars[1], 1);
+      tc::mbar_init(&bars[2], 1);
+      tc::mbar_init(&bars[3], 1);
+      tc::mbar_init_fence();
+    }
+    if (warp == 0) {
+      __syncwarp();
+      tc::tmem_alloc(tslot, tcols);
+    }
+    tc::fence_before_sync();
+  }
+  __syncthreads();
+  if (use_mma) {
+    tc::fence_after_sync();
+    tmem = *tslot;
+  }
+
+  // persistent over tiles (MM launches use at most two CTAs per SM; the exact-fp32 engine launches one CTA per tile)
+  int tile_iter = 0;
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tile_iter) {
+  const int mol0 = tile * a.MT;
+  const int nm = min(a.MT, a.B - mol0);
+  const int rows = nm * N;
+  const size_t row0 = (size_t)mol0 * N;
 
   // ---- stage neighbour records (made tile-relative), masks and per-molecule flags ---------------------------
   for (int r = tid; r < TR; r += NT) {
@@ -212,24 +238,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
     sRow[idx] = a.rowmask[row0 * NW + idx];
     sCol[idx] = a.colmask[row0 * NW + idx];
   }
-  if (use_mma) {
-    if (tid == 0) {
-      tc::mbar_init(&bars[0], 1);
-      tc::mbar_init(&bars[1], 1);
-      tc::mbar_init(&bars[2], 1);
-      tc::mbar_init_fence();
-    }
-    if (warp == 0) {
-      __syncwarp();
-      tc::tmem_alloc(tslot, tcols);
-    }
-    tc::fence_before_sync();
-  }
   __syncthreads();
-  if (use_mma) {
-    tc::fence_after_sync();
-    tmem = *tslot;
-  }
 
   float acc[MM ? 1 : 8][MM ? 1 : 8];
 
@@ -258,13 +267,17 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
         }
         // producer-only launches (skip_gemm) need no lo image: odd chunks use its space as a second hi image, so the
         // bulk store of one chunk overlaps the production of the next and the wait is only needed every other chunk
-        const bool reuse = !a.skip_gemm || (k0 / KC) >= 2;
+        const bool reuse = !a.skip_gemm || do_dw || (k0 / KC) >= 2;
         if (store_pending && reuse) {
           if (tid == 0) tc::bulk_wait_read0();   // the previous chunks' images have been read by the bulk stores
           if (PROD == P_DZ || PROD == P_DU) __syncthreads();   // these producers write the image in their first stage
           store_pending = false;
         }
-        if (use_mma && tid == 0 && !(PROD == P_MID)) {   // buf0 is free for the whole chunk: fetch the weight pieces now
+        if (do_dw && k0 == 0 && tid == 0) {   // this tile's saved operand image (S_l or H_L) -> buf1 (free in these producers)
+          tc::mbar_expect_tx(&bars[3], (uint32_t)a.dw_chunks * 2048u);
+          tc::bulk_g2s(buf1, reinterpret_cast<const unsigned char*>(a.dw_img) + (size_t)tile * a.dw_chunks * 2048, (uint32_t)a.dw_chunks * 2048u, &bars[3]);
+        }
+        if (use_mma && !a.skip_gemm && tid == 0 && !(PROD == P_MID)) {   // buf0 is free for the whole chunk: fetch the weight pieces now
           const unsigned char* src = reinterpret_cast<const unsigned char*>(a.wimg) +
                                      ((size_t)(k0 / KC) * a.ncb + (cb / TC)) * 2 * kWPiece;
           tc::mbar_expect_tx(&bars[0], 2 * kWPiece);
@@ -296,7 +309,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
           uint32_t hi, lo;
           tc::split2_bf16(val.x, val.y, hi, lo);
           const uint32_t off = img_lane_off + (uint32_t)r * 16;
-          if (a.skip_gemm) {
+          if (a.skip_gemm && !do_dw) {
             *reinterpret_cast<uint32_t*>(((k0 / KC) & 1 ? imgLo : imgHi) + off) = hi;
           } else {
             *reinterpret_cast<uint32_t*>(imgHi + off) = hi;
@@ -536,27 +549,42 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
             const int kleft = K - k0;
             const int nks = (kleft >= KC) ? KC / 16 : (kleft + 15) / 16;
             const bool two = a.ncb > 1;
-            if (two) {   // second column block's weight pieces -> buf1 (dead since the barrier above), overlapping the first block's MMAs
-              const unsigned char* src1 = reinterpret_cast<const unsigned char*>(a.wimg) + ((size_t)(k0 / KC) * a.ncb + 1) * 2 * kWPiece;
-              tc::mbar_expect_tx(&bars[2], 2 * kWPiece);
-              tc::bulk_g2s(buf1, src1, kWPiece, &bars[2]);
-              tc::bulk_g2s(reinterpret_cast<unsigned char*>(buf1) + kWPiece, src1 + kWPiece, kWPiece, &bars[2]);
-            }
-            constexpr uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, 128, false, false);
             const uint32_t aHi = tc::smem_u32(imgHi), aLo = tc::smem_u32(imgLo);
-            for (int cbi = 0; cbi < (two ? 2 : 1); ++cbi) {
-              if (cbi == 0) tc::mbar_wait(&bars[0], ph_w);
-              else tc::mbar_wait(&bars[2], ph_w1);
-              tc::fence_after_sync();
-              const uint32_t bHi = cbi ? tc::smem_u32(buf1) : tc::smem_u32(wHi), bLo = bHi + kWPiece;
+            if (!a.skip_gemm) {
+              if (two) {   // second column block's weight pieces -> buf1 (dead since the barrier above), overlapping the first block's MMAs
+                const unsigned char* src1 = reinterpret_cast<const unsigned char*>(a.wimg) + ((size_t)(k0 / KC) * a.ncb + 1) * 2 * kWPiece;
+                tc::mbar_expect_tx(&bars[2], 2 * kWPiece);
+                tc::bulk_g2s(buf1, src1, kWPiece, &bars[2]);
+                tc::bulk_g2s(reinterpret_cast<unsigned char*>(buf1) + kWPiece, src1 + kWPiece, kWPiece, &bars[2]);
+              }
+              constexpr uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, 128, false, false);
+              for (int cbi = 0; cbi < (two ? 2 : 1); ++cbi) {
+                if (cbi == 0) tc::mbar_wait(&bars[0], ph_w);
+                else tc::mbar_wait(&bars[2], ph_w1);
+                tc::fence_after_sync();
+                const uint32_t bHi = cbi ? tc::smem_u32(buf1) : tc::smem_u32(wHi), bLo = bHi + kWPiece;
 #pragma unroll
-              for (int p = 0; p < NPASS; ++p) {
-                const uint32_t ab = (p & 1) ? aLo : aHi, bb = (p & 2) ? bLo : bHi;
-                for (int ks = 0; ks < nks; ++ks) {
-                  const uint64_t da = tc::make_desc(ab + ks * 2 * kImgPitch, kImgPitch, 128);
-                  const uint64_t db = tc::make_desc(bb + ks * 2 * (128 * 16), 128 * 16, 128);
-                  tc::mma_ss<false>(tmem + (uint32_t)(cbi * kTmemCols), da, db, idesc, (k0 > 0 || p > 0 || ks > 0) ? 1u : 0u);
+                for (int p = 0; p < NPASS; ++p) {
+                  const uint32_t ab = (p & 1) ? aLo : aHi, bb = (p & 2) ? bLo : bHi;
+                  for (int ks = 0; ks < nks; ++ks) {
+                    const uint64_t da = tc::make_desc(ab + ks * 2 * kImgPitch, kImgPitch, 128);
+                    const uint64_t db = tc::make_desc(bb + ks * 2 * (128 * 16), 128 * 16, 128);
+                    tc::mma_ss<false>(tmem + (uint32_t)(cbi * kTmemCols), da, db, idesc, (k0 > 0 || p > 0 || ks > 0) ? 1u : 0u);
+                  }
                 }
+              }
+            }
+            if (do_dw) {
+              // dW[m][n] += sum over the tile's 128 rows of saved[row][m] * produced[row][k0 + n]: both operands MN-major (rows = K),
+              // A = the saved image in buf1 (chunk pitch 2048), B = this chunk's hi image (chunk pitch kImgPitch); single bf16 pass
+              if (k0 == 0) tc::mbar_wait(&bars[3], ph_s);
+              tc::fence_after_sync();
+              constexpr uint32_t idw = tc::make_idesc(tc::FMT_BF16, 128, KC, true, true);
+              const uint32_t sa = tc::smem_u32(buf1);
+              for (int ks = 0; ks < 8; ++ks) {
+                const uint64_t da = tc::make_desc(sa + ks * 256, 128, 2048);
+                const uint64_t db = tc::make_desc(aHi + ks * 256, 128, kImgPitch);
+                tc::mma_ss<false>(tmem + (uint32_t)(kTmemCols + k0), da, db, idw, (tile_iter > 0 || ks > 0) ? 1u : 0u);
               }
             }
             tc::mma_commit(&bars[1]);
@@ -565,12 +593,16 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
             // the hi image of this chunk is the formatted operand of the weight-gradient GEMM: tile image [K/8][128][8] bf16
             unsigned char* dst = reinterpret_cast<unsigned char*>(a.prod_img) + ((size_t)tile * a.img_chunks + (k0 / 8)) * 2048;
             const int nch = min(8, a.img_chunks - k0 / 8);
-            const unsigned char* simg = (a.skip_gemm && ((k0 / KC) & 1)) ? imgLo : imgHi;
+            const unsigned char* simg = (a.skip_gemm && !do_dw && ((k0 / KC) & 1)) ? imgLo : imgHi;
             for (int q = 0; q < nch; ++q) tc::bulk_s2g(dst + (size_t)q * 2048, simg + q * kImgPitch, 2048);
             tc::bulk_commit();
           }
         }
-        if (use_mma) { ph_w ^= 1; mma_pending = true; if (a.ncb > 1) ph_w1 ^= 1; }
+        if (use_mma) {
+          mma_pending = true;
+          if (!a.skip_gemm) { ph_w ^= 1; if (a.ncb > 1) ph_w1 ^= 1; }
+          if (do_dw && k0 == 0) ph_s ^= 1;
+        }
         if (first_pass && a.prod_img) store_pending = true;
       } else if (!a.skip_gemm) {
 #pragma unroll 2
@@ -1056,8 +1088,41 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
     } else if (MM) {
       __syncthreads();   // the staging tile aliases the chunk buffers of the next column pass
     }
-  }
+  }   // column passes
+  __syncthreads();   // the next tile restages the neighbour records and reuses every buffer
+  }   // tiles of this CTA
 
+  if (do_dw) {
+    // this CTA's partial weight gradient: TMEM columns [128, 256) -> dw_partial[cta][m][n] (merged in fixed order afterwards)
+    if (mma_pending) {
+      tc::mbar_wait(&bars[1], ph_mma);
+      ph_mma ^= 1;
+      mma_pending = false;
+    }
+    tc::fence_after_sync();
+    constexpr int CPG = TC / (NWARP / 4);
+    const int q = warp & 3, hsel = warp >> 2;
+    const int m = q * 32 + lane;
+    float* outp = a.dw_partial + (size_t)blockIdx.x * a.dw_M * K;
+    const bool vec4 = (K % 4 == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < CPG; c0 += 32) {
+      const int cl = hsel * CPG + c0;
+      float v[32];
+      tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(kTmemCols + cl), v);
+      if (blockIdx.x < (unsigned)a.ntiles && m < a.dw_M && cl < K) {
+        float* dst = outp + (size_t)m * K + cl;
+        if (vec4 && cl + 32 <= K) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (cl + i < K) dst[i] = v[i];
+        }
+      }
+    }
+  }
   if (MM && use_mma) {
     tc::fence_before_sync();
     __syncthreads();
