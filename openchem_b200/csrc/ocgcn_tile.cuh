@@ -258,8 +258,11 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
       const bool v0 = c < K, v1 = c + 1 < K;
       const float* opnd = buf0;
 
-      if (MM) {
-        // the previous chunk's MMAs read the weight image (buf0) and the operand images: wait before touching them
+      // MM: the previous chunk's MMAs read the weight image (buf0 / buf1) and the operand images, and a bulk store may still
+      // read the hi image. Every producer first ISSUES its global loads of this chunk, then calls chunk_sync() before its
+      // first shared-memory write: the MMA tail hides behind the load latency. Thread 0 then starts this chunk's bulk loads.
+      auto chunk_sync = [&]() {
+        if (!MM) return;
         if (mma_pending) {
           tc::mbar_wait(&bars[1], ph_mma);
           ph_mma ^= 1;
@@ -284,6 +287,8 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
           tc::bulk_g2s(wHi, src, kWPiece, &bars[0]);
           tc::bulk_g2s(wHi + kWPiece, src + kWPiece, kWPiece, &bars[0]);
         }
+      };
+      if (MM) {
       } else if (!a.skip_gemm) {
         // weight chunk [KC][TC] (independent of the producer; sW is free after the previous trailing sync)
         if (NC % 4 == 0) {
@@ -336,6 +341,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
               if (v1) v[q].y = __ldg(px + a.xs2);
             }
           }
+          if (h == 0) chunk_sync();
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float2*>(&buf1[(warp + (h * 8 + q) * NWARP) * BS + 2 * lane]) = v[q];
@@ -355,6 +361,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
               const int r = warp + (h * TB + q) * NWARP;
               v[q] = (r < rows && v0) ? ldg2(&a.in0[(row0 + r) * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
             }
+            if (h == 0) chunk_sync();
 #pragma unroll
             for (int q = 0; q < TB; ++q) {
               const int r = warp + (h * TB + q) * NWARP;
@@ -446,6 +453,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
             zv[q] = ok ? ldg2(&a.in1[(row0 + r) * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
             dv[q] = ok ? ldg2(&a.in0[(row0 + r) * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
           }
+          if (h == 0) chunk_sync();
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const int r = warp + (h * 8 + q) * NWARP;
@@ -481,6 +489,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
             const int r = warp + (h * 8 + q) * NWARP;
             dv[q] = (r < rows && v0) ? ldg2(&a.in0[(row0 + r) * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
           }
+          if (h == 0) chunk_sync();
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const int r = warp + (h * 8 + q) * NWARP;
