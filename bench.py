@@ -362,14 +362,16 @@ def run_native(args, w, wname):
         mid, R = F[1], B * w["n_max"]
         tc = args.precision != "fp32"
         simg = 2 if tc else 4                      # bytes/element of the saved S / dZ operand (bf16 image vs fp32)
-        alg = {   # kernel -> (flops, bytes) per launch, mid layers (F_in = F_out = mid)
+        fused = tc and max(F + [E]) <= 128            # weight gradients accumulated inside the backward tile kernels
+        alg = {   # kernel -> (dense GEMM flops, boundary-tensor bytes) per launch, mid layers (F_in = F_out = mid)
             "fwd_mid": (B * (2 * N * N * mid + 2 * N * mid * mid), R * mid * (4 + 4 + 1 + simg)),            # Z in; Z, arg, S out
             "fwd_first": (B * (2 * N * N * F[0] + 2 * N * F[0] * F[1]), R * (F[0] * (4 + simg) + F[1] * 4)),
-            "bwd_dz": (B * (2 * N * mid * mid + 2 * N * N * mid), R * mid * (4 + 4 + 4 + 1 + 4 + simg)),    # dY, Z, Z_prev, arg in; dY_prev, dZ out
+            # dY, Z, Z_prev, arg (+ S image when dW is fused) in; dY_prev (+ dZ image when it is not) out
+            "bwd_dz": (B * (2 * N * mid * mid + 2 * N * N * mid + (2 * N * mid * mid if fused else 0)), R * mid * (4 + 4 + 4 + 1 + 4 + simg)),
             "gemm_tn": (B * (2 * N * mid * mid), R * mid * 8),
             "dw_mma": (B * (2 * N * mid * mid), R * mid * 4),
             "fwd_readout": (B * (2 * N * F[-1] * E), R * (F[-1] * (4 + 1 + simg) + E * 4)),
-            "bwd_readout": (B * (2 * N * F[-1] * E), R * (E * (4 + simg) + F[-1] * (4 + 1 + 4))),
+            "bwd_readout": (B * (2 * N * F[-1] * E * (2 if fused else 1)), R * (E * 4 + F[-1] * (4 + 1 + 4 + simg))),
             "bwd_dy": (0, R * mid * (4 + 4 + 1 + 4)),
         }.get(top)
         if alg is not None:
