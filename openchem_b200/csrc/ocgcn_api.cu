@@ -82,7 +82,7 @@ struct Layout {
   size_t HL, D, O;
   size_t saved_total;
   // scratch
-  size_t partials, prodpart, WT[OCGCN_MAX_LAYERS], WdT, G[3], dU, coef, gemm_partial;
+  size_t partials, prodpart[OCGCN_MAX_LAYERS + 1], WT[OCGCN_MAX_LAYERS], WdT, G[3], dU, coef, gemm_partial[OCGCN_MAX_LAYERS + 1];   // [L] = readout
   size_t Wf[OCGCN_MAX_LAYERS], Wro, Wb[OCGCN_MAX_LAYERS], Wrob, dZimg, dUimg;   // mm: weight operand images, dZ / dU tile images
   size_t scratch_total;
   int max_splits;
@@ -151,7 +151,7 @@ static int make_layout(const ocgcn_desc* d, bool layer_only, Layout* lo) {
 
   off = 0;
   lo->partials = take((size_t)lo->tiles * 2 * Fmax * 4);
-  lo->prodpart = take((size_t)lo->tiles * Fmax * 4);
+  for (int l = 0; l <= d->L; ++l) lo->prodpart[l] = take((size_t)lo->tiles * Fmax * 4);   // per layer: merged by ONE reduction launch at the end
   int max_splits = 1;
   size_t max_partial = 0;
   for (int l = 0; l < d->L; ++l) {
@@ -184,7 +184,7 @@ static int make_layout(const ocgcn_desc* d, bool layer_only, Layout* lo) {
     const size_t p = (size_t)kMaxPersistent * KPmax * (lo->KPE > KPmax ? lo->KPE : KPmax) * 4;   // per-CTA dW partials (dw_mma_kernel / fused)
     max_partial = p > max_partial ? p : max_partial;
   }
-  lo->gemm_partial = take(max_partial);
+  for (int l = 0; l <= d->L; ++l) lo->gemm_partial[l] = take(max_partial);
   lo->max_splits = max_splits;
   lo->scratch_total = off;
   return OCGCN_OK;
@@ -341,16 +341,17 @@ static int run_gemm_tn(const float* A, const float* Bm, size_t R, int M, int Nn,
   return OCGCN_OK;
 }
 
-static int run_reduce(const Layout& lo, char* scratch, const float* p0, float* o0, int P0, int c0, const float* p1, float* o1, int P1,
-                      int c1, cudaStream_t st, int tr_cols = 0) {
-  (void)lo; (void)scratch;
+static void add_reduce(ReduceJobs& j, const float* partial, float* out, int P, int count, int matrix, int tr_cols) {
+  if (!out || count <= 0) return;
+  const int n = j.n;
+  j.partial[n] = partial; j.out[n] = out; j.P[n] = P; j.count[n] = count; j.matrix[n] = matrix; j.tr_cols[n] = tr_cols;
+  j.first_cta[n + 1] = j.first_cta[n] + (reduce_job_vec4(matrix, tr_cols, count) ? (count + 127) / 128 : matrix ? (count + 31) / 32 : (count + kChanCols - 1) / kChanCols);
+  j.n = n + 1;
+}
+static int run_reduce(const ReduceJobs& j, cudaStream_t st) {
+  if (j.n == 0) return OCGCN_OK;
   ProfScope prof(KK_REDUCE, st);
-  ReduceJobs j;
-  j.tr_cols = tr_cols;
-  j.partial[0] = p0; j.out[0] = o0; j.P[0] = P0; j.count[0] = c0;
-  j.partial[1] = p1; j.out[1] = o1; j.P[1] = P1; j.count[1] = o1 ? c1 : 0;
-  const int nblk = (c0 + 31) / 32 + (o1 ? (c1 + kChanCols - 1) / kChanCols : 0);
-  reduce_partials_kernel<<<nblk, kRedThreads, 0, st>>>(j);
+  reduce_partials_kernel<<<j.first_cta[j.n], kRedThreads, 0, st>>>(j);
   LAUNCH_CHECK();
   return OCGCN_OK;
 }
@@ -408,12 +409,12 @@ static void set_prev_layer(TileArgs& a, const ocgcn_desc* d, const Layout& lo, i
 // Produces dgamma/dbeta/dW/db, and dHprev (= dX) in `g_out` unless skip_dx.
 static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float* adj, const ocgcn_params* p, const ocgcn_grads* g,
                               int l, bool plain, float* g_in, float* g_dz, float* g_out, bool skip_dx, char* saved, char* scratch,
-                              cudaStream_t st) {
+                              cudaStream_t st, ReduceJobs& rj) {
   const int Fin = d->F[l], Fout = d->F[l + 1];
   const float* stats = reinterpret_cast<const float*>(saved + lo.stats[l]);
   float* coef = reinterpret_cast<float*>(scratch + lo.coef);
   float* partials = reinterpret_cast<float*>(scratch + lo.partials);
-  float* prodpart = reinterpret_cast<float*>(scratch + lo.prodpart);
+  float* prodpart = reinterpret_cast<float*>(scratch + lo.prodpart[l]);
   const float* Z = reinterpret_cast<const float*>(saved + lo.Z[l]);
 
   BwdDyArgs y;
@@ -448,7 +449,7 @@ static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float
   a.Bm = reinterpret_cast<const float*>(scratch + lo.WT[l]);
   a.out0 = g_out;
   a.skip_gemm = skip_dx ? 1 : 0;
-  float* gp = reinterpret_cast<float*>(scratch + lo.gemm_partial);
+  float* gp = reinterpret_cast<float*>(scratch + lo.gemm_partial[l]);
   if (lo.mm) {
     a.prod_out = nullptr;
     a.prod_img = scratch + lo.dZimg; a.img_chunks = lo.KP[l + 1] / 8;
@@ -469,7 +470,8 @@ static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float
   if (lo.fuse_dw) splits = mm_grid(lo.tiles);
   else if (lo.mm) ST_TRY(run_dw_mma(lo, saved + lo.S[l], scratch + lo.dZimg, lo.KP[l], lo.KP[l + 1], Fin, Fout, gp, st, &splits));
   else ST_TRY(run_gemm_tn(reinterpret_cast<const float*>(saved + lo.S[l]), g_dz, lo.rows, Fin, Fout, gp, st, &splits));
-  ST_TRY(run_reduce(lo, scratch, gp, g->dW[l], splits, Fin * Fout, prodpart, (d->has_bias ? g->db[l] : nullptr), lo.tiles, Fout, st));
+  add_reduce(rj, gp, g->dW[l], splits, Fin * Fout, 1, 0);
+  add_reduce(rj, prodpart, (d->has_bias ? g->db[l] : nullptr), lo.tiles, Fout, 0, 0);
   return OCGCN_OK;
 }
 
@@ -645,9 +647,11 @@ int ocgcn_encoder_backward(const ocgcn_desc* d, const float* grad_out, const flo
 
   float* G[3] = {reinterpret_cast<float*>(scratch + lo.G[0]), reinterpret_cast<float*>(scratch + lo.G[1]),
                  reinterpret_cast<float*>(scratch + lo.G[2])};
-  float* prodpart = reinterpret_cast<float*>(scratch + lo.prodpart);
+  float* prodpart = reinterpret_cast<float*>(scratch + lo.prodpart[L]);
   float* dU = reinterpret_cast<float*>(scratch + lo.dU);
-  float* gp = reinterpret_cast<float*>(scratch + lo.gemm_partial);
+  float* gp = reinterpret_cast<float*>(scratch + lo.gemm_partial[L]);
+  ReduceJobs rj;
+  memset(&rj, 0, sizeof(rj));
 
   // readout backward: dU = dO(1-O^2)(1-D^2); dH_L = dU.Wd; dWd = dU^T.H_L; dbd = sum dU
   TileArgs a = base_tile_args(d, lo, adj, saved);
@@ -674,15 +678,16 @@ int ocgcn_encoder_backward(const ocgcn_desc* d, const float* grad_out, const flo
   if (lo.fuse_dw) splits = mm_grid(lo.tiles);
   else if (lo.mm) ST_TRY(run_dw_mma(lo, scratch + lo.dUimg, saved + lo.HL, lo.KPE, lo.KP[L], d->E, d->F[L], gp, st, &splits));
   else ST_TRY(run_gemm_tn(dU, reinterpret_cast<const float*>(saved + lo.HL), lo.rows, d->E, d->F[L], gp, st, &splits));
-  ST_TRY(run_reduce(lo, scratch, gp, g->dWd, splits, d->E * d->F[L], prodpart, g->dbd, lo.tiles, d->E, st, lo.fuse_dw ? d->F[L] : 0));
+  add_reduce(rj, gp, g->dWd, splits, d->E * d->F[L], 1, lo.fuse_dw ? d->F[L] : 0);
+  add_reduce(rj, prodpart, g->dbd, lo.tiles, d->E, 0, 0);
 
   int cur = 0;
   for (int l = L - 1; l >= 0; --l) {
     const int dz = (cur + 1) % 3, nxt = (cur + 2) % 3;
-    ST_TRY(run_layer_backward(d, lo, adj, p, g, l, false, G[cur], G[dz], G[nxt], l == 0, saved, scratch, st));
+    ST_TRY(run_layer_backward(d, lo, adj, p, g, l, false, G[cur], G[dz], G[nxt], l == 0, saved, scratch, st, rj));
     cur = nxt;
   }
-  return OCGCN_OK;
+  return run_reduce(rj, st);   // every dW_l, db_l, dWd, dbd in one fixed-order reduction launch
 }
 
 int ocgcn_layer_forward(const ocgcn_desc* d, const float* x, const float* adj, const ocgcn_params* p, void* saved_v, void* scratch_v,
@@ -748,7 +753,10 @@ int ocgcn_layer_backward(const ocgcn_desc* d, const float* grad_y, const float* 
     ST_TRY(run_transposes(tj, 1, st));
   }
   float* dz = reinterpret_cast<float*>(scratch + lo.G[0]);
-  return run_layer_backward(d, lo, adj, p, g, 0, true, const_cast<float*>(grad_y), dz, grad_x, !d->need_dx, saved, scratch, st);
+  ReduceJobs rj;
+  memset(&rj, 0, sizeof(rj));
+  ST_TRY(run_layer_backward(d, lo, adj, p, g, 0, true, const_cast<float*>(grad_y), dz, grad_x, !d->need_dx, saved, scratch, st, rj));
+  return run_reduce(rj, st);
 }
 
 }  // extern "C"

@@ -108,12 +108,15 @@ __global__ void transpose_kernel(const TransposeJobs jobs) {
 // finaliser. The summation order depends only on the shape -> bit-reproducible.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kRedThreads = 1024;
+// shared-memory doubles wide_reduce<NV, COLS> needs
+template <int NV, int COLS>
+__host__ __device__ constexpr int wide_reduce_smem() { return NV * kRedThreads + NV * 16 * COLS; }
 template <int NV, int COLS, typename Job>
-__device__ __forceinline__ void wide_reduce(const Job& job, int P, int cnt, int cgroup) {
+__device__ __forceinline__ void wide_reduce(const Job& job, int P, int cnt, int cgroup, double* sbuf) {
   constexpr int RL = kRedThreads / COLS;
   static_assert(RL >= 16 && RL % 16 == 0, "row lanes are folded 16 groups at a time");
-  __shared__ double sred[NV][RL][COLS];
-  __shared__ double sred2[NV][16][COLS];
+  double (*sred)[RL][COLS] = reinterpret_cast<double (*)[RL][COLS]>(sbuf);
+  double (*sred2)[16][COLS] = reinterpret_cast<double (*)[16][COLS]>(sbuf + NV * kRedThreads);
   const int col = threadIdx.x % COLS, rl = threadIdx.x / COLS;
   const int c = cgroup * COLS + col;
   const bool valid = c < cnt;
@@ -213,8 +216,9 @@ __global__ void __launch_bounds__(kRedThreads) bn_finalize_kernel(const BnFinali
     a.shift[c] = a.beta[c] - (float)mean * sc;
     return;
   }
+  __shared__ double sbuf[wide_reduce_smem<2, kChanCols>()];
   BnJob job{a};
-  wide_reduce<2, kChanCols>(job, a.T, a.F, blockIdx.x);
+  wide_reduce<2, kChanCols>(job, a.T, a.F, blockIdx.x, sbuf);
 }
 
 // y = scale*z + shift (standalone GraphConvolution output, gcn.py:40)
@@ -451,8 +455,9 @@ struct BwdFinJob {
   }
 };
 __global__ void __launch_bounds__(kRedThreads) bwd_finalize_kernel(const BwdFinalizeArgs a) {
+  __shared__ double sbuf[wide_reduce_smem<2, kChanCols>()];
   BwdFinJob job{a};
-  wide_reduce<2, kChanCols>(job, a.T, a.F, blockIdx.x);
+  wide_reduce<2, kChanCols>(job, a.T, a.F, blockIdx.x, sbuf);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -511,36 +516,72 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tn_kernel(const float* __res
   }
 }
 
-// out[i] = sum_p partial[p][i] (fixed order). Two jobs per launch: job 0 = a matrix of split-K partials (few rows, many
-// outputs: 32 columns x 32 row lanes per CTA), job 1 = a per-channel vector of per-tile partials (many rows, few outputs).
+// out[i] = sum_p partial[p][i] (fixed order) for a LIST of jobs in one launch (every dW_l / db_l / dWd / dbd of a backward
+// call): "matrix" jobs = few partial rows (per-CTA split-K partials), many outputs -> 32 columns x 32 row lanes per CTA;
+// "vector" jobs = many partial rows (per tile), few outputs -> 8 columns x 128 row lanes per CTA.
+constexpr int kMaxReduceJobs = 2 * OCGCN_MAX_LAYERS + 2;
 struct ReduceJobs {
-  const float* partial[2];
-  float* out[2];
-  int P[2];
-  int count[2];
-  int tr_cols;   // job 0 only: > 0 = the partials hold the TRANSPOSE ([tr_cols][count/tr_cols]... see SumJob) of the output matrix
+  const float* partial[kMaxReduceJobs];
+  float* out[kMaxReduceJobs];
+  int P[kMaxReduceJobs];
+  int count[kMaxReduceJobs];
+  int tr_cols[kMaxReduceJobs];    // > 0: each partial holds the TRANSPOSE of the output ([tr_cols][count / tr_cols]) — fused readout gradient dWd^T
+  int matrix[kMaxReduceJobs];     // 1: matrix job (32 columns per CTA), 0: vector job (8 columns per CTA)
+  int first_cta[kMaxReduceJobs + 1];
+  int n;
 };
 struct SumJob {
   const float* p;
   float* out;
   int cnt;
-  int tr_cols;   // output is [R][tr_cols] row-major while each partial is [tr_cols][R] (fused readout gradient dWd^T); 0 = same layout
+  int tr_cols;
   __device__ __forceinline__ void add(int q, int c, double* acc) const {
     const int src = tr_cols ? (c % tr_cols) * (cnt / tr_cols) + c / tr_cols : c;
     acc[0] += (double)__ldg(&p[(size_t)q * cnt + src]);
   }
   __device__ __forceinline__ void finish(int c, const double* acc) const { out[c] = (float)acc[0]; }
 };
-// 1-D grid: the first ceil(count[0]/32) CTAs serve job 0, the following ceil(count[1]/8) CTAs job 1
-__global__ void __launch_bounds__(kRedThreads) reduce_partials_kernel(const ReduceJobs jobs) {
-  const int n0 = (jobs.count[0] + 31) / 32;
-  if ((int)blockIdx.x < n0) {
-    SumJob job{jobs.partial[0], jobs.out[0], jobs.count[0], jobs.tr_cols};
-    wide_reduce<1, 32>(job, jobs.P[0], jobs.count[0], blockIdx.x);
-  } else {
-    SumJob job{jobs.partial[1], jobs.out[1], jobs.count[1], 0};
-    wide_reduce<1, kChanCols>(job, jobs.P[1], jobs.count[1], blockIdx.x - n0);
+// matrix job, 16-byte loads: a CTA owns 128 consecutive outputs (32 threads x float4) x 32 row lanes; fixed-order fp64 folds
+__device__ __forceinline__ void wide_reduce_vec4(const float* __restrict__ p, float* __restrict__ out, int P, int cnt, int cgroup, double* sbuf) {
+  double (*sred4)[128] = reinterpret_cast<double (*)[128]>(sbuf);   // [32][128]
+  const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = cgroup * 128 + cq * 4;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  if (c < cnt) {
+    for (int q = rl; q < P; q += 32 * 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = (q + u * 32 < P) ? __ldg(reinterpret_cast<const float4*>(&p[(size_t)(q + u * 32) * cnt + c])) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { acc[0] += (double)v[u].x; acc[1] += (double)v[u].y; acc[2] += (double)v[u].z; acc[3] += (double)v[u].w; }
+    }
   }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) sred4[rl][cq * 4 + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < 128 && cgroup * 128 + (int)threadIdx.x < cnt) {
+    double t = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) t += sred4[k][threadIdx.x];
+    out[cgroup * 128 + threadIdx.x] = (float)t;
+  }
+}
+static inline bool reduce_job_vec4(int matrix, int tr_cols, int count) { return matrix && tr_cols == 0 && count % 4 == 0; }
+
+__global__ void __launch_bounds__(kRedThreads) reduce_partials_kernel(const ReduceJobs jobs) {
+  int jb = 0;
+  while (jb + 1 < jobs.n && (int)blockIdx.x >= jobs.first_cta[jb + 1]) ++jb;
+  const int cg = (int)blockIdx.x - jobs.first_cta[jb];
+  __shared__ double sbuf[32 * 128];   // one buffer for whichever path this CTA takes
+  static_assert(wide_reduce_smem<1, 32>() <= 32 * 128 && wide_reduce_smem<1, kChanCols>() <= 32 * 128, "shared reduction buffer");
+  if (jobs.matrix[jb] && jobs.tr_cols[jb] == 0 && jobs.count[jb] % 4 == 0) {
+    wide_reduce_vec4(jobs.partial[jb], jobs.out[jb], jobs.P[jb], jobs.count[jb], cg, sbuf);
+    return;
+  }
+  SumJob job{jobs.partial[jb], jobs.out[jb], jobs.count[jb], jobs.tr_cols[jb]};
+  if (jobs.matrix[jb]) wide_reduce<1, 32>(job, jobs.P[jb], jobs.count[jb], cg, sbuf);
+  else wide_reduce<1, kChanCols>(job, jobs.P[jb], jobs.count[jb], cg, sbuf);
 }
 
 }  // namespace ocgcn
