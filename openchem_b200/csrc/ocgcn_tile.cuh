@@ -134,11 +134,11 @@ __device__ __forceinline__ float4 rec_sum4(const uint4& rec, const float* colp) 
 
 // two adjacent channels of one row from global memory (8-byte access when the row pitch allows it)
 __device__ __forceinline__ float2 ldg2(const float* p, bool v0, bool v1, bool vec) {
-  if (vec && v1) return __ldg(reinterpret_cast<const float2*>(p));
+  if (vec) return v0 ? __ldg(reinterpret_cast<const float2*>(p)) : make_float2(0.f, 0.f);   // even width: v1 == v0
   return make_float2(v0 ? __ldg(p) : 0.f, v1 ? __ldg(p + 1) : 0.f);
 }
 __device__ __forceinline__ void stg2(float* p, float2 v, bool v0, bool v1, bool vec) {
-  if (vec && v1) { *reinterpret_cast<float2*>(p) = v; return; }
+  if (vec) { if (v0) *reinterpret_cast<float2*>(p) = v; return; }
   if (v0) p[0] = v.x;
   if (v1) p[1] = v.y;
 }
@@ -222,6 +222,16 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
   const int nm = min(a.MT, a.B - mol0);
   const int rows = nm * N;
   const size_t row0 = (size_t)mol0 * N;
+  // tile base pointers: the 64-bit products are formed once per tile, the loops below add 32-bit offsets (rows * width < 2^16)
+  const float* const in0_t = (PROD == P_X || !a.in0) ? a.in0 : a.in0 + row0 * K;
+  const float* const in1_t = (PROD == P_DZ) ? a.in1 + row0 * K : a.in1;
+  unsigned char* const argo_t = a.arg_out ? a.arg_out + row0 * K : nullptr;
+  float* const prodo_t = a.prod_out ? a.prod_out + row0 * K : nullptr;
+  float* const out0_t = a.out0 ? a.out0 + row0 * NC : nullptr;
+  const unsigned char* const argi_t = a.arg_in ? a.arg_in + row0 * NC : nullptr;
+  const float* const zprev_t = a.zprev ? a.zprev + row0 * NC : nullptr;
+  const float* const o_t = (PROD == P_DU) ? a.in2 + (size_t)mol0 * K : nullptr;
+  const float* const do_t = (PROD == P_DU) ? a.in1 + (size_t)mol0 * K : nullptr;
 
   // ---- stage neighbour records (made tile-relative), masks and per-molecule flags ---------------------------
   for (int r = tid; r < TR; r += NT) {
@@ -359,7 +369,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
 #pragma unroll
             for (int q = 0; q < TB; ++q) {
               const int r = warp + (h * TB + q) * NWARP;
-              v[q] = (r < rows && v0) ? ldg2(&a.in0[(row0 + r) * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
+              v[q] = (r < rows && v0) ? ldg2(&in0_t[r * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
             }
             if (h == 0) chunk_sync();
 #pragma unroll
@@ -417,14 +427,14 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
               }
             }
             if (first_pass && v0) {
-              unsigned char* ap = a.arg_out + (row0 + r) * K + c;
+              unsigned char* ap = argo_t + (r * K + c);
               if (kvec2) {
                 *reinterpret_cast<uchar2*>(ap) = make_uchar2((unsigned char)(a0 - mb), (unsigned char)(a1 - mb));
               } else {
                 ap[0] = (unsigned char)(a0 - mb);
                 if (v1) ap[1] = (unsigned char)(a1 - mb);
               }
-              if (!MM && PROD == P_RO) stg2(a.prod_out + (row0 + r) * K + c, make_float2(b0, b1), v0, v1, kvec2);
+              if (!MM && PROD == P_RO) stg2(prodo_t + (r * K + c), make_float2(b0, b1), v0, v1, kvec2);
             }
           }
           if (PROD == P_RO) put_operand(bufH, r, make_float2(b0, b1));   // readout: the pooled H is the GEMM operand
@@ -450,8 +460,8 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
           for (int q = 0; q < 8; ++q) {
             const int r = warp + (h * 8 + q) * NWARP;
             const bool ok = r < rows && v0;
-            zv[q] = ok ? ldg2(&a.in1[(row0 + r) * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
-            dv[q] = ok ? ldg2(&a.in0[(row0 + r) * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
+            zv[q] = ok ? ldg2(&in1_t[r * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
+            dv[q] = ok ? ldg2(&in0_t[r * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
           }
           if (h == 0) chunk_sync();
 #pragma unroll
@@ -462,7 +472,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
               dz.x = g.x * (dv[q].x - c1.x - (zv[q].x - mu.x) * is.x * c2.x);
               if (v1) dz.y = g.y * (dv[q].y - c1.y - (zv[q].y - mu.y) * is.y * c2.y);
               if (first_pass) {
-                if (!MM) stg2(a.prod_out + (row0 + r) * K + c, dz, v0, v1, kvec2);
+                if (!MM) stg2(prodo_t + (r * K + c), dz, v0, v1, kvec2);
                 colsum.x += dz.x; colsum.y += dz.y;
               }
             }
@@ -487,7 +497,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const int r = warp + (h * 8 + q) * NWARP;
-            dv[q] = (r < rows && v0) ? ldg2(&a.in0[(row0 + r) * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
+            dv[q] = (r < rows && v0) ? ldg2(&in0_t[r * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
           }
           if (h == 0) chunk_sync();
 #pragma unroll
@@ -496,12 +506,12 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
             float2 du = make_float2(0.f, 0.f);
             if (r < rows && v0) {
               const int m = rec_m(sRec[r]);
-              const size_t ob = (size_t)(mol0 + m) * K + c;
-              const float2 ov = ldg2(&a.in2[ob], v0, v1, kvec2), go = ldg2(&a.in1[ob], v0, v1, kvec2);
+              const int ob = m * K + c;   // (molecule-of-the-tile, channel) in the per-molecule O / dO tensors
+              const float2 ov = ldg2(&o_t[ob], v0, v1, kvec2), go = ldg2(&do_t[ob], v0, v1, kvec2);
               du.x = go.x * (1.f - ov.x * ov.x) * (1.f - dv[q].x * dv[q].x);
               if (v1) du.y = go.y * (1.f - ov.y * ov.y) * (1.f - dv[q].y * dv[q].y);
               if (first_pass) {
-                if (!MM) stg2(a.prod_out + (row0 + r) * K + c, du, v0, v1, kvec2);
+                if (!MM) stg2(prodo_t + (r * K + c), du, v0, v1, kvec2);
                 colsum.x += du.x; colsum.y += du.y;
               }
             }
@@ -542,7 +552,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
                 s.y = fmaf(aj, hv.y, s.y);
               }
             }
-            if (!MM && first_pass && v0 && a.prod_out) stg2(a.prod_out + (row0 + r) * K + c, s, v0, v1, kvec2);
+            if (!MM && first_pass && v0 && a.prod_out) stg2(prodo_t + (r * K + c), s, v0, v1, kvec2);
           }
           put_operand(buf0, r, s);
         }
@@ -686,7 +696,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
           if (gc >= NC) continue;
           float4 v = *reinterpret_cast<const float4*>(&sC[r * TCP + cl]);
           v.x += bb[0]; v.y += bb[1]; v.z += bb[2]; v.w += bb[3];
-          float* dst = a.out0 + (row0 + r) * NC + gc;
+          float* dst = out0_t + (r * NC + gc);
           if (vec_ok && gc + 3 < NC) {
             *reinterpret_cast<float4*>(dst) = v;
           } else {
@@ -755,7 +765,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
 #pragma unroll
           for (int q = 0; q < 4; ++q) acc[r][(MM ? 0 : h * 4 + q)] += bb[q];
           if (row < rows) {
-            float* dst = a.out0 + (row0 + row) * NC + gc;
+            float* dst = out0_t + (row * NC + gc);
             if (vec_ok && gc + 3 < NC) {
               *reinterpret_cast<float4*>(dst) = make_float4(acc[r][(MM ? 0 : h * 4 + 0)], acc[r][(MM ? 0 : h * 4 + 1)], acc[r][(MM ? 0 : h * 4 + 2)], acc[r][(MM ? 0 : h * 4 + 3)]);
             } else {
@@ -828,7 +838,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
             if (EPI == E_READOUT) v[q] = (row < rows && gc + q < NC) ? fast_tanh(v[q] + bb[q]) : 0.f;   // gcn_encoder.py:51
           }
           if (EPI == E_READOUT && row < rows) {
-            float* dst = a.out0 + (row0 + row) * NC + gc;
+            float* dst = out0_t + (row * NC + gc);
             if (NC % 4 == 0 && gc + 3 < NC) {
               *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
             } else {
@@ -880,7 +890,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
               s.x = fmaf(ai, dv.x, s.x); s.y = fmaf(ai, dv.y, s.y); s.z = fmaf(ai, dv.z, s.z); s.w = fmaf(ai, dv.w, s.w);
             }
           }
-          float* dst = a.out0 + (row0 + r) * NC + cb + cl;
+          float* dst = out0_t + (r * NC + cb + cl);
           if (NC % 4 == 0 && cb + cl + 3 < NC) {
             *reinterpret_cast<float4*>(dst) = s;
           } else {
@@ -909,7 +919,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
           const int gc = cb + c16;
           pv[u] = make_uint4(0u, 0u, 0u, 0u);
           if (r < rows && gc < NC) {
-            const unsigned char* src = a.arg_in + (row0 + r) * NC + gc;
+            const unsigned char* src = argi_t + (r * NC + gc);
             if (vec) {
               pv[u] = __ldg(reinterpret_cast<const uint4*>(src));
             } else {
@@ -984,7 +994,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
         auto load_z = [&](int r) -> float4 {
           float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
           if (act && r < rows) {
-            const float* zp = a.zprev + (row0 + r) * NC + gc;
+            const float* zp = zprev_t + (r * NC + gc);
             if (vec4) z = __ldg(reinterpret_cast<const float4*>(zp));
             else { z.x = __ldg(zp); if (gc + 1 < NC) z.y = __ldg(zp + 1); if (gc + 2 < NC) z.z = __ldg(zp + 2); if (gc + 3 < NC) z.w = __ldg(zp + 3); }
           }
@@ -1060,7 +1070,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
             s1[e] += dy[e];
             s2[e] = fmaf(dy[e], (zz[e] - mu[e]) * is[e], s2[e]);
           }
-          float* dst = a.out0 + (row0 + r) * NC + gc;
+          float* dst = out0_t + (r * NC + gc);
           if (vec4) {
             *reinterpret_cast<float4*>(dst) = make_float4(dy[0], dy[1], dy[2], dy[3]);
           } else {
