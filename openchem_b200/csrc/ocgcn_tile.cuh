@@ -179,7 +179,10 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
   uint64_t* bars = reinterpret_cast<uint64_t*>(sWarp + 2 * NWARP * 32);   // MM: [0] weight image landed, [1] MMAs complete, [2] second column block's weight image landed, [3] see tslot
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4);   // ([3]: saved operand image of the fused dW GEMM landed)
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // warp index through a shuffle: the compiler then KNOWS it is warp-uniform, keeps everything derived from it (row index,
+  // neighbour record, its flags and counts) on the uniform datapath and emits uniform branches instead of divergence scaffolding
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int tx = tid % TXN, ty = tid / TXN;
   const bool kvec2 = (K % 2 == 0);
   // T goes to the buffer the weight image does NOT alias while the pool still reads it
