@@ -102,7 +102,7 @@ template <int Q>
 __device__ __forceinline__ int rec_idx(const uint4& r) {
   constexpr int byte = 3 + Q;
   const unsigned w = (byte >> 2) == 0 ? r.x : (byte >> 2) == 1 ? r.y : (byte >> 2) == 2 ? r.z : r.w;
-  return (w >> ((byte & 3) * 8)) & 0xff;
+  return (int)__byte_perm(w, 0u, 0x4440u | (unsigned)(byte & 3));   // one PRMT: byte -> bits 0-7, zeros above
 }
 __device__ __forceinline__ uint4 rec_stage(uint4 r, int m, int mb) {   // molecule-relative -> tile-relative indices
   const unsigned add = (unsigned)mb * 0x01010101u;
@@ -111,6 +111,19 @@ __device__ __forceinline__ uint4 rec_stage(uint4 r, int m, int mb) {   // molecu
   r.z = __vadd4(r.z, add);
   r.w = __vadd4(r.w, add);
   return r;
+}
+// as rec_stage, and every unused neighbour slot (>= count) points at tile row `dummy`: a row the staged buffers keep at the
+// neutral element (-inf for the max-pool, 0 for the gather), so the first neighbour steps need no count checks at all
+__device__ __forceinline__ uint4 rec_stage_padded(uint4 r, int m, int mb, int dummy) {
+  r = rec_stage(r, m, mb);
+  const int cnt = (r.x & 0x80u) ? kMaxNbr : (int)(r.x & 0xfu);
+  unsigned w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int q = 0; q < kMaxNbr; ++q) {
+    const int byte = 3 + q;
+    if (q >= cnt) w[byte >> 2] = (w[byte >> 2] & ~(0xffu << ((byte & 3) * 8))) | ((unsigned)dummy << ((byte & 3) * 8));
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 __device__ __forceinline__ int first_zero_bit(const u64* m, int NW, int N) {

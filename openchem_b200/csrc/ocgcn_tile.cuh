@@ -114,6 +114,56 @@ __device__ __forceinline__ float2 rec_sum2(const uint4& rec, const float* colp, 
   return make_float2(s0, s1);
 }
 
+// Variants for records staged with rec_stage_padded (tensor-core engine): unused slots read the neutral dummy row
+template <int STRIDE>
+__device__ __forceinline__ void rec_max2_padded(const uint4& rec, const float* colp, float& b0, float& b1, int& a0, int& a1) {
+  const int cnt = rec_cnt(rec);
+  const int j0 = rec_idx<0>(rec), j1 = rec_idx<1>(rec), j2 = rec_idx<2>(rec), j3 = rec_idx<3>(rec);
+  const float2 v0 = *reinterpret_cast<const float2*>(colp + j0 * STRIDE);
+  const float2 v1 = *reinterpret_cast<const float2*>(colp + j1 * STRIDE);
+  const float2 v2 = *reinterpret_cast<const float2*>(colp + j2 * STRIDE);
+  const float2 v3 = *reinterpret_cast<const float2*>(colp + j3 * STRIDE);
+  b0 = v0.x; b1 = v0.y; a0 = j0; a1 = j0;
+  if (v1.x > b0) { b0 = v1.x; a0 = j1; }
+  if (v1.y > b1) { b1 = v1.y; a1 = j1; }
+  if (v2.x > b0) { b0 = v2.x; a0 = j2; }
+  if (v2.y > b1) { b1 = v2.y; a1 = j2; }
+  if (v3.x > b0) { b0 = v3.x; a0 = j3; }
+  if (v3.y > b1) { b1 = v3.y; a1 = j3; }
+#define OCGCN_MAX_STEP(Q)                                                        \
+  if (cnt > Q) {                                                                 \
+    const int jr = rec_idx<Q>(rec);                                              \
+    const float2 v = *reinterpret_cast<const float2*>(colp + jr * STRIDE);       \
+    if (v.x > b0) { b0 = v.x; a0 = jr; }                                         \
+    if (v.y > b1) { b1 = v.y; a1 = jr; }                                         \
+  }
+  if (cnt > 4) {
+    OCGCN_MAX_STEP(4) OCGCN_MAX_STEP(5) OCGCN_MAX_STEP(6) OCGCN_MAX_STEP(7) OCGCN_MAX_STEP(8)
+    if (cnt > 9) { OCGCN_MAX_STEP(9) OCGCN_MAX_STEP(10) OCGCN_MAX_STEP(11) OCGCN_MAX_STEP(12) }
+  }
+#undef OCGCN_MAX_STEP
+}
+template <int STRIDE>
+__device__ __forceinline__ float2 rec_sum2_padded(const uint4& rec, const float* colp) {
+  const int cnt = rec_cnt(rec);
+  const float2 v0 = *reinterpret_cast<const float2*>(colp + rec_idx<0>(rec) * STRIDE);
+  const float2 v1 = *reinterpret_cast<const float2*>(colp + rec_idx<1>(rec) * STRIDE);
+  const float2 v2 = *reinterpret_cast<const float2*>(colp + rec_idx<2>(rec) * STRIDE);
+  const float2 v3 = *reinterpret_cast<const float2*>(colp + rec_idx<3>(rec) * STRIDE);
+  float s0 = ((v0.x + v1.x) + v2.x) + v3.x, s1 = ((v0.y + v1.y) + v2.y) + v3.y;   // ascending neighbour order; dummies add 0
+#define OCGCN_SUM_STEP(Q)                                                                       \
+  if (cnt > Q) {                                                                                \
+    const float2 v = *reinterpret_cast<const float2*>(colp + rec_idx<Q>(rec) * STRIDE);         \
+    s0 += v.x; s1 += v.y;                                                                       \
+  }
+  if (cnt > 4) {
+    OCGCN_SUM_STEP(4) OCGCN_SUM_STEP(5) OCGCN_SUM_STEP(6) OCGCN_SUM_STEP(7) OCGCN_SUM_STEP(8)
+    if (cnt > 9) { OCGCN_SUM_STEP(9) OCGCN_SUM_STEP(10) OCGCN_SUM_STEP(11) OCGCN_SUM_STEP(12) }
+  }
+#undef OCGCN_SUM_STEP
+  return make_float2(s0, s1);
+}
+
 template <int STRIDE>
 __device__ __forceinline__ float4 rec_sum4(const uint4& rec, const float* colp) {
   const int cnt = rec_cnt(rec);
@@ -164,8 +214,9 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
   u64* sRow = reinterpret_cast<u64*>(sCRec + TR);
   u64* sCol = sRow + (size_t)TR * NW;
   float* mainp = reinterpret_cast<float*>(sCol + (size_t)TR * NW);
+  constexpr int BROWS = MM ? TR + 1 : TR;   // MM: row TR of each chunk buffer is the neutral dummy row of the padded neighbour records
   float* buf0 = mainp;
-  float* buf1 = buf0 + TR * BS;
+  float* buf1 = buf0 + BROWS * BS;
   float* sW = buf1 + TR * BS;                                          // MM == 0: weight chunk
   unsigned char* imgHi = reinterpret_cast<unsigned char*>(mainp + TR * TCP);  // MM == 1: operand images [8][kImgPitch], after the staging tile
   unsigned char* imgLo = imgHi + 8 * kImgPitch;
@@ -241,7 +292,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
     uint4 rec = make_uint4(0u, 0u, 0u, 0u), crec = make_uint4(0u, 0u, 0u, 0u);
     if (r < rows) {
       const int m = r / N, mb = m * N;
-      rec = rec_stage(__ldg(&a.nbr[row0 + r]), m, mb);
+      rec = MM ? rec_stage_padded(__ldg(&a.nbr[row0 + r]), m, mb, TR) : rec_stage(__ldg(&a.nbr[row0 + r]), m, mb);
       crec = rec_stage(__ldg(&a.cnbr[row0 + r]), m, mb);
     }
     sRec[r] = rec;
@@ -359,6 +410,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float2*>(&buf1[(warp + (h * 8 + q) * NWARP) * BS + 2 * lane]) = v[q];
         }
+        if (MM && warp == 0) *reinterpret_cast<float2*>(&buf1[TR * BS + 2 * lane]) = make_float2(0.f, 0.f);   // dummy row of the padded records
         __syncthreads();
       } else if (PROD == P_MID || PROD == P_RO) {
         float2 sc = make_float2(0.f, 0.f), sh = make_float2(0.f, 0.f);
@@ -387,6 +439,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
             }
           }
         }
+        if (MM && warp == 0) *reinterpret_cast<float2*>(&bufT[TR * BS + 2 * lane]) = make_float2(-INFINITY, -INFINITY);   // dummy row: never wins a max
         __syncthreads();
         // neighbour max-pool: P[i,c] = max_j A[i,j]*T[j,c], first index wins ties (gcn_encoder.py:44-50)
         for (int r = warp; r < TR; r += NWARP) {
@@ -397,7 +450,8 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
             int a0 = mb, a1 = mb;  // tile rows of the arg-max
             const bool flag = rec_binary(rec);
             if (flag && !rec_fallback(rec)) {
-              rec_max2<BS>(rec, &bufT[2 * lane], r, b0, b1, a0, a1);
+              if (MM) rec_max2_padded<BS>(rec, &bufT[2 * lane], b0, b1, a0, a1);
+              else rec_max2<BS>(rec, &bufT[2 * lane], r, b0, b1, a0, a1);
               if (rec_has_zero(rec)) {  // a zero entry A[i,jz] contributes the candidate 0*T = 0
                 const int jz = mb + rec_jz(rec);
                 if (!(b0 > 0.f)) { if (b0 < 0.f || jz < a0) a0 = jz; b0 = 0.f; }
@@ -443,6 +497,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
           if (PROD == P_RO) put_operand(bufH, r, make_float2(b0, b1));   // readout: the pooled H is the GEMM operand
           else *reinterpret_cast<float2*>(&bufH[r * BS + 2 * lane]) = make_float2(b0, b1);
         }
+        if (MM && PROD == P_MID && warp == 0) *reinterpret_cast<float2*>(&bufH[TR * BS + 2 * lane]) = make_float2(0.f, 0.f);   // dummy row: adds nothing
         if (MM && PROD == P_RO) tc::fence_async_smem();
         __syncthreads();
         if (MM && PROD == P_MID && use_mma && tid == 0) {   // T (buf0) is dead now: fetch the weight pieces over it
@@ -542,7 +597,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
             const int m = rec_m(rec), mb = m * N;
             const bool flag = rec_binary(rec);
             if (flag && !rec_fallback(rec)) {
-              s = rec_sum2<BS>(rec, &buf1[2 * lane], r);
+              s = MM ? rec_sum2_padded<BS>(rec, &buf1[2 * lane]) : rec_sum2<BS>(rec, &buf1[2 * lane], r);
             } else if (flag) {
               s.x = masked_sum(&sRow[(size_t)r * NW], NW, &buf1[mb * BS + 2 * lane], BS);
               s.y = masked_sum(&sRow[(size_t)r * NW], NW, &buf1[mb * BS + 2 * lane + 1], BS);
