@@ -42,7 +42,7 @@ __host__ __device__ inline size_t tile_smem_bytes(int NW) {
   size_t masks = (size_t)2 * TR * NW * sizeof(u64);
   size_t main_a = MM ? (size_t)TR * (TC + 4) * 4 + (size_t)2 * 8 * kImgPitch   // [chunk buffers | pad] = staging tile, then operand images
                      : (size_t)2 * TR * KCP * 4 + (size_t)KC * TC * 4;          // two chunk buffers + weight chunk
-  size_t main_b = (size_t)TR * (TC + 4) * 4 + (size_t)TR * TC;          // epilogue staging tile + arg-max tile (E_DY / E_ATG_DY)
+  size_t main_b = (size_t)(TR + 1) * (TC + 4) * 4 + (size_t)(TR + 1) * TC;   // epilogue staging tile + arg-max tile (E_DY / E_ATG_DY), dummy rows
   size_t mainsz = main_a > main_b ? main_a : main_b;
   return recs + masks + mainsz + (size_t)TR * 4 /*molecule flags*/ + (size_t)2 * (NT / 32) * 32 * 4 /*warp partials*/ + 64;
 }
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
   unsigned char* wHi = reinterpret_cast<unsigned char*>(buf0);                 // MM == 1: weight image pieces (hi, lo) alias buf0
   float* sC = mainp;  // epilogue staging, aliases buf0/buf1/sW
   constexpr size_t main_a = MM ? (size_t)TR * TCP + (size_t)2 * 8 * kImgPitch / 4 : (size_t)2 * TR * KCP + (size_t)KC * TC;
-  constexpr size_t main_b = (size_t)TR * TCP + (size_t)TR * TC / 4;
+  constexpr size_t main_b = (size_t)(TR + 1) * TCP + (size_t)(TR + 1) * TC / 4;
   constexpr size_t mainsz = main_a > main_b ? main_a : main_b;
   unsigned* sFlag = reinterpret_cast<unsigned*>(mainp + mainsz);
   float* sWarp = reinterpret_cast<float*>(sFlag + TR);
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
     if (r < rows) {
       const int m = r / N, mb = m * N;
       rec = MM ? rec_stage_padded(__ldg(&a.nbr[row0 + r]), m, mb, TR) : rec_stage(__ldg(&a.nbr[row0 + r]), m, mb);
-      crec = rec_stage(__ldg(&a.cnbr[row0 + r]), m, mb);
+      crec = MM ? rec_stage_padded(__ldg(&a.cnbr[row0 + r]), m, mb, TR) : rec_stage(__ldg(&a.cnbr[row0 + r]), m, mb);
     }
     sRec[r] = rec;
     sCRec[r] = crec;
@@ -735,6 +735,8 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
 #pragma unroll
         for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(&sC[row * TCP + cl + i]) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
+      if ((EPI == E_DY || EPI == E_ATG_DY) && warp == 0)   // all-zero dummy row of the padded column records
+        *reinterpret_cast<float4*>(&sC[TR * TCP + lane * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
       tc::fence_before_sync();
       __syncthreads();
       if (EPI == E_ZSTATS || EPI == E_STORE || EPI == E_READOUT) {
@@ -963,7 +965,10 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
     } else if (EPI == E_DY || EPI == E_ATG_DY) {
       // ---- fused first half of the previous layer's backward (gcn_encoder.py:43-50 differentiated) ----
       // staged tile -> dH (A^T gather, in place) -> dT = pool scatter through the saved arg-max -> dY = dT*(1-T^2)
-      unsigned char* sArg = reinterpret_cast<unsigned char*>(sC + TR * TCP);   // [TR][TC] arg-max of the previous layer
+      // MM: row TR of the staged tile is the all-zero dummy row of the padded column records, row TR of the arg-max tile holds 0xff
+      // (no atom index) so a dummy neighbour never matches
+      unsigned char* sArg = reinterpret_cast<unsigned char*>(sC + (MM ? TR + 1 : TR) * TCP);   // [TR (+1)][TC] arg-max of the previous layer
+      if (MM && warp == 0) *reinterpret_cast<unsigned*>(&sArg[TR * TC + lane * 4]) = 0xffffffffu;   // (the zero row of sC is written with the staging)
       {
         // TR * (TC / 16) / NT sixteen-byte pieces per thread: all loads first, then the stores
         constexpr int PPT = TR * (TC / 16) / NT;
@@ -1008,7 +1013,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
               const uint4 crec = sCRec[r];
               const int m = rec_m(crec), mb = m * N;
               if (rec_binary(crec) && !rec_fallback(crec)) {
-                sv = rec_sum2<TCP>(crec, &sC[cs + 2 * lane], r);
+                sv = MM ? rec_sum2_padded<TCP>(crec, &sC[cs + 2 * lane]) : rec_sum2<TCP>(crec, &sC[cs + 2 * lane], r);
               } else if (rec_binary(crec)) {
                 const u64* mk = &sCol[(size_t)r * NW];
                 sv.x = masked_sum(mk, NW, &sC[mb * TCP + cs + 2 * lane], TCP);
@@ -1072,8 +1077,9 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
             if (OK && ((AG >> 16) & 0xffu) == jrel) dt[2] += G.z;                             \
             if (OK && (AG >> 24) == jrel) dt[3] += G.w;
             {   // first four neighbours without branches: all eight shared-memory loads in flight at once
-              const int i0 = cnt > 0 ? rec_idx<0>(crec) : r, i1 = cnt > 1 ? rec_idx<1>(crec) : i0;
-              const int i2 = cnt > 2 ? rec_idx<2>(crec) : i0, i3 = cnt > 3 ? rec_idx<3>(crec) : i0;
+              // (MM: padded records — unused slots point at the dummy rows, no count checks; FFMA engine: re-read a valid row, masked)
+              const int i0 = (MM || cnt > 0) ? rec_idx<0>(crec) : r, i1 = (MM || cnt > 1) ? rec_idx<1>(crec) : i0;
+              const int i2 = (MM || cnt > 2) ? rec_idx<2>(crec) : i0, i3 = (MM || cnt > 3) ? rec_idx<3>(crec) : i0;
               const float4 g0 = *reinterpret_cast<const float4*>(&sC[i0 * TCP + cl]);
               const float4 g1 = *reinterpret_cast<const float4*>(&sC[i1 * TCP + cl]);
               const float4 g2 = *reinterpret_cast<const float4*>(&sC[i2 * TCP + cl]);
@@ -1082,7 +1088,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
               const unsigned q1 = *reinterpret_cast<const unsigned*>(&sArg[i1 * TC + cl]);
               const unsigned q2 = *reinterpret_cast<const unsigned*>(&sArg[i2 * TC + cl]);
               const unsigned q3 = *reinterpret_cast<const unsigned*>(&sArg[i3 * TC + cl]);
-              const bool k0 = cnt > 0, k1 = cnt > 1, k2 = cnt > 2, k3 = cnt > 3;
+              const bool k0 = MM || cnt > 0, k1 = MM || cnt > 1, k2 = MM || cnt > 2, k3 = MM || cnt > 3;
               OCGCN_SCAT_ADD(g0, q0, k0) OCGCN_SCAT_ADD(g1, q1, k1) OCGCN_SCAT_ADD(g2, q2, k2) OCGCN_SCAT_ADD(g3, q3, k3)
             }
 #define OCGCN_SCAT_STEP(Q)                                                                    \
