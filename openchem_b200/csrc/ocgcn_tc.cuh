@@ -139,13 +139,12 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {  // a -> low half (lower address)
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
-// two fp32 -> packed bf16x2 hi and lo words (element 0 in the low half)
+// two fp32 -> packed bf16x2 hi and lo words (element 0 in the low half): two packed conversions (round to nearest even,
+// identical to the scalar split), the hi halves are re-expanded with one shift / one mask
 __device__ __forceinline__ void split2_bf16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 h0, l0, h1, l1;
-  split_bf16(x0, h0, l0);
-  split_bf16(x1, h1, l1);
-  hi = pack_bf16(h0, h1);
-  lo = pack_bf16(l0, l1);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
 }
 // tf32: hi keeps the top 19 bits (the MMA ignores the low 13 mantissa bits), lo = x - hi (exact in fp32)
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
