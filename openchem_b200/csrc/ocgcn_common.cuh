@@ -188,11 +188,13 @@ __device__ __forceinline__ float masked_sum(const u64* mk, int NW, const float* 
 
 // tanh(x) = 1 - 2/(exp(2x)+1) on the SFU (MUFU.EX2 + MUFU.RCP): absolute error <~ 3e-7 over the whole range,
 // saturates correctly (+-1) for large |x|. Same function in forward and backward.
-__device__ __forceinline__ float fast_tanh(float x) {
+constexpr float kTanhScale = 2.8853900817779268f;   // 2 * log2(e)
+__device__ __forceinline__ float fast_tanh_scaled(float xs) {   // tanh(x) given xs = x * kTanhScale
   float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xs));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
   return fmaf(-2.f, r, 1.f);
 }
+__device__ __forceinline__ float fast_tanh(float x) { return fast_tanh_scaled(x * kTanhScale); }
 
 }  // namespace ocgcn

@@ -416,6 +416,8 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
         float2 sc = make_float2(0.f, 0.f), sh = make_float2(0.f, 0.f);
         if (v0) { sc.x = __ldg(&a.vec0[c]); sh.x = __ldg(&a.vec1[c]); }
         if (v1) { sc.y = __ldg(&a.vec0[c + 1]); sh.y = __ldg(&a.vec1[c + 1]); }
+        // (the 2*log2(e) factor of the exp2-based tanh is folded into the lane's scale / shift: one multiply less per element)
+        const float2 scs = make_float2(sc.x * kTanhScale, sc.y * kTanhScale), shs = make_float2(sh.x * kTanhScale, sh.y * kTanhScale);
         {
           constexpr int TB = (RPW > 16) ? 16 : RPW;   // rows per batch: all their loads are in flight before the first tanh
 #pragma unroll
@@ -432,8 +434,8 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
               const int r = warp + (h * TB + q) * NWARP;
               float2 t = make_float2(0.f, 0.f);
               if (r < rows) {
-                if (v0) t.x = fast_tanh(fmaf(v[q].x, sc.x, sh.x));
-                if (v1) t.y = fast_tanh(fmaf(v[q].y, sc.y, sh.y));
+                if (v0) t.x = fast_tanh_scaled(fmaf(v[q].x, scs.x, shs.x));
+                if (v1) t.y = fast_tanh_scaled(fmaf(v[q].y, scs.y, shs.y));
               }
               *reinterpret_cast<float2*>(&bufT[r * BS + 2 * lane]) = t;
             }
@@ -643,10 +645,12 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
 #pragma unroll
                 for (int p = 0; p < NPASS; ++p) {
                   const uint32_t ab = (p & 1) ? aLo : aHi, bb = (p & 2) ? bLo : bHi;
+                  // (descriptor of K step ks = base + ks * step: only the 14-bit start-address field moves, it cannot carry out)
+                  uint64_t da = tc::make_desc(ab, kImgPitch, 128), db = tc::make_desc(bb, 128 * 16, 128);
                   for (int ks = 0; ks < nks; ++ks) {
-                    const uint64_t da = tc::make_desc(ab + ks * 2 * kImgPitch, kImgPitch, 128);
-                    const uint64_t db = tc::make_desc(bb + ks * 2 * (128 * 16), 128 * 16, 128);
                     tc::mma_ss<false>(tmem + (uint32_t)(cbi * kTmemCols), da, db, idesc, (k0 > 0 || p > 0 || ks > 0) ? 1u : 0u);
+                    da += (uint64_t)((2 * kImgPitch) >> 4);
+                    db += (uint64_t)((2 * 128 * 16) >> 4);
                   }
                 }
               }
@@ -1043,12 +1047,12 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
         const int cl = lane * 4, gc = cb + cl;
         const bool act = cl < TC && gc < NC;
         const bool vec4 = (NC % 4 == 0);
-        float sc[4], sh[4], mu[4], is[4], s1[4], s2[4];
+        float scs[4], shs[4], mu[4], is[4], s1[4], s2[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const bool ok = act && gc + e < NC;
-          sc[e] = ok ? __ldg(&a.pv_scale[gc + e]) : 0.f;
-          sh[e] = ok ? __ldg(&a.pv_shift[gc + e]) : 0.f;
+          scs[e] = ok ? __ldg(&a.pv_scale[gc + e]) * kTanhScale : 0.f;   // (tanh scale folded in, as in the forward)
+          shs[e] = ok ? __ldg(&a.pv_shift[gc + e]) * kTanhScale : 0.f;
           mu[e] = ok ? __ldg(&a.pv_mean[gc + e]) : 0.f;
           is[e] = ok ? __ldg(&a.pv_invstd[gc + e]) : 0.f;
           s1[e] = 0.f;
@@ -1129,7 +1133,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
           float dy[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float t = fast_tanh(fmaf(zz[e], sc[e], sh[e]));
+            const float t = fast_tanh_scaled(fmaf(zz[e], scs[e], shs[e]));
             dy[e] = (gc + e < NC) ? dt[e] * (1.f - t * t) : 0.f;
             s1[e] += dy[e];
             s2[e] = fmaf(dy[e], (zz[e] - mu[e]) * is[e], s2[e]);

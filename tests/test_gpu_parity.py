@@ -214,22 +214,56 @@ TC_SHAPES = [
 ]
 
 
+TC_TIE = 1e-4   # forward resolution of the tensor-core classes (outputs agree to ~3e-5): two pool candidates closer than this are a near-tie
+
+
 def _tc_check(x, adj, p, dO, cfg, precision, label):
+    """Tensor-core classes vs the fp64 oracle. The max-pool routes gradients through an arg-max, so two candidates closer than
+    the forward's resolution may legitimately be ordered differently (the reference's own fp32 run differs from its fp64 run in
+    the same way: ~10 routings of 360 k at the C1 shape, worth 3e-3 on the gradients). Same method as the fp32-class test:
+    (1) every routing that differs from the oracle's must be such a near-tie and they must be rare, (2) outputs within 1e-2,
+    (3) gradients within 1e-2 of the oracle's gradients evaluated with the routing the kernel used, (4) the raw, un-overridden
+    gradient deviation stays bounded as well."""
     from oracle import gcn_oracle as orc
+    from openchem_b200 import functional
     dev = _dev()
+    B, N = x.shape[0], x.shape[1]
     L = cfg["n_layers"]
     p64 = orc.cast_params(p, np.float64)
     x64, a64 = x.astype(np.float64), adj.astype(np.float64)
     O, cache, rms, rvs = orc.encoder_forward(x64, a64, p64, training=True)
     Oe = orc.encoder_forward(x64, a64, dict(p64, running_mean=rms, running_var=rvs), training=False)[0]
-    gr = orc.encoder_backward(dO.astype(np.float64), cache)
-    ref = dict(out_train=O, out_eval=Oe, dWd=gr["dWd"], dbd=gr["dbd"])
-    for l in range(L):
-        ref.update({f"dW{l}": gr["dW"][l], f"db{l}": gr["db"][l], f"dgamma{l}": gr["dgamma"][l], f"dbeta{l}": gr["dbeta"][l],
-                    f"rm{l}": rms[l], f"rv{l}": rvs[l]})
     enc = build_encoder(cfg, p, dev, precision=precision)
-    res = _run_encoder(enc, x, adj, dO, dev)
-    return _compare(res, ref, L, TC_TOL, f"{label} [{precision}]")
+    functional.debug_keep["on"] = True
+    try:
+        enc.train()
+        tx, ta = torch.from_numpy(x).to(dev), torch.from_numpy(adj).to(dev)
+        out = enc((tx, ta))
+        args = [functional.saved_tensor("argmax", l).cpu().numpy().reshape(B, N, -1).astype(np.int64) for l in range(L)]
+    finally:
+        functional.debug_keep.update(on=False, saved=None, desc=None)
+    n_mism = 0
+    for l in range(L):
+        T, oarg = cache["layers"][l]["T"], cache["layers"][l]["arg"]
+        for b, i, c in np.argwhere(args[l] != oarg):
+            ja, jo = args[l][b, i, c], oarg[b, i, c]
+            va, vo = a64[b, i, ja] * T[b, ja, c], a64[b, i, jo] * T[b, jo, c]
+            assert abs(va - vo) < TC_TIE, f"{label} layer {l} {(b, i, c)}: arg-max {ja} vs oracle {jo} is not a near-tie ({va} vs {vo})"
+            n_mism += 1
+    assert n_mism <= 2e-4 * sum(a.size for a in args) + 2, n_mism
+    res = _run_encoder(enc, x, adj, dO, dev, fwd_out=out)
+
+    def ref_with(routing):
+        gr = orc.encoder_backward(dO.astype(np.float64), cache, arg_override=routing)
+        ref = dict(out_train=O, out_eval=Oe, dWd=gr["dWd"], dbd=gr["dbd"])
+        for l in range(L):
+            ref.update({f"dW{l}": gr["dW"][l], f"db{l}": gr["db"][l], f"dgamma{l}": gr["dgamma"][l], f"dbeta{l}": gr["dbeta"][l],
+                        f"rm{l}": rms[l], f"rv{l}": rvs[l]})
+        return ref
+
+    worst = _compare(res, ref_with(args), L, TC_TOL, f"{label} [{precision}] ({n_mism} near-tie routings)")
+    _compare(res, ref_with(None), L, 5 * TC_TOL, f"{label} [{precision}] raw, no routing override")
+    return worst
 
 
 @pytest.mark.parametrize("precision", ["bf16", "tf32"])
