@@ -1075,11 +1075,17 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
           if (rec_binary(crec) && !rec_fallback(crec)) {
             // dT[j,c] = sum over rows i that list j as a neighbour and whose arg-max in channel c is j
             const int cnt = rec_cnt(crec);
+            // one XOR per neighbour turns "arg-max byte == my index" into "byte of x is zero": a single logic op with predicate
+            // output per channel instead of extract + compare
+            const unsigned jrel4 = jrel * 0x01010101u;
 #define OCGCN_SCAT_ADD(G, AG, OK)                                                             \
-            if (OK && (AG & 0xffu) == jrel) dt[0] += G.x;                                     \
-            if (OK && ((AG >> 8) & 0xffu) == jrel) dt[1] += G.y;                              \
-            if (OK && ((AG >> 16) & 0xffu) == jrel) dt[2] += G.z;                             \
-            if (OK && (AG >> 24) == jrel) dt[3] += G.w;
+            {                                                                                 \
+              const unsigned x_ = (AG) ^ jrel4;                                               \
+              if (OK && !(x_ & 0x000000ffu)) dt[0] += G.x;                                    \
+              if (OK && !(x_ & 0x0000ff00u)) dt[1] += G.y;                                    \
+              if (OK && !(x_ & 0x00ff0000u)) dt[2] += G.z;                                    \
+              if (OK && !(x_ & 0xff000000u)) dt[3] += G.w;                                    \
+            }
             {   // first four neighbours without branches: all eight shared-memory loads in flight at once
               // (MM: padded records — unused slots point at the dummy rows, no count checks; FFMA engine: re-read a valid row, masked)
               const int i0 = (MM || cnt > 0) ? rec_idx<0>(crec) : r, i1 = (MM || cnt > 1) ? rec_idx<1>(crec) : i0;
