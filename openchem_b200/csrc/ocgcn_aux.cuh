@@ -43,7 +43,6 @@ __global__ void __launch_bounds__(kThreads) adj_pack_kernel(const float* __restr
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* ab = adj + (long long)b * as0;
   int nonbin = 0;
-  for (int idx = tid; idx < N * NW; idx += kThreads) sCm[idx] = 0ull;
   for (int i = warp; i < N; i += kWarps) {
     for (int w = 0; w < NW; ++w) {
       const int j0 = 64 * w + lane, j1 = j0 + 32;
@@ -59,20 +58,21 @@ __global__ void __launch_bounds__(kThreads) adj_pack_kernel(const float* __restr
     }
   }
   nonbin = __syncthreads_or(nonbin);
-  // column masks = bit transpose of the row masks: every thread gathers 16 bits of one word, OR-merged in shared memory
-  for (int idx = tid; idx < N * NW * 4; idx += kThreads) {
-    const int word = idx >> 2, part = idx & 3;
-    const int j = word / NW, w = word - j * NW;
-    u64 bitsv = 0;
-#pragma unroll 4
-    for (int ii = 16 * part; ii < 16 * part + 16; ++ii) {
-      const int i = 64 * w + ii;
-      if (i < N) bitsv |= ((sR[i * NW + (j >> 6)] >> (j & 63)) & 1ull) << ii;
+  // column masks = bit transpose of the row masks, by ballots: lane = row inside a group of 32 rows, one vote per column
+  for (int j = warp; j < N; j += kWarps) {
+    const int jw = j >> 6, jb = j & 63;
+    for (int w = 0; w < NW; ++w) {
+      const int i0 = 64 * w + lane, i1 = i0 + 32;
+      const unsigned b0 = __ballot_sync(0xffffffffu, i0 < N && ((sR[i0 * NW + jw] >> jb) & 1ull));
+      const unsigned b1 = __ballot_sync(0xffffffffu, i1 < N && ((sR[i1 * NW + jw] >> jb) & 1ull));
+      if (lane == 0) {
+        const u64 word = (u64)b0 | ((u64)b1 << 32);
+        sCm[j * NW + w] = word;
+        colmask[((size_t)b * N + j) * NW + w] = word;
+      }
     }
-    if (bitsv) atomicOr(reinterpret_cast<unsigned long long*>(&sCm[word]), bitsv);
   }
   __syncthreads();
-  for (int idx = tid; idx < N * NW; idx += kThreads) colmask[(size_t)b * N * NW + idx] = sCm[idx];
   for (int i = tid; i < 2 * N; i += kThreads) {   // one 16-byte neighbour record per row and per column
     if (i < N) nbr[(size_t)b * N + i] = build_record(&sR[i * NW], NW, N, !nonbin);
     else cnbr[(size_t)b * N + (i - N)] = build_record(&sCm[(i - N) * NW], NW, N, !nonbin);
@@ -542,7 +542,10 @@ struct SumJob {
   __device__ __forceinline__ void finish(int c, const double* acc) const { out[c] = (float)acc[0]; }
 };
 // matrix job, 16-byte loads: a CTA owns 128 consecutive outputs (32 threads x float4) x 32 row lanes; fixed-order fp64 folds
-__device__ __forceinline__ void wide_reduce_vec4(const float* __restrict__ p, float* __restrict__ out, int P, int cnt, int cgroup, double* sbuf) {
+// tr_cols > 0: each partial holds the transpose [tr_cols][cnt / tr_cols] of the [cnt / tr_cols][tr_cols] output (fused readout
+// gradient dWd^T): the 16-byte loads run along the partial's rows, the (few) results are stored transposed
+__device__ __forceinline__ void wide_reduce_vec4(const float* __restrict__ p, float* __restrict__ out, int P, int cnt, int cgroup, double* sbuf,
+                                                 int tr_cols) {
   double (*sred4)[128] = reinterpret_cast<double (*)[128]>(sbuf);   // [32][128]
   const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = cgroup * 128 + cq * 4;
@@ -564,10 +567,12 @@ __device__ __forceinline__ void wide_reduce_vec4(const float* __restrict__ p, fl
     double t = 0.0;
 #pragma unroll 8
     for (int k = 0; k < 32; ++k) t += sred4[k][threadIdx.x];
-    out[cgroup * 128 + threadIdx.x] = (float)t;
+    const int c = cgroup * 128 + (int)threadIdx.x;          // index in the partial's layout
+    const int tr_rows = tr_cols ? cnt / tr_cols : 0;        // partial is [tr_cols][tr_rows] -> out[(c % tr_rows) * tr_cols + c / tr_rows]
+    out[tr_cols ? (c % tr_rows) * tr_cols + c / tr_rows : c] = (float)t;
   }
 }
-static inline bool reduce_job_vec4(int matrix, int tr_cols, int count) { return matrix && tr_cols == 0 && count % 4 == 0; }
+static inline bool reduce_job_vec4(int matrix, int tr_cols, int count) { return matrix && count % 4 == 0 && (tr_cols == 0 || (count / tr_cols) % 4 == 0); }
 
 __global__ void __launch_bounds__(kRedThreads) reduce_partials_kernel(const ReduceJobs jobs) {
   int jb = 0;
@@ -575,8 +580,8 @@ __global__ void __launch_bounds__(kRedThreads) reduce_partials_kernel(const Redu
   const int cg = (int)blockIdx.x - jobs.first_cta[jb];
   __shared__ double sbuf[32 * 128];   // one buffer for whichever path this CTA takes
   static_assert(wide_reduce_smem<1, 32>() <= 32 * 128 && wide_reduce_smem<1, kChanCols>() <= 32 * 128, "shared reduction buffer");
-  if (jobs.matrix[jb] && jobs.tr_cols[jb] == 0 && jobs.count[jb] % 4 == 0) {
-    wide_reduce_vec4(jobs.partial[jb], jobs.out[jb], jobs.P[jb], jobs.count[jb], cg, sbuf);
+  if (jobs.matrix[jb] && jobs.count[jb] % 4 == 0 && (jobs.tr_cols[jb] == 0 || (jobs.count[jb] / jobs.tr_cols[jb]) % 4 == 0)) {
+    wide_reduce_vec4(jobs.partial[jb], jobs.out[jb], jobs.P[jb], jobs.count[jb], cg, sbuf, jobs.tr_cols[jb]);
     return;
   }
   SumJob job{jobs.partial[jb], jobs.out[jb], jobs.count[jb], jobs.tr_cols[jb]};
