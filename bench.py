@@ -402,6 +402,14 @@ def run_native(args, w, wname):
         }.get(top)
         if alg is not None:
             flops_launch, bytes_launch = alg
+            if top == "bwd_dz":
+                # its L launches are not alike: the one for layer 0 has no dS product, no fused epilogue and a narrower S image.
+                # Use the mean algorithmic work per launch (sum over the L launches / L), matching the mean launch time below.
+                nL = len(F) - 1
+                light_b = R * (F[1] * 8 + (F[0] * simg if fused else F[1] * simg))
+                light_f = B * (2 * N * F[0] * F[1]) if fused else 0
+                bytes_launch = ((nL - 1) * bytes_launch + light_b) / nL
+                flops_launch = ((nL - 1) * flops_launch + light_f) / nL
             t_hbm = bytes_launch / (peaks["hbm_gbs"] * 1e9)
             t_tensor = flops_launch / (peaks["bf16_burst"] * 1e12)
             traffic = None
