@@ -164,3 +164,40 @@ def test_namespace_shadow_resolves_to_this_package():
         for k in [k for k in sys.modules if k == "openchem" or k.startswith("openchem.")]:
             sys.modules.pop(k)
         sys.modules.update(saved)
+
+
+def test_header_compiles_as_plain_c_and_links(tmp_path):
+    """include/ocgcn.h is a C header (no C++/torch types): a C translation unit including it must compile with gcc, link
+    against libocgcn.so and get sane answers from the host-only entry points."""
+    import shutil
+    import subprocess
+    from openchem_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    _lib.load()
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "ocgcn.h"
+int main(void) {
+  ocgcn_desc d;
+  memset(&d, 0, sizeof d);
+  d.B = 8; d.N = 20; d.L = 2; d.E = 12; d.F[0] = 33; d.F[1] = 16; d.F[2] = 8;
+  d.mode = OCGCN_BF16; d.training = 1; d.has_bias = 1; d.eps = 1e-5f; d.momentum = 0.1f;
+  size_t saved = 0, scratch = 0;
+  int rc = ocgcn_query_workspace(&d, &saved, &scratch);
+  printf("%d %d %zu %zu %s\n", ocgcn_abi_version(), rc, saved, scratch, ocgcn_status_string(OCGCN_EARCH));
+  d.N = 1000;
+  printf("%d\n", ocgcn_query_workspace(&d, &saved, &scratch));
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:libocgcn.so", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    first = out[0].split(" ", 4)
+    assert first[0] == "1" and first[1] == "0" and int(first[2]) > 0 and int(first[3]) > 0 and "sm_100" in first[4]
+    assert out[1].strip() == "2"      # N > 256: OCGCN_EUNSUPPORTED
