@@ -245,7 +245,12 @@ static int run_dw_mma(const Layout& lo, const void* Aimg, const void* Bimg, int 
   int splits = lo.tiles < 148 ? lo.tiles : 148;
   g.tiles_per_cta = (lo.tiles + splits - 1) / splits;
   splits = (lo.tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
-  const size_t stage = dw_stage_bytes(g.chA, g.chB);
+  g.rows_per_stage = 128;
+  size_t stage = dw_stage_bytes(g.chA, g.chB, 128);
+  if ((size_t)(200 * 1024) / stage < 2) {   // wide layers: half-tile stages keep the copy / MMA pipeline at least three deep
+    g.rows_per_stage = 64;
+    stage = dw_stage_bytes(g.chA, g.chB, 64);
+  }
   int stages = (int)((size_t)(200 * 1024) / stage);
   stages = stages < 1 ? 1 : stages > 4 ? 4 : stages;
   g.stages = stages;

@@ -52,15 +52,21 @@ struct DwArgs {
   int tiles, chA, chB;
   int M, Nn;          // true output extents
   int tiles_per_cta, stages;
+  int rows_per_stage; // 128: one stage = one whole tile image (one bulk copy per operand); 64: half tiles (one 1 KB copy per chunk),
+                      // used when a whole-tile stage would leave room for only one stage
   float* partial;     // [gridDim.x][M][Nn]
 };
-static inline size_t dw_stage_bytes(int chA, int chB) { return (size_t)(chA > 16 ? chA : 16) * 2048 + (size_t)chB * 2048; }
+static inline size_t dw_stage_bytes(int chA, int chB, int rows_per_stage) {
+  return ((size_t)(chA > 16 ? chA : 16) + (size_t)chB) * 16 * rows_per_stage;
+}
 
 __global__ void __launch_bounds__(128) dw_mma_kernel(const DwArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int chA = a.chA, chB = a.chB, S = a.stages;
-  const uint32_t aBytes = (uint32_t)chA * 2048u, aAlloc = (uint32_t)(chA > 16 ? chA : 16) * 2048u, bBytes = (uint32_t)chB * 2048u;
+  const int RS = a.rows_per_stage, halves = 128 / RS;
+  const uint32_t cpitch = (uint32_t)RS * 16u;   // bytes of one 16-byte-wide channel chunk inside a stage
+  const uint32_t aBytes = (uint32_t)chA * cpitch, aAlloc = (uint32_t)(chA > 16 ? chA : 16) * cpitch, bBytes = (uint32_t)chB * cpitch;
   const uint32_t stageBytes = aAlloc + bBytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stageBytes);
   uint64_t* empty = full + S;
@@ -91,29 +97,37 @@ __global__ void __launch_bounds__(128) dw_mma_kernel(const DwArgs a) {
   const uint32_t tmem = *slot;
 
   if (warp == 0 && lane == 0) {
-    // producer: one bulk copy per operand image and tile
-    const unsigned char* ga = reinterpret_cast<const unsigned char*>(a.Aimg) + (size_t)t0 * aBytes;
-    const unsigned char* gb = reinterpret_cast<const unsigned char*>(a.Bimg) + (size_t)t0 * bBytes;
-    for (int i = 0; i < nt; ++i) {
+    // producer: stage i = rows [RS*(i % halves), +RS) of tile t0 + i / halves; one bulk copy per operand image (whole tiles) or
+    // per 16-byte channel chunk (half tiles: the chunk's rows are contiguous in the tile image)
+    const unsigned char* ga = reinterpret_cast<const unsigned char*>(a.Aimg) + (size_t)t0 * chA * 2048;
+    const unsigned char* gb = reinterpret_cast<const unsigned char*>(a.Bimg) + (size_t)t0 * chB * 2048;
+    for (int i = 0; i < nt * halves; ++i) {
       const int s = i % S;
       if (i >= S) tc::mbar_wait(&empty[s], (uint32_t)((i / S) - 1) & 1u);
       unsigned char* st = smem + (size_t)s * stageBytes;
+      const size_t ta = (size_t)(i / halves) * chA * 2048 + (size_t)(i % halves) * cpitch;
+      const size_t tb = (size_t)(i / halves) * chB * 2048 + (size_t)(i % halves) * cpitch;
       tc::mbar_expect_tx(&full[s], aBytes + bBytes);
-      tc::bulk_g2s(st, ga + (size_t)i * aBytes, aBytes, &full[s]);
-      tc::bulk_g2s(st + aAlloc, gb + (size_t)i * bBytes, bBytes, &full[s]);
+      if (halves == 1) {
+        tc::bulk_g2s(st, ga + ta, aBytes, &full[s]);
+        tc::bulk_g2s(st + aAlloc, gb + tb, bBytes, &full[s]);
+      } else {
+        for (int c = 0; c < chA; ++c) tc::bulk_g2s(st + (size_t)c * cpitch, ga + ta + (size_t)c * 2048, cpitch, &full[s]);
+        for (int c = 0; c < chB; ++c) tc::bulk_g2s(st + aAlloc + (size_t)c * cpitch, gb + tb + (size_t)c * 2048, cpitch, &full[s]);
+      }
     }
   } else if (warp == 1 && lane == 0) {
     // MMA issuer: D[m][n] += sum over the tile's 128 rows of A[row][m] * B[row][n]  (both operands MN-major)
     const uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, ncols, true, true);
-    for (int i = 0; i < nt; ++i) {
+    for (int i = 0; i < nt * halves; ++i) {
       const int s = i % S;
       tc::mbar_wait(&full[s], (uint32_t)(i / S) & 1u);
       tc::fence_after_sync();
       const uint32_t sa = tc::smem_u32(smem + (size_t)s * stageBytes), sb = sa + aAlloc;
       for (int mb = 0; mb < mblocks; ++mb)
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t da = tc::make_desc(sa + (uint32_t)mb * 16u * 2048u + (uint32_t)ks * 256u, 128, 2048);
-          const uint64_t db = tc::make_desc(sb + (uint32_t)ks * 256u, 128, 2048);
+        for (int ks = 0; ks < RS / 16; ++ks) {
+          const uint64_t da = tc::make_desc(sa + (uint32_t)mb * 16u * cpitch + (uint32_t)ks * 256u, 128, cpitch);
+          const uint64_t db = tc::make_desc(sb + (uint32_t)ks * 256u, 128, cpitch);
           tc::mma_ss<false>(tmem + (uint32_t)(mb * ncols), da, db, idesc, (i > 0 || ks > 0) ? 1u : 0u);
         }
       tc::mma_commit(&empty[s]);
