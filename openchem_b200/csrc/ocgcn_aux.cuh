@@ -43,17 +43,27 @@ __global__ void __launch_bounds__(kThreads) adj_pack_kernel(const float* __restr
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* ab = adj + (long long)b * as0;
   int nonbin = 0;
-  for (int i = warp; i < N; i += kWarps) {
+  // rows in batches of four per warp: the eight loads of a batch are in flight together (the kernel is latency-bound otherwise)
+  for (int i0 = warp; i0 < N; i0 += 4 * kWarps) {
     for (int w = 0; w < NW; ++w) {
       const int j0 = 64 * w + lane, j1 = j0 + 32;
-      const float v0 = (j0 < N) ? __ldg(&ab[(long long)i * as1 + (long long)j0 * as2]) : 0.f;
-      const float v1 = (j1 < N) ? __ldg(&ab[(long long)i * as1 + (long long)j1 * as2]) : 0.f;
-      nonbin |= (v0 != 0.f && v0 != 1.f) | (v1 != 0.f && v1 != 1.f);
-      const unsigned b0 = __ballot_sync(0xffffffffu, v0 != 0.f), b1 = __ballot_sync(0xffffffffu, v1 != 0.f);
-      if (lane == 0) {
-        const u64 word = (u64)b0 | ((u64)b1 << 32);
-        sR[i * NW + w] = word;
-        rowmask[((size_t)b * N + i) * NW + w] = word;
+      float v0[4], v1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kWarps;
+        v0[u] = (i < N && j0 < N) ? __ldg(&ab[(long long)i * as1 + (long long)j0 * as2]) : 0.f;
+        v1[u] = (i < N && j1 < N) ? __ldg(&ab[(long long)i * as1 + (long long)j1 * as2]) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kWarps;
+        nonbin |= (v0[u] != 0.f && v0[u] != 1.f) | (v1[u] != 0.f && v1[u] != 1.f);
+        const unsigned b0 = __ballot_sync(0xffffffffu, v0[u] != 0.f), b1 = __ballot_sync(0xffffffffu, v1[u] != 0.f);
+        if (lane == 0 && i < N) {
+          const u64 word = (u64)b0 | ((u64)b1 << 32);
+          sR[i * NW + w] = word;
+          rowmask[((size_t)b * N + i) * NW + w] = word;
+        }
       }
     }
   }
