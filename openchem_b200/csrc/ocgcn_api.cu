@@ -330,7 +330,8 @@ static int run_bn_finalize(const ocgcn_desc* d, const Layout& lo, const ocgcn_pa
   f.running_mean = p->running_mean[l]; f.running_var = p->running_var[l];
   f.nbt = reinterpret_cast<long long*>(p->num_batches_tracked[l]);
   f.mean = stats; f.invstd = stats + F; f.scale = stats + 2 * F; f.shift = stats + 3 * F;
-  bn_finalize_kernel<<<(F + kChanCols - 1) / kChanCols, kRedThreads, 0, st>>>(f);
+  if (d->training && chan_wide(lo.tiles)) bn_finalize_kernel<kChanColsWide><<<(F + kChanColsWide - 1) / kChanColsWide, kRedThreads, 0, st>>>(f);
+  else bn_finalize_kernel<kChanCols><<<(F + kChanCols - 1) / kChanCols, kRedThreads, 0, st>>>(f);
   LAUNCH_CHECK();
   return OCGCN_OK;
 }
@@ -441,7 +442,8 @@ static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float
   f.g = coef; f.c1 = coef + lo.Fmax; f.c2 = coef + 2 * lo.Fmax;
   {
     ProfScope prof(KK_BWD_FINALIZE, st);
-    bwd_finalize_kernel<<<(Fout + kChanCols - 1) / kChanCols, kRedThreads, 0, st>>>(f);
+    if (chan_wide(lo.tiles)) bwd_finalize_kernel<kChanColsWide><<<(Fout + kChanColsWide - 1) / kChanColsWide, kRedThreads, 0, st>>>(f);
+    else bwd_finalize_kernel<kChanCols><<<(Fout + kChanCols - 1) / kChanCols, kRedThreads, 0, st>>>(f);
     LAUNCH_CHECK();
   }
 

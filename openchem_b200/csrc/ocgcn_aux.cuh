@@ -212,11 +212,15 @@ struct BnJob {
     a.shift[c] = a.beta[c] - (float)mean * sc;
   }
 };
-constexpr int kChanCols = 8;   // per-channel jobs: 8 channels x 128 row lanes per CTA
+constexpr int kChanCols = 8;      // per-channel jobs: 8 channels x 128 row lanes per CTA
+constexpr int kChanColsWide = 2;  // ... or 2 channels x 512 row lanes when there are many partial rows (the job is a latency chain:
+                                  // more CTAs and fewer rows per thread shorten it)
+static inline bool chan_wide(int rows) { return rows >= 1024; }
+template <int COLS>
 __global__ void __launch_bounds__(kRedThreads) bn_finalize_kernel(const BnFinalizeArgs a) {
   if (!a.training) {   // eval: running statistics
-    const int c = blockIdx.x * kChanCols + (threadIdx.x % kChanCols);
-    if (threadIdx.x >= kChanCols || c >= a.F) return;
+    const int c = blockIdx.x * COLS + (threadIdx.x % COLS);
+    if (threadIdx.x >= COLS || c >= a.F) return;
     const double mean = (double)a.running_mean[c], var = (double)a.running_var[c];
     const float invstd = (float)(1.0 / sqrt(var + (double)a.eps));
     const float sc = a.gamma[c] * invstd;
@@ -226,9 +230,9 @@ __global__ void __launch_bounds__(kRedThreads) bn_finalize_kernel(const BnFinali
     a.shift[c] = a.beta[c] - (float)mean * sc;
     return;
   }
-  __shared__ double sbuf[wide_reduce_smem<2, kChanCols>()];
+  __shared__ double sbuf[wide_reduce_smem<2, COLS>()];
   BnJob job{a};
-  wide_reduce<2, kChanCols>(job, a.T, a.F, blockIdx.x, sbuf);
+  wide_reduce<2, COLS>(job, a.T, a.F, blockIdx.x, sbuf);
 }
 
 // y = scale*z + shift (standalone GraphConvolution output, gcn.py:40)
@@ -464,10 +468,11 @@ struct BwdFinJob {
     a.c2[c] = a.training ? (float)(acc[1] / a.n) : 0.f;
   }
 };
+template <int COLS>
 __global__ void __launch_bounds__(kRedThreads) bwd_finalize_kernel(const BwdFinalizeArgs a) {
-  __shared__ double sbuf[wide_reduce_smem<2, kChanCols>()];
+  __shared__ double sbuf[wide_reduce_smem<2, COLS>()];
   BwdFinJob job{a};
-  wide_reduce<2, kChanCols>(job, a.T, a.F, blockIdx.x, sbuf);
+  wide_reduce<2, COLS>(job, a.T, a.F, blockIdx.x, sbuf);
 }
 
 // ---------------------------------------------------------------------------------------------------------
