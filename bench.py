@@ -416,14 +416,16 @@ def run_native(args, w, wname):
             tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
             if os.path.exists(tpath):
                 traffic = json.load(open(tpath)).get("%s/%s/%s" % (wname, args.precision, top))
+            tnote = "dram__bytes_read+write of ONE launch from the committed ncu --set full capture (profiles/r1_traffic.json); for bwd_dz that " \
+                    "is a full-layer launch, while achieved/algorithmic figures are means over the L launches (the layer-0 one is lighter)"
             if t_hbm >= t_tensor:
                 ach = bytes_launch / (ms_launch * 1e-3) / 1e9
-                roofline = dict(bound="hbm", kernel=top, achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"],
+                roofline = dict(bound="hbm", kernel=top, traffic_note=tnote, achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"],
                                 traffic=traffic, ms_per_launch=ms_launch, algorithmic_bytes_per_launch=bytes_launch,
                                 algorithmic_flops_per_launch=flops_launch, peak_source=peaks["source"] + ", STREAM-style copy")
             else:
                 ach = flops_launch / (ms_launch * 1e-3) / 1e12
-                roofline = dict(bound="tensor", kernel=top, achieved=ach, peak=peaks["bf16_burst"], unit="TFLOP/s", frac=ach / peaks["bf16_burst"],
+                roofline = dict(bound="tensor", kernel=top, traffic_note=tnote, achieved=ach, peak=peaks["bf16_burst"], unit="TFLOP/s", frac=ach / peaks["bf16_burst"],
                                 traffic=traffic, ms_per_launch=ms_launch, algorithmic_bytes_per_launch=bytes_launch,
                                 algorithmic_flops_per_launch=flops_launch, peak_source=peaks["source"] + ", burst bf16")
 
