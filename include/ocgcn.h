@@ -123,6 +123,20 @@ int ocgcn_layer_backward(const ocgcn_desc* desc, const float* grad_y, const floa
                          const ocgcn_params* params, const ocgcn_grads* grads, float* grad_x, void* saved,
                          void* scratch, void* stream);
 
+/* Compact batch format (replaces the dense fp32 upload of Graph2Label.cast_inputs, openchem/models/Graph2Label.py:41-57,
+ * for 0/1 adjacency and 0/1 node features — what utils/graph.py:57-63,80-84 produces). Bit (c & 31) of word
+ * bits[(mol*N + row)*ceil(C/32) + (c >> 5)] is set iff dense[mol][row][c] == 1.0f; C = N for adj_bits, F0 for x_bits.
+ *
+ * ocgcn_expand_compact writes the contiguous dense fp32 x (B,N,F0) and adj (B,N,N) the entry points above take (bit-exact).
+ * `index` (device, B int32, or NULL) gathers molecule index[b] of a compact data set resident in device memory into
+ * batch slot b. Either output (with its bits) may be NULL to skip it.
+ * ocgcn_pack_compact is the inverse for strided dense inputs (element strides, molecule/row/column); *nonbinary (device
+ * int32, zeroed by the call) is set to 1 if any entry is neither 0 nor 1 — such batches must use the dense entry points. */
+int ocgcn_expand_compact(int B, int N, int F0, const uint32_t* x_bits, const uint32_t* adj_bits, const int32_t* index,
+                         float* x, float* adj, void* stream);
+int ocgcn_pack_compact(int B, int N, int F0, const float* x, const int64_t* x_stride, const float* adj,
+                       const int64_t* adj_stride, uint32_t* x_bits, uint32_t* adj_bits, int32_t* nonbinary, void* stream);
+
 /* Opt-in, process-wide per-kernel timing (used by bench.py's roofline leg, never by training):
  * while enabled every kernel launch is bracketed by CUDA events recorded on the launching stream.
  * ocgcn_profile_collect synchronises those events, sums milliseconds and launch counts per kernel kind

@@ -14,7 +14,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libocgcn.so")
-SOURCES = ["ocgcn_api.cu", "ocgcn_tile.cuh", "ocgcn_aux.cuh", "ocgcn_common.cuh", "ocgcn_tc.cuh", "ocgcn_dw.cuh"]
+SOURCES = ["ocgcn_api.cu", "ocgcn_tile.cuh", "ocgcn_aux.cuh", "ocgcn_common.cuh", "ocgcn_tc.cuh", "ocgcn_dw.cuh", "ocgcn_compact.cuh"]
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "ocgcn.h")
 
 MAX_LAYERS = 16
@@ -55,7 +55,7 @@ EXPORTS = [
     "ocgcn_query_workspace", "ocgcn_encoder_forward", "ocgcn_encoder_backward", "ocgcn_layer_forward",
     "ocgcn_layer_backward", "ocgcn_last_launch_count", "ocgcn_last_cuda_error", "ocgcn_status_string",
     "ocgcn_abi_version", "ocgcn_profile_enable", "ocgcn_profile_kinds", "ocgcn_profile_kind_name", "ocgcn_profile_collect",
-    "ocgcn_saved_tensor",
+    "ocgcn_saved_tensor", "ocgcn_expand_compact", "ocgcn_pack_compact",
 ]
 
 
@@ -118,6 +118,11 @@ def load():
         lib.ocgcn_layer_backward.argtypes = [ctypes.POINTER(Desc), vp, vp, vp, ctypes.POINTER(Params), ctypes.POINTER(Grads), vp, vp, vp, vp]
         lib.ocgcn_saved_tensor.argtypes = [ctypes.POINTER(Desc), ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]
         lib.ocgcn_saved_tensor.restype = ctypes.c_int
+        i64p = ctypes.POINTER(ctypes.c_int64)
+        lib.ocgcn_expand_compact.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+        lib.ocgcn_expand_compact.restype = ctypes.c_int
+        lib.ocgcn_pack_compact.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, i64p, vp, i64p, vp, vp, vp, vp]
+        lib.ocgcn_pack_compact.restype = ctypes.c_int
         lib.ocgcn_profile_kind_name.restype = ctypes.c_char_p
         lib.ocgcn_profile_kind_name.argtypes = [ctypes.c_int]
         lib.ocgcn_profile_enable.argtypes = [ctypes.c_int]

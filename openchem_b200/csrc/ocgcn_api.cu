@@ -10,6 +10,7 @@
 
 #include "ocgcn_aux.cuh"
 #include "ocgcn_common.cuh"
+#include "ocgcn_compact.cuh"
 #include "ocgcn_dw.cuh"
 #include "ocgcn_tile.cuh"
 
@@ -21,11 +22,11 @@ static thread_local int tl_cuda_err = 0;
 // ---- opt-in per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream ----------
 enum KernelKind : int {
   KK_ADJ_PACK = 0, KK_TRANSPOSE, KK_FWD_FIRST, KK_FWD_MID, KK_BN_FINALIZE, KK_FWD_READOUT, KK_BWD_READOUT, KK_BWD_DY,
-  KK_BWD_FINALIZE, KK_BWD_DZ, KK_GEMM_TN, KK_REDUCE, KK_BN_APPLY, KK_WPREP, KK_DW_MMA, KK_COUNT
+  KK_BWD_FINALIZE, KK_BWD_DZ, KK_GEMM_TN, KK_REDUCE, KK_BN_APPLY, KK_WPREP, KK_DW_MMA, KK_EXPAND, KK_PACK, KK_COUNT
 };
 static const char* const kKindNames[KK_COUNT] = {"adj_pack", "transpose", "fwd_first", "fwd_mid", "bn_finalize", "fwd_readout",
                                                  "bwd_readout", "bwd_dy", "bwd_finalize", "bwd_dz", "gemm_tn", "reduce", "bn_apply",
-                                                 "wprep", "dw_mma"};
+                                                 "wprep", "dw_mma", "expand_compact", "pack_compact"};
 struct ProfRec { int kind; cudaEvent_t e0, e1; };
 // process-wide (autograd runs backward on its own thread), guarded by a mutex; off by default
 static std::atomic<bool> g_prof_on{false};
@@ -764,6 +765,66 @@ int ocgcn_layer_backward(const ocgcn_desc* d, const float* grad_y, const float* 
   memset(&rj, 0, sizeof(rj));
   ST_TRY(run_layer_backward(d, lo, adj, p, g, 0, true, const_cast<float*>(grad_y), dz, grad_x, !d->need_dx, saved, scratch, st, rj));
   return run_reduce(rj, st);
+}
+
+static int bits_grid(long long work_items) {
+  long long g = (work_items + 255) / 256;
+  const long long cap = 148 * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+int ocgcn_expand_compact(int B, int N, int F0, const uint32_t* x_bits, const uint32_t* adj_bits, const int32_t* index, float* x,
+                         float* adj, void* stream) {
+  tl_launches = 0;
+  if (B <= 0 || N <= 0 || F0 <= 0) return OCGCN_EINVAL;
+  if ((x != nullptr) != (x_bits != nullptr) || (adj != nullptr) != (adj_bits != nullptr) || (!x && !adj)) return OCGCN_EINVAL;
+  ST_TRY(check_device());
+  if (x) { ST_TRY(check_device_ptr(x)); ST_TRY(check_device_ptr(x_bits)); }
+  if (adj) { ST_TRY(check_device_ptr(adj)); ST_TRY(check_device_ptr(adj_bits)); }
+  if (index) ST_TRY(check_device_ptr(index));
+  if (((uintptr_t)x & 15) || ((uintptr_t)adj & 15)) return OCGCN_EALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long rows = (long long)B * N;
+  if (adj) {
+    ProfScope ps(KK_EXPAND, st);
+    expand_bits_kernel<<<bits_grid(rows * ((N + 3) / 4)), 256, 0, st>>>(adj_bits, index, N, N, (N + 31) / 32, rows, adj);
+    LAUNCH_CHECK();
+  }
+  if (x) {
+    ProfScope ps(KK_EXPAND, st);
+    expand_bits_kernel<<<bits_grid(rows * ((F0 + 3) / 4)), 256, 0, st>>>(x_bits, index, N, F0, (F0 + 31) / 32, rows, x);
+    LAUNCH_CHECK();
+  }
+  return OCGCN_OK;
+}
+
+int ocgcn_pack_compact(int B, int N, int F0, const float* x, const int64_t* x_stride, const float* adj, const int64_t* adj_stride,
+                       uint32_t* x_bits, uint32_t* adj_bits, int32_t* nonbinary, void* stream) {
+  tl_launches = 0;
+  if (B <= 0 || N <= 0 || F0 <= 0 || !nonbinary) return OCGCN_EINVAL;
+  if ((x != nullptr) != (x_bits != nullptr) || (adj != nullptr) != (adj_bits != nullptr) || (!x && !adj)) return OCGCN_EINVAL;
+  if ((x && !x_stride) || (adj && !adj_stride)) return OCGCN_EINVAL;
+  ST_TRY(check_device());
+  ST_TRY(check_device_ptr(nonbinary));
+  if (x) { ST_TRY(check_device_ptr(x)); ST_TRY(check_device_ptr(x_bits)); }
+  if (adj) { ST_TRY(check_device_ptr(adj)); ST_TRY(check_device_ptr(adj_bits)); }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU_TRY(cudaMemsetAsync(nonbinary, 0, sizeof(int32_t), st));
+  const long long rows = (long long)B * N;
+  if (adj) {
+    ProfScope ps(KK_PACK, st);
+    const int W = (N + 31) / 32;
+    pack_bits_kernel<<<bits_grid(rows * W * 32), 256, 0, st>>>(adj, adj_stride[0], adj_stride[1], adj_stride[2], N, N, W, rows, adj_bits,
+                                                              nonbinary);
+    LAUNCH_CHECK();
+  }
+  if (x) {
+    ProfScope ps(KK_PACK, st);
+    const int W = (F0 + 31) / 32;
+    pack_bits_kernel<<<bits_grid(rows * W * 32), 256, 0, st>>>(x, x_stride[0], x_stride[1], x_stride[2], N, F0, W, rows, x_bits, nonbinary);
+    LAUNCH_CHECK();
+  }
+  return OCGCN_OK;
 }
 
 }  // extern "C"

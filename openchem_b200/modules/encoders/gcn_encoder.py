@@ -1,7 +1,8 @@
 """GraphCNNEncoder with the reference's surface (openchem/modules/encoders/gcn_encoder.py:9-53), executed as
 one fused autograd node by libocgcn.so.
 
-forward(inp) with inp = (x (B,N,F0), adj (B,N,N)) returns (B, encoder_dim):
+forward(inp) with inp = (x (B,N,F0), adj (B,N,N)) — or a bit-packed `openchem_b200.compact.CompactGraphBatch` — returns
+(B, encoder_dim):
 per layer  tanh(BN((adj x) W + b)) -> neighbour max-pool  (gcn_encoder.py:41-50), then
 tanh(dense(.)) -> sum over ALL N rows (unmasked) -> tanh  (:51-53). dropout_layer is constructed but, as in the
 reference (:22, :38-53), never applied.
@@ -13,6 +14,7 @@ from __future__ import annotations
 
 import torch.nn as nn
 
+from ...compact import CompactGraphBatch
 from ...functional import EncoderFn, LayerSpec
 from ...layers.gcn import GraphConvolution
 from ...utils import check_params
@@ -45,7 +47,10 @@ class GraphCNNEncoder(OpenChemEncoder):
         return {"n_layers": int, "hidden_size": list}
 
     def forward(self, inp):
-        x, adj = inp[0], inp[1]
+        if isinstance(inp, CompactGraphBatch):   # bit-packed batch: rebuilt as dense fp32 on the device (bit-exact)
+            x, adj = inp.expand()
+        else:
+            x, adj = inp[0], inp[1]
         gcs = list(self.graph_convolutions)
         bn0 = gcs[0].bn
         spec = LayerSpec(self.hidden_size, self.encoder_dim, self.precision, self.training, gcs[0].bias is not None,

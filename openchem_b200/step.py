@@ -76,6 +76,13 @@ class TrainStep:
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
 
+    def load_compact(self, batch):
+        """Expand a device CompactGraphBatch (openchem_b200.compact) straight into the static dense inputs: no dense
+        staging copy, and only the bit words crossed the host link."""
+        batch.expand(out=(self.inputs[0], self.inputs[1]))
+        if batch.labels is not None:
+            self.inputs[2].copy_(batch.labels, non_blocking=True)
+
     def __call__(self, x=None, adj=None, y=None):
         if x is not None:
             self.load(x, adj, y)

@@ -1,0 +1,126 @@
+"""Compact batch format on the device (ocgcn_expand_compact / ocgcn_pack_compact through the C ABI): bit-exact against the
+dense reference-format tensors for ragged sizes, gathers, strided inputs; the encoder gives identical results from either
+format."""
+import numpy as np
+import pytest
+import torch
+
+from openchem_b200 import compact
+from _util import build_encoder, random_params
+from openchem_b200.synthetic import make_graph_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _case(B, N, F0, hidden, E, seed):
+    g = make_graph_batch(B, N, F0, occupancy="molecular", seed=seed)
+    p = random_params([F0] + list(hidden), E, seed=seed + 1)
+    cfg = {"input_size": F0, "encoder_dim": E, "n_layers": len(hidden), "hidden_size": list(hidden)}
+    return g, p, cfg
+
+
+def _rand_binary(B, N, F0, seed):
+    rng = np.random.RandomState(seed)
+    return (rng.rand(B, N, F0) < 0.2).astype(np.float32), (rng.rand(B, N, N) < 0.1).astype(np.float32)
+
+
+@pytest.mark.parametrize("B,N,F0", [(1, 1, 1), (3, 37, 33), (5, 64, 64), (2, 85, 75), (2, 132, 33), (7, 50, 130), (4, 256, 64)])
+def test_expand_is_bit_exact(B, N, F0):
+    x, adj = _rand_binary(B, N, F0, B * 1000 + N)
+    cb = compact.pack_graph_batch(x, adj).to(_dev())
+    xe, ae = cb.expand()
+    assert xe.dtype == torch.float32 and tuple(xe.shape) == (B, N, F0) and tuple(ae.shape) == (B, N, N)
+    assert np.array_equal(xe.cpu().numpy(), x) and np.array_equal(ae.cpu().numpy(), adj)
+    # into preallocated outputs (poisoned first)
+    xo = torch.full((B, N, F0), 7.0, device=_dev())
+    ao = torch.full((B, N, N), 7.0, device=_dev())
+    cb.expand(out=(xo, ao))
+    assert torch.equal(xo, xe) and torch.equal(ao, ae)
+
+
+def test_expand_gather_from_resident_dataset():
+    x, adj = _rand_binary(40, 30, 33, 11)
+    y = torch.arange(40, dtype=torch.float32).reshape(40, 1)
+    ds = compact.ResidentCompactDataset(compact.pack_graph_batch(x, adj, y), _dev())
+    assert len(ds) == 40
+    idx = torch.tensor([39, 0, 7, 7, 12], dtype=torch.int64)
+    xb, ab, yb = ds.batch(idx)
+    assert np.array_equal(xb.cpu().numpy(), x[idx.numpy()]) and np.array_equal(ab.cpu().numpy(), adj[idx.numpy()])
+    assert torch.equal(yb.cpu(), y[idx])
+
+
+@pytest.mark.parametrize("B,N,F0", [(3, 37, 33), (4, 64, 64), (2, 132, 70)])
+def test_device_pack_matches_host_pack_and_handles_strides(B, N, F0):
+    x, adj = _rand_binary(B, N, F0, 5)
+    host = compact.pack_graph_batch(x, adj)
+    xd, ad = torch.from_numpy(x).to(_dev()), torch.from_numpy(adj).to(_dev())
+    dev = compact.pack_graph_batch_device(xd, ad)
+    assert torch.equal(dev.x_bits.cpu(), host.x_bits) and torch.equal(dev.adj_bits.cpu(), host.adj_bits)
+    # transposed (non-contiguous) adjacency view
+    dev_t = compact.pack_graph_batch_device(xd, ad.transpose(1, 2))
+    assert torch.equal(dev_t.adj_bits.cpu(), compact.pack_graph_batch(x, adj.transpose(0, 2, 1)).adj_bits)
+
+
+def test_device_pack_rejects_non_binary():
+    x, adj = _rand_binary(2, 16, 8, 1)
+    adj[1, 3, 4] = 0.25
+    with pytest.raises(ValueError):
+        compact.pack_graph_batch_device(torch.from_numpy(x).to(_dev()), torch.from_numpy(adj).to(_dev()))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_encoder_accepts_compact_batch_with_identical_results(precision):
+    g, p, cfg = _case(B=12, N=30, F0=33, hidden=(64, 64), E=32, seed=2)
+    dev = _dev()
+    enc = build_encoder(cfg, p, dev, precision=precision).train()
+    x, adj = torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["adj"]).to(dev)
+    state = {k: v.clone() for k, v in enc.state_dict().items()}
+    out_d = enc((x, adj))
+    out_d.sum().backward()
+    gd = [q.grad.clone() for q in enc.parameters()]
+    enc.load_state_dict(state)
+    enc.zero_grad()
+    cb = compact.pack_graph_batch(g["x"], g["adj"]).to(dev)
+    out_c = enc(cb)
+    out_c.sum().backward()
+    assert torch.equal(out_c, out_d)
+    for a, b in zip(gd, [q.grad for q in enc.parameters()]):
+        assert torch.equal(a, b)
+
+
+class _Model(torch.nn.Module):
+    def __init__(self, enc, E):
+        super().__init__()
+        self.enc, self.head = enc, torch.nn.Linear(E, 1)
+
+    def forward(self, inp):
+        return self.head(self.enc(inp))
+
+
+def test_train_step_load_compact_equals_dense_load():
+    from openchem_b200.step import TrainStep
+    g, p, cfg = _case(16, 20, 16, (32,), 16, seed=4)
+    g2 = make_graph_batch(16, 20, 16, seed=9)
+    dev = _dev()
+    y = torch.from_numpy(np.random.RandomState(1).randn(16, 1).astype(np.float32))
+    losses = []
+    for use_compact in (False, True):
+        torch.manual_seed(0)
+        model = _Model(build_encoder(cfg, p, dev, precision="bf16"), 16).to(dev).train()
+        ex = (torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["adj"]).to(dev), y.to(dev))
+        step = TrainStep(model, torch.nn.MSELoss(), lambda ps: torch.optim.Adam(ps, lr=1e-3, fused=True, capturable=True), ex,
+                         use_graph=True, warmup=1)
+        assert step.graph is not None, step.graph_error
+        run = []
+        for data in (g2, g):
+            if use_compact:
+                step.load_compact(compact.pack_graph_batch(data["x"], data["adj"], y).to(dev))
+                run.append(float(step()))
+            else:
+                run.append(float(step(torch.from_numpy(data["x"]).to(dev), torch.from_numpy(data["adj"]).to(dev), y.to(dev))))
+        losses.append(run)
+    assert losses[0] == losses[1], losses
