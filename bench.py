@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -331,18 +332,50 @@ def run_native(args, w, wname):
     h2d = hx.numel() * 4 + hadj.numel() * 4 + hy.numel() * 4
     host_batches = [(hx, hadj, hy)] * (2 + args.steps)
     feed = DevicePrefetcher(host_batches, dev)
+    from openchem_b200.step import DelayedLoss
     for _ in range(2):
         xb, adjb, yb = next(feed)
         float(step(xb, adjb, yb).item())
     barrier()
+    reader, host_losses = DelayedLoss(dev), []
     e0.record()
     for _ in range(args.steps):
         xb, adjb, yb = next(feed)
-        loss = step(xb, adjb, yb)
-        float(loss.item())
+        host_losses.append(reader.push(step(xb, adjb, yb)))     # step t's loss reaches the host while step t+1 runs
+    host_losses.append(reader.flush())                           # ... and the last one before the clock stops
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    assert len([v for v in host_losses if v is not None]) == args.steps and all(math.isfinite(v) for v in host_losses[1:])
+
+    # ---- the same end-to-end region fed in the package's compact batch format (openchem_b200.compact: bit-packed adjacency
+    # and features, 32x fewer host bytes; expanded bit-exactly on the device into the step's static inputs). Reported
+    # beside `e2e`, which stays on the reference's dense fp32 host format ----
+    from openchem_b200.compact import CompactGraphBatch, pack_graph_batch
+    cb_host = pack_graph_batch(g["x"], g["adj"], hy).pin_memory()
+    feed_c = DevicePrefetcher([cb_host.tensors()] * (2 + args.steps), dev)
+
+    def compact_step():
+        xbits, abits, yb = next(feed_c)
+        cb = CompactGraphBatch(xbits, abits, w["f0"], yb)
+        if stepper is not None:
+            stepper.load_compact(cb)
+            return stepper()
+        xe, ae = cb.expand()
+        return step(xe, ae, yb)
+
+    for _ in range(2):
+        float(compact_step().item())
+    barrier()
+    reader, host_losses = DelayedLoss(dev), []
+    e0.record()
+    for _ in range(args.steps):
+        host_losses.append(reader.push(compact_step()))
+    host_losses.append(reader.flush())
+    e1.record()
+    barrier()
+    assert len([v for v in host_losses if v is not None]) == args.steps and all(math.isfinite(v) for v in host_losses[1:])
+    ms_e2e_compact = max_over_ranks(e0.elapsed_time(e1))
 
     # ---- per-kernel timing (CUDA events around every launch, on the launching stream) ----
     # (every rank runs the steps - they contain the DDP all-reduce - but only rank 0 records events)
@@ -451,7 +484,13 @@ def run_native(args, w, wname):
                             encoder_dim=w["encoder_dim"], occupancy=args.occupancy, precision=args.precision, parallelism="dp%d" % world,
                             optimizer="Adam(fused)", runtime=runtime, l2_policy="inputs+saved state per step (>1 GB at c3) exceed the 126 MB L2; no explicit flush"),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps,
-                         feeder="openchem_b200.loader.DevicePrefetcher (pinned host -> device on a copy stream, one batch ahead)"),
+                         feeder="openchem_b200.loader.DevicePrefetcher (pinned host -> device on a copy stream, one batch ahead)",
+                         loss_readback="every step's loss is copied to pinned host memory and read there, one step delayed "
+                                       "(openchem_b200.step.DelayedLoss); the last read is inside the timed region"),
+                e2e_compact=dict(value=world * B * args.steps / (ms_e2e_compact * 1e-3), unit=UNIT, h2d_bytes_per_step=cb_host.nbytes(),
+                                 d2h_bytes_per_step=4, ms_per_step=ms_e2e_compact / args.steps,
+                                 format="openchem_b200.compact.CompactGraphBatch: bit-packed adj/features from pinned host memory, "
+                                        "expanded on the device (ocgcn_expand_compact) inside the timed region"),
                 gpu_launches=launches, clocks=clocks, roofline=roofline,
                 step_roofline=dict(frac=step_frac, t_roof_us=B * t_roof_mol * 1e6, flops_per_molecule=work["flops"],
                                    bytes_per_molecule=work["bytes"], tensor_peak_tflops=tensor_peak, hbm_gbs=peaks["hbm_gbs"],

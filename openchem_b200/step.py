@@ -19,6 +19,33 @@ import torch
 import torch.distributed as dist
 
 
+class DelayedLoss:
+    """Reads every step's loss on the host without stalling the device: the device -> host copy of step t's scalar is
+    enqueued behind step t, and its VALUE is collected while step t+1 is already running (the reference's `fit` loop calls
+    `.item()` right after `backward`, openchem/models/openchem_model.py:159-163, which idles the GPU for the host's
+    launch latency every iteration). `push` returns the previous step's loss (None on the first call); `flush` the last."""
+
+    def __init__(self, device, depth=2):
+        self.host = torch.zeros(depth, dtype=torch.float32).pin_memory()
+        self.events = [torch.cuda.Event() for _ in range(depth)]
+        self.device, self.depth, self.n = torch.device(device), depth, 0
+
+    def _collect(self, k):
+        self.events[k].synchronize()
+        return float(self.host[k])
+
+    def push(self, loss):
+        prev = self._collect((self.n - 1) % self.depth) if self.n > 0 else None
+        k = self.n % self.depth
+        self.host[k:k + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        self.events[k].record(torch.cuda.current_stream(self.device))
+        self.n += 1
+        return prev
+
+    def flush(self):
+        return self._collect((self.n - 1) % self.depth) if self.n > 0 else None
+
+
 class TrainStep:
     def __init__(self, model, criterion, make_optimizer, example_batch, use_graph=True, warmup=3):
         """model((x, adj)) -> predictions; criterion(pred, y) -> scalar; make_optimizer(params) -> torch optimizer that is

@@ -214,3 +214,16 @@ def test_training_trajectory_matches_reference_op_sequence(precision, tol):
     # implementations (the reference on two machines included) while everything the loss sees agrees
     rv_gpu = enc.graph_convolutions[0].bn.running_var.cpu().numpy()
     assert rel_l2(rv_gpu, pt["running_var"][0].numpy()) < 10 * tol
+
+
+def test_delayed_loss_returns_every_value_in_order():
+    from openchem_b200.step import DelayedLoss
+    dev = _dev()
+    reader = DelayedLoss(dev)
+    static = torch.zeros((), device=dev)          # like TrainStep.loss: one device scalar overwritten every step
+    got = []
+    for t in range(7):
+        static.fill_(float(t) + 0.5)
+        got.append(reader.push(static))
+    got.append(reader.flush())
+    assert got[0] is None and got[1:] == [t + 0.5 for t in range(7)]
