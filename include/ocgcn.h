@@ -137,6 +137,63 @@ int ocgcn_expand_compact(int B, int N, int F0, const uint32_t* x_bits, const uin
 int ocgcn_pack_compact(int B, int N, int F0, const float* x, const int64_t* x_stride, const float* adj,
                        const int64_t* adj_stride, uint32_t* x_bits, uint32_t* adj_bits, int32_t* nonbinary, void* stream);
 
+/* ---- MLP head + loss (Graph2Label.forward's `self.MLP(output)` and the criterion `fit` applies to it) -------------------
+ * ocgcn_head_forward   <- OpenChemMLP.forward                      openchem/modules/mlp/openchem_mlp.py:51-61
+ *                         (+ nn.MSELoss / MultitaskLoss.forward    openchem/criterion/multitask_loss.py:40-49 when loss != NONE)
+ * ocgcn_head_backward  <- autograd of the above
+ * Layer i: Linear(width[i] -> width[i+1]); every layer but the last is followed by BatchNorm1d over the B rows and act[i],
+ * the last by act[n_layers-1] only. Exact fp32 arithmetic. Dropout must be inactive (p = 0 or eval mode). */
+#define OCGCN_HEAD_MAX_LAYERS 4
+#define OCGCN_HEAD_MAX_WIDTH 256
+#define OCGCN_ACT_IDENTITY 0
+#define OCGCN_ACT_RELU 1
+#define OCGCN_ACT_SIGMOID 2
+#define OCGCN_ACT_TANH 3
+#define OCGCN_LOSS_NONE 0      /* forward returns predictions only; backward takes grad_pred (B,T)                     */
+#define OCGCN_LOSS_MSE 1       /* nn.MSELoss(): mean over B*T                                                         */
+#define OCGCN_LOSS_MULTITASK 2 /* MultitaskLoss(ignore_index, n_tasks = T): masked BCE, per-task mean, mean over tasks */
+
+typedef struct ocgcn_head_desc {
+  int32_t B;
+  int32_t n_layers;                          /* 1..OCGCN_HEAD_MAX_LAYERS                                  */
+  int32_t width[OCGCN_HEAD_MAX_LAYERS + 1];  /* input_size, hidden_size[0..n_layers-1] (last = T)         */
+  int32_t act[OCGCN_HEAD_MAX_LAYERS];        /* OCGCN_ACT_*                                               */
+  int32_t training;                          /* BatchNorm: batch statistics + running-stat update         */
+  int32_t loss;                              /* OCGCN_LOSS_*                                              */
+  int32_t need_dx;                           /* backward: also produce grad_inp (B, width[0])             */
+  float eps, momentum;                       /* BatchNorm1d                                               */
+  float ignore_index;                        /* MultitaskLoss                                             */
+} ocgcn_head_desc;
+
+/* state_dict names: layers.{i}.weight (width[i+1], width[i]) [nn.Linear layout], layers.{i}.bias, bn.{i}.weight/.bias/
+ * .running_mean/.running_var/.num_batches_tracked for i < n_layers-1 */
+typedef struct ocgcn_head_params {
+  const float* W[OCGCN_HEAD_MAX_LAYERS];
+  const float* b[OCGCN_HEAD_MAX_LAYERS];
+  const float* gamma[OCGCN_HEAD_MAX_LAYERS];
+  const float* beta[OCGCN_HEAD_MAX_LAYERS];
+  float* running_mean[OCGCN_HEAD_MAX_LAYERS];
+  float* running_var[OCGCN_HEAD_MAX_LAYERS];
+  int64_t* num_batches_tracked[OCGCN_HEAD_MAX_LAYERS];
+} ocgcn_head_params;
+
+typedef struct ocgcn_head_grads {
+  float* dW[OCGCN_HEAD_MAX_LAYERS];
+  float* db[OCGCN_HEAD_MAX_LAYERS];
+  float* dgamma[OCGCN_HEAD_MAX_LAYERS];
+  float* dbeta[OCGCN_HEAD_MAX_LAYERS];
+} ocgcn_head_grads;
+
+int ocgcn_head_query_workspace(const ocgcn_head_desc* desc, size_t* saved_bytes, size_t* scratch_bytes);
+/* inp (B,width[0]) contiguous; pred (B,T) written; target (B,T) and loss (device scalar) used when desc->loss != NONE. */
+int ocgcn_head_forward(const ocgcn_head_desc* desc, const float* inp, const ocgcn_head_params* params, const float* target,
+                       void* saved, void* scratch, float* pred, float* loss, void* stream);
+/* grad: desc->loss == NONE: grad_pred (B,T); otherwise a device scalar dLoss (NULL = 1). pred = what forward wrote.
+ * Writes every gradient in `grads` and, when desc->need_dx, grad_inp (B,width[0]). */
+int ocgcn_head_backward(const ocgcn_head_desc* desc, const float* grad, const float* inp, const float* pred, const float* target,
+                        const ocgcn_head_params* params, const ocgcn_head_grads* grads, float* grad_inp, void* saved,
+                        void* scratch, void* stream);
+
 /* Opt-in, process-wide per-kernel timing (used by bench.py's roofline leg, never by training):
  * while enabled every kernel launch is bracketed by CUDA events recorded on the launching stream.
  * ocgcn_profile_collect synchronises those events, sums milliseconds and launch counts per kernel kind

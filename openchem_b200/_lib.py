@@ -14,7 +14,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libocgcn.so")
-SOURCES = ["ocgcn_api.cu", "ocgcn_tile.cuh", "ocgcn_aux.cuh", "ocgcn_common.cuh", "ocgcn_tc.cuh", "ocgcn_dw.cuh", "ocgcn_compact.cuh"]
+SOURCES = ["ocgcn_api.cu", "ocgcn_tile.cuh", "ocgcn_aux.cuh", "ocgcn_common.cuh", "ocgcn_tc.cuh", "ocgcn_dw.cuh", "ocgcn_compact.cuh", "ocgcn_head.cuh"]
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "ocgcn.h")
 
 MAX_LAYERS = 16
@@ -51,11 +51,36 @@ class Grads(ctypes.Structure):
     ]
 
 
+HEAD_MAX_LAYERS = 4
+HEAD_MAX_WIDTH = 256
+ACTS = {"identity": 0, "relu": 1, "sigmoid": 2, "tanh": 3}
+LOSSES = {"none": 0, "mse": 1, "multitask": 2}
+
+
+class HeadDesc(ctypes.Structure):
+    _fields_ = [
+        ("B", ctypes.c_int32), ("n_layers", ctypes.c_int32),
+        ("width", ctypes.c_int32 * (HEAD_MAX_LAYERS + 1)), ("act", ctypes.c_int32 * HEAD_MAX_LAYERS),
+        ("training", ctypes.c_int32), ("loss", ctypes.c_int32), ("need_dx", ctypes.c_int32),
+        ("eps", ctypes.c_float), ("momentum", ctypes.c_float), ("ignore_index", ctypes.c_float),
+    ]
+
+
+class HeadParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p * HEAD_MAX_LAYERS) for n in
+                ("W", "b", "gamma", "beta", "running_mean", "running_var", "num_batches_tracked")]
+
+
+class HeadGrads(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p * HEAD_MAX_LAYERS) for n in ("dW", "db", "dgamma", "dbeta")]
+
+
 EXPORTS = [
     "ocgcn_query_workspace", "ocgcn_encoder_forward", "ocgcn_encoder_backward", "ocgcn_layer_forward",
     "ocgcn_layer_backward", "ocgcn_last_launch_count", "ocgcn_last_cuda_error", "ocgcn_status_string",
     "ocgcn_abi_version", "ocgcn_profile_enable", "ocgcn_profile_kinds", "ocgcn_profile_kind_name", "ocgcn_profile_collect",
     "ocgcn_saved_tensor", "ocgcn_expand_compact", "ocgcn_pack_compact",
+    "ocgcn_head_query_workspace", "ocgcn_head_forward", "ocgcn_head_backward",
 ]
 
 
@@ -123,6 +148,12 @@ def load():
         lib.ocgcn_expand_compact.restype = ctypes.c_int
         lib.ocgcn_pack_compact.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, i64p, vp, i64p, vp, vp, vp, vp]
         lib.ocgcn_pack_compact.restype = ctypes.c_int
+        lib.ocgcn_head_query_workspace.argtypes = [ctypes.POINTER(HeadDesc), ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]
+        lib.ocgcn_head_forward.argtypes = [ctypes.POINTER(HeadDesc), vp, ctypes.POINTER(HeadParams), vp, vp, vp, vp, vp, vp]
+        lib.ocgcn_head_backward.argtypes = [ctypes.POINTER(HeadDesc), vp, vp, vp, vp, ctypes.POINTER(HeadParams), ctypes.POINTER(HeadGrads),
+                                            vp, vp, vp, vp]
+        for name in ("ocgcn_head_query_workspace", "ocgcn_head_forward", "ocgcn_head_backward"):
+            getattr(lib, name).restype = ctypes.c_int
         lib.ocgcn_profile_kind_name.restype = ctypes.c_char_p
         lib.ocgcn_profile_kind_name.argtypes = [ctypes.c_int]
         lib.ocgcn_profile_enable.argtypes = [ctypes.c_int]

@@ -12,6 +12,7 @@
 #include "ocgcn_common.cuh"
 #include "ocgcn_compact.cuh"
 #include "ocgcn_dw.cuh"
+#include "ocgcn_head.cuh"
 #include "ocgcn_tile.cuh"
 
 namespace ocgcn {
@@ -22,11 +23,11 @@ static thread_local int tl_cuda_err = 0;
 // ---- opt-in per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream ----------
 enum KernelKind : int {
   KK_ADJ_PACK = 0, KK_TRANSPOSE, KK_FWD_FIRST, KK_FWD_MID, KK_BN_FINALIZE, KK_FWD_READOUT, KK_BWD_READOUT, KK_BWD_DY,
-  KK_BWD_FINALIZE, KK_BWD_DZ, KK_GEMM_TN, KK_REDUCE, KK_BN_APPLY, KK_WPREP, KK_DW_MMA, KK_EXPAND, KK_PACK, KK_COUNT
+  KK_BWD_FINALIZE, KK_BWD_DZ, KK_GEMM_TN, KK_REDUCE, KK_BN_APPLY, KK_WPREP, KK_DW_MMA, KK_EXPAND, KK_PACK, KK_HEAD_FWD, KK_HEAD_LOSS, KK_HEAD_BWD, KK_COUNT
 };
 static const char* const kKindNames[KK_COUNT] = {"adj_pack", "transpose", "fwd_first", "fwd_mid", "bn_finalize", "fwd_readout",
                                                  "bwd_readout", "bwd_dy", "bwd_finalize", "bwd_dz", "gemm_tn", "reduce", "bn_apply",
-                                                 "wprep", "dw_mma", "expand_compact", "pack_compact"};
+                                                 "wprep", "dw_mma", "expand_compact", "pack_compact", "head_fwd", "head_loss", "head_bwd"};
 struct ProfRec { int kind; cudaEvent_t e0, e1; };
 // process-wide (autograd runs backward on its own thread), guarded by a mutex; off by default
 static std::atomic<bool> g_prof_on{false};
@@ -825,6 +826,201 @@ int ocgcn_pack_compact(int B, int N, int F0, const float* x, const int64_t* x_st
     LAUNCH_CHECK();
   }
   return OCGCN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// MLP head + loss
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct HeadLayout {
+  int L, ntiles, grid, T;
+  // saved
+  size_t U[OCGCN_HEAD_MAX_LAYERS], stat[OCGCN_HEAD_MAX_LAYERS], ncount, saved_total;
+  // scratch
+  size_t part[OCGCN_HEAD_MAX_LAYERS], loss_part, dY[OCGCN_HEAD_MAX_LAYERS], dpart[OCGCN_HEAD_MAX_LAYERS], dWpart[OCGCN_HEAD_MAX_LAYERS],
+      dbpart[OCGCN_HEAD_MAX_LAYERS], scratch_total;
+};
+int head_layout(const ocgcn_head_desc* d, HeadLayout* lo) {
+  memset(lo, 0, sizeof(*lo));
+  if (!d || d->B <= 0 || d->n_layers <= 0 || d->n_layers > OCGCN_HEAD_MAX_LAYERS) return OCGCN_EINVAL;
+  for (int i = 0; i <= d->n_layers; ++i) {
+    if (d->width[i] <= 0) return OCGCN_EINVAL;
+    if (d->width[i] > OCGCN_HEAD_MAX_WIDTH) return OCGCN_EUNSUPPORTED;
+  }
+  for (int i = 0; i < d->n_layers; ++i)
+    if (d->act[i] < OCGCN_ACT_IDENTITY || d->act[i] > OCGCN_ACT_TANH) return OCGCN_EINVAL;
+  if (d->loss < OCGCN_LOSS_NONE || d->loss > OCGCN_LOSS_MULTITASK) return OCGCN_EINVAL;
+  if (d->training && d->n_layers > 1 && d->B < 2) return OCGCN_EINVAL;   // BatchNorm1d needs more than one value per channel
+  const int L = d->n_layers;
+  lo->L = L;
+  lo->T = d->width[L];
+  lo->ntiles = (d->B + HR - 1) / HR;
+  lo->grid = lo->ntiles < kMaxPersistent ? lo->ntiles : kMaxPersistent;
+  size_t off = 0;
+  for (int i = 0; i + 1 < L; ++i) {
+    lo->U[i] = off; off = align_up(off + (size_t)d->B * d->width[i + 1] * 4);
+    lo->stat[i] = off; off = align_up(off + (size_t)2 * d->width[i + 1] * 4);
+  }
+  lo->ncount = off; off = align_up(off + (size_t)lo->T * 4);
+  lo->saved_total = off;
+  off = 0;
+  for (int i = 0; i + 1 < L; ++i) {
+    lo->part[i] = off; off = align_up(off + (size_t)lo->ntiles * 2 * d->width[i + 1] * 4);
+    lo->dY[i] = off; off = align_up(off + (size_t)d->B * d->width[i + 1] * 4);
+    lo->dpart[i] = off; off = align_up(off + (size_t)lo->ntiles * 2 * d->width[i + 1] * 4);
+  }
+  lo->loss_part = off; off = align_up(off + (size_t)lo->ntiles * 2 * lo->T * 4);
+  for (int i = 0; i < L; ++i) {
+    lo->dWpart[i] = off; off = align_up(off + (size_t)lo->grid * d->width[i] * d->width[i + 1] * 4);
+    lo->dbpart[i] = off; off = align_up(off + (size_t)lo->grid * d->width[i + 1] * 4);
+  }
+  lo->scratch_total = off;
+  return OCGCN_OK;
+}
+int head_validate(const ocgcn_head_desc* d, const ocgcn_head_params* p) {
+  if (!p) return OCGCN_EINVAL;
+  for (int i = 0; i < d->n_layers; ++i) {
+    if (!p->W[i]) return OCGCN_EINVAL;
+    if (i + 1 < d->n_layers && (!p->gamma[i] || !p->beta[i] || !p->running_mean[i] || !p->running_var[i])) return OCGCN_EINVAL;
+  }
+  return OCGCN_OK;
+}
+HeadBN head_bn(const ocgcn_head_desc* d, const ocgcn_head_params* p, const HeadLayout& lo, int i, char* saved, char* scratch) {
+  HeadBN bn;
+  bn.part = reinterpret_cast<const float*>(scratch + lo.part[i]);
+  bn.gamma = p->gamma[i]; bn.beta = p->beta[i];
+  bn.running_mean = p->running_mean[i]; bn.running_var = p->running_var[i];
+  bn.nbt = reinterpret_cast<long long*>(p->num_batches_tracked[i]);
+  bn.stat = reinterpret_cast<float*>(saved + lo.stat[i]);
+  bn.act = d->act[i];
+  return bn;
+}
+}  // namespace
+
+int ocgcn_head_query_workspace(const ocgcn_head_desc* desc, size_t* saved_bytes, size_t* scratch_bytes) {
+  HeadLayout lo;
+  ST_TRY(head_layout(desc, &lo));
+  if (saved_bytes) *saved_bytes = lo.saved_total;
+  if (scratch_bytes) *scratch_bytes = lo.scratch_total;
+  return OCGCN_OK;
+}
+
+int ocgcn_head_forward(const ocgcn_head_desc* d, const float* inp, const ocgcn_head_params* p, const float* target, void* saved_v,
+                       void* scratch_v, float* pred, float* loss, void* stream) {
+  tl_launches = 0;
+  HeadLayout lo;
+  ST_TRY(head_layout(d, &lo));
+  ST_TRY(head_validate(d, p));
+  if (!saved_v || !scratch_v || !pred) return OCGCN_EINVAL;
+  ST_TRY(check_device());
+  ST_TRY(check_device_ptr(inp));
+  ST_TRY(check_device_ptr(pred));
+  if (d->loss != OCGCN_LOSS_NONE) {
+    ST_TRY(check_device_ptr(target));
+    ST_TRY(check_device_ptr(loss));
+  }
+  if (((uintptr_t)saved_v & 255) || ((uintptr_t)scratch_v & 255)) return OCGCN_EALIGN;
+  char* saved = static_cast<char*>(saved_v);
+  char* scratch = static_cast<char*>(scratch_v);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int L = lo.L;
+  for (int i = 0; i < L; ++i) {
+    HeadFwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.Kin = d->width[i]; a.Nout = d->width[i + 1];
+    a.in = i == 0 ? inp : reinterpret_cast<const float*>(saved + lo.U[i - 1]);
+    a.prev_bn = i > 0;
+    if (i > 0) a.bn = head_bn(d, p, lo, i - 1, saved, scratch);
+    a.W = p->W[i]; a.b = p->b[i];
+    a.has_bn = i + 1 < L;
+    a.out = a.has_bn ? reinterpret_cast<float*>(saved + lo.U[i]) : pred;
+    a.part_out = a.has_bn ? reinterpret_cast<float*>(scratch + lo.part[i]) : nullptr;
+    a.act = d->act[i];
+    a.B = d->B; a.ntiles = lo.ntiles; a.training = d->training; a.eps = d->eps; a.momentum = d->momentum;
+    if (!a.has_bn) {
+      a.loss = d->loss; a.target = target; a.ignore = d->ignore_index;
+      a.loss_part = reinterpret_cast<float*>(scratch + lo.loss_part);
+    }
+    const size_t smem = head_fwd_smem(a.Kin, a.Nout);
+    CU_TRY(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_fwd_smem(kHeadMaxWidth, kHeadMaxWidth)));
+    ProfScope prof(KK_HEAD_FWD, st);
+    head_fwd_kernel<<<lo.grid, HT, smem, st>>>(a);
+    LAUNCH_CHECK();
+  }
+  if (d->loss != OCGCN_LOSS_NONE) {
+    ProfScope prof(KK_HEAD_LOSS, st);
+    head_loss_kernel<<<1, HT, 0, st>>>(reinterpret_cast<const float*>(scratch + lo.loss_part), lo.ntiles, lo.T, d->B, d->loss, loss,
+                                       reinterpret_cast<float*>(saved + lo.ncount));
+    LAUNCH_CHECK();
+  }
+  return OCGCN_OK;
+}
+
+int ocgcn_head_backward(const ocgcn_head_desc* d, const float* grad, const float* inp, const float* pred, const float* target,
+                        const ocgcn_head_params* p, const ocgcn_head_grads* g, float* grad_inp, void* saved_v, void* scratch_v,
+                        void* stream) {
+  tl_launches = 0;
+  HeadLayout lo;
+  ST_TRY(head_layout(d, &lo));
+  ST_TRY(head_validate(d, p));
+  if (!g || !saved_v || !scratch_v) return OCGCN_EINVAL;
+  for (int i = 0; i < lo.L; ++i) {
+    if (!g->dW[i]) return OCGCN_EINVAL;
+    if (i + 1 < lo.L && (!g->dgamma[i] || !g->dbeta[i])) return OCGCN_EINVAL;
+  }
+  if (d->need_dx && !grad_inp) return OCGCN_EINVAL;
+  ST_TRY(check_device());
+  ST_TRY(check_device_ptr(inp));
+  ST_TRY(check_device_ptr(pred));
+  if (d->loss == OCGCN_LOSS_NONE) ST_TRY(check_device_ptr(grad));
+  else ST_TRY(check_device_ptr(target));
+  if (((uintptr_t)saved_v & 255) || ((uintptr_t)scratch_v & 255)) return OCGCN_EALIGN;
+  char* saved = static_cast<char*>(saved_v);
+  char* scratch = static_cast<char*>(scratch_v);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int L = lo.L;
+  ReduceJobs rj;
+  memset(&rj, 0, sizeof(rj));
+  for (int i = L - 1; i >= 0; --i) {
+    HeadBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = d->B; a.ntiles = lo.ntiles; a.training = d->training;
+    a.W = p->W[i]; a.Nout = d->width[i + 1]; a.Kin = d->width[i];
+    a.has_bn = i + 1 < L;
+    if (a.has_bn) {
+      a.dY = reinterpret_cast<const float*>(scratch + lo.dY[i]);
+      a.dpart = reinterpret_cast<const float*>(scratch + lo.dpart[i]);
+      a.U = reinterpret_cast<const float*>(saved + lo.U[i]);
+      a.stat = reinterpret_cast<const float*>(saved + lo.stat[i]);
+      a.gamma = p->gamma[i]; a.dgamma = g->dgamma[i]; a.dbeta = g->dbeta[i];
+    } else {
+      a.pred = pred; a.act = d->act[i]; a.loss = d->loss; a.target = target; a.ignore = d->ignore_index;
+      if (d->loss == OCGCN_LOSS_NONE) a.grad_pred = grad; else a.gloss = grad;
+      a.ncount = reinterpret_cast<const float*>(saved + lo.ncount);
+    }
+    a.prev = i == 0 ? inp : reinterpret_cast<const float*>(saved + lo.U[i - 1]);
+    a.prev_bn = i > 0;
+    if (i > 0) {
+      a.pstat = reinterpret_cast<const float*>(saved + lo.stat[i - 1]);
+      a.pgamma = p->gamma[i - 1]; a.pbeta = p->beta[i - 1]; a.pact = d->act[i - 1];
+      a.dprev = reinterpret_cast<float*>(scratch + lo.dY[i - 1]);
+      a.dpart_out = reinterpret_cast<float*>(scratch + lo.dpart[i - 1]);
+    } else {
+      a.dprev = d->need_dx ? grad_inp : nullptr;
+    }
+    a.dWpart = reinterpret_cast<float*>(scratch + lo.dWpart[i]);
+    a.dbpart = reinterpret_cast<float*>(scratch + lo.dbpart[i]);
+    const size_t smem = head_bwd_smem(a.Kin, a.Nout);
+    CU_TRY(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_bwd_smem(kHeadMaxWidth, kHeadMaxWidth)));
+    {
+      ProfScope prof(KK_HEAD_BWD, st);
+      head_bwd_kernel<<<lo.grid, HT, smem, st>>>(a);
+      LAUNCH_CHECK();
+    }
+    add_reduce(rj, a.dWpart, g->dW[i], lo.grid, a.Nout * a.Kin, 1, 0);
+    add_reduce(rj, a.dbpart, g->db[i], lo.grid, a.Nout, 0, 0);
+  }
+  return run_reduce(rj, st);
 }
 
 }  // extern "C"

@@ -226,3 +226,125 @@ class LayerFn(torch.autograd.Function):
                                                 saved.data_ptr(), scratch.data_ptr(), _stream_ptr(x.device)))
             _count(lib)
         return gx, None, None, gW, gbias, gg, gb_
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# MLP head (+ criterion) — ocgcn_head_forward / ocgcn_head_backward
+# ---------------------------------------------------------------------------------------------------------------------
+class HeadSpec:
+    """Non-tensor arguments + in-place updated BatchNorm buffers of one head call."""
+
+    def __init__(self, widths, acts, training, eps, momentum, running_mean, running_var, nbt, loss="none", ignore_index=0.0):
+        self.widths, self.acts = [int(w) for w in widths], list(acts)
+        self.training, self.eps, self.momentum = bool(training), float(eps), float(momentum)
+        self.running_mean, self.running_var, self.nbt = running_mean, running_var, nbt
+        self.loss, self.ignore_index = loss, float(ignore_index)
+
+
+def _head_desc(spec, B, need_dx):
+    L = len(spec.widths) - 1
+    if L < 1 or L > _lib.HEAD_MAX_LAYERS or max(spec.widths) > _lib.HEAD_MAX_WIDTH:
+        raise RuntimeError("openchem_b200: the fused MLP head supports 1..%d layers of width <= %d (got %s)" %
+                           (_lib.HEAD_MAX_LAYERS, _lib.HEAD_MAX_WIDTH, spec.widths))
+    if spec.training and L > 1 and B < 2:
+        raise ValueError("Expected more than 1 value per channel when training, got input size [%d, %d]" % (B, spec.widths[1]))
+    d = _lib.HeadDesc()
+    d.B, d.n_layers = B, L
+    for i, w in enumerate(spec.widths):
+        d.width[i] = w
+    for i, a in enumerate(spec.acts):
+        d.act[i] = _lib.ACTS[a]
+    d.training, d.loss, d.need_dx = int(spec.training), _lib.LOSSES[spec.loss], int(need_dx)
+    d.eps, d.momentum, d.ignore_index = spec.eps, spec.momentum, spec.ignore_index
+    return d
+
+
+def _head_params(spec, Ws, bs, gammas, betas):
+    p = _lib.HeadParams()
+    for i in range(len(Ws)):
+        p.W[i] = Ws[i].data_ptr()
+        p.b[i] = bs[i].data_ptr() if bs[i] is not None else None
+    for i in range(len(gammas)):
+        p.gamma[i], p.beta[i] = gammas[i].data_ptr(), betas[i].data_ptr()
+        p.running_mean[i], p.running_var[i] = spec.running_mean[i].data_ptr(), spec.running_var[i].data_ptr()
+        p.num_batches_tracked[i] = spec.nbt[i].data_ptr() if spec.nbt[i] is not None else None
+    return p
+
+
+class HeadFn(torch.autograd.Function):
+    """OpenChemMLP.forward (openchem_mlp.py:51-61), optionally fused with the criterion, as ONE autograd node.
+    inputs: inp (B, widths[0]), target (B,T) or None, spec, then W_0..W_{L-1}, b_0..b_{L-1}, gamma_0.., beta_0.. (L-1 each).
+    Returns predictions (spec.loss == 'none') or (loss scalar, predictions)."""
+
+    @staticmethod
+    def forward(ctx, inp, target, spec, *tensors):
+        lib = _lib.load()
+        _require_cuda(inp, "inp")
+        L = len(spec.widths) - 1
+        need_dx = bool(inp.requires_grad)
+        inp = _f32(inp.detach()).contiguous()
+        if inp.dim() != 2 or inp.shape[1] != spec.widths[0]:
+            raise RuntimeError("openchem_b200: MLP input must be (B, %d); got %s" % (spec.widths[0], tuple(inp.shape)))
+        tensors = [None if t is None else t.detach().contiguous() for t in tensors]
+        Ws, bs = tensors[0:L], tensors[L:2 * L]
+        gammas, betas = tensors[2 * L:3 * L - 1], tensors[3 * L - 1:4 * L - 2]
+        B, T = inp.shape[0], spec.widths[-1]
+        fused = spec.loss != "none"
+        if fused:
+            _require_cuda(target, "target")
+            target = _f32(target.detach()).contiguous()
+            if tuple(target.shape) != (B, T):
+                raise RuntimeError("openchem_b200: target must be (B, %d); got %s" % (T, tuple(target.shape)))
+        with torch.cuda.device(inp.device):
+            desc = _head_desc(spec, B, need_dx)
+            params = _head_params(spec, Ws, bs, gammas, betas)
+            sb, cb = ctypes.c_size_t(0), ctypes.c_size_t(0)
+            _lib.check(lib.ocgcn_head_query_workspace(ctypes.byref(desc), ctypes.byref(sb), ctypes.byref(cb)))
+            saved, scratch = _alloc(sb.value, inp.device), _alloc(cb.value, inp.device)
+            pred = torch.empty((B, T), dtype=torch.float32, device=inp.device)
+            loss = torch.empty((), dtype=torch.float32, device=inp.device) if fused else None
+            _lib.check(lib.ocgcn_head_forward(ctypes.byref(desc), inp.data_ptr(), ctypes.byref(params),
+                                              target.data_ptr() if fused else None, saved.data_ptr(), scratch.data_ptr(),
+                                              pred.data_ptr(), loss.data_ptr() if fused else None, _stream_ptr(inp.device)))
+            _count(lib)
+        ctx.spec, ctx.cbytes, ctx.need_dx, ctx.fused = spec, cb.value, need_dx, fused
+        ctx.none_mask = [t is None for t in tensors]
+        ctx.save_for_backward(inp, pred, saved, *([target] if fused else []), *[t for t in tensors if t is not None])
+        if fused:
+            ctx.mark_non_differentiable(pred)
+            return loss, pred
+        return pred
+
+    @staticmethod
+    def backward(ctx, *grad_outputs):
+        lib = _lib.load()
+        spec = ctx.spec
+        L = len(spec.widths) - 1
+        inp, pred, saved, *rest = ctx.saved_tensors
+        target = rest.pop(0) if ctx.fused else None
+        it = iter(rest)
+        tensors = [None if isnone else next(it) for isnone in ctx.none_mask]
+        Ws, bs = tensors[0:L], tensors[L:2 * L]
+        gammas, betas = tensors[2 * L:3 * L - 1], tensors[3 * L - 1:4 * L - 2]
+        grad = _f32(grad_outputs[0]).contiguous()
+        with torch.cuda.device(inp.device):
+            desc = _head_desc(spec, inp.shape[0], ctx.need_dx)
+            params = _head_params(spec, Ws, bs, gammas, betas)
+            grads = _lib.HeadGrads()
+            gW = [torch.empty_like(w) for w in Ws]
+            gb = [None if b is None else torch.empty_like(b) for b in bs]
+            gg = [torch.empty_like(t) for t in gammas]
+            gbt = [torch.empty_like(t) for t in betas]
+            for i in range(L):
+                grads.dW[i] = gW[i].data_ptr()
+                grads.db[i] = gb[i].data_ptr() if gb[i] is not None else None
+            for i in range(L - 1):
+                grads.dgamma[i], grads.dbeta[i] = gg[i].data_ptr(), gbt[i].data_ptr()
+            gx = torch.empty_like(inp) if ctx.need_dx else None
+            scratch = _alloc(ctx.cbytes, inp.device)
+            _lib.check(lib.ocgcn_head_backward(ctypes.byref(desc), grad.data_ptr(), inp.data_ptr(), pred.data_ptr(),
+                                               target.data_ptr() if target is not None else None, ctypes.byref(params),
+                                               ctypes.byref(grads), gx.data_ptr() if gx is not None else None, saved.data_ptr(),
+                                               scratch.data_ptr(), _stream_ptr(inp.device)))
+            _count(lib)
+        return (gx, None, None, *gW, *gb, *gg, *gbt)
