@@ -100,10 +100,11 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------------------
 # the model of the step
 # --------------------------------------------------------------------------------------------------------------
-def build_model(w, precision, device):
+def build_model(w, precision, device, head="fused"):
     import torch
     import torch.nn as nn
     from openchem_b200.modules.encoders.gcn_encoder import GraphCNNEncoder
+    from openchem_b200.modules.mlp.openchem_mlp import OpenChemMLP
 
     class Graph2LabelStep(nn.Module):
         """Encoder -> MLP head, the shape of openchem/models/Graph2Label.py:21-37 with OpenChemMLP
@@ -114,29 +115,40 @@ def build_model(w, precision, device):
             self.Encoder = GraphCNNEncoder({"input_size": w["f0"], "encoder_dim": w["encoder_dim"], "n_layers": len(w["hidden"]),
                                             "hidden_size": list(w["hidden"]), "precision": precision}, True)
             hs = w["mlp_hidden"]
-            self.MLP = nn.Sequential(nn.Linear(w["encoder_dim"], hs[0]), nn.BatchNorm1d(hs[0]), nn.ReLU(), nn.Linear(hs[0], hs[1]))
             self.sigmoid_out = w["task"] == "multitask"
+            if head == "fused":      # the package's OpenChemMLP (libocgcn head kernels)
+                self.MLP = OpenChemMLP({"input_size": w["encoder_dim"], "n_layers": 2, "hidden_size": list(hs),
+                                        "activation": [torch.relu, torch.sigmoid if self.sigmoid_out else "identity"]})
+            else:                    # plain torch modules (eager kernels), for comparison
+                self.MLP = nn.Sequential(nn.Linear(w["encoder_dim"], hs[0]), nn.BatchNorm1d(hs[0]), nn.ReLU(), nn.Linear(hs[0], hs[1]))
+            self.head = head
 
         def forward(self, inp):
             out = self.MLP(self.Encoder(inp))
-            return torch.sigmoid(out) if self.sigmoid_out else out
+            return torch.sigmoid(out) if (self.sigmoid_out and self.head != "fused") else out
 
     torch.manual_seed(0)
     return Graph2LabelStep().to(device)
 
 
+def head_loss_fn(args, crit):
+    """loss_fn for TrainStep: criterion evaluated inside the head's last kernel (None with --head torch)."""
+    if args.head != "fused":
+        return None
+    from openchem_b200.modules.mlp.openchem_mlp import fused_head_loss
+
+    def loss_fn(model, inp, y):
+        return fused_head_loss(model.MLP, model.Encoder(inp), y, crit)[0]
+
+    return loss_fn
+
+
 def make_criterion(w):
     import torch
-    import torch.nn.functional as F
     if w["task"] != "multitask":
         return torch.nn.MSELoss()
-
-    def masked_bce(inp, target):  # semantics of openchem/criterion/multitask_loss.py:40-49 (ignore_index = 9)
-        mask = (target != 9).to(inp.dtype)
-        loss = F.binary_cross_entropy(inp, mask * target, reduction="none") * mask
-        return (loss.sum(dim=0) / mask.sum(dim=0).clamp_min(1)).mean()
-
-    return masked_bce
+    from openchem_b200.criterion.multitask_loss import MultitaskLoss     # openchem/criterion/multitask_loss.py:40-49 as executed
+    return MultitaskLoss(ignore_index=9, n_tasks=w["mlp_hidden"][-1])
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -216,9 +228,10 @@ def measure_other(wname, args, dev, steps, warmup):
     g = make_graph_batch(B, w["n_max"], w["f0"], occupancy="molecular" if wname in ("c1_logp", "c2_tox21") else "full", seed=99)
     labels = make_labels(B, T, w["task"] if w["task"] == "multitask" else "regression", seed=98)
     x, adj, y = (torch.from_numpy(a).to(dev) for a in (g["x"], g["adj"], labels))
-    model = build_model(w, args.precision, dev)
-    st = TrainStep(model, make_criterion(w), lambda ps: torch.optim.Adam(ps, lr=5e-4, fused=True, capturable=True), (x, adj, y),
-                   use_graph=(args.runtime == "graph"))
+    model = build_model(w, args.precision, dev, args.head)
+    crit = make_criterion(w)
+    st = TrainStep(model, crit, lambda ps: torch.optim.Adam(ps, lr=5e-4, fused=True, capturable=True), (x, adj, y),
+                   use_graph=(args.runtime == "graph"), loss_fn=head_loss_fn(args, crit))
     for _ in range(warmup):
         st()
     torch.cuda.synchronize()
@@ -262,13 +275,14 @@ def run_native(args, w, wname):
     hx, hadj, hy = (torch.from_numpy(a).pin_memory() for a in (g["x"], g["adj"], labels))
     x, adj, y = hx.to(dev), hadj.to(dev), hy.to(dev)
 
-    model = build_model(w, args.precision, dev)
+    model = build_model(w, args.precision, dev, args.head)
     crit = make_criterion(w)
     stepper, runtime = None, "eager (torch autograd + DistributedDataParallel, as run.py drives it)"
     if args.runtime == "graph":
         # the package's step runtime: fwd + loss + bwd + NCCL grad all-reduce + Adam captured in one CUDA graph
         from openchem_b200.step import TrainStep
-        stepper = TrainStep(model, crit, lambda ps: torch.optim.Adam(ps, lr=5e-4, fused=True, capturable=True), (x, adj, y))
+        stepper = TrainStep(model, crit, lambda ps: torch.optim.Adam(ps, lr=5e-4, fused=True, capturable=True), (x, adj, y),
+                            loss_fn=head_loss_fn(args, crit))
         runtime = "openchem_b200.step.TrainStep: one CUDA graph per step (flat-gradient NCCL all-reduce inside)" if stepper.graph is not None \
             else "openchem_b200.step.TrainStep eager (graph capture failed: %s)" % stepper.graph_error
         opt = stepper.opt
@@ -482,7 +496,8 @@ def run_native(args, w, wname):
                 data="synthetic",
                 config=dict(workload=wname, per_gpu_batch=B, global_batch=B * world, n_max=w["n_max"], f0=w["f0"], hidden=w["hidden"],
                             encoder_dim=w["encoder_dim"], occupancy=args.occupancy, precision=args.precision, parallelism="dp%d" % world,
-                            optimizer="Adam(fused)", runtime=runtime, l2_policy="inputs+saved state per step (>1 GB at c3) exceed the 126 MB L2; no explicit flush"),
+                            optimizer="Adam(fused)", runtime=runtime,
+                            head="openchem_b200 OpenChemMLP + criterion (libocgcn head kernels)" if args.head == "fused" else "torch modules", l2_policy="inputs+saved state per step (>1 GB at c3) exceed the 126 MB L2; no explicit flush"),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps,
                          feeder="openchem_b200.loader.DevicePrefetcher (pinned host -> device on a copy stream, one batch ahead)",
                          loss_readback="every step's loss is copied to pinned host memory and read there, one step delayed "
@@ -510,6 +525,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--occupancy", default="full", choices=["full", "molecular"])
     ap.add_argument("--runtime", default="graph", choices=["graph", "eager"])
+    ap.add_argument("--head", default="fused", choices=["fused", "torch"], help="MLP head + criterion: libocgcn kernels or torch modules")
     ap.add_argument("--profile-steps", type=int, default=3)
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")

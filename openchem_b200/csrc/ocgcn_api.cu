@@ -942,9 +942,10 @@ int ocgcn_head_forward(const ocgcn_head_desc* d, const float* inp, const ocgcn_h
       a.loss_part = reinterpret_cast<float*>(scratch + lo.loss_part);
     }
     const size_t smem = head_fwd_smem(a.Kin, a.Nout);
-    CU_TRY(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_fwd_smem(kHeadMaxWidth, kHeadMaxWidth)));
+    auto kern = a.Nout > 128 ? head_fwd_kernel<2> : head_fwd_kernel<1>;
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_fwd_smem(kHeadMaxWidth, kHeadMaxWidth)));
     ProfScope prof(KK_HEAD_FWD, st);
-    head_fwd_kernel<<<lo.grid, HT, smem, st>>>(a);
+    kern<<<lo.grid, HT, smem, st>>>(a);
     LAUNCH_CHECK();
   }
   if (d->loss != OCGCN_LOSS_NONE) {
@@ -1011,10 +1012,11 @@ int ocgcn_head_backward(const ocgcn_head_desc* d, const float* grad, const float
     a.dWpart = reinterpret_cast<float*>(scratch + lo.dWpart[i]);
     a.dbpart = reinterpret_cast<float*>(scratch + lo.dbpart[i]);
     const size_t smem = head_bwd_smem(a.Kin, a.Nout);
-    CU_TRY(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_bwd_smem(kHeadMaxWidth, kHeadMaxWidth)));
+    auto kern = a.Kin > 128 ? head_bwd_kernel<2> : head_bwd_kernel<1>;
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_bwd_smem(kHeadMaxWidth, kHeadMaxWidth)));
     {
       ProfScope prof(KK_HEAD_BWD, st);
-      head_bwd_kernel<<<lo.grid, HT, smem, st>>>(a);
+      kern<<<lo.grid, HT, smem, st>>>(a);
       LAUNCH_CHECK();
     }
     add_reduce(rj, a.dWpart, g->dW[i], lo.grid, a.Nout * a.Kin, 1, 0);

@@ -60,23 +60,85 @@ struct HeadBN {
   int act;
 };
 
-// every CTA folds the per-tile partials of column c in the same fixed order (fp64): bit-identical scale / shift everywhere
-__device__ __forceinline__ void head_fold_stats(const float* __restrict__ part, int ntiles, int C, int B, int c, double* mean_out,
-                                                double* m2_out) {
-  double s = 0.0;
-  for (int t = 0; t < ntiles; ++t) {
-    const int nv = min(HR, B - t * HR);
-    s += (double)nv * (double)__ldg(&part[((size_t)t * 2) * C + c]);
+// Every CTA folds the per-tile partial pairs part[t][0..1][c] over all tiles in the same fixed order (fp64), so all CTAs hold
+// bit-identical results without a finalize launch: warp w takes tiles w, w+8, ... with its lanes across the columns (coalesced
+// 128-byte rows, independent loads in flight), then the eight warp sums are added in order.
+//   STATS: p0 = tile mean, p1 = tile M2 -> out0 = sum n_t*p0, out1 = sum (p1 + n_t*p0^2)   (mean = out0/B, M2 = out1 - out0^2/B)
+//   else : plain sums of both
+constexpr size_t kHeadFoldBytes = (size_t)(8 * 2 + 2) * kHeadMaxWidth * sizeof(double);
+template <bool STATS>
+__device__ __forceinline__ void head_fold(const float* __restrict__ part, int ntiles, int C, int B, double* sred, double* out0, double* out1) {
+  constexpr int NJ = kHeadMaxWidth / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if ((C & 3) == 0 && C <= 128) {
+    // common widths: one 16-byte load per (tile, row of the pair) and lane, eight tiles (16 loads) in flight per thread
+    double b0[4] = {0.0, 0.0, 0.0, 0.0}, b1[4] = {0.0, 0.0, 0.0, 0.0};
+    const int c4 = 4 * lane;
+    if (c4 < C) {
+      for (int t0 = warp; t0 < ntiles; t0 += 64) {
+        float4 p0[8], p1[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int t = t0 + 8 * u;
+          p0[u] = p1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (t < ntiles) {
+            p0[u] = __ldg(reinterpret_cast<const float4*>(&part[((size_t)t * 2) * C + c4]));
+            p1[u] = __ldg(reinterpret_cast<const float4*>(&part[((size_t)t * 2 + 1) * C + c4]));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int t = t0 + 8 * u;
+          if (t < ntiles) {
+            const double nv = (double)min(HR, B - t * HR);
+            const float q0[4] = {p0[u].x, p0[u].y, p0[u].z, p0[u].w}, q1[4] = {p1[u].x, p1[u].y, p1[u].z, p1[u].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (STATS) { b0[i] += nv * (double)q0[i]; b1[i] += (double)q1[i] + nv * (double)q0[i] * (double)q0[i]; }
+              else { b0[i] += (double)q0[i]; b1[i] += (double)q1[i]; }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sred[(warp * 2) * kHeadMaxWidth + c4 + i] = b0[i];
+        sred[(warp * 2 + 1) * kHeadMaxWidth + c4 + i] = b1[i];
+      }
+    }
+  } else {
+  double a0[NJ], a1[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) a0[j] = a1[j] = 0.0;
+#pragma unroll 4
+  for (int t = warp; t < ntiles; t += 8) {
+    const double nv = (double)min(HR, B - t * HR);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c = lane + 32 * j;
+      if (c < C) {
+        const double p0 = (double)__ldg(&part[((size_t)t * 2) * C + c]), p1 = (double)__ldg(&part[((size_t)t * 2 + 1) * C + c]);
+        if (STATS) { a0[j] += nv * p0; a1[j] += p1 + nv * p0 * p0; }
+        else { a0[j] += p0; a1[j] += p1; }
+      }
+    }
   }
-  const double mean = s / (double)B;
-  double m2 = 0.0;
-  for (int t = 0; t < ntiles; ++t) {
-    const int nv = min(HR, B - t * HR);
-    const double d = (double)__ldg(&part[((size_t)t * 2) * C + c]) - mean;
-    m2 += (double)__ldg(&part[((size_t)t * 2 + 1) * C + c]) + (double)nv * d * d;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int c = lane + 32 * j;
+    sred[(warp * 2) * kHeadMaxWidth + c] = a0[j];
+    sred[(warp * 2 + 1) * kHeadMaxWidth + c] = a1[j];
   }
-  *mean_out = mean;
-  *m2_out = m2;
+  }
+  __syncthreads();
+  if (tid < C) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { s0 += sred[(w * 2) * kHeadMaxWidth + tid]; s1 += sred[(w * 2 + 1) * kHeadMaxWidth + tid]; }
+    out0[tid] = s0;
+    out1[tid] = s1;
+  }
+  __syncthreads();
 }
 
 struct HeadFwdArgs {
@@ -98,26 +160,60 @@ struct HeadFwdArgs {
   float* loss_part;       // MSE: [ntiles]; multitask: [ntiles][2][Nout] (BCE sums, valid-label counts)
 };
 
-static inline size_t head_fwd_smem(int Kin, int Nout) {
-  return ((size_t)2 * kHeadMaxWidth + (size_t)HR * head_pitch(Kin) + (size_t)HKC * head_pitch(Nout) + (size_t)HR * head_pitch(Nout)) * 4;
+// Register-tiled fp32 GEMM core shared by the three GEMMs of the head: both operands in shared memory with the REDUCTION index
+// outermost ("k-major"), so that one 16-byte load fetches a thread's four rows (broadcast inside the warp) and one its four
+// columns (consecutive lanes, conflict-free): 2 LDS.128 per 16 FFMA.
+//   acc[r][4*p + c] += sum_k Ak[k][4*ty + r] * Bk[k][128*p + 4*tx + c]        r, c < 4; p < NCP (column passes of 128)
+// Bk must be zero-padded to 128*NCP columns, Ak to the 32 rows.
+constexpr int HAP = HR + 4;                                   // pitch of a k-major 32-row operand
+__host__ __device__ inline int head_cw(int n) { return n > 128 ? 256 : 128; }   // padded column extent of a B operand
+template <int NCP>
+__device__ __forceinline__ void head_mma(const float* __restrict__ sAk, int apitch, const float* __restrict__ sBk, int bpitch, int K, int ty, int tx,
+                                         float (&acc)[4][4 * NCP]) {
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 av = *reinterpret_cast<const float4*>(&sAk[k * apitch + 4 * ty]);
+    const float ar[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+    for (int p = 0; p < NCP; ++p) {
+      const float4 bv = *reinterpret_cast<const float4*>(&sBk[k * bpitch + 128 * p + 4 * tx]);
+      const float bc[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][4 * p + c] = fmaf(ar[r], bc[c], acc[r][4 * p + c]);
+    }
+  }
 }
 
-__global__ void __launch_bounds__(HT) head_fwd_kernel(const HeadFwdArgs a) {
+static inline size_t head_fwd_smem(int Kin, int Nout) {
+  const size_t gemm = ((size_t)Kin * HAP + (size_t)HKC * (head_cw(Nout) + 4) + (size_t)HR * head_pitch(Nout)) * 4;
+  return (size_t)2 * kHeadMaxWidth * 4 + (gemm > kHeadFoldBytes ? gemm : kHeadFoldBytes);
+}
+
+template <int NCP>
+__global__ void __launch_bounds__(HT, 2) head_fwd_kernel(const HeadFwdArgs a) {
   extern __shared__ __align__(16) float hsm[];
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  const int Kin = a.Kin, Nout = a.Nout, KP = head_pitch(Kin), NP = head_pitch(Nout);
+  const int Kin = a.Kin, Nout = a.Nout, NP = head_pitch(Nout);
+  constexpr int CW = 128 * NCP, BP = CW + 4;
   float* sScale = hsm;
   float* sShift = sScale + kHeadMaxWidth;
-  float* sA = sShift + kHeadMaxWidth;          // [HR][KP]
-  float* sW = sA + (size_t)HR * KP;            // [HKC][NP]
-  float* sO = sW + (size_t)HKC * NP;           // [HR][NP]
+  float* sAk = sShift + kHeadMaxWidth;         // [Kin][HAP]  A_{i-1} tile, k-major
+  float* sBk = sAk + (size_t)Kin * HAP;        // [HKC][BP]   chunk of W^T, zero-padded to CW columns
+  float* sO = sBk + (size_t)HKC * BP;          // [HR][NP]    staged outputs for the column reductions
   if (a.prev_bn) {
+    double* sred = reinterpret_cast<double*>(sAk);     // the GEMM region is free until the first tile
+    double* f0 = sred + 16 * kHeadMaxWidth;
+    double* f1 = f0 + kHeadMaxWidth;
+    if (a.training) head_fold<true>(a.bn.part, a.ntiles, Kin, a.B, sred, f0, f1);
     if (tid < Kin) {
       const int c = tid;
       float mean, invstd;
       if (a.training) {
-        double m, m2;
-        head_fold_stats(a.bn.part, a.ntiles, Kin, a.B, c, &m, &m2);
+        const double m = f0[c] / (double)a.B;
+        double m2 = f1[c] - f0[c] * m;
+        m2 = m2 > 0.0 ? m2 : 0.0;
         const double var = m2 / (double)a.B;
         mean = (float)m;
         invstd = (float)(1.0 / sqrt(var + (double)a.eps));
@@ -138,69 +234,60 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(const HeadFwdArgs a) {
     }
     __syncthreads();
   }
-  constexpr int NJ = kHeadMaxWidth / 32;
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const int row0 = tile * HR, nv = min(HR, a.B - row0);
+    // A tile, k-major: lane = row (conflict-free stores; the strided global reads of one warp are re-used from L1 by the next k)
     for (int e = tid; e < HR * Kin; e += HT) {
-      const int r = e / Kin, k = e - r * Kin;
+      const int r = e & (HR - 1), k = e >> 5;
       float v = 0.f;
       if (r < nv) {
         v = __ldg(&a.in[(size_t)(row0 + r) * Kin + k]);
         if (a.prev_bn) v = head_act(fmaf(v, sScale[k], sShift[k]), a.bn.act);
       }
-      sA[r * KP + k] = v;
+      sAk[k * HAP + r] = v;
     }
-    float acc[4][NJ];
+    float acc[4][4 * NCP];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) acc[r][j] = 0.f;
+      for (int c = 0; c < 4 * NCP; ++c) acc[r][c] = 0.f;
     for (int k0 = 0; k0 < Kin; k0 += HKC) {
       __syncthreads();
-      for (int e = tid; e < Nout * HKC; e += HT) {
-        const int o = e / HKC, k = e - o * HKC;
-        sW[k * NP + o] = (k0 + k < Kin) ? __ldg(&a.W[(size_t)o * Kin + k0 + k]) : 0.f;
+      for (int e = tid; e < HKC * CW; e += HT) {     // lane = output column: conflict-free stores, zero padding beyond Nout / Kin
+        const int o = e % CW, kk = e / CW;
+        sBk[kk * BP + o] = (o < Nout && k0 + kk < Kin) ? __ldg(&a.W[(size_t)o * Kin + k0 + kk]) : 0.f;
       }
       __syncthreads();
-      const int kn = min(HKC, Kin - k0);
-      for (int k = 0; k < kn; ++k) {
-        float av[4], wv[NJ];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) av[r] = sA[(ty * 4 + r) * KP + k0 + k];
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) wv[j] = (tx + 32 * j < Nout) ? sW[k * NP + tx + 32 * j] : 0.f;
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) acc[r][j] = fmaf(av[r], wv[j], acc[r][j]);
-      }
+      head_mma<NCP>(sAk + (size_t)k0 * HAP, HAP, sBk, BP, min(HKC, Kin - k0), ty, tx, acc);
     }
     // epilogue: bias (+ activation), store, stage for the column reductions
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const int o = tx + 32 * j;
-      if (o < Nout) {
-        const float bias = a.b ? __ldg(&a.b[o]) : 0.f;
+    for (int p = 0; p < NCP; ++p)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int rr = ty * 4 + r;
-          float u = acc[r][j] + bias;
-          if (!a.has_bn) u = head_act(u, a.act);
-          if (rr < nv) a.out[(size_t)(row0 + rr) * Nout + o] = u;
-          float staged = u;
-          if (!a.has_bn && a.loss != HLOSS_NONE && rr < nv) {
-            const float y = __ldg(&a.target[(size_t)(row0 + rr) * Nout + o]);
-            if (a.loss == HLOSS_MSE) {
-              staged = (u - y) * (u - y);
-            } else {   // BCE against the masked target; ignored labels count as class 0 (see head_loss_kernel)
-              const float t = (y == a.ignore) ? 0.f : y;
-              staged = -(t * fmaxf(logf(u), -100.f) + (1.f - t) * fmaxf(logf(1.f - u), -100.f));
+      for (int c = 0; c < 4; ++c) {
+        const int o = 128 * p + 4 * tx + c;
+        if (o < Nout) {
+          const float bias = a.b ? __ldg(&a.b[o]) : 0.f;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int rr = ty * 4 + r;
+            float u = acc[r][4 * p + c] + bias;
+            if (!a.has_bn) u = head_act(u, a.act);
+            if (rr < nv) a.out[(size_t)(row0 + rr) * Nout + o] = u;
+            float staged = u;
+            if (!a.has_bn && a.loss != HLOSS_NONE && rr < nv) {
+              const float y = __ldg(&a.target[(size_t)(row0 + rr) * Nout + o]);
+              if (a.loss == HLOSS_MSE) {
+                staged = (u - y) * (u - y);
+              } else {   // BCE against the masked target; ignored labels count as class 0 (see head_loss_kernel)
+                const float t = (y == a.ignore) ? 0.f : y;
+                staged = -(t * fmaxf(logf(u), -100.f) + (1.f - t) * fmaxf(logf(1.f - u), -100.f));
+              }
             }
+            sO[rr * NP + o] = staged;
           }
-          sO[rr * NP + o] = staged;
         }
       }
-    }
     __syncthreads();
     if (a.has_bn) {
       if (tid < Nout) {     // per-tile mean and M2 over the valid rows (two passes over the staged tile)
@@ -311,47 +398,54 @@ struct HeadBwdArgs {
   float* dbpart;           // [gridDim.x][Nout]
 };
 
+static inline int head_pad32(int n) { return (n + 31) / 32 * 32; }
 static inline size_t head_bwd_smem(int Kin, int Nout) {
-  return ((size_t)4 * kHeadMaxWidth + (size_t)HR * head_pitch(Nout) + (size_t)HR * head_pitch(Kin) + (size_t)HKC * head_pitch(Kin)) * 4;
+  const size_t gemm = ((size_t)HR * (head_pad32(Nout) + 4) + (size_t)head_pad32(Nout) * HAP + (size_t)2 * HR * (head_cw(Kin) + 4)) * 4;
+  return (size_t)4 * kHeadMaxWidth * 4 + (gemm > kHeadFoldBytes ? gemm : kHeadFoldBytes);
 }
 
-__global__ void __launch_bounds__(HT) head_bwd_kernel(const HeadBwdArgs a) {
+template <int NCP>
+__global__ void __launch_bounds__(HT, 2) head_bwd_kernel(const HeadBwdArgs a) {
   extern __shared__ __align__(16) float hsm[];
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  const int Kin = a.Kin, Nout = a.Nout, KP = head_pitch(Kin), NP = head_pitch(Nout);
+  const int Kin = a.Kin, Nout = a.Nout;
+  const int NO32 = (Nout + 31) / 32 * 32, NOP = NO32 + 4;
+  constexpr int CW = 128 * NCP, BP = CW + 4;
   float* sC0 = hsm;                              // hidden: gamma*invstd          (per output column)
   float* sC1 = sC0 + kHeadMaxWidth;              // hidden: dbeta / B
   float* sC2 = sC1 + kHeadMaxWidth;              // hidden: dgamma / B
-  float* sPs = sC2 + kHeadMaxWidth;              // previous layer: scale (first Kin) ... shift kept in registers-free form below
-  float* sdU = sPs + kHeadMaxWidth;              // [HR][NP]
-  float* sAp = sdU + (size_t)HR * NP;            // [HR][KP]  A_{i-1}
-  float* sWc = sAp + (size_t)HR * KP;            // [HKC][KP] chunk of W rows; reused as the dY_{i-1} staging tile [HR][KP]
+  float* sPs = sC2 + kHeadMaxWidth;              // (spare)
+  float* sdUr = sPs + kHeadMaxWidth;             // [HR][NOP]   dU tile, row-major (= k-major for dW, k = row), zero-padded to NO32 columns
+  float* sdUk = sdUr + (size_t)HR * NOP;         // [NO32][HAP] dU tile, k-major for dA (k = output column)
+  float* sAp = sdUk + (size_t)NO32 * HAP;        // [HR][BP]    A_{i-1} tile, row-major, zero-padded to CW columns
+  float* sWc = sAp + (size_t)HR * BP;            // [HKC][BP]   chunk of W rows; reused as the dY_{i-1} staging tile
   const float inv_B = 1.f / (float)a.B;
-  if (a.has_bn && tid < Nout) {
-    const int c = tid;
-    double dg = 0.0, db = 0.0;
-    for (int t = 0; t < a.ntiles; ++t) {
-      dg += (double)__ldg(&a.dpart[((size_t)t * 2) * Nout + c]);
-      db += (double)__ldg(&a.dpart[((size_t)t * 2 + 1) * Nout + c]);
+  if (a.has_bn) {
+    double* sred = reinterpret_cast<double*>(sdUr);    // the GEMM region is free until the first tile
+    double* f0 = sred + 16 * kHeadMaxWidth;
+    double* f1 = f0 + kHeadMaxWidth;
+    head_fold<false>(a.dpart, a.ntiles, Nout, a.B, sred, f0, f1);
+    if (tid < Nout) {
+      const int c = tid;
+      const double dg = f0[c], db = f1[c];
+      if (blockIdx.x == 0) { a.dgamma[c] = (float)dg; a.dbeta[c] = (float)db; }
+      sC0[c] = __ldg(&a.gamma[c]) * __ldg(&a.stat[Nout + c]);
+      sC1[c] = a.training ? (float)db * inv_B : 0.f;
+      sC2[c] = a.training ? (float)dg * inv_B : 0.f;
     }
-    if (blockIdx.x == 0) { a.dgamma[c] = (float)dg; a.dbeta[c] = (float)db; }
-    sC0[c] = __ldg(&a.gamma[c]) * __ldg(&a.stat[Nout + c]);
-    sC1[c] = a.training ? (float)db * inv_B : 0.f;
-    sC2[c] = a.training ? (float)dg * inv_B : 0.f;
   }
   const float gl = a.gloss ? __ldg(a.gloss) : 1.f;
   __syncthreads();
-  constexpr int NJ = kHeadMaxWidth / 32;
   float* dWp = a.dWpart + (size_t)blockIdx.x * Nout * Kin;
   float* dbp = a.dbpart + (size_t)blockIdx.x * Nout;
   int iter = 0;
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++iter) {
     const int row0 = tile * HR, nv = min(HR, a.B - row0);
-    // dU tile
-    for (int e = tid; e < HR * Nout; e += HT) {
-      const int r = e / Nout, o = e - r * Nout;
+    // dU tile (lane = output column: coalesced global reads), stored in both layouts
+    for (int e = tid; e < HR * NO32; e += HT) {
+      const int r = e / NO32, o = e - r * NO32;
       float du = 0.f;
-      if (r < nv) {
+      if (r < nv && o < Nout) {
         const size_t g = (size_t)(row0 + r) * Nout + o;
         if (a.has_bn) {
           const float yhat = (__ldg(&a.U[g]) - __ldg(&a.stat[o])) * __ldg(&a.stat[Nout + o]);
@@ -372,113 +466,95 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const HeadBwdArgs a) {
           du = dp * head_act_grad(p, a.act);
         }
       }
-      sdU[r * NP + o] = du;
+      sdUr[r * NOP + o] = du;
+      sdUk[o * HAP + r] = du;
     }
-    // A_{i-1} tile (recomputed from the saved pre-BN activations for hidden layers)
-    for (int e = tid; e < HR * Kin; e += HT) {
-      const int r = e / Kin, k = e - r * Kin;
+    // A_{i-1} tile (recomputed from the saved pre-BN activations for hidden layers), zero-padded to CW columns
+    for (int e = tid; e < HR * CW; e += HT) {
+      const int r = e / CW, k = e - r * CW;
       float v = 0.f;
-      if (r < nv) {
+      if (r < nv && k < Kin) {
         v = __ldg(&a.prev[(size_t)(row0 + r) * Kin + k]);
         if (a.prev_bn) {
           const float sc = __ldg(&a.pgamma[k]) * __ldg(&a.pstat[Kin + k]);
           v = head_act(fmaf(v, sc, __ldg(&a.pbeta[k]) - __ldg(&a.pstat[k]) * sc), a.pact);
         }
       }
-      sAp[r * KP + k] = v;
+      sAp[r * BP + k] = v;
     }
     __syncthreads();
     // db partial
     if (tid < Nout) {
       float s = 0.f;
-      for (int r = 0; r < nv; ++r) s += sdU[r * NP + tid];
+      for (int r = 0; r < nv; ++r) s += sdUr[r * NOP + tid];
       dbp[tid] = iter ? dbp[tid] + s : s;
     }
-    // dW partial: out[o][i] = sum_r dU[r][o] * A[r][i]; o = ty + 8*(4*pass + q), i = tx + 32*j
-    for (int pass = 0; pass * 32 < Nout; ++pass) {
-      float acc[4][NJ];
+    // dW partial, 32 output rows (o) per pass: out[o][i] = sum_r dU[r][o] * A[r][i]   (k = tile row; padded rows are zero)
+    for (int ob = 0; ob < NO32; ob += 32) {
+      float acc[4][4 * NCP];
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) acc[q][j] = 0.f;
-      for (int r = 0; r < nv; ++r) {
-        float dv[4], av[NJ];
+        for (int c = 0; c < 4 * NCP; ++c) acc[r][c] = 0.f;
+      head_mma<NCP>(sdUr + ob, NOP, sAp, BP, HR, ty, tx, acc);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int o = ty + 8 * (4 * pass + q);
-          dv[q] = o < Nout ? sdU[r * NP + o] : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) av[j] = (tx + 32 * j < Kin) ? sAp[r * KP + tx + 32 * j] : 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) acc[q][j] = fmaf(dv[q], av[j], acc[q][j]);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int o = ty + 8 * (4 * pass + q);
+      for (int r = 0; r < 4; ++r) {
+        const int o = ob + 4 * ty + r;
         if (o < Nout) {
 #pragma unroll
-          for (int j = 0; j < NJ; ++j) {
-            const int i = tx + 32 * j;
-            if (i < Kin) {
-              float* dst = &dWp[(size_t)o * Kin + i];
-              *dst = iter ? *dst + acc[q][j] : acc[q][j];
+          for (int p = 0; p < NCP; ++p)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int i = 128 * p + 4 * tx + c;
+              if (i < Kin) {
+                float* dst = &dWp[(size_t)o * Kin + i];
+                *dst = iter ? *dst + acc[r][4 * p + c] : acc[r][4 * p + c];
+              }
             }
-          }
         }
       }
     }
     if (a.dprev) {
       // dA_{i-1}[r][i] = sum_o dU[r][o] * W[o][i]
-      float acc[4][NJ];
+      float acc[4][4 * NCP];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) acc[r][j] = 0.f;
+        for (int c = 0; c < 4 * NCP; ++c) acc[r][c] = 0.f;
       for (int o0 = 0; o0 < Nout; o0 += HKC) {
         __syncthreads();
         const int on = min(HKC, Nout - o0);
-        for (int e = tid; e < on * Kin; e += HT) {
-          const int oo = e / Kin, i = e - oo * Kin;
-          sWc[oo * KP + i] = __ldg(&a.W[(size_t)(o0 + oo) * Kin + i]);
+        for (int e = tid; e < on * CW; e += HT) {
+          const int oo = e / CW, i = e - oo * CW;
+          sWc[oo * BP + i] = i < Kin ? __ldg(&a.W[(size_t)(o0 + oo) * Kin + i]) : 0.f;
         }
         __syncthreads();
-        for (int oo = 0; oo < on; ++oo) {
-          float dv[4], wv[NJ];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) dv[r] = sdU[(ty * 4 + r) * NP + o0 + oo];
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) wv[j] = (tx + 32 * j < Kin) ? sWc[oo * KP + tx + 32 * j] : 0.f;
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) acc[r][j] = fmaf(dv[r], wv[j], acc[r][j]);
-        }
+        head_mma<NCP>(sdUk + (size_t)o0 * HAP, HAP, sWc, BP, on, ty, tx, acc);
       }
       __syncthreads();     // all reads of sWc done: reuse it as the dY_{i-1} staging tile
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const int i = tx + 32 * j;
-        if (i < Kin) {
+      for (int p = 0; p < NCP; ++p)
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const int rr = ty * 4 + r;
-            float d = acc[r][j];
-            if (a.prev_bn) d *= head_act_grad(sAp[rr * KP + i], a.pact);
-            if (rr < nv) a.dprev[(size_t)(row0 + rr) * Kin + i] = d;
-            if (a.prev_bn) sWc[rr * KP + i] = (rr < nv) ? d : 0.f;
+        for (int c = 0; c < 4; ++c) {
+          const int i = 128 * p + 4 * tx + c;
+          if (i < Kin) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const int rr = ty * 4 + r;
+              float d = acc[r][4 * p + c];
+              if (a.prev_bn) d *= head_act_grad(sAp[rr * BP + i], a.pact);
+              if (rr < nv) a.dprev[(size_t)(row0 + rr) * Kin + i] = d;
+              if (a.prev_bn) sWc[rr * BP + i] = (rr < nv) ? d : 0.f;
+            }
           }
         }
-      }
       if (a.prev_bn) {
         __syncthreads();
         if (tid < Kin) {     // per-tile partial dgamma_{i-1} = sum_r dY * yhat, dbeta_{i-1} = sum_r dY
           const float mean = __ldg(&a.pstat[tid]), invstd = __ldg(&a.pstat[Kin + tid]);
           float dg = 0.f, db = 0.f;
           for (int r = 0; r < nv; ++r) {
-            const float d = sWc[r * KP + tid];
+            const float d = sWc[r * BP + tid];
             const float yhat = (__ldg(&a.prev[(size_t)(row0 + r) * Kin + tid]) - mean) * invstd;
             dg = fmaf(d, yhat, dg);
             db += d;

@@ -47,10 +47,12 @@ class DelayedLoss:
 
 
 class TrainStep:
-    def __init__(self, model, criterion, make_optimizer, example_batch, use_graph=True, warmup=3):
+    def __init__(self, model, criterion, make_optimizer, example_batch, use_graph=True, warmup=3, loss_fn=None):
         """model((x, adj)) -> predictions; criterion(pred, y) -> scalar; make_optimizer(params) -> torch optimizer that is
-        CUDA-graph capturable (e.g. Adam(fused=True, capturable=True)); example_batch = (x, adj, y) device tensors."""
-        self.model, self.criterion = model, criterion
+        CUDA-graph capturable (e.g. Adam(fused=True, capturable=True)); example_batch = (x, adj, y) device tensors.
+        loss_fn(model, (x, adj), y) -> scalar, optional: replaces criterion(model(inp), y), e.g. to evaluate the criterion
+        inside the MLP head's last kernel (openchem_b200.modules.mlp.openchem_mlp.fused_head_loss)."""
+        self.model, self.criterion, self.loss_fn = model, criterion, loss_fn
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         dev = example_batch[0].device
         self.params = [p for p in model.parameters() if p.requires_grad]
@@ -90,7 +92,7 @@ class TrainStep:
     def _body(self):
         self.flat_grad.zero_()
         x, adj, y = self.inputs
-        loss = self.criterion(self.model((x, adj)), y)
+        loss = self.loss_fn(self.model, (x, adj), y) if self.loss_fn is not None else self.criterion(self.model((x, adj)), y)
         loss.backward()
         if self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
