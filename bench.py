@@ -476,13 +476,18 @@ def run_native(args, w, wname):
                                 traffic=traffic, ms_per_launch=ms_launch, algorithmic_bytes_per_launch=bytes_launch,
                                 algorithmic_flops_per_launch=flops_launch, peak_source=peaks["source"] + ", burst bf16")
 
-    # ---- secondary device-resident numbers for the reference's own small-batch configuration (BASELINE configs[1]) ----
+    # ---- secondary device-resident numbers for the other named configurations (BASELINE configs[0], [1], [4] shapes at
+    # their per-GPU batch) with the same runtime ----
     others = {}
-    if world == 1 and not args.no_extra and wname != "c2_tox21":
-        try:
-            others["c2_tox21"] = measure_other("c2_tox21", args, dev, steps=100, warmup=10)
-        except Exception as exc:  # noqa: BLE001 - secondary numbers must never cost the headline line
-            others["c2_tox21"] = dict(error=repr(exc)[:200])
+    if world == 1 and not args.no_extra:
+        for other, n_steps in (("c1_logp", 100), ("c2_tox21", 100), ("c5_large", 20)):
+            if other == wname:
+                continue
+            try:
+                others[other] = measure_other(other, args, dev, steps=n_steps, warmup=10)
+            except Exception as exc:  # noqa: BLE001 - secondary numbers must never cost the headline line
+                others[other] = dict(error=repr(exc)[:200])
+            torch.cuda.empty_cache()
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
