@@ -272,7 +272,7 @@ static int run_wprep(const WPrepJobs& jobs, int n, cudaStream_t st) {
     const int p = ((jobs.K[j] + 63) / 64) * ((jobs.Nn[j] + 127) / 128);
     pieces = p > pieces ? p : pieces;
   }
-  wprep_kernel<<<dim3(pieces, n), 256, 0, st>>>(jobs);
+  wprep_kernel<<<dim3(8 * pieces, n), 256, 0, st>>>(jobs);
   LAUNCH_CHECK();
   return OCGCN_OK;
 }

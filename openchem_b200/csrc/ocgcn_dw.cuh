@@ -24,22 +24,31 @@ struct WPrepJobs {
   int form[kMaxPrepJobs];   // 0: element(n,k) = src[k*Nn + n] (src is [K][Nn]);  1: element(n,k) = src[n*K + k] (src is [Nn][K])
   int parts[kMaxPrepJobs];  // 2: hi and lo images, 1: hi only
 };
-// grid = (max pieces, jobs); one CTA writes the hi(/lo) piece pair (q, cbi)
+// grid = (8 * max pieces, jobs): one CTA writes one 16-byte-chunk row block (k-chunk kc = blockIdx.x % 8) of the hi(/lo) piece pair
+// (q, cbi) — four elements per thread, so the kernel is one load latency deep instead of 32
 __global__ void __launch_bounds__(256) wprep_kernel(const WPrepJobs jobs) {
   const int jb = blockIdx.y;
   const int K = jobs.K[jb], Nn = jobs.Nn[jb], parts = jobs.parts[jb];
   const int nq = (K + 63) / 64, ncb = (Nn + 127) / 128;
-  if ((int)blockIdx.x >= nq * ncb) return;
-  const int q = blockIdx.x / ncb, cbi = blockIdx.x % ncb;
+  const int piece = blockIdx.x >> 3, kc = blockIdx.x & 7;
+  if (piece >= nq * ncb) return;
+  const int q = piece / ncb, cbi = piece % ncb;
   const float* src = jobs.src[jb];
-  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(jobs.dst[jb]) + (size_t)blockIdx.x * parts * 8192;
-  for (int idx = threadIdx.x; idx < 8192; idx += 256) {
-    const int kc = idx >> 10, n = (idx >> 3) & 127, ke = idx & 7;
+  const int form = jobs.form[jb];
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(jobs.dst[jb]) + (size_t)piece * parts * 8192 + kc * 1024;
+  float v[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int idx = threadIdx.x + 256 * u;
+    const int n = idx >> 3, ke = idx & 7;
     const int k = q * 64 + kc * 8 + ke, ng = cbi * 128 + n;
-    float v = 0.f;
-    if (k < K && ng < Nn) v = jobs.form[jb] ? __ldg(&src[(size_t)ng * K + k]) : __ldg(&src[(size_t)k * Nn + ng]);
+    v[u] = (k < K && ng < Nn) ? (form ? __ldg(&src[(size_t)ng * K + k]) : __ldg(&src[(size_t)k * Nn + ng])) : 0.f;
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int idx = threadIdx.x + 256 * u;
     __nv_bfloat16 hi, lo;
-    tc::split_bf16(v, hi, lo);
+    tc::split_bf16(v[u], hi, lo);
     dst[idx] = hi;
     if (parts == 2) dst[8192 + idx] = lo;
   }
