@@ -43,43 +43,67 @@ __global__ void __launch_bounds__(kThreads) adj_pack_kernel(const float* __restr
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* ab = adj + (long long)b * as0;
   int nonbin = 0;
-  // rows in batches of four per warp: the eight loads of a batch are in flight together (the kernel is latency-bound otherwise)
+  // Row masks. Rows in batches of four per warp: the 8*NW loads of a batch are in flight together (the kernel is latency-bound
+  // otherwise). The ballots of a batch are parked in lanes 0 .. 4*NW-1 (slot = u*NW + w) and written with ONE store each to
+  // shared and global memory per batch instead of one predicated lane-0 store per word.
   for (int i0 = warp; i0 < N; i0 += 4 * kWarps) {
+    u64 mine = 0;
     for (int w = 0; w < NW; ++w) {
       const int j0 = 64 * w + lane, j1 = j0 + 32;
+      const long long o0 = (long long)j0 * as2, o1 = (long long)j1 * as2;
       float v0[4], v1[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int i = i0 + u * kWarps;
-        v0[u] = (i < N && j0 < N) ? __ldg(&ab[(long long)i * as1 + (long long)j0 * as2]) : 0.f;
-        v1[u] = (i < N && j1 < N) ? __ldg(&ab[(long long)i * as1 + (long long)j1 * as2]) : 0.f;
+        const float* rp = ab + (long long)i * as1;
+        v0[u] = (i < N && j0 < N) ? __ldg(rp + o0) : 0.f;
+        v1[u] = (i < N && j1 < N) ? __ldg(rp + o1) : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * kWarps;
-        nonbin |= (v0[u] != 0.f && v0[u] != 1.f) | (v1[u] != 0.f && v1[u] != 1.f);
+        // v*(v-1) == 0 exactly for v in {0, 1} (and -0), non-zero (or NaN) for everything else
+        nonbin |= (fabsf(v0[u] * (v0[u] - 1.f)) + fabsf(v1[u] * (v1[u] - 1.f)) != 0.f);
         const unsigned b0 = __ballot_sync(0xffffffffu, v0[u] != 0.f), b1 = __ballot_sync(0xffffffffu, v1[u] != 0.f);
-        if (lane == 0 && i < N) {
-          const u64 word = (u64)b0 | ((u64)b1 << 32);
-          sR[i * NW + w] = word;
-          rowmask[((size_t)b * N + i) * NW + w] = word;
-        }
+        if (lane == u * NW + w) mine = (u64)b0 | ((u64)b1 << 32);
+      }
+    }
+    if (lane < 4 * NW) {
+      const int u = lane / NW, w = lane - u * NW, i = i0 + u * kWarps;
+      if (i < N) {
+        sR[i * NW + w] = mine;
+        rowmask[((size_t)b * N + i) * NW + w] = mine;
       }
     }
   }
   nonbin = __syncthreads_or(nonbin);
-  // column masks = bit transpose of the row masks, by ballots: lane = row inside a group of 32 rows, one vote per column
-  for (int j = warp; j < N; j += kWarps) {
-    const int jw = j >> 6, jb = j & 63;
-    for (int w = 0; w < NW; ++w) {
-      const int i0 = 64 * w + lane, i1 = i0 + 32;
-      const unsigned b0 = __ballot_sync(0xffffffffu, i0 < N && ((sR[i0 * NW + jw] >> jb) & 1ull));
-      const unsigned b1 = __ballot_sync(0xffffffffu, i1 < N && ((sR[i1 * NW + jw] >> jb) & 1ull));
-      if (lane == 0) {
-        const u64 word = (u64)b0 | ((u64)b1 << 32);
-        sCm[j * NW + w] = word;
-        colmask[((size_t)b * N + j) * NW + w] = word;
+  // Column masks = bit transpose of the row masks, by ballots. A warp takes (row group g of 32 rows, block of 16 columns): every
+  // lane fetches the 16 bits of its row ONCE, the 16 votes are parked in lanes 0..15 and written as the g-th 32-bit half-word of
+  // the column's mask row with one store (little-endian: half-word g of a row of NW 64-bit words).
+  {
+    const int RG = (N + 31) >> 5, CB = (N + 15) >> 4;
+    unsigned* sCm32 = reinterpret_cast<unsigned*>(sCm);
+    unsigned* col32 = reinterpret_cast<unsigned*>(colmask) + (size_t)b * N * NW * 2;
+    for (int combo = warp; combo < RG * CB; combo += kWarps) {
+      const int g = combo / CB, c0 = (combo - g * CB) << 4;
+      const int i = 32 * g + lane;
+      const unsigned bits16 = i < N ? (unsigned)(sR[i * NW + (c0 >> 6)] >> (c0 & 63)) & 0xffffu : 0u;
+      unsigned parked = 0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const unsigned v = __ballot_sync(0xffffffffu, (bits16 >> k) & 1u);
+        if (lane == k) parked = v;
       }
+      const int j = c0 + lane;
+      if (lane < 16 && j < N) {
+        sCm32[j * NW * 2 + g] = parked;
+        col32[(size_t)j * NW * 2 + g] = parked;
+      }
+    }
+    // rows N .. 64*NW-1 do not exist: the upper half-words of the last mask word that no row group covered are zero
+    for (int idx = tid; idx < N * (NW * 2 - RG); idx += kThreads) {
+      const int j = idx / (NW * 2 - RG), h = RG + idx - j * (NW * 2 - RG);
+      sCm32[j * NW * 2 + h] = 0u;
+      col32[(size_t)j * NW * 2 + h] = 0u;
     }
   }
   __syncthreads();
