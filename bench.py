@@ -337,7 +337,6 @@ def run_native(args, w, wname):
     launches = functional.launch_counter["n"]
     if stepper is not None and stepper.graph is not None:
         launches = launches_per_body * args.steps     # replays re-issue the captured launches; count them from one eager body
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end region: every step's inputs come from pinned HOST memory (reference layout: dense fp32 adj / features /
     # labels) through the package's feeder (openchem_b200.loader.DevicePrefetcher: upload of batch t+1 overlaps step t), and
@@ -390,6 +389,11 @@ def run_native(args, w, wname):
     barrier()
     assert len([v for v in host_losses if v is not None]) == args.steps and all(math.isfinite(v) for v in host_losses[1:])
     ms_e2e_compact = max_over_ranks(e0.elapsed_time(e1))
+    # the clock / throttle sampler (nvidia-smi, ~20 Hz at best) ran through the device-resident AND the two end-to-end timed
+    # regions: the same load, enough samples for a median even when K steps last only tens of milliseconds
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "device-resident + end-to-end timed regions"
 
     # ---- per-kernel timing (CUDA events around every launch, on the launching stream) ----
     # (every rank runs the steps - they contain the DDP all-reduce - but only rank 0 records events)
