@@ -209,11 +209,12 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = a.N, NW = a.NW, K = a.K, NC = a.NC;
+  // Layout: [records][main region][flags][warp partials][barriers][tmem slot][row masks][column masks]. Only the bit masks have
+  // a run-time size (NW words per row); they come LAST so that every other region sits at a compile-time offset and its
+  // addresses fold into instruction immediates instead of being re-formed from NW inside the loops.
   uint4* sRec = reinterpret_cast<uint4*>(smem_raw);
   uint4* sCRec = sRec + TR;
-  u64* sRow = reinterpret_cast<u64*>(sCRec + TR);
-  u64* sCol = sRow + (size_t)TR * NW;
-  float* mainp = reinterpret_cast<float*>(sCol + (size_t)TR * NW);
+  float* mainp = reinterpret_cast<float*>(sCRec + TR);
   constexpr int BROWS = MM ? TR + 1 : TR;   // MM: row TR of each chunk buffer is the neutral dummy row of the padded neighbour records
   float* buf0 = mainp;
   float* buf1 = buf0 + BROWS * BS;
@@ -229,6 +230,8 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
   float* sWarp = reinterpret_cast<float*>(sFlag + TR);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sWarp + 2 * NWARP * 32);   // MM: [0] weight image landed, [1] MMAs complete, [2] second column block's weight image landed, [3] see tslot
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4);   // ([3]: saved operand image of the fused dW GEMM landed)
+  u64* sRow = reinterpret_cast<u64*>(bars + 8);               // (bars + 4 .. + 8: tslot and padding, 64 bytes after the warp partials in all)
+  u64* sCol = sRow + (size_t)TR * NW;
 
   const int tid = threadIdx.x, lane = tid & 31;
   // warp index through a shuffle: the compiler then KNOWS it is warp-uniform, keeps everything derived from it (row index,
