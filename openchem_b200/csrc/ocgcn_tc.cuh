@@ -104,11 +104,13 @@ __device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
   const uint32_t addr = smem_u32(bar);
+  // the suspend-time hint lets the hardware park the warp until the phase completes (or the hint expires) instead of returning to
+  // the loop every few hundred cycles: the polling instructions of 16 waiting warps otherwise take issue slots from the co-resident CTA
   do {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(0x989680u)
         : "memory");
   } while (!done);
 }
