@@ -291,12 +291,14 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
   const float* const do_t = (PROD == P_DU) ? a.in1 + (size_t)mol0 * K : nullptr;
 
   // ---- stage neighbour records (made tile-relative), masks and per-molecule flags ---------------------------
+  int simple = 1;   // every row AND column of the tile is a binary record with <= kMaxNbr neighbours (any molecular graph)
   for (int r = tid; r < TR; r += NT) {
     uint4 rec = make_uint4(0u, 0u, 0u, 0u), crec = make_uint4(0u, 0u, 0u, 0u);
     if (r < rows) {
       const int m = r / N, mb = m * N;
       rec = MM ? rec_stage_padded(__ldg(&a.nbr[row0 + r]), m, mb, TR) : rec_stage(__ldg(&a.nbr[row0 + r]), m, mb);
       crec = MM ? rec_stage_padded(__ldg(&a.cnbr[row0 + r]), m, mb, TR) : rec_stage(__ldg(&a.cnbr[row0 + r]), m, mb);
+      simple &= (int)(rec_binary(rec) && !rec_fallback(rec) && rec_binary(crec) && !rec_fallback(crec));
     }
     sRec[r] = rec;
     sCRec[r] = crec;
@@ -305,7 +307,9 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
     sRow[idx] = a.rowmask[row0 * NW + idx];
     sCol[idx] = a.colmask[row0 * NW + idx];
   }
-  __syncthreads();
+  // tile_simple selects row loops that contain ONLY the padded-record walk and are unrolled over the warp's RPW rows (their
+  // record, buffer and image addresses become immediates); hub rows / float adjacency take the general loops
+  const bool tile_simple = __syncthreads_and(simple) != 0 && MM;
 
   float acc[MM ? 1 : 8][MM ? 1 : 8];
 
@@ -447,6 +451,35 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
         if (MM && warp == 0) *reinterpret_cast<float2*>(&bufT[TR * BS + 2 * lane]) = make_float2(-INFINITY, -INFINITY);   // dummy row: never wins a max
         __syncthreads();
         // neighbour max-pool: P[i,c] = max_j A[i,j]*T[j,c], first index wins ties (gcn_encoder.py:44-50)
+        if (tile_simple) {
+#pragma unroll 2
+          for (int q = 0; q < RPW; ++q) {
+            const int r = warp + q * NWARP;
+            float b0 = 0.f, b1 = 0.f;
+            if (r < rows) {
+              const uint4 rec = sRec[r];
+              const int mb = rec_m(rec) * N;
+              int a0 = mb, a1 = mb;
+              rec_max2_padded<BS>(rec, &bufT[2 * lane], b0, b1, a0, a1);
+              if (rec_has_zero(rec)) {  // a zero entry A[i,jz] contributes the candidate 0*T = 0
+                const int jz = mb + rec_jz(rec);
+                if (!(b0 > 0.f)) { if (b0 < 0.f || jz < a0) a0 = jz; b0 = 0.f; }
+                if (!(b1 > 0.f)) { if (b1 < 0.f || jz < a1) a1 = jz; b1 = 0.f; }
+              }
+              if (first_pass && v0) {
+                unsigned char* ap = argo_t + (r * K + c);
+                if (kvec2) {
+                  *reinterpret_cast<uchar2*>(ap) = make_uchar2((unsigned char)(a0 - mb), (unsigned char)(a1 - mb));
+                } else {
+                  ap[0] = (unsigned char)(a0 - mb);
+                  if (v1) ap[1] = (unsigned char)(a1 - mb);
+                }
+              }
+            }
+            if (PROD == P_RO) put_operand(bufH, r, make_float2(b0, b1));
+            else *reinterpret_cast<float2*>(&bufH[r * BS + 2 * lane]) = make_float2(b0, b1);
+          }
+        } else
         for (int r = warp; r < TR; r += NWARP) {
           float b0 = 0.f, b1 = 0.f;
           if (r < rows) {
@@ -595,6 +628,15 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
 
       if (PROD == P_X || PROD == P_MID) {
         // S = A.H for this chunk (gcn.py:34): over the dead T buffer (FFMA) or into the operand images (MMA)
+        if (tile_simple) {
+#pragma unroll 2
+          for (int q = 0; q < RPW; ++q) {
+            const int r = warp + q * NWARP;
+            float2 s = make_float2(0.f, 0.f);
+            if (r < rows) s = rec_sum2_padded<BS>(sRec[r], &buf1[2 * lane]);
+            put_operand(buf0, r, s);
+          }
+        } else
         for (int r = warp; r < TR; r += NWARP) {
           float2 s = make_float2(0.f, 0.f);
           if (r < rows) {
