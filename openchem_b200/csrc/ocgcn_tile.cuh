@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
       if (PROD == P_X || PROD == P_MID) {
         // S = A.H for this chunk (gcn.py:34): over the dead T buffer (FFMA) or into the operand images (MMA)
         if (tile_simple) {
-#pragma unroll 2
+#pragma unroll 4
           for (int q = 0; q < RPW; ++q) {
             const int r = warp + q * NWARP;
             float2 s = make_float2(0.f, 0.f);
