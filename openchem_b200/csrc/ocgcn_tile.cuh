@@ -1054,6 +1054,13 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
 #pragma unroll 1
         for (int cs = 0; cs < TC; cs += 64) {
           float2 hv[RPW];
+          if (tile_simple) {
+#pragma unroll
+            for (int q = 0; q < RPW; ++q) {
+              const int r = warp + q * NWARP;
+              hv[q] = (r < rows) ? rec_sum2_padded<TCP>(sCRec[r], &sC[cs + 2 * lane]) : make_float2(0.f, 0.f);
+            }
+          } else
 #pragma unroll
           for (int q = 0; q < RPW; ++q) {
             const int r = warp + q * NWARP;
