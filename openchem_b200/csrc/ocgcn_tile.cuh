@@ -549,20 +549,21 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
         if (v0) { g.x = __ldg(&a.vec0[c]); c1.x = __ldg(&a.vec1[c]); c2.x = __ldg(&a.vec2[c]); mu.x = __ldg(&a.vec3[c]); is.x = __ldg(&a.vec4[c]); }
         if (v1) { g.y = __ldg(&a.vec0[c + 1]); c1.y = __ldg(&a.vec1[c + 1]); c2.y = __ldg(&a.vec2[c + 1]); mu.y = __ldg(&a.vec3[c + 1]); is.y = __ldg(&a.vec4[c + 1]); }
         float2 colsum = make_float2(0.f, 0.f);
+        constexpr int PB = MM ? 4 : 8;   // rows in flight per lane: 2*PB float2 registers (8 rows spill at 64 registers per thread)
 #pragma unroll
-        for (int h = 0; h < RPW / 8; ++h) {
-          float2 zv[8], dv[8];
+        for (int h = 0; h < RPW / PB; ++h) {
+          float2 zv[PB], dv[PB];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int r = warp + (h * 8 + q) * NWARP;
+          for (int q = 0; q < PB; ++q) {
+            const int r = warp + (h * PB + q) * NWARP;
             const bool ok = r < rows && v0;
             zv[q] = ok ? ldg2(&in1_t[r * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
             dv[q] = ok ? ldg2(&in0_t[r * K + c], v0, v1, kvec2) : make_float2(0.f, 0.f);
           }
           if (h == 0) chunk_sync();
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int r = warp + (h * 8 + q) * NWARP;
+          for (int q = 0; q < PB; ++q) {
+            const int r = warp + (h * PB + q) * NWARP;
             float2 dz = make_float2(0.f, 0.f);
             if (r < rows && v0) {
               dz.x = g.x * (dv[q].x - c1.x - (zv[q].x - mu.x) * is.x * c2.x);
