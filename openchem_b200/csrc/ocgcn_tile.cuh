@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
         __syncthreads();
         // neighbour max-pool: P[i,c] = max_j A[i,j]*T[j,c], first index wins ties (gcn_encoder.py:44-50)
         if (tile_simple) {
-#pragma unroll 2
+#pragma unroll 4
           for (int q = 0; q < RPW; ++q) {
             const int r = warp + q * NWARP;
             float b0 = 0.f, b1 = 0.f;
