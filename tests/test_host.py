@@ -190,6 +190,16 @@ int main(void) {
   printf("%d %d %zu %zu %s\n", ocgcn_abi_version(), rc, saved, scratch, ocgcn_status_string(OCGCN_EARCH));
   d.N = 1000;
   printf("%d\n", ocgcn_query_workspace(&d, &saved, &scratch));
+  /* MLP head: struct sizes (the ctypes mirrors in openchem_b200/_lib.py must agree) and the host-only workspace query */
+  ocgcn_head_desc h;
+  memset(&h, 0, sizeof h);
+  h.B = 64; h.n_layers = 2; h.width[0] = 128; h.width[1] = 128; h.width[2] = 1;
+  h.act[0] = OCGCN_ACT_RELU; h.act[1] = OCGCN_ACT_IDENTITY; h.training = 1; h.loss = OCGCN_LOSS_MSE; h.eps = 1e-5f; h.momentum = 0.1f;
+  rc = ocgcn_head_query_workspace(&h, &saved, &scratch);
+  printf("%zu %zu %zu %zu %d %zu %zu\n", sizeof(ocgcn_desc), sizeof(ocgcn_head_desc), sizeof(ocgcn_head_params), sizeof(ocgcn_head_grads),
+         rc, saved, scratch);
+  h.width[1] = 300;
+  printf("%d\n", ocgcn_head_query_workspace(&h, &saved, &scratch));
   return 0;
 }
 ''')
@@ -201,3 +211,9 @@ int main(void) {
     first = out[0].split(" ", 4)
     assert first[0] == "1" and first[1] == "0" and int(first[2]) > 0 and int(first[3]) > 0 and "sm_100" in first[4]
     assert out[1].strip() == "2"      # N > 256: OCGCN_EUNSUPPORTED
+    import ctypes
+    sizes = out[2].split()
+    assert [int(v) for v in sizes[:4]] == [ctypes.sizeof(_lib.Desc), ctypes.sizeof(_lib.HeadDesc), ctypes.sizeof(_lib.HeadParams),
+                                           ctypes.sizeof(_lib.HeadGrads)]
+    assert sizes[4] == "0" and int(sizes[5]) > 0 and int(sizes[6]) > 0
+    assert out[3].strip() == "2"      # head width > 256: OCGCN_EUNSUPPORTED
