@@ -1,4 +1,11 @@
-"""Encoder base class with the reference's surface (openchem/modules/encoders/openchem_encoder.py:7-28)."""
+"""Common base of the encoders on this path, behaviour-compatible with the reference's
+openchem/modules/encoders/openchem_encoder.py:7-28 (what subclasses and `Graph2Label` rely on):
+
+* `params` is kept as given; `input_size` / `encoder_dim` are read from it and exposed as attributes;
+* `use_cuda=None` means "whatever torch reports";
+* the dict returned by the (possibly overridden) `get_required_params()` is validated as BOTH the required and the optional
+  specification — the reference passes it twice (:11); subclasses then validate their own optional keys themselves.
+"""
 from __future__ import annotations
 
 import torch
@@ -6,23 +13,26 @@ from torch import nn
 
 from ...utils import check_params
 
+_SIZE_KEYS = ("input_size", "encoder_dim")
+
 
 class OpenChemEncoder(nn.Module):
     def __init__(self, params, use_cuda=None):
-        super().__init__()
-        check_params(params, self.get_required_params(), self.get_required_params())
+        nn.Module.__init__(self)
+        spec = self.get_required_params()
+        check_params(params, spec, spec)
         self.params = params
-        self.use_cuda = torch.cuda.is_available() if use_cuda is None else use_cuda
-        self.input_size = self.params["input_size"]
-        self.encoder_dim = self.params["encoder_dim"]
+        self.use_cuda = use_cuda if use_cuda is not None else torch.cuda.is_available()
+        for key in _SIZE_KEYS:
+            setattr(self, key, params[key])
 
     @staticmethod
     def get_required_params():
-        return {"input_size": int, "encoder_dim": int}
+        return dict.fromkeys(_SIZE_KEYS, int)
 
     @staticmethod
     def get_optional_params():
-        return {}
+        return dict()
 
     def forward(self, inp):
-        raise NotImplementedError
+        raise NotImplementedError("OpenChemEncoder is abstract")
