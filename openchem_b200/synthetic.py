@@ -120,3 +120,28 @@ WORKLOADS = {
     "c4_ddp":   dict(batch=2048, n_max=64, f0=64, hidden=[128] * 4, encoder_dim=128, mlp_hidden=[128, 1], task="regression"),
     "c5_large": dict(batch=1024, n_max=128, f0=64, hidden=[256] * 6, encoder_dim=256, mlp_hidden=[256, 1], task="regression"),
 }
+
+
+class SyntheticGraphDataset:
+    """A map-style data set with the sample layout of the reference's GraphDataset.__getitem__
+    (openchem/data/graph_data_layer.py:116-156): dicts of fp32 numpy arrays `adj_matrix` (N,N), `node_feature_matrix` (N,F0)
+    and `labels` (T,), which the default collate of run.py's DataLoader batches and `Graph2Label.cast_inputs`
+    (Graph2Label.py:39-64) uploads. Used by configs/*.py so the unmodified run.py / launch.py can be driven without RDKit."""
+
+    def __init__(self, size, n_max, f0, n_tasks=1, kind="regression", occupancy="molecular", seed=1234):
+        g = make_graph_batch(size, n_max, f0, occupancy=occupancy, seed=seed)
+        self.adj, self.x, self.n_atoms = g["adj"], g["x"], g["n_atoms"]
+        if kind == "regression":     # a learnable target: a fixed random linear readout of the atom-type counts, plus noise
+            rng = np.random.RandomState(seed + 1)
+            w = rng.randn(f0, n_tasks).astype(np.float32)
+            y = self.x.sum(axis=1) @ w / np.sqrt(n_max)
+            self.target = (y + 0.05 * rng.randn(size, n_tasks)).astype(np.float32)
+        else:
+            self.target = make_labels(size, n_tasks, kind=kind, seed=seed + 1)
+        self.max_size = int(n_max)
+
+    def __len__(self):
+        return self.adj.shape[0]
+
+    def __getitem__(self, index):
+        return {"adj_matrix": self.adj[index], "node_feature_matrix": self.x[index], "labels": self.target[index]}

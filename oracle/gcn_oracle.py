@@ -24,10 +24,49 @@ float64 arrays for the "fp64-promoted reference".
 """
 from __future__ import annotations
 
+import ctypes
+import os
+
 import numpy as np
 
 EPS = 1e-5
 MOMENTUM = 0.1
+
+# Optional plain-C scan of the max-pool (oracle/pool_scan.c: same arithmetic and scan order, OpenMP over molecules),
+# built by __graft_entry__.build() into oracle/_build/. Used only for large batches; the numpy loops below are the
+# definition and tests/test_oracle.py checks the two agree bit for bit.
+_POOL_LIB = None
+POOL_C_MIN_ELEMS = 1 << 22      # B*N*D above which the C scan is used (when the library is built)
+
+
+def pool_lib():
+    global _POOL_LIB
+    if _POOL_LIB is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libpool_scan.so")
+        _POOL_LIB = ctypes.CDLL(path) if os.path.exists(path) else False
+    return _POOL_LIB or None
+
+
+def _pool_c(name, T, adj, arg=None):
+    lib = pool_lib()
+    dt = T.dtype
+    if lib is None or dt not in (np.float64, np.float32) or adj.dtype != dt:
+        return None
+    B, N, D = T.shape
+    T = np.ascontiguousarray(T)
+    adj = np.ascontiguousarray(adj)
+    suffix = "f64" if dt == np.float64 else "f32"
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    dims = (ctypes.c_long(B), ctypes.c_long(N), ctypes.c_long(D))
+    if name == "fwd":
+        P = np.empty_like(T)
+        arg = np.empty((B, N, D), dtype=np.int64)
+        getattr(lib, "pool_fwd_" + suffix)(ptr(T), ptr(adj), *dims, ptr(P), ptr(arg))
+        return P, arg
+    arg = np.ascontiguousarray(arg, dtype=np.int64)
+    dT = np.empty_like(T)
+    getattr(lib, "pool_bwd_" + suffix)(ptr(T), ptr(adj), ptr(arg), *dims, ptr(dT))
+    return dT
 
 
 # --------------------------------------------------------------------------- #
@@ -90,7 +129,7 @@ def graph_conv_backward(dY, cache, need_dx=True):
 # --------------------------------------------------------------------------- #
 # Neighbour max-pool  (gcn_encoder.py:44-50)
 # --------------------------------------------------------------------------- #
-def neighbour_max_pool(T, adj):
+def neighbour_max_pool(T, adj, use_c=None):
     """P[b,i,c] = max_j adj[b,i,j] * T[b,j,c]; returns (P, first-argmax j*).
 
     The reference materialises a (B,N,N,D) tensor (x.repeat -> view -> * adj.expand
@@ -98,6 +137,12 @@ def neighbour_max_pool(T, adj):
     We scan j ascending with a strict '>' instead of materialising.
     """
     B, N, D = T.shape
+    if use_c is None:
+        use_c = B * N * D >= POOL_C_MIN_ELEMS
+    if use_c:
+        r = _pool_c("fwd", T, adj)
+        if r is not None:
+            return r
     best = adj[:, :, 0, None] * T[:, 0, None, :]
     arg = np.zeros((B, N, D), dtype=np.int64)
     for j in range(1, N):
@@ -108,9 +153,15 @@ def neighbour_max_pool(T, adj):
     return best, arg
 
 
-def neighbour_max_pool_backward(dP, adj, arg):
+def neighbour_max_pool_backward(dP, adj, arg, use_c=None):
     """dT[b,j,c] = sum_{i: j*[b,i,c]==j} adj[b,i,j] * dP[b,i,c]."""
     B, N, D = dP.shape
+    if use_c is None:
+        use_c = B * N * D >= POOL_C_MIN_ELEMS
+    if use_c:
+        r = _pool_c("bwd", dP, adj, arg)
+        if r is not None:
+            return r
     dT = np.zeros_like(dP)
     for j in range(N):
         sel = (arg == j)

@@ -1,5 +1,6 @@
 """The oracle (oracle/gcn_oracle.py) against the fixtures produced by the unmodified reference, plus
 reference-independent checks (hand-computed tie rule, finite differences). CPU only."""
+import os
 import numpy as np
 import pytest
 
@@ -161,3 +162,38 @@ def test_torch_restatement_matches_reference_fixture(case):
         assert rel_l2(p["running_var"][l].numpy(), g[f"ref32_rv{l}"]) < 1e-6
     assert rel_l2(p["Wd"].grad.numpy(), g["ref32_dWd"]) < 1e-5
     assert rel_l2(tr.encoder(x, adj, p, False).detach().numpy(), g["ref32_out_eval"]) < 1e-6
+
+
+def test_c_pool_scan_is_bit_identical_to_the_numpy_definition():
+    """oracle/pool_scan.c (used for benchmark-sized parity cases) vs the numpy loops that define the oracle: ties, signed
+    zeros, float adjacency, fully connected and empty rows, fp32 and fp64."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import __graft_entry__ as ge
+    if orc.pool_lib() is None:
+        try:
+            ge.build_oracle()
+        except (OSError, subprocess.CalledProcessError) as e:   # no gcc: the numpy definition is used everywhere
+            pytest.skip("cannot build oracle/pool_scan.c: %s" % e)
+        orc._POOL_LIB = None
+    assert orc.pool_lib() is not None
+    rs = np.random.RandomState(0)
+    for dt in (np.float64, np.float32):
+        for B, N, D in ((5, 17, 9), (3, 64, 33), (2, 1, 4)):
+            T = rs.randn(B, N, D).astype(dt)
+            if N > 5:
+                T[0, 3] = T[0, 5]                      # exact ties -> first index
+            T[-1] = -np.abs(T[-1])                     # all negative: the 0 * T candidates (signed zeros) win
+            adj = (rs.rand(B, N, N) < 0.2).astype(dt)
+            adj[0, 0] = 0                              # empty row
+            if B > 2:
+                adj[1] = rs.rand(N, N).astype(dt)      # float adjacency
+                adj[2] = 1                             # fully connected: no zero candidate
+            P0, a0 = orc.neighbour_max_pool(T, adj, use_c=False)
+            P1, a1 = orc.neighbour_max_pool(T, adj, use_c=True)
+            assert np.array_equal(a0, a1) and np.array_equal(P0, P1)
+            dP = rs.randn(B, N, D).astype(dt)
+            d0 = orc.neighbour_max_pool_backward(dP, adj, a0, use_c=False)
+            d1 = orc.neighbour_max_pool_backward(dP, adj, a0, use_c=True)
+            assert np.array_equal(d0, d1)
