@@ -54,14 +54,21 @@ def test_unmodified_run_py_through_both_routes_matches_the_reference_run(tmp_pat
     assert all(k.startswith("module.") for k in r1)
     for k in r1:
         assert torch.equal(r1[k], r2[k]), "routes 1 and 2 differ in " + k
-    worst = 0.0
+    # 16 Adam steps from identical initial weights (same --random_seed consumption order): the trajectories stay together.
+    # Exception: GraphConvolution.bias. Its gradient is analytically ZERO (BatchNorm removes the mean right after the bias is
+    # added), so every implementation feeds Adam pure round-off noise, which Adam normalises to +-lr steps: the reference's own
+    # CPU and GPU runs disagree there as well. For those the only meaningful bound is Adam's: |delta| <= 2 * steps * lr.
+    errs = {}
     for k in ref:
-        if ref[k].dtype.is_floating_point and ref[k].numel() > 1:
-            worst = max(worst, _rel(r1[k], ref[k]))
-        else:
-            assert torch.equal(r1[k].cpu(), ref[k].cpu()) or ref[k].dtype.is_floating_point, k
-    # 16 Adam steps from identical initial weights (same --random_seed consumption order): the trajectories stay together
-    assert worst < 2e-3, worst
+        if not ref[k].dtype.is_floating_point:
+            assert torch.equal(r1[k], ref[k]), k
+        elif ".graph_convolutions." in k and k.endswith(".bias") and ".bn." not in k:
+            assert float((r1[k] - ref[k]).abs().max()) <= 2 * 16 * 0.0005 * 1.01, k
+        elif ref[k].numel() > 1:
+            errs[k] = _rel(r1[k], ref[k])
+    worst = max(errs, key=errs.get)
+    print("drop-in vs reference run, worst tensors:", sorted(errs.items(), key=lambda kv: -kv[1])[:4])
+    assert errs[worst] < 2e-3, (worst, errs[worst])
     # --mode=eval reloads the `module.`-prefixed checkpoint into the wrapped model and evaluates (run.py:240-243, 258)
     r = run_reference_driver("shadow", "logp_gcnn_reference_imports.py", logs["shadow"], mode="eval", env_extra=SMALL)
     assert r.returncode == 0 and "EVALUATION" in r.stdout + r.stderr, r.stderr[-3000:]
