@@ -129,11 +129,13 @@ int ocgcn_layer_backward(const ocgcn_desc* desc, const float* grad_y, const floa
  *
  * ocgcn_expand_compact writes the contiguous dense fp32 x (B,N,F0) and adj (B,N,N) the entry points above take (bit-exact).
  * `index` (device, B int32, or NULL) gathers molecule index[b] of a compact data set resident in device memory into
- * batch slot b. Either output (with its bits) may be NULL to skip it.
+ * batch slot b; the data set holds n_src molecules. An index outside [0, n_src) is never dereferenced: that molecule is written
+ * as zeros and *index_oob (device int32, zeroed by the call; required with `index`) is set to 1. Either output (with its bits)
+ * may be NULL to skip it.
  * ocgcn_pack_compact is the inverse for strided dense inputs (element strides, molecule/row/column); *nonbinary (device
  * int32, zeroed by the call) is set to 1 if any entry is neither 0 nor 1 — such batches must use the dense entry points. */
-int ocgcn_expand_compact(int B, int N, int F0, const uint32_t* x_bits, const uint32_t* adj_bits, const int32_t* index,
-                         float* x, float* adj, void* stream);
+int ocgcn_expand_compact(int B, int N, int F0, const uint32_t* x_bits, const uint32_t* adj_bits, const int32_t* index, int n_src,
+                         int32_t* index_oob, float* x, float* adj, void* stream);
 int ocgcn_pack_compact(int B, int N, int F0, const float* x, const int64_t* x_stride, const float* adj,
                        const int64_t* adj_stride, uint32_t* x_bits, uint32_t* adj_bits, int32_t* nonbinary, void* stream);
 
@@ -209,6 +211,9 @@ int ocgcn_last_launch_count(void);
 int ocgcn_last_cuda_error(void);
 const char* ocgcn_status_string(int status);
 /* ABI version; bumped whenever a struct above changes. */
+/* Bumped whenever a struct layout or an entry-point signature changes (2: ocgcn_expand_compact gained n_src / index_oob;
+ * head and compact entry points exist). Bindings must refuse a library that reports another value. */
+#define OCGCN_ABI_VERSION 2
 int ocgcn_abi_version(void);
 
 #ifdef __cplusplus

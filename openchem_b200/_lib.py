@@ -98,16 +98,34 @@ def _stale():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
+ABI_VERSION = 2     # include/ocgcn.h OCGCN_ABI_VERSION: bump both whenever a struct layout or an entry-point signature changes
+
+
 def build(force=False, verbose=False):
-    """Compile csrc/*.cu for sm_100a into csrc/libocgcn.so (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a into csrc/libocgcn.so (nvcc cross-compiles without a GPU).
+
+    Ranks started together (torchrun / launch.py) may all find the library stale: the build is serialised with an advisory file
+    lock, written to a temporary path and renamed into place, so no process can dlopen a half-written file."""
     if not force and not _stale():
         return LIB_PATH
-    cmd = nvcc_command(extra=("-Xptxas", "-v") if verbose else ())
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():      # another process built it while we waited
+                return LIB_PATH
+            tmp = "%s.tmp.%d" % (LIB_PATH, os.getpid())
+            cmd = nvcc_command(out=tmp, extra=("-Xptxas", "-v") if verbose else ())
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, LIB_PATH)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
@@ -131,6 +149,9 @@ def load():
                     raise RuntimeError(
                         "openchem_b200: libocgcn.so is missing and could not be built (%s). "
                         "There is no CPU/PyTorch fallback for this path; run `python -c 'import __graft_entry__ as g; g.build()'`." % exc)
+                import warnings
+                warnings.warn("openchem_b200: libocgcn.so is older than its sources and the rebuild failed (%s); loading the STALE "
+                              "library (its ABI version is still checked)" % (str(exc)[:200],), RuntimeWarning)
         lib = ctypes.CDLL(LIB_PATH)
         for name in EXPORTS:
             if not hasattr(lib, name):
@@ -144,7 +165,7 @@ def load():
         lib.ocgcn_saved_tensor.argtypes = [ctypes.POINTER(Desc), ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]
         lib.ocgcn_saved_tensor.restype = ctypes.c_int
         i64p = ctypes.POINTER(ctypes.c_int64)
-        lib.ocgcn_expand_compact.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+        lib.ocgcn_expand_compact.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, vp, vp, vp]
         lib.ocgcn_expand_compact.restype = ctypes.c_int
         lib.ocgcn_pack_compact.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, i64p, vp, i64p, vp, vp, vp, vp]
         lib.ocgcn_pack_compact.restype = ctypes.c_int
@@ -163,8 +184,9 @@ def load():
         for name in ("ocgcn_query_workspace", "ocgcn_encoder_forward", "ocgcn_encoder_backward", "ocgcn_layer_forward",
                      "ocgcn_layer_backward", "ocgcn_last_launch_count", "ocgcn_last_cuda_error", "ocgcn_abi_version"):
             getattr(lib, name).restype = ctypes.c_int
-        if lib.ocgcn_abi_version() != 1:
-            raise RuntimeError("libocgcn.so ABI version mismatch; rebuild it")
+        if lib.ocgcn_abi_version() != ABI_VERSION:
+            raise RuntimeError("libocgcn.so reports ABI version %d, this binding needs %d; rebuild it "
+                               "(python -c 'import __graft_entry__ as g; g.build()')" % (lib.ocgcn_abi_version(), ABI_VERSION))
         _lib = lib
     return _lib
 

@@ -101,10 +101,10 @@ class CompactGraphBatch:
             raise RuntimeError("openchem_b200.compact: expand() runs on the device (there is no CPU path); call .to('cuda') first")
         xb, ab = self.x_bits.contiguous(), self.adj_bits.contiguous()
         N, F0 = self.n_atoms, self.n_features
+        oob = None
         if index is not None:
-            if index.dtype != torch.int32 or not index.is_cuda or index.dim() != 1:
-                raise TypeError("openchem_b200.compact: index must be a 1-D int32 CUDA tensor")
-            index = index.contiguous()
+            index = self._checked_index(index)
+            oob = torch.empty(1, dtype=torch.int32, device=self.device)
         B = self.batch_size if index is None else index.shape[0]
         if out is None:
             x = torch.empty((B, N, F0), dtype=torch.float32, device=self.device)
@@ -118,10 +118,31 @@ class CompactGraphBatch:
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             _lib.check(lib.ocgcn_expand_compact(B, N, F0, xb.data_ptr(), ab.data_ptr(), index.data_ptr() if index is not None else None,
+                                                self.batch_size, oob.data_ptr() if oob is not None else None,
                                                 x.data_ptr(), adj.data_ptr(), stream))
         from . import functional
         functional.launch_counter["n"] += lib.ocgcn_last_launch_count()
+        self.last_index_oob = oob      # device flag of this gather (1 = some index was out of range and expanded to zeros)
         return x, adj
+
+    def _checked_index(self, index):
+        """-> 1-D int32 CUDA index. Host indices (list / numpy / CPU tensor: the usual case, a sampler's permutation) are
+        bounds-checked on the host before the upload; a CUDA index is checked by the kernel itself, which never dereferences
+        an out-of-range entry and raises `last_index_oob` (read it with .item() when a synchronisation is acceptable)."""
+        n = self.batch_size
+        if not (isinstance(index, torch.Tensor) and index.is_cuda):
+            host = torch.as_tensor(index)
+            if host.dim() != 1 or host.dtype not in (torch.int32, torch.int64, torch.int16, torch.uint8, torch.int8):
+                raise TypeError("openchem_b200.compact: index must be a 1-D integer tensor")
+            if host.numel() and (int(host.min()) < 0 or int(host.max()) >= n):
+                raise IndexError("openchem_b200.compact: index out of range for a data set of %d molecules (min %d, max %d)" %
+                                 (n, int(host.min()), int(host.max())))
+            return host.to(torch.int32).to(self.device).contiguous()
+        if index.dim() != 1 or index.dtype not in (torch.int32, torch.int64):
+            raise TypeError("openchem_b200.compact: index must be a 1-D int32 / int64 CUDA tensor")
+        if index.dtype == torch.int64:      # values that do not fit in int32 must not wrap into range
+            index = index.clamp(min=-1, max=2 ** 31 - 1).to(torch.int32)
+        return index.to(self.device).contiguous()
 
 
 def pack_graph_batch(x, adj, labels=None):
@@ -180,7 +201,9 @@ class ResidentCompactDataset:
         return self.data.batch_size
 
     def batch(self, index, out=None):
-        index = index.to(device=self.data.device, dtype=torch.int32)
+        index = self.data._checked_index(index)
         x, adj = self.data.expand(out=out, index=index)
-        labels = None if self.data.labels is None else self.data.labels.index_select(0, index.long())
+        labels = None
+        if self.data.labels is not None:      # (clamped: an out-of-range entry was already flagged / expanded to zeros above)
+            labels = self.data.labels.index_select(0, index.long().clamp(0, len(self) - 1))
         return x, adj, labels

@@ -173,7 +173,7 @@ static int make_layout(const ocgcn_desc* d, bool layer_only, Layout* lo) {
     lo->dU = take(rows * d->E * 4);
   }
   for (int i = 0; i < 3; ++i) lo->G[i] = take(rows * Fmax * 4);
-  lo->coef = take((size_t)3 * Fmax * 4);
+  lo->coef = take((size_t)3 * ((Fmax + 3) / 4 * 4) * 4);   // three vectors at a 16-byte aligned stride (float4 loads)
   if (lo->mm) {
     for (int l = 0; l < d->L; ++l) {
       lo->Wf[l] = take(wimg_bytes(d->F[l], d->F[l + 1], 2));
@@ -192,17 +192,29 @@ static int make_layout(const ocgcn_desc* d, bool layer_only, Layout* lo) {
   return OCGCN_OK;
 }
 
+constexpr int kMaxDevices = 64;
 static int check_device() {
+  static std::atomic<int> major_of[kMaxDevices];   // 0 = not asked yet (immutable per device afterwards)
   int dev = 0, major = 0;
   CU_TRY(cudaGetDevice(&dev));
-  CU_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (dev >= 0 && dev < kMaxDevices) major = major_of[dev].load(std::memory_order_relaxed);
+  if (major == 0) {
+    CU_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (dev >= 0 && dev < kMaxDevices) major_of[dev].store(major, std::memory_order_relaxed);
+  }
   if (major != 10) return OCGCN_EARCH;
   return OCGCN_OK;
 }
 
+// Is `p` device (or managed) memory? cudaPointerGetAttributes costs ~1 us; a training loop passes the same few dozen parameter
+// and workspace addresses every step, so validated addresses are remembered in a small per-thread direct-mapped table. (Unified
+// virtual addressing: an address that was device memory once can only ever be device memory again, never a host allocation.)
 static int check_device_ptr(const void* p) {
   if (!p) return OCGCN_EINVAL;
   if (((uintptr_t)p & 3) != 0) return OCGCN_EALIGN;
+  static thread_local const void* seen[256];
+  const size_t slot = ((uintptr_t)p >> 4) * 0x9E3779B97F4A7C15ull >> 56;
+  if (seen[slot] == p) return OCGCN_OK;
   cudaPointerAttributes at;
   cudaError_t e = cudaPointerGetAttributes(&at, p);
   if (e != cudaSuccess) {
@@ -210,6 +222,20 @@ static int check_device_ptr(const void* p) {
     return OCGCN_EINVAL;
   }
   if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) return OCGCN_EINVAL;  // no CPU fallback
+  seen[slot] = p;
+  return OCGCN_OK;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) and size class instead of on every launch
+template <auto Kern>
+static int ensure_dynamic_smem(size_t smem) {
+  static std::atomic<size_t> granted[kMaxDevices];
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  const bool track = dev >= 0 && dev < kMaxDevices;
+  if (track && granted[dev].load(std::memory_order_relaxed) >= smem) return OCGCN_OK;
+  CU_TRY(cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (track) granted[dev].store(smem, std::memory_order_relaxed);
   return OCGCN_OK;
 }
 
@@ -224,7 +250,7 @@ static int launch_tile_t(const TileArgs& a, int tiles, cudaStream_t st) {
   ProfScope prof(PROD == P_X ? KK_FWD_FIRST : PROD == P_MID ? KK_FWD_MID : PROD == P_RO ? KK_FWD_READOUT : PROD == P_DZ ? KK_BWD_DZ : KK_BWD_READOUT, st);
   auto kern = tile_kernel<TR, TC, PROD, EPI, MM, NT>;
   const size_t smem = tile_smem_bytes<TR, TC, MM, NT>(a.NW);
-  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ST_TRY((ensure_dynamic_smem<tile_kernel<TR, TC, PROD, EPI, MM, NT>>(smem)));
   // persistent (two CTAs per SM looping over tiles) only where the CTA accumulates the weight gradient across its tiles;
   // everything else launches one CTA per tile (dynamic scheduling balances and de-phases the co-resident CTAs better)
   kern<<<((MM && a.dw_img) ? mm_grid(tiles) : tiles), NT, smem, st>>>(a);
@@ -257,7 +283,7 @@ static int run_dw_mma(const Layout& lo, const void* Aimg, const void* Bimg, int 
   stages = stages < 1 ? 1 : stages > 4 ? 4 : stages;
   g.stages = stages;
   const size_t smem = stage * stages + (size_t)(2 * stages + 1) * 8 + 16;
-  CU_TRY(cudaFuncSetAttribute(dw_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ST_TRY((ensure_dynamic_smem<dw_mma_kernel>(smem)));
   dw_mma_kernel<<<splits, 128, smem, st>>>(g);
   LAUNCH_CHECK();
   *splits_out = splits;
@@ -285,11 +311,11 @@ static int launch_bwd_dy(const Layout& lo, const BwdDyArgs& a, cudaStream_t st) 
   ProfScope prof(KK_BWD_DY, st);
   if (lo.TR == 128) {
     const size_t smem = bwd_dy_smem_bytes<128>(a.NW);
-    CU_TRY(cudaFuncSetAttribute(bwd_dy_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ST_TRY((ensure_dynamic_smem<bwd_dy_kernel<128>>(smem)));
     bwd_dy_kernel<128><<<lo.tiles, kThreads, smem, st>>>(a);
   } else {
     const size_t smem = bwd_dy_smem_bytes<256>(a.NW);
-    CU_TRY(cudaFuncSetAttribute(bwd_dy_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ST_TRY((ensure_dynamic_smem<bwd_dy_kernel<256>>(smem)));
     bwd_dy_kernel<256><<<lo.tiles, kThreads, smem, st>>>(a);
   }
   LAUNCH_CHECK();
@@ -364,13 +390,22 @@ static int run_reduce(const ReduceJobs& j, cudaStream_t st) {
   return OCGCN_OK;
 }
 
+// every parameter / buffer pointer must be non-null DEVICE memory (a module left on the host is an error, not a fault)
 static int validate_params(const ocgcn_desc* d, const ocgcn_params* p, bool layer_only) {
   if (!p) return OCGCN_EINVAL;
   for (int l = 0; l < d->L; ++l) {
-    if (!p->W[l] || !p->gamma[l] || !p->beta[l] || !p->running_mean[l] || !p->running_var[l]) return OCGCN_EINVAL;
-    if (d->has_bias && !p->b[l]) return OCGCN_EINVAL;
+    ST_TRY(check_device_ptr(p->W[l]));
+    ST_TRY(check_device_ptr(p->gamma[l]));
+    ST_TRY(check_device_ptr(p->beta[l]));
+    ST_TRY(check_device_ptr(p->running_mean[l]));
+    ST_TRY(check_device_ptr(p->running_var[l]));
+    if (d->has_bias) ST_TRY(check_device_ptr(p->b[l]));
+    if (p->num_batches_tracked[l]) ST_TRY(check_device_ptr(p->num_batches_tracked[l]));
   }
-  if (!layer_only && (!p->Wd || !p->bd)) return OCGCN_EINVAL;
+  if (!layer_only) {
+    ST_TRY(check_device_ptr(p->Wd));
+    ST_TRY(check_device_ptr(p->bd));
+  }
   return OCGCN_OK;
 }
 
@@ -441,7 +476,8 @@ static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float
   f.partials = partials; f.T = lo.tiles; f.F = Fout; f.training = d->training; f.n = (double)lo.rows;
   f.gamma = p->gamma[l]; f.invstd = stats + Fout;
   f.dgamma = g->dgamma[l]; f.dbeta = g->dbeta[l];
-  f.g = coef; f.c1 = coef + lo.Fmax; f.c2 = coef + 2 * lo.Fmax;
+  const int cstride = (lo.Fmax + 3) / 4 * 4;
+  f.g = coef; f.c1 = coef + cstride; f.c2 = coef + 2 * cstride;
   {
     ProfScope prof(KK_BWD_FINALIZE, st);
     if (chan_wide(lo.tiles)) bwd_finalize_kernel<kChanColsWide><<<(Fout + kChanColsWide - 1) / kChanColsWide, kRedThreads, 0, st>>>(f);
@@ -452,7 +488,7 @@ static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float
   TileArgs a = base_tile_args(d, lo, adj, saved);
   a.K = Fout; a.NC = Fin;
   a.in0 = g_in; a.in1 = Z;
-  a.vec0 = coef; a.vec1 = coef + lo.Fmax; a.vec2 = coef + 2 * lo.Fmax; a.vec3 = stats; a.vec4 = stats + Fout;
+  a.vec0 = coef; a.vec1 = coef + cstride; a.vec2 = coef + 2 * cstride; a.vec3 = stats; a.vec4 = stats + Fout;
   a.prod_out = g_dz;
   a.prod_partials = (d->has_bias && g->db[l]) ? prodpart : nullptr;
   a.Bm = reinterpret_cast<const float*>(scratch + lo.WT[l]);
@@ -499,7 +535,7 @@ using namespace ocgcn;
 
 extern "C" {
 
-int ocgcn_abi_version(void) { return 1; }
+int ocgcn_abi_version(void) { return OCGCN_ABI_VERSION; }
 
 int ocgcn_profile_enable(int on) {
   g_prof_on.store(on != 0);
@@ -774,26 +810,28 @@ static int bits_grid(long long work_items) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-int ocgcn_expand_compact(int B, int N, int F0, const uint32_t* x_bits, const uint32_t* adj_bits, const int32_t* index, float* x,
-                         float* adj, void* stream) {
+int ocgcn_expand_compact(int B, int N, int F0, const uint32_t* x_bits, const uint32_t* adj_bits, const int32_t* index, int n_src,
+                         int32_t* index_oob, float* x, float* adj, void* stream) {
   tl_launches = 0;
   if (B <= 0 || N <= 0 || F0 <= 0) return OCGCN_EINVAL;
   if ((x != nullptr) != (x_bits != nullptr) || (adj != nullptr) != (adj_bits != nullptr) || (!x && !adj)) return OCGCN_EINVAL;
+  if (index && (n_src <= 0 || !index_oob)) return OCGCN_EINVAL;
   ST_TRY(check_device());
   if (x) { ST_TRY(check_device_ptr(x)); ST_TRY(check_device_ptr(x_bits)); }
   if (adj) { ST_TRY(check_device_ptr(adj)); ST_TRY(check_device_ptr(adj_bits)); }
-  if (index) ST_TRY(check_device_ptr(index));
+  if (index) { ST_TRY(check_device_ptr(index)); ST_TRY(check_device_ptr(index_oob)); }
   if (((uintptr_t)x & 15) || ((uintptr_t)adj & 15)) return OCGCN_EALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (index) CU_TRY(cudaMemsetAsync(index_oob, 0, sizeof(int32_t), st));
   const long long rows = (long long)B * N;
   if (adj) {
     ProfScope ps(KK_EXPAND, st);
-    expand_bits_kernel<<<bits_grid(rows * ((N + 3) / 4)), 256, 0, st>>>(adj_bits, index, N, N, (N + 31) / 32, rows, adj);
+    expand_bits_kernel<<<bits_grid(rows * ((N + 3) / 4)), 256, 0, st>>>(adj_bits, index, n_src, index_oob, N, N, (N + 31) / 32, rows, adj);
     LAUNCH_CHECK();
   }
   if (x) {
     ProfScope ps(KK_EXPAND, st);
-    expand_bits_kernel<<<bits_grid(rows * ((F0 + 3) / 4)), 256, 0, st>>>(x_bits, index, N, F0, (F0 + 31) / 32, rows, x);
+    expand_bits_kernel<<<bits_grid(rows * ((F0 + 3) / 4)), 256, 0, st>>>(x_bits, index, n_src, index_oob, N, F0, (F0 + 31) / 32, rows, x);
     LAUNCH_CHECK();
   }
   return OCGCN_OK;

@@ -17,8 +17,11 @@
 namespace ocgcn {
 
 // one thread per group of four consecutive columns; rows = B*N output rows of C columns
-__global__ void __launch_bounds__(256) expand_bits_kernel(const uint32_t* __restrict__ bits, const int* __restrict__ index, int N,
-                                                          int C, int W, long long rows, float* __restrict__ out) {
+// `index` entries outside [0, n_src) are never dereferenced: the molecule is written as zeros and *oob (integer flag, order-independent)
+// is raised, like pack_bits_kernel's non-binary flag
+__global__ void __launch_bounds__(256) expand_bits_kernel(const uint32_t* __restrict__ bits, const int* __restrict__ index, int n_src,
+                                                          int* __restrict__ oob, int N, int C, int W, long long rows,
+                                                          float* __restrict__ out) {
   const int C4 = (C + 3) >> 2;
   const long long total = rows * C4;
   const bool vec = (C & 3) == 0;
@@ -26,11 +29,15 @@ __global__ void __launch_bounds__(256) expand_bits_kernel(const uint32_t* __rest
     const long long row = idx / C4;
     const int c = (int)(idx - row * C4) << 2;
     long long srow = row;
+    bool ok = true;
     if (index) {
       const long long b = row / N;
-      srow = (long long)__ldg(&index[b]) * N + (row - b * N);
+      const int src = __ldg(&index[b]);
+      ok = src >= 0 && src < n_src;
+      if (!ok && c == 0 && row == b * N) atomicOr(oob, 1);
+      srow = (long long)src * N + (row - b * N);
     }
-    const uint32_t nib = (__ldg(&bits[srow * W + (c >> 5)]) >> (c & 31)) & 0xfu;   // c is a multiple of 4: one word holds all four
+    const uint32_t nib = ok ? (__ldg(&bits[srow * W + (c >> 5)]) >> (c & 31)) & 0xfu : 0u;   // c is a multiple of 4: one word holds all four
     const float v0 = (nib & 1u) ? 1.f : 0.f, v1 = (nib & 2u) ? 1.f : 0.f, v2 = (nib & 4u) ? 1.f : 0.f, v3 = (nib & 8u) ? 1.f : 0.f;
     float* dst = out + row * C + c;
     if (vec) {

@@ -148,6 +148,11 @@ __device__ __forceinline__ void split2_bf16(float x0, float x1, uint32_t& hi, ui
   const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
 }
+// four fp32 -> two packed hi words and two packed lo words (8 bytes of an operand image row each)
+__device__ __forceinline__ void split4_bf16(const float4& x, uint2& hi, uint2& lo) {
+  split2_bf16(x.x, x.y, hi.x, lo.x);
+  split2_bf16(x.z, x.w, hi.y, lo.y);
+}
 // tf32: hi keeps the top 19 bits (the MMA ignores the low 13 mantissa bits), lo = x - hi (exact in fp32)
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);

@@ -164,6 +164,62 @@ __device__ __forceinline__ float2 rec_sum2_padded(const uint4& rec, const float*
   return make_float2(s0, s1);
 }
 
+// ---- four adjacent channels (LDS.128) per lane over PADDED records: the walks of the tensor-core engine's fast paths --------
+// A warp covers two tile rows at once (half-warp = one row x 64 channels), or one row x 128 channels; `colp` already points at
+// this lane's four channels of buffer row 0. Unused neighbour slots of a padded record point at the buffer's neutral dummy row
+// (-inf for the max, 0 for the sums), so the first four steps need no count checks. Same candidate / summation order as the
+// two-channel walks above (ascending neighbour index, first index wins ties).
+template <int STRIDE>
+__device__ __forceinline__ void rec_max4_padded(const uint4& rec, const float* colp, float (&b)[4], int (&a)[4]) {
+  const int cnt = rec_cnt(rec);
+  const int j0 = rec_idx<0>(rec), j1 = rec_idx<1>(rec), j2 = rec_idx<2>(rec), j3 = rec_idx<3>(rec);
+  const float4 v0 = *reinterpret_cast<const float4*>(colp + j0 * STRIDE);
+  const float4 v1 = *reinterpret_cast<const float4*>(colp + j1 * STRIDE);
+  const float4 v2 = *reinterpret_cast<const float4*>(colp + j2 * STRIDE);
+  const float4 v3 = *reinterpret_cast<const float4*>(colp + j3 * STRIDE);
+  b[0] = v0.x; b[1] = v0.y; b[2] = v0.z; b[3] = v0.w;
+  a[0] = a[1] = a[2] = a[3] = j0;
+#define OCGCN_MAX4(V, J)                          \
+  if (V.x > b[0]) { b[0] = V.x; a[0] = J; }       \
+  if (V.y > b[1]) { b[1] = V.y; a[1] = J; }       \
+  if (V.z > b[2]) { b[2] = V.z; a[2] = J; }       \
+  if (V.w > b[3]) { b[3] = V.w; a[3] = J; }
+  OCGCN_MAX4(v1, j1) OCGCN_MAX4(v2, j2) OCGCN_MAX4(v3, j3)
+#define OCGCN_MAX_STEP(Q)                                                        \
+  if (cnt > Q) {                                                                 \
+    const int jr = rec_idx<Q>(rec);                                              \
+    const float4 v = *reinterpret_cast<const float4*>(colp + jr * STRIDE);       \
+    OCGCN_MAX4(v, jr)                                                            \
+  }
+  if (cnt > 4) {
+    OCGCN_MAX_STEP(4) OCGCN_MAX_STEP(5) OCGCN_MAX_STEP(6) OCGCN_MAX_STEP(7) OCGCN_MAX_STEP(8)
+    if (cnt > 9) { OCGCN_MAX_STEP(9) OCGCN_MAX_STEP(10) OCGCN_MAX_STEP(11) OCGCN_MAX_STEP(12) }
+  }
+#undef OCGCN_MAX_STEP
+#undef OCGCN_MAX4
+}
+template <int STRIDE>
+__device__ __forceinline__ float4 rec_sum4_padded(const uint4& rec, const float* colp) {
+  const int cnt = rec_cnt(rec);
+  const float4 v0 = *reinterpret_cast<const float4*>(colp + rec_idx<0>(rec) * STRIDE);
+  const float4 v1 = *reinterpret_cast<const float4*>(colp + rec_idx<1>(rec) * STRIDE);
+  const float4 v2 = *reinterpret_cast<const float4*>(colp + rec_idx<2>(rec) * STRIDE);
+  const float4 v3 = *reinterpret_cast<const float4*>(colp + rec_idx<3>(rec) * STRIDE);
+  float4 s = make_float4(((v0.x + v1.x) + v2.x) + v3.x, ((v0.y + v1.y) + v2.y) + v3.y, ((v0.z + v1.z) + v2.z) + v3.z,
+                         ((v0.w + v1.w) + v2.w) + v3.w);   // ascending neighbour order; dummies add 0
+#define OCGCN_SUM_STEP(Q)                                                                       \
+  if (cnt > Q) {                                                                                \
+    const float4 v = *reinterpret_cast<const float4*>(colp + rec_idx<Q>(rec) * STRIDE);         \
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;                                             \
+  }
+  if (cnt > 4) {
+    OCGCN_SUM_STEP(4) OCGCN_SUM_STEP(5) OCGCN_SUM_STEP(6) OCGCN_SUM_STEP(7) OCGCN_SUM_STEP(8)
+    if (cnt > 9) { OCGCN_SUM_STEP(9) OCGCN_SUM_STEP(10) OCGCN_SUM_STEP(11) OCGCN_SUM_STEP(12) }
+  }
+#undef OCGCN_SUM_STEP
+  return s;
+}
+
 template <int STRIDE>
 __device__ __forceinline__ float4 rec_sum4(const uint4& rec, const float* colp) {
   const int cnt = rec_cnt(rec);
@@ -310,6 +366,10 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
   // tile_simple selects row loops that contain ONLY the padded-record walk and are unrolled over the warp's RPW rows (their
   // record, buffer and image addresses become immediates); hub rows / float adjacency take the general loops
   const bool tile_simple = __syncthreads_and(simple) != 0 && MM;
+  // fast paths of the tensor-core engine (any molecular graph, widths that are multiples of four): FOUR adjacent channels per
+  // lane (LDS.128 / LDG.128); a half-warp owns one tile row of the 64-channel chunk, so one warp instruction covers two rows
+  const bool fast4 = tile_simple && (K % 4 == 0);
+  const int hl = lane & 15, hh = lane >> 4;
 
   float acc[MM ? 1 : 8][MM ? 1 : 8];
 
@@ -334,19 +394,24 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
       // first shared-memory write: the MMA tail hides behind the load latency. Thread 0 then starts this chunk's bulk loads.
       auto chunk_sync = [&]() {
         if (!MM) return;
+        // ONE warp polls the mbarrier, everybody else parks at the hardware barrier: waiting warps then take no issue slots from the
+        // co-resident CTA (16 polling warps were 7-10 % of the executed instructions)
+        bool resync = false;
         if (mma_pending) {
-          tc::mbar_wait(&bars[1], ph_mma);
+          if (warp == 0) tc::mbar_wait(&bars[1], ph_mma);
           ph_mma ^= 1;
           mma_pending = false;
+          resync = true;
         }
         // producer-only launches (skip_gemm) need no lo image: odd chunks use its space as a second hi image, so the
         // bulk store of one chunk overlaps the production of the next and the wait is only needed every other chunk
         const bool reuse = !a.skip_gemm || do_dw || (k0 / KC) >= 2;
         if (store_pending && reuse) {
           if (tid == 0) tc::bulk_wait_read0();   // the previous chunks' images have been read by the bulk stores
-          if (PROD == P_DZ || PROD == P_DU) __syncthreads();   // these producers write the image in their first stage
+          if (PROD == P_DZ || PROD == P_DU) resync = true;   // these producers write the image in their first stage
           store_pending = false;
         }
+        if (resync) __syncthreads();
         if (do_dw && k0 == 0 && tid == 0) {   // this tile's saved operand image (S_l or H_L) -> buf1 (free in these producers)
           tc::mbar_expect_tx(&bars[3], (uint32_t)a.dw_chunks * 2048u);
           tc::bulk_g2s(buf1, reinterpret_cast<const unsigned char*>(a.dw_img) + (size_t)tile * a.dw_chunks * 2048, (uint32_t)a.dw_chunks * 2048u, &bars[3]);
@@ -396,6 +461,22 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
         }
       };
 
+      // fast4: this lane's four channels of row r -> 8 bytes of the hi image and 8 bytes of the lo image
+      const uint32_t img_lane_off4 = (uint32_t)(hl >> 1) * kImgPitch + (uint32_t)(hl & 1) * 8;
+      auto put_operand4 = [&](int r, const float4& val) {
+        uint2 hi, lo;
+        tc::split4_bf16(val, hi, lo);
+        const uint32_t off = img_lane_off4 + (uint32_t)r * 16;
+        if (a.skip_gemm && !do_dw) {
+          *reinterpret_cast<uint2*>(((k0 / KC) & 1 ? imgLo : imgHi) + off) = hi;
+        } else {
+          *reinterpret_cast<uint2*>(imgHi + off) = hi;
+          *reinterpret_cast<uint2*>(imgLo + off) = lo;
+        }
+      };
+      const int c4 = k0 + 4 * hl;   // fast4: this lane's first channel
+      const bool cv = c4 < K;       // (K % 4 == 0: all four channels valid, or none)
+
       // =========================== PRODUCER ===========================
       if (PROD == P_X) {
 #pragma unroll
@@ -425,7 +506,31 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
         if (v1) { sc.y = __ldg(&a.vec0[c + 1]); sh.y = __ldg(&a.vec1[c + 1]); }
         // (the 2*log2(e) factor of the exp2-based tanh is folded into the lane's scale / shift: one multiply less per element)
         const float2 scs = make_float2(sc.x * kTanhScale, sc.y * kTanhScale), shs = make_float2(sh.x * kTanhScale, sh.y * kTanhScale);
-        {
+        if (MM && fast4) {
+          float4 sc4 = make_float4(0.f, 0.f, 0.f, 0.f), sh4 = sc4;
+          if (cv) { sc4 = __ldg(reinterpret_cast<const float4*>(&a.vec0[c4])); sh4 = __ldg(reinterpret_cast<const float4*>(&a.vec1[c4])); }
+          sc4.x *= kTanhScale; sc4.y *= kTanhScale; sc4.z *= kTanhScale; sc4.w *= kTanhScale;
+          sh4.x *= kTanhScale; sh4.y *= kTanhScale; sh4.z *= kTanhScale; sh4.w *= kTanhScale;
+          float4 v[RPW / 2];
+#pragma unroll
+          for (int sI = 0; sI < RPW / 2; ++sI) {
+            const int r = warp + (2 * sI + hh) * NWARP;
+            v[sI] = (r < rows && cv) ? __ldg(reinterpret_cast<const float4*>(&in0_t[r * K + c4])) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          chunk_sync();
+#pragma unroll
+          for (int sI = 0; sI < RPW / 2; ++sI) {
+            const int r = warp + (2 * sI + hh) * NWARP;
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < rows && cv) {
+              t.x = fast_tanh_scaled(fmaf(v[sI].x, sc4.x, sh4.x));
+              t.y = fast_tanh_scaled(fmaf(v[sI].y, sc4.y, sh4.y));
+              t.z = fast_tanh_scaled(fmaf(v[sI].z, sc4.z, sh4.z));
+              t.w = fast_tanh_scaled(fmaf(v[sI].w, sc4.w, sh4.w));
+            }
+            *reinterpret_cast<float4*>(&bufT[r * BS + 4 * hl]) = t;
+          }
+        } else {
           constexpr int TB = (RPW > 16) ? 16 : RPW;   // rows per batch: all their loads are in flight before the first tanh
 #pragma unroll
           for (int h = 0; h < RPW / TB; ++h) {
@@ -451,7 +556,31 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
         if (MM && warp == 0) *reinterpret_cast<float2*>(&bufT[TR * BS + 2 * lane]) = make_float2(-INFINITY, -INFINITY);   // dummy row: never wins a max
         __syncthreads();
         // neighbour max-pool: P[i,c] = max_j A[i,j]*T[j,c], first index wins ties (gcn_encoder.py:44-50)
-        if (tile_simple) {
+        if (MM && fast4) {
+#pragma unroll
+          for (int sI = 0; sI < RPW / 2; ++sI) {
+            const int r = warp + (2 * sI + hh) * NWARP;
+            float bq[4] = {0.f, 0.f, 0.f, 0.f};
+            if (r < rows) {
+              const uint4 rec = sRec[r];
+              const int mb = rec_m(rec) * N;
+              int aq[4];
+              rec_max4_padded<BS>(rec, &bufT[4 * hl], bq, aq);
+              if (rec_has_zero(rec)) {  // a zero entry A[i,jz] contributes the candidate 0*T = 0
+                const int jz = mb + rec_jz(rec);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (!(bq[e] > 0.f)) { if (bq[e] < 0.f || jz < aq[e]) aq[e] = jz; bq[e] = 0.f; }
+              }
+              if (first_pass && cv)
+                *reinterpret_cast<uchar4*>(argo_t + (r * K + c4)) =
+                    make_uchar4((unsigned char)(aq[0] - mb), (unsigned char)(aq[1] - mb), (unsigned char)(aq[2] - mb), (unsigned char)(aq[3] - mb));
+            }
+            const float4 h4 = cv ? make_float4(bq[0], bq[1], bq[2], bq[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (PROD == P_RO) put_operand4(r, h4);
+            else *reinterpret_cast<float4*>(&bufH[r * BS + 4 * hl]) = h4;
+          }
+        } else if (tile_simple) {
 #pragma unroll 4
           for (int q = 0; q < RPW; ++q) {
             const int r = warp + q * NWARP;
@@ -549,6 +678,59 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
         if (v0) { g.x = __ldg(&a.vec0[c]); c1.x = __ldg(&a.vec1[c]); c2.x = __ldg(&a.vec2[c]); mu.x = __ldg(&a.vec3[c]); is.x = __ldg(&a.vec4[c]); }
         if (v1) { g.y = __ldg(&a.vec0[c + 1]); c1.y = __ldg(&a.vec1[c + 1]); c2.y = __ldg(&a.vec2[c + 1]); mu.y = __ldg(&a.vec3[c + 1]); is.y = __ldg(&a.vec4[c + 1]); }
         float2 colsum = make_float2(0.f, 0.f);
+        if (MM && fast4) {
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          // dZ = g*(dY - c1 - (Z - mean)*invstd*c2) folded per channel into dZ = ca*dY + cb*Z + cc (12 coefficient registers instead of 20)
+          float4 ca = z4, cb = z4, cc = z4, cs4 = z4;
+          if (cv) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(&a.vec0[c4])), c14 = __ldg(reinterpret_cast<const float4*>(&a.vec1[c4]));
+            const float4 c24 = __ldg(reinterpret_cast<const float4*>(&a.vec2[c4])), mu4 = __ldg(reinterpret_cast<const float4*>(&a.vec3[c4]));
+            const float4 is4 = __ldg(reinterpret_cast<const float4*>(&a.vec4[c4]));
+            ca = g4;
+            cb = make_float4(-g4.x * is4.x * c24.x, -g4.y * is4.y * c24.y, -g4.z * is4.z * c24.z, -g4.w * is4.w * c24.w);
+            cc = make_float4(-fmaf(cb.x, mu4.x, g4.x * c14.x), -fmaf(cb.y, mu4.y, g4.y * c14.y), -fmaf(cb.z, mu4.z, g4.z * c14.z),
+                             -fmaf(cb.w, mu4.w, g4.w * c14.w));
+          }
+          constexpr int HB = RPW / 4;   // two load batches of HB row pairs: 4*HB float4 registers in flight
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            float4 zv[HB], dv[HB];
+#pragma unroll
+            for (int u = 0; u < HB; ++u) {
+              const int r = warp + (2 * (hb * HB + u) + hh) * NWARP;
+              const bool ok = r < rows && cv;
+              zv[u] = ok ? __ldg(reinterpret_cast<const float4*>(&in1_t[r * K + c4])) : z4;
+              dv[u] = ok ? __ldg(reinterpret_cast<const float4*>(&in0_t[r * K + c4])) : z4;
+            }
+            if (hb == 0) chunk_sync();
+#pragma unroll
+            for (int u = 0; u < HB; ++u) {
+              const int r = warp + (2 * (hb * HB + u) + hh) * NWARP;
+              float4 dz = z4;
+              if (r < rows && cv) {
+                dz.x = fmaf(ca.x, dv[u].x, fmaf(cb.x, zv[u].x, cc.x));
+                dz.y = fmaf(ca.y, dv[u].y, fmaf(cb.y, zv[u].y, cc.y));
+                dz.z = fmaf(ca.z, dv[u].z, fmaf(cb.z, zv[u].z, cc.z));
+                dz.w = fmaf(ca.w, dv[u].w, fmaf(cb.w, zv[u].w, cc.w));
+                cs4.x += dz.x; cs4.y += dz.y; cs4.z += dz.z; cs4.w += dz.w;
+              }
+              put_operand4(r, dz);
+            }
+          }
+          if (first_pass && a.prod_partials) {   // column sums (db): the two half-warps hold the same channels, then across warps
+            cs4.x += __shfl_xor_sync(0xffffffffu, cs4.x, 16); cs4.y += __shfl_xor_sync(0xffffffffu, cs4.y, 16);
+            cs4.z += __shfl_xor_sync(0xffffffffu, cs4.z, 16); cs4.w += __shfl_xor_sync(0xffffffffu, cs4.w, 16);
+            if (hh == 0) *reinterpret_cast<float4*>(&sWarp[(warp * 16 + hl) * 4]) = cs4;
+          }
+          tc::fence_async_smem();
+          __syncthreads();
+          if (first_pass && a.prod_partials && warp == 0 && hh == 0 && cv) {
+            float4 t = z4;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) { const float4 u = *reinterpret_cast<const float4*>(&sWarp[(w * 16 + hl) * 4]); t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+            *reinterpret_cast<float4*>(&a.prod_partials[(size_t)tile * K + c4]) = t;
+          }
+        } else {
         constexpr int PB = MM ? 4 : 8;   // rows in flight per lane: 2*PB float2 registers (8 rows spill at 64 registers per thread)
 #pragma unroll
         for (int h = 0; h < RPW / PB; ++h) {
@@ -586,8 +768,48 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
           a.prod_partials[(size_t)tile * K + c] = s.x;
           if (v1) a.prod_partials[(size_t)tile * K + c + 1] = s.y;
         }
+        }   // !fast4
       } else if (PROD == P_DU) {
         float2 colsum = make_float2(0.f, 0.f);
+        if (MM && fast4) {
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 cs4 = z4;
+          float4 dv[RPW / 2];
+#pragma unroll
+          for (int sI = 0; sI < RPW / 2; ++sI) {
+            const int r = warp + (2 * sI + hh) * NWARP;
+            dv[sI] = (r < rows && cv) ? __ldg(reinterpret_cast<const float4*>(&in0_t[r * K + c4])) : z4;
+          }
+          chunk_sync();
+#pragma unroll
+          for (int sI = 0; sI < RPW / 2; ++sI) {
+            const int r = warp + (2 * sI + hh) * NWARP;
+            float4 du = z4;
+            if (r < rows && cv) {
+              const int ob = rec_m(sRec[r]) * K + c4;   // (molecule-of-the-tile, channel) in the per-molecule O / dO tensors
+              const float4 ov = __ldg(reinterpret_cast<const float4*>(&o_t[ob])), go = __ldg(reinterpret_cast<const float4*>(&do_t[ob]));
+              du.x = go.x * (1.f - ov.x * ov.x) * (1.f - dv[sI].x * dv[sI].x);
+              du.y = go.y * (1.f - ov.y * ov.y) * (1.f - dv[sI].y * dv[sI].y);
+              du.z = go.z * (1.f - ov.z * ov.z) * (1.f - dv[sI].z * dv[sI].z);
+              du.w = go.w * (1.f - ov.w * ov.w) * (1.f - dv[sI].w * dv[sI].w);
+              cs4.x += du.x; cs4.y += du.y; cs4.z += du.z; cs4.w += du.w;
+            }
+            put_operand4(r, du);
+          }
+          if (first_pass && a.prod_partials) {
+            cs4.x += __shfl_xor_sync(0xffffffffu, cs4.x, 16); cs4.y += __shfl_xor_sync(0xffffffffu, cs4.y, 16);
+            cs4.z += __shfl_xor_sync(0xffffffffu, cs4.z, 16); cs4.w += __shfl_xor_sync(0xffffffffu, cs4.w, 16);
+            if (hh == 0) *reinterpret_cast<float4*>(&sWarp[(warp * 16 + hl) * 4]) = cs4;
+          }
+          tc::fence_async_smem();
+          __syncthreads();
+          if (first_pass && a.prod_partials && warp == 0 && hh == 0 && cv) {
+            float4 t = z4;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) { const float4 u = *reinterpret_cast<const float4*>(&sWarp[(w * 16 + hl) * 4]); t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+            *reinterpret_cast<float4*>(&a.prod_partials[(size_t)tile * K + c4]) = t;
+          }
+        } else {
 #pragma unroll
         for (int h = 0; h < RPW / 8; ++h) {
           float2 dv[8];
@@ -625,11 +847,20 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
           a.prod_partials[(size_t)tile * K + c] = s.x;
           if (v1) a.prod_partials[(size_t)tile * K + c + 1] = s.y;
         }
+        }   // !fast4
       }
 
       if (PROD == P_X || PROD == P_MID) {
         // S = A.H for this chunk (gcn.py:34): over the dead T buffer (FFMA) or into the operand images (MMA)
-        if (tile_simple) {
+        if (MM && fast4) {
+#pragma unroll
+          for (int sI = 0; sI < RPW / 2; ++sI) {
+            const int r = warp + (2 * sI + hh) * NWARP;
+            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < rows) s4 = rec_sum4_padded<BS>(sRec[r], &buf1[4 * hl]);
+            put_operand4(r, s4);
+          }
+        } else if (tile_simple) {
 #pragma unroll 4
           for (int q = 0; q < RPW; ++q) {
             const int r = warp + q * NWARP;
@@ -761,9 +992,10 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
     if (MM) {
       // accumulator tile: TMEM -> registers (thread = row) -> bias / activation -> staging tile in shared memory
       if (mma_pending) {
-        tc::mbar_wait(&bars[1], ph_mma);
+        if (warp == 0) tc::mbar_wait(&bars[1], ph_mma);
         ph_mma ^= 1;
         mma_pending = false;
+        __syncthreads();
       }
       tc::fence_after_sync();
       constexpr int CPG = TC / (NWARP / 4);   // columns per warp group (the four warps of a group cover the 128 TMEM lanes)
@@ -1055,6 +1287,21 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
 #pragma unroll 1
         for (int cs = 0; cs < TC; cs += 64) {
           float2 hv[RPW];
+          if (MM && tile_simple && NC % 4 == 0) {   // half-warp per row, four channels per lane
+            float4 h4[RPW / 2];
+#pragma unroll
+            for (int sI = 0; sI < RPW / 2; ++sI) {
+              const int r = warp + (2 * sI + hh) * NWARP;
+              h4[sI] = (r < rows) ? rec_sum4_padded<TCP>(sCRec[r], &sC[cs + 4 * hl]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int sI = 0; sI < RPW / 2; ++sI) {
+              const int r = warp + (2 * sI + hh) * NWARP;
+              if (r < rows) *reinterpret_cast<float4*>(&sC[r * TCP + cs + 4 * hl]) = h4[sI];
+            }
+            continue;
+          }
           if (tile_simple) {
 #pragma unroll
             for (int q = 0; q < RPW; ++q) {

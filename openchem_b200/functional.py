@@ -24,6 +24,35 @@ def _f32(t):
     return t if t.dtype == torch.float32 else t.to(torch.float32)
 
 
+def _check_state(ref, named):
+    """Every parameter / BatchNorm buffer handed to the kernels by raw pointer must live on the inputs' device, in the dtype the
+    kernels read (float32; num_batches_tracked int64) and contiguous - the same class of error the reference raises from ATen
+    when a module was left on the CPU, on another GPU, or cast with .double()/.half(). Without this the kernels would
+    dereference host or wrong-typed memory."""
+    for name, t, dtype in named:
+        if t is None:
+            continue
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or t.device != ref.device:
+            raise RuntimeError("openchem_b200: %s is on %s but the input is on %s (move the module with .to(device); this path has "
+                               "no CPU fallback)" % (name, getattr(t, "device", type(t).__name__), ref.device))
+        if t.dtype != dtype:
+            raise RuntimeError("openchem_b200: %s has dtype %s, the kernels need %s" % (name, t.dtype, dtype))
+        if not t.is_contiguous():
+            raise RuntimeError("openchem_b200: %s must be contiguous" % name)
+
+
+def _layer_state(spec, Ws, bs, gammas, betas, Wd=None, bd=None):
+    named = []
+    for l in range(len(Ws)):
+        named += [("weight[%d]" % l, Ws[l], torch.float32), ("bias[%d]" % l, bs[l], torch.float32),
+                  ("bn.weight[%d]" % l, gammas[l], torch.float32), ("bn.bias[%d]" % l, betas[l], torch.float32),
+                  ("bn.running_mean[%d]" % l, spec.running_mean[l], torch.float32),
+                  ("bn.running_var[%d]" % l, spec.running_var[l], torch.float32),
+                  ("bn.num_batches_tracked[%d]" % l, spec.nbt[l], torch.int64)]
+    named += [("dense.weight", Wd, torch.float32), ("dense.bias", bd, torch.float32)]
+    return named
+
+
 class LayerSpec:
     """Non-tensor arguments + in-place updated buffers of one call (kept out of autograd's sight)."""
 
@@ -126,6 +155,9 @@ class EncoderFn(torch.autograd.Function):
         tensors = [None if t is None else t.detach().contiguous() for t in tensors]
         Ws, bs, gammas, betas = tensors[0:4 * L:4], tensors[1:4 * L:4], tensors[2:4 * L:4], tensors[3:4 * L:4]
         Wd, bd = tensors[4 * L], tensors[4 * L + 1]
+        if adj.device != x.device:
+            raise RuntimeError("openchem_b200: x is on %s but adj is on %s" % (x.device, adj.device))
+        _check_state(x, _layer_state(spec, Ws, bs, gammas, betas, Wd, bd))
         with torch.cuda.device(x.device):
             desc = _make_desc(spec, x, adj)
             params = _make_params(spec, Ws, bs, gammas, betas, Wd, bd)
@@ -190,6 +222,9 @@ class LayerFn(torch.autograd.Function):
         x, adj = _f32(x.detach()), _f32(adj)
         W, gamma, beta = W.detach().contiguous(), gamma.detach().contiguous(), beta.detach().contiguous()
         b = None if b is None else b.detach().contiguous()
+        if adj.device != x.device:
+            raise RuntimeError("openchem_b200: x is on %s but adj is on %s" % (x.device, adj.device))
+        _check_state(x, _layer_state(spec, [W], [b], [gamma], [beta]))
         with torch.cuda.device(x.device):
             desc = _make_desc(spec, x, adj, need_dx)
             params = _make_params(spec, [W], [b], [gamma], [beta])
@@ -295,6 +330,14 @@ class HeadFn(torch.autograd.Function):
             target = _f32(target.detach()).contiguous()
             if tuple(target.shape) != (B, T):
                 raise RuntimeError("openchem_b200: target must be (B, %d); got %s" % (T, tuple(target.shape)))
+        named = [("layers[%d].weight" % i, Ws[i], torch.float32) for i in range(L)] + [("layers[%d].bias" % i, bs[i], torch.float32) for i in range(L)]
+        for i in range(L - 1):
+            named += [("bn[%d].weight" % i, gammas[i], torch.float32), ("bn[%d].bias" % i, betas[i], torch.float32),
+                      ("bn[%d].running_mean" % i, spec.running_mean[i], torch.float32), ("bn[%d].running_var" % i, spec.running_var[i], torch.float32),
+                      ("bn[%d].num_batches_tracked" % i, spec.nbt[i], torch.int64)]
+        if fused:
+            named.append(("target", target, torch.float32))
+        _check_state(inp, named)
         with torch.cuda.device(inp.device):
             desc = _head_desc(spec, B, need_dx)
             params = _head_params(spec, Ws, bs, gammas, betas)

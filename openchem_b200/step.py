@@ -51,7 +51,9 @@ class TrainStep:
         """model((x, adj)) -> predictions; criterion(pred, y) -> scalar; make_optimizer(params) -> torch optimizer that is
         CUDA-graph capturable (e.g. Adam(fused=True, capturable=True)); example_batch = (x, adj, y) device tensors.
         loss_fn(model, (x, adj), y) -> scalar, optional: replaces criterion(model(inp), y), e.g. to evaluate the criterion
-        inside the MLP head's last kernel (openchem_b200.modules.mlp.openchem_mlp.fused_head_loss)."""
+        inside the MLP head's last kernel (openchem_b200.modules.mlp.openchem_mlp.fused_head_loss).
+        Construction runs `warmup` real steps and the capture on `example_batch`, then restores the model / optimizer state it was
+        given (see the snapshot note below): the first __call__ is training step 1."""
         self.model, self.criterion, self.loss_fn = model, criterion, loss_fn
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         dev = example_batch[0].device
@@ -71,6 +73,11 @@ class TrainStep:
         if self.world > 1:   # identical initial weights on every rank (DDP does this at construction)
             for t in list(model.parameters()) + list(model.buffers()):
                 dist.broadcast(t.data, src=0)
+        # Warm-up and capture must not advance training: the warm-up bodies below are real optimizer steps on `example_batch`. The
+        # model's parameters and buffers (BatchNorm running statistics, num_batches_tracked) are snapshotted here and restored IN
+        # PLACE afterwards, and the optimizer's state tensors are zeroed in place (the captured graph holds their addresses), so a
+        # freshly built TrainStep starts from exactly the state it was given - a reloaded checkpoint gets no hidden extra updates.
+        snapshot = {k: v.detach().clone() for k, v in model.state_dict().items()}
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(cur)
@@ -88,6 +95,16 @@ class TrainStep:
             except Exception as exc:  # noqa: BLE001 - capture is an optimisation; the eager body is the same work
                 self.graph, self.graph_error = None, repr(exc)[:300]
                 torch.cuda.synchronize(dev)
+        with torch.no_grad():
+            for k, v in model.state_dict().items():
+                v.copy_(snapshot[k])
+            for st in self.opt.state.values():
+                for v in st.values():
+                    if isinstance(v, torch.Tensor):
+                        v.zero_()
+            self.flat_grad.zero_()
+            self.loss.zero_()
+        torch.cuda.synchronize(dev)
 
     def _body(self):
         self.flat_grad.zero_()

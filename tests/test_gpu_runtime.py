@@ -141,12 +141,27 @@ def test_graph_step_matches_eager_steps():
     crit = torch.nn.MSELoss()
     mk = lambda ps: torch.optim.Adam(ps, lr=1e-3, fused=True, capturable=True)  # noqa: E731
     m_graph, m_eager = Wrap(make()), Wrap(make())
+    before = {k: v.clone() for k, v in m_graph.state_dict().items()}
     st_g = TrainStep(m_graph, crit, mk, (x, adj, y), use_graph=True, warmup=2)
     st_e = TrainStep(m_eager, crit, mk, (x, adj, y), use_graph=False, warmup=2)
     assert st_g.graph is not None, st_g.graph_error
-    for _ in range(3):
+    # construction (warm-up steps + capture) leaves the model and the optimizer exactly as they were handed over
+    for k, v in m_graph.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    assert all(float(t.abs().sum()) == 0.0 for st in st_g.opt.state.values() for t in st.values() if isinstance(t, torch.Tensor))
+    # ... so the first call is training step 1: it equals one plain eager torch step from the same state
+    m_plain = Wrap(make())
+    opt = mk([q for q in m_plain.parameters()])
+    loss = crit(m_plain((x, adj)), y)
+    loss.backward()
+    opt.step()
+    for it in range(3):
         lg, le = float(st_g(x, adj, y)), float(st_e(x, adj, y))
         assert lg == le
+        if it == 0:
+            assert lg == float(loss)
+            for a, b in zip(m_graph.parameters(), m_plain.parameters()):
+                assert torch.equal(a, b)
     for a, b in zip(m_graph.parameters(), m_eager.parameters()):
         assert torch.equal(a, b)
 
@@ -227,3 +242,29 @@ def test_delayed_loss_returns_every_value_in_order():
         got.append(reader.push(static))
     got.append(reader.flush())
     assert got[0] is None and got[1:] == [t + 0.5 for t in range(7)]
+
+
+def test_module_left_on_the_cpu_or_cast_raises_cleanly():
+    """CUDA inputs with a module whose parameters are on the host / in another dtype: a clear RuntimeError before any kernel
+    runs (the kernels take raw pointers), like the reference's ATen device / dtype errors - and the context stays usable."""
+    from _util import build_encoder, random_params
+    from openchem_b200.layers.gcn import GraphConvolution
+    from openchem_b200.synthetic import make_graph_batch
+    dev = torch.device("cuda:0")
+    g = make_graph_batch(4, 10, 8, seed=1)
+    x, adj = torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["adj"]).to(dev)
+    cfg = {"input_size": 8, "encoder_dim": 6, "n_layers": 2, "hidden_size": [12, 12]}
+    enc = build_encoder(cfg, random_params([8, 12, 12], 6, seed=0), "cpu")
+    with pytest.raises(RuntimeError, match="is on cpu"):
+        enc((x, adj))
+    enc = enc.to(dev)
+    enc.graph_convolutions[1].bn.running_var.data = enc.graph_convolutions[1].bn.running_var.data.cpu()   # one stray buffer
+    with pytest.raises(RuntimeError, match="running_var"):
+        enc((x, adj))
+    with pytest.raises(RuntimeError, match="dtype"):
+        build_encoder(cfg, random_params([8, 12, 12], 6, seed=0), dev).double()((x, adj))
+    with pytest.raises(RuntimeError, match="is on cpu"):
+        GraphConvolution(8, 5)(x, adj)
+    out = build_encoder(cfg, random_params([8, 12, 12], 6, seed=0), dev)((x, adj))      # the context is still healthy
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ocgcn_abi_version() == 1
+    assert lib.ocgcn_abi_version() == 2
     assert lib.ocgcn_status_string(0) == b"ok"
     assert b"unsupported" in lib.ocgcn_status_string(2)
 
@@ -209,7 +209,7 @@ int main(void) {
                     "-L", libdir, "-l:libocgcn.so", "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
     first = out[0].split(" ", 4)
-    assert first[0] == "1" and first[1] == "0" and int(first[2]) > 0 and int(first[3]) > 0 and "sm_100" in first[4]
+    assert first[0] == str(_lib.ABI_VERSION) and first[1] == "0" and int(first[2]) > 0 and int(first[3]) > 0 and "sm_100" in first[4]
     assert out[1].strip() == "2"      # N > 256: OCGCN_EUNSUPPORTED
     import ctypes
     sizes = out[2].split()
