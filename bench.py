@@ -154,40 +154,103 @@ def make_criterion(w):
 # --------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's CPU op sequence (oracle/torch_restatement.py) on host cores
 # --------------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(w, steps, warmup, chunk=256, seed=1234):
-    """molecules/s of the reference's eager CPU path (fwd + loss + bwd + Adam) on a bounded sample: chunks of `chunk`
-    molecules of the same workload (the reference materialises (B,N,N,D) temporaries, ~8.6 GB each at B=4096)."""
+def _reference_stepper(w, B, g, y):
+    """The UNMODIFIED reference (staged under baseline/_ref by oracle/stage_reference.py) on the host cores: its own Graph2Label
+    (reference GraphCNNEncoder + OpenChemMLP), criterion, OpenChemOptimizer(Adam) and `train_step` (anomaly mode included,
+    openchem_model.py:102-121) through its public API. Returns a zero-argument step function, or None if it is not staged."""
     import torch
-    from oracle import torch_restatement as tr
+    from oracle import stage_reference
+    ref = stage_reference.staged_path()
+    if ref is None:
+        return None
+    stubs = os.path.join(ROOT, "tests", "stubs")          # rdkit import stub (RDKit is not in this image; never called here)
+    for pth in (stubs, ref):
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
+    for k in [k for k in sys.modules if k == "openchem" or k.startswith("openchem.")]:
+        sys.modules.pop(k)                                   # (this repo's namespace shadow must not win: reference first)
+    from openchem.models.Graph2Label import Graph2Label
+    from openchem.models.openchem_model import build_training, train_step
+    from openchem.modules.encoders.gcn_encoder import GraphCNNEncoder
+    from openchem.modules.mlp.openchem_mlp import OpenChemMLP
+    from openchem.utils.utils import identity
+    assert GraphCNNEncoder.__module__ == "openchem.modules.encoders.gcn_encoder" and os.path.realpath(
+        sys.modules[GraphCNNEncoder.__module__].__file__).startswith(os.path.realpath(ref)), "reference arm must run the reference's own encoder"
+    multitask = w["task"] == "multitask"
+    if multitask:     # the reference's MultitaskLoss hard-codes .cuda() (multitask_loss.py:43-44): unusable on the host; BCE as executed
+        crit = torch.nn.BCELoss()
+    else:
+        crit = torch.nn.MSELoss()
+    params = {
+        "task": "regression", "batch_size": B, "num_epochs": 1, "train_data_layer": None, "val_data_layer": None, "use_cuda": False,
+        "eval_metrics": None, "logdir": "/tmp/ocb200_ref_arm", "random_seed": 0, "print_every": 1, "save_every": 1,
+        "criterion": crit, "optimizer": torch.optim.Adam, "optimizer_params": {"lr": 5e-4},
+        "encoder": GraphCNNEncoder,
+        "encoder_params": {"input_size": w["f0"], "encoder_dim": w["encoder_dim"], "n_layers": len(w["hidden"]), "hidden_size": list(w["hidden"])},
+        "mlp": OpenChemMLP,
+        "mlp_params": {"input_size": w["encoder_dim"], "n_layers": 2, "hidden_size": list(w["mlp_hidden"]),
+                       "activation": [torch.nn.functional.relu, torch.sigmoid if multitask else identity]},
+    }
+    torch.manual_seed(0)
+    model = Graph2Label(params)
+    criterion, optimizer, _ = build_training(model, params)
+    sample = {"adj_matrix": torch.from_numpy(g["adj"]), "node_feature_matrix": torch.from_numpy(g["x"]), "labels": torch.from_numpy(y)}
+    if multitask:
+        sample["labels"] = (sample["labels"] == 1).float()
+
+    def step():
+        inp, target = Graph2Label.cast_inputs(sample, "regression", False)       # Graph2Label.py:39-64, as fit() calls it every batch
+        return float(train_step(model, optimizer, criterion, inp, target).item())
+
+    return step
+
+
+def cpu_reference_rate(w, steps, warmup, chunk=256, seed=1234):
+    """molecules/s of the reference's CPU path (fwd + loss + bwd + Adam) on a bounded sample: chunks of `chunk` molecules of the
+    same workload (the reference materialises (B,N,N,D) temporaries, ~8.6 GB each at B=4096). kind "reference": the unmodified
+    reference itself (baseline/_ref); kind "port" (only when it is not staged): oracle/torch_restatement.py, the same ATen op
+    sequence."""
+    import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     B = min(chunk, w["batch"])
     g = make_graph_batch(B, w["n_max"], w["f0"], occupancy="full", seed=seed)
-    x, adj = torch.from_numpy(g["x"]), torch.from_numpy(g["adj"])
     T = w["mlp_hidden"][-1]
-    y = torch.from_numpy(make_labels(B, T, "regression"))
-    p = tr.params_to_torch(random_params([w["f0"]] + list(w["hidden"]), w["encoder_dim"], seed=0))
-    H1 = w["mlp_hidden"][0]
-    hp = dict(W1=torch.randn(H1, w["encoder_dim"]) * 0.05, b1=torch.zeros(H1), g=torch.ones(H1), be=torch.zeros(H1),
-              rm=torch.zeros(H1), rv=torch.ones(H1), W2=torch.randn(T, H1) * 0.05, b2=torch.zeros(T))
-    leaves = [t for k in ("W", "b", "gamma", "beta") for t in p[k]] + [p["Wd"], p["bd"]]
-    for k in ("W1", "b1", "g", "be", "W2", "b2"):
-        hp[k].requires_grad_(True)
-        leaves.append(hp[k])
-    opt = torch.optim.Adam(leaves, lr=5e-4)
+    ynp = make_labels(B, T, w["task"] if w["task"] == "multitask" else "regression")
+    step, kind = _reference_stepper(w, B, g, ynp), "reference"
+    if step is None:
+        kind = "port"
+        from oracle import torch_restatement as tr
+        x, adj, y = torch.from_numpy(g["x"]), torch.from_numpy(g["adj"]), torch.from_numpy(make_labels(B, T, "regression"))
+        p = tr.params_to_torch(random_params([w["f0"]] + list(w["hidden"]), w["encoder_dim"], seed=0))
+        H1 = w["mlp_hidden"][0]
+        hp = dict(W1=torch.randn(H1, w["encoder_dim"]) * 0.05, b1=torch.zeros(H1), g=torch.ones(H1), be=torch.zeros(H1),
+                  rm=torch.zeros(H1), rv=torch.ones(H1), W2=torch.randn(T, H1) * 0.05, b2=torch.zeros(T))
+        leaves = [t for k in ("W", "b", "gamma", "beta") for t in p[k]] + [p["Wd"], p["bd"]]
+        for k in ("W1", "b1", "g", "be", "W2", "b2"):
+            hp[k].requires_grad_(True)
+            leaves.append(hp[k])
+        opt = torch.optim.Adam(leaves, lr=5e-4)
+
+        def step():
+            opt.zero_grad()
+            loss = torch.nn.functional.mse_loss(tr.mlp_head(tr.encoder(x, adj, p, True), hp, True), y)
+            loss.backward()
+            opt.step()
+            return float(loss)
+
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        opt.zero_grad()
-        out = tr.mlp_head(tr.encoder(x, adj, p, True), hp, True)
-        loss = torch.nn.functional.mse_loss(out, y)
-        loss.backward()
-        opt.step()
+        step()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     total = sum(times)
-    return dict(value=B * len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores, chunk=B, steps=len(times))
+    what = ("the unmodified reference (baseline/_ref): Graph2Label + train_step (anomaly mode) through its own API" if kind == "reference"
+            else "oracle/torch_restatement.py (the reference's ATen op sequence; baseline/_ref not staged)")
+    sample = "%d steps of a %d-molecule chunk of %%s (full occupancy), fwd+loss+bwd+Adam, %s, torch CPU, %d threads" % (len(times), B, what, cores)
+    return dict(value=B * len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores, chunk=B, steps=len(times), kind=kind, sample=sample)
 
 
 def run_reference_arm(args, w, wname):
@@ -195,12 +258,10 @@ def run_reference_arm(args, w, wname):
     if rank != 0:
         return
     r = cpu_reference_rate(w, args.steps, args.warmup)
-    sample = "%d steps of a %d-molecule chunk of %s (full occupancy), fwd+loss+bwd+Adam, torch CPU eager, %d threads" % (
-        r["steps"], r["chunk"], wname, r["cores"])
     line = dict(impl="reference", metric=METRIC, value=r["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload=wname, chunk=r["chunk"], n_max=w["n_max"], f0=w["f0"], hidden=w["hidden"], encoder_dim=w["encoder_dim"]),
-                cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=sample),
+                cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"] % wname),
                 e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
@@ -246,6 +307,96 @@ def measure_other(wname, args, dev, steps, warmup):
                 occupancy="molecular", steps=steps, graph=st.graph is not None)
 
 
+def kernel_algorithmic_flops(w, B, fused_dw):
+    """Dense-GEMM flops of ONE launch of each tile-kernel kind (mean over that kind's launches in a step), SURVEY 8(d) counting:
+    products of the reference's algorithm only - split-operand passes, recomputation and padding are not counted."""
+    N, F, E = w["n_max"], [w["f0"]] + list(w["hidden"]), w["encoder_dim"]
+    L = len(F) - 1
+    fwd = [B * (2 * N * N * F[l] + 2 * N * F[l] * F[l + 1]) for l in range(L)]
+    dz = [B * ((2 * N * F[l] * F[l + 1] + 2 * N * N * F[l]) if l > 0 else 0) + (B * 2 * N * F[l] * F[l + 1] if fused_dw else 0) for l in range(L)]
+    dw = [B * 2 * N * F[l] * F[l + 1] for l in range(L)] + [B * 2 * N * F[L] * E]
+    return {
+        "fwd_first": fwd[0], "fwd_mid": sum(fwd[1:]) / max(L - 1, 1), "fwd_readout": B * 2 * N * F[L] * E,
+        "bwd_readout": B * 2 * N * F[L] * E * (2 if fused_dw else 1), "bwd_dz": sum(dz) / L,
+        "dw_mma": sum(dw) / len(dw), "gemm_tn": sum(dw) / len(dw),
+    }
+
+
+def kernel_boundary_bytes(w, B, tc, fused_dw):
+    """Bytes of the boundary tensors one launch of each kind reads + writes in THIS implementation (saved activations, arg-max,
+    operand images, gradient ping-pong): the numerator of `hbm_achieved_gbs`, NOT the roofline's compulsory bytes."""
+    N, F, E = w["n_max"], [w["f0"]] + list(w["hidden"]), w["encoder_dim"]
+    L, R = len(F) - 1, B * w["n_max"]
+    simg = 2 if tc else 4
+    mid = [R * (F[l] * (4 + 1 + simg) + F[l + 1] * 4) for l in range(1, L)]
+    dzb = [R * (F[l + 1] * 8 + F[l] * simg + (F[l] * (4 + 1 + 4) if l > 0 else 0)) for l in range(L)]
+    return {
+        "fwd_first": R * (F[0] * (4 + simg) + F[1] * 4), "fwd_mid": sum(mid) / max(L - 1, 1),
+        "fwd_readout": R * (F[L] * (4 + 1 + simg) + E * 4), "bwd_readout": R * (E * 4 + F[L] * (4 + 1 + 4 + simg)),
+        "bwd_dz": sum(dzb) / L,
+    }
+
+
+def parity_block(w, g, precision, dev):
+    """Parity of the TIMED configuration (same batch, same widths), computed outside every timed region: one train-mode
+    forward + backward of the encoder against the fp64 oracle (oracle/ is used here strictly as the checker). Reports the
+    rel-L2 of the output and the worst parameter-gradient rel-L2, raw (oracle's own pool routing) and with the kernel's
+    routing, plus how many pool routings differ (all of them must be near-ties)."""
+    import torch
+    from oracle import gcn_oracle as orc
+    from openchem_b200 import functional
+    from openchem_b200.modules.encoders.gcn_encoder import GraphCNNEncoder
+    t0 = time.perf_counter()
+    F, E = [w["f0"]] + list(w["hidden"]), w["encoder_dim"]
+    L, B, N = len(F) - 1, g["x"].shape[0], w["n_max"]
+    if B * N * max(F) >= orc.POOL_C_MIN_ELEMS and orc.pool_lib() is None:
+        return dict(skipped="oracle/_build/libpool_scan.so not built (run __graft_entry__.build())")
+    p = random_params(F, E, seed=0)
+    enc = GraphCNNEncoder({"input_size": F[0], "encoder_dim": E, "n_layers": L, "hidden_size": list(w["hidden"]), "precision": precision}, True)
+    with torch.no_grad():
+        for l, gc in enumerate(enc.graph_convolutions):
+            gc.weight.copy_(torch.from_numpy(p["W"][l])); gc.bias.copy_(torch.from_numpy(p["b"][l]))
+            gc.bn.weight.copy_(torch.from_numpy(p["gamma"][l])); gc.bn.bias.copy_(torch.from_numpy(p["beta"][l]))
+            gc.bn.running_mean.copy_(torch.from_numpy(p["running_mean"][l])); gc.bn.running_var.copy_(torch.from_numpy(p["running_var"][l]))
+        enc.dense.weight.copy_(torch.from_numpy(p["Wd"])); enc.dense.bias.copy_(torch.from_numpy(p["bd"]))
+    enc = enc.to(dev).train()
+    dO = np.random.RandomState(7).randn(B, E).astype(np.float32)
+    x, adj = torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["adj"]).to(dev)
+    functional.debug_keep["on"] = True
+    try:
+        out = enc((x, adj))
+        args = [functional.saved_tensor("argmax", l).cpu().numpy().reshape(B, N, -1).astype(np.int64) for l in range(L)]
+    finally:
+        functional.debug_keep.update(on=False, saved=None, desc=None)
+    out.backward(torch.from_numpy(dO).to(dev))
+    torch.cuda.synchronize()
+    p64 = orc.cast_params(p, np.float64)
+    O, cache, _, _ = orc.encoder_forward(g["x"].astype(np.float64), g["adj"].astype(np.float64), p64, training=True)
+    flips = int(sum((args[l] != cache["layers"][l]["arg"]).sum() for l in range(L)))
+    res = {"dWd": enc.dense.weight.grad, "dbd": enc.dense.bias.grad}
+    for l, gc in enumerate(enc.graph_convolutions):
+        res.update({"dW%d" % l: gc.weight.grad, "dgamma%d" % l: gc.bn.weight.grad, "dbeta%d" % l: gc.bn.bias.grad})
+    res = {k: v.detach().cpu().numpy() for k, v in res.items()}
+
+    def worst(routing):
+        gr = orc.encoder_backward(dO.astype(np.float64), cache, arg_override=routing)
+        ref = {"dWd": gr["dWd"], "dbd": gr["dbd"]}
+        for l in range(L):
+            ref.update({"dW%d" % l: gr["dW"][l], "dgamma%d" % l: gr["dgamma"][l], "dbeta%d" % l: gr["dbeta"][l]})
+        errs = {k: orc.rel_l2(res[k], ref[k]) for k in ref}
+        k = max(errs, key=errs.get)
+        return k, errs[k]
+
+    k_raw, e_raw = worst(None)
+    k_rt, e_rt = worst(args) if flips else (k_raw, e_raw)
+    tol = 1e-5 if precision == "fp32" else 1e-2
+    return dict(oracle="oracle/gcn_oracle.py fp64 (pinned to the unmodified reference by tests/golden)", batch=B, tolerance=tol,
+                out_rel_l2=orc.rel_l2(out.detach().cpu().numpy(), O), worst_grad_rel_l2=e_raw, worst_grad=k_raw,
+                worst_grad_rel_l2_kernel_routing=e_rt, worst_grad_kernel_routing=k_rt,
+                pool_routings_differing=flips, pool_routings=int(sum(a.size for a in args)),
+                ok=bool(orc.rel_l2(out.detach().cpu().numpy(), O) < tol and e_rt < tol), seconds=time.perf_counter() - t0)
+
+
 def run_native(args, w, wname):
     import torch
     import torch.distributed as dist
@@ -277,12 +428,12 @@ def run_native(args, w, wname):
 
     model = build_model(w, args.precision, dev, args.head)
     crit = make_criterion(w)
+    adam = lambda ps: torch.optim.Adam(ps, lr=5e-4, fused=True, capturable=True)  # noqa: E731
     stepper, runtime = None, "eager (torch autograd + DistributedDataParallel, as run.py drives it)"
     if args.runtime == "graph":
         # the package's step runtime: fwd + loss + bwd + NCCL grad all-reduce + Adam captured in one CUDA graph
         from openchem_b200.step import TrainStep
-        stepper = TrainStep(model, crit, lambda ps: torch.optim.Adam(ps, lr=5e-4, fused=True, capturable=True), (x, adj, y),
-                            loss_fn=head_loss_fn(args, crit))
+        stepper = TrainStep(model, crit, adam, (x, adj, y), loss_fn=head_loss_fn(args, crit))
         runtime = "openchem_b200.step.TrainStep: one CUDA graph per step (flat-gradient NCCL all-reduce inside)" if stepper.graph is not None \
             else "openchem_b200.step.TrainStep eager (graph capture failed: %s)" % stepper.graph_error
         opt = stepper.opt
@@ -310,6 +461,17 @@ def run_native(args, w, wname):
     def max_over_ranks(ms):
         return ocd.max_over_ranks(ms, dev)
 
+    def timed(fn, n):
+        """exactly n calls of fn bracketed by barrier + synchronize, CUDA events on the current stream, max over ranks -> ms"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
     launches_per_body = 0
     if stepper is not None:
         x, adj, y = stepper.inputs          # device-resident static inputs: a step is one graph replay
@@ -326,50 +488,68 @@ def run_native(args, w, wname):
     if rank == 0:
         sampler.start()
     functional.launch_counter["n"] = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step(x, adj, y)
-    e1.record()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_total = timed(lambda: step(x, adj, y), args.steps)
     launches = functional.launch_counter["n"]
     if stepper is not None and stepper.graph is not None:
         launches = launches_per_body * args.steps     # replays re-issue the captured launches; count them from one eager body
 
-    # ---- end-to-end region: every step's inputs come from pinned HOST memory (reference layout: dense fp32 adj / features /
-    # labels) through the package's feeder (openchem_b200.loader.DevicePrefetcher: upload of batch t+1 overlaps step t), and
-    # the loss is read back to the host every step ----
-    from openchem_b200.loader import DevicePrefetcher
-    h2d = hx.numel() * 4 + hadj.numel() * 4 + hy.numel() * 4
-    host_batches = [(hx, hadj, hy)] * (2 + args.steps)
-    feed = DevicePrefetcher(host_batches, dev)
-    from openchem_b200.step import DelayedLoss
-    for _ in range(2):
-        xb, adjb, yb = next(feed)
-        float(step(xb, adjb, yb).item())
-    barrier()
-    reader, host_losses = DelayedLoss(dev), []
-    e0.record()
-    for _ in range(args.steps):
-        xb, adjb, yb = next(feed)
-        host_losses.append(reader.push(step(xb, adjb, yb)))     # step t's loss reaches the host while step t+1 runs
-    host_losses.append(reader.flush())                           # ... and the last one before the clock stops
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    assert len([v for v in host_losses if v is not None]) == args.steps and all(math.isfinite(v) for v in host_losses[1:])
+    # ---- replicas stayed identical (N > 1): bitwise checksum of every parameter after the timed steps, gathered on all ranks ----
+    replica_check = None
+    if world > 1:
+        flat = torch.cat([q.detach().reshape(-1).double() for q in model.parameters()])
+        mine = torch.stack([flat.sum(), (flat * flat).sum(), flat.abs().max()])
+        allv = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        replica_check = dict(identical=bool(all(torch.equal(v, allv[0]) for v in allv)), checksum=[float(v) for v in allv[0]],
+                             what="sum, sum of squares and max |p| (fp64) of all parameters on every rank after the timed steps")
+        assert replica_check["identical"], "data-parallel replicas diverged: %s" % ([v.tolist() for v in allv],)
 
-    # ---- the same end-to-end region fed in the package's compact batch format (openchem_b200.compact: bit-packed adjacency
-    # and features, 32x fewer host bytes; expanded bit-exactly on the device into the step's static inputs). Reported
-    # beside `e2e`, which stays on the reference's dense fp32 host format ----
-    from openchem_b200.compact import CompactGraphBatch, pack_graph_batch
-    cb_host = pack_graph_batch(g["x"], g["adj"], hy).pin_memory()
-    feed_c = DevicePrefetcher([cb_host.tensors()] * (2 + args.steps), dev)
+    from openchem_b200.loader import DevicePrefetcher
+    from openchem_b200.step import DelayedLoss
+
+    def e2e_region(next_batch_step):
+        """K steps whose inputs start in HOST memory and whose loss is read on the host every step, inside the timed region."""
+        for _ in range(2):
+            float(next_batch_step().item())
+        reader, host_losses = DelayedLoss(dev), []
+
+        def one():
+            host_losses.append(reader.push(next_batch_step()))     # step t's loss reaches the host while step t+1 runs
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            one()
+        host_losses.append(reader.flush())                          # ... and the last one before the clock stops
+        e1.record()
+        barrier()
+        assert len([v for v in host_losses if v is not None]) == args.steps and all(math.isfinite(v) for v in host_losses[1:])
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- e2e (headline): the package's data path. A featurised data set cached on the host in the compact format
+    # (openchem_b200.compact.CompactGraphDataset: packed ONCE, like any featurisation cache); EVERY step inside the timed region a
+    # sampler's index batch is collated from it into pinned memory (row gather), uploaded on the copy stream, expanded on the
+    # device into the step's static inputs, the step runs and its loss is read back on the host ----
+    from openchem_b200.compact import CompactGraphBatch, CompactGraphDataset
+    n_set = 4 * B
+    gset = make_graph_batch(n_set, w["n_max"], w["f0"], occupancy=args.occupancy, seed=ocd.shard_seed(777, rank))
+    yset = make_labels(n_set, T, w["task"] if w["task"] == "multitask" else "regression", seed=ocd.shard_seed(778, rank))
+    host_set = CompactGraphDataset.from_dense(gset["x"], gset["adj"], yset, pinned_slots=6)
+    del gset
+    perm = np.random.RandomState(5 + rank)
+
+    def compact_batches(n):
+        for _ in range(n):
+            yield host_set.collate(perm.permutation(n_set)[:B]).tensors()      # per-step host work: the sampler + the collate
+
+    from openchem_b200.loader import BackgroundIterator
+    feed_c = DevicePrefetcher(BackgroundIterator(compact_batches(2 + args.steps), depth=2), dev)
+    e2e_h2d = [0]
 
     def compact_step():
         xbits, abits, yb = next(feed_c)
+        e2e_h2d[0] = (xbits.numel() + abits.numel()) * 4 + yb.numel() * 4
         cb = CompactGraphBatch(xbits, abits, w["f0"], yb)
         if stepper is not None:
             stepper.load_compact(cb)
@@ -377,19 +557,30 @@ def run_native(args, w, wname):
         xe, ae = cb.expand()
         return step(xe, ae, yb)
 
-    for _ in range(2):
-        float(compact_step().item())
-    barrier()
-    reader, host_losses = DelayedLoss(dev), []
-    e0.record()
-    for _ in range(args.steps):
-        host_losses.append(reader.push(compact_step()))
-    host_losses.append(reader.flush())
-    e1.record()
-    barrier()
-    assert len([v for v in host_losses if v is not None]) == args.steps and all(math.isfinite(v) for v in host_losses[1:])
-    ms_e2e_compact = max_over_ranks(e0.elapsed_time(e1))
-    # the clock / throttle sampler (nvidia-smi, ~20 Hz at best) ran through the device-resident AND the two end-to-end timed
+    ms_e2e = e2e_region(compact_step)
+
+    # ---- e2e_dense: the same region fed in the REFERENCE's host format (dense fp32 adjacency / features / labels from pinned
+    # memory, Graph2Label.cast_inputs' layout) through the same feeder ----
+    h2d_dense = hx.numel() * 4 + hadj.numel() * 4 + hy.numel() * 4
+    feed = DevicePrefetcher([(hx, hadj, hy)] * (2 + args.steps), dev)
+    ms_e2e_dense = e2e_region(lambda: step(*next(feed)))
+
+    # ---- the same per-GPU workload without the gradient exchange (N > 1 only): every rank steps a purely local replica.
+    # This is the single-GPU number the N-GPU value should be read against (BASELINE config 4 is quoted at 2048 per GPU) ----
+    local_only = None
+    if world > 1 and stepper is not None:
+        from openchem_b200.step import TrainStep
+        torch.manual_seed(0)
+        lmodel = build_model(w, args.precision, dev, args.head)
+        lstep = TrainStep(lmodel, crit, adam, (x, adj, y), loss_fn=head_loss_fn(args, crit), exchange=False)
+        for _ in range(args.warmup):
+            lstep()
+        ms_local = timed(lstep, args.steps)
+        local_only = dict(value=B * args.steps / (ms_local * 1e-3), unit=UNIT, ms_per_step=ms_local / args.steps,
+                          what="one GPU, same per-GPU batch, no gradient exchange (slowest rank)")
+        del lstep, lmodel
+
+    # the clock / throttle sampler (nvidia-smi, ~20 Hz at best) ran through the device-resident AND the end-to-end timed
     # regions: the same load, enough samples for a median even when K steps last only tens of milliseconds
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
@@ -412,6 +603,31 @@ def run_native(args, w, wname):
             _lib.profile_enable(False)
     barrier()
 
+    # ---- the route an unmodified run.py takes: eager autograd (+ DDP) + per-step .item(), same model class ----
+    eager = None
+    if args.runtime == "graph" and not args.no_extra:
+        torch.manual_seed(0)
+        emodel = build_model(w, args.precision, dev, args.head)
+        estep_model = ocd.wrap_ddp(emodel, local) if world > 1 else emodel
+        eopt = torch.optim.Adam(emodel.parameters(), lr=5e-4)
+        eloss = head_loss_fn(args, crit)
+
+        def eager_step():
+            with torch.autograd.set_detect_anomaly(True):        # openchem_model.py:103
+                eopt.zero_grad()
+                loss = crit(estep_model((x, adj)), y)
+                loss.backward()
+                eopt.step()
+            return loss.item()                                   # openchem_model.py:159-163
+
+        for _ in range(3):
+            eager_step()
+        ms_eager = timed(eager_step, max(args.steps // 2, 5))
+        eager = dict(value=world * B * max(args.steps // 2, 5) / (ms_eager * 1e-3), unit=UNIT, ms_per_step=ms_eager / max(args.steps // 2, 5),
+                     what="device-resident batch; eager autograd + torch Adam + anomaly mode + loss.item() every step, as the reference's "
+                          "train_step/fit drive the model (DistributedDataParallel when N > 1)")
+        del eloss, estep_model, emodel
+
     if rank != 0:
         finish(world)
         return
@@ -420,85 +636,81 @@ def run_native(args, w, wname):
     work = algorithmic_work(w)
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
-    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
-    tensor_peak = peaks["bf16_sustained"] * (0.5 if args.precision == "tf32" else 1.0)
+    tensor_scale = 0.5 if args.precision == "tf32" else 1.0
+    tensor_peak = peaks["bf16_sustained"] * tensor_scale
     t_roof_mol = max(work["bytes"] / (peaks["hbm_gbs"] * 1e9), work["flops"] / (tensor_peak * 1e12))
     step_frac = (B * t_roof_mol) / (ms_step * 1e-3)
 
-    # dominant kernel: the one with the largest share of the profiled steps. Its roofline is the slower of
-    # (algorithmic bytes / measured HBM bandwidth) and (algorithmic flops / measured tensor peak) for ONE launch
-    # (DESIGN.md section 5 states the per-launch figures: boundary tensors only, dense GEMM flops only).
+    # ---- roofline of the dominant kernel, SURVEY 8(d): ALGORITHMIC work of one launch (dense-GEMM flops of the reference's
+    # products; compulsory bytes) / its mean duration, against the measured peak. The tile kernels are tensor-bound on paper
+    # (flops at tensor peak take longer than their share of the compulsory bytes at HBM peak), so `bound` is "tensor";
+    # what the implementation actually moves is reported separately (hbm_achieved_gbs, traffic, traffic_ratio) ----
     roofline, shares = None, {}
     tot_ms = sum(v[0] for v in kern.values()) or 1.0
     for k, (ms, n) in sorted(kern.items(), key=lambda kv: -kv[1][0]):
         shares[k] = dict(ms_per_step=ms / max(args.profile_steps, 1), launches_per_step=n / max(args.profile_steps, 1), share=ms / tot_ms)
+    tc = args.precision != "fp32"
+    Fall = [w["f0"]] + list(w["hidden"]) + [w["encoder_dim"]]
+    fused_dw = tc and max(Fall) <= 128 and w["n_max"] <= 128
+    traffic_tab = {}
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if os.path.exists(tpath):
+        traffic_tab = json.load(open(tpath))
     if kern:
-        top = max(kern, key=lambda k: kern[k][0])
-        ms_launch = kern[top][0] / kern[top][1]
-        N, F, E = w["n_max"], [w["f0"]] + list(w["hidden"]), w["encoder_dim"]
-        mid, R = F[1], B * w["n_max"]
-        tc = args.precision != "fp32"
-        simg = 2 if tc else 4                      # bytes/element of the saved S / dZ operand (bf16 image vs fp32)
-        fused = tc and max(F + [E]) <= 128            # weight gradients accumulated inside the backward tile kernels
-        alg = {   # kernel -> (dense GEMM flops, boundary-tensor bytes) per launch, mid layers (F_in = F_out = mid)
-            "fwd_mid": (B * (2 * N * N * mid + 2 * N * mid * mid), R * mid * (4 + 4 + 1 + simg)),            # Z in; Z, arg, S out
-            "fwd_first": (B * (2 * N * N * F[0] + 2 * N * F[0] * F[1]), R * (F[0] * (4 + simg) + F[1] * 4)),
-            # dY, Z, Z_prev, arg (+ S image when dW is fused) in; dY_prev (+ dZ image when it is not) out
-            "bwd_dz": (B * (2 * N * mid * mid + 2 * N * N * mid + (2 * N * mid * mid if fused else 0)), R * mid * (4 + 4 + 4 + 1 + 4 + simg)),
-            "gemm_tn": (B * (2 * N * mid * mid), R * mid * 8),
-            "dw_mma": (B * (2 * N * mid * mid), R * mid * 4),
-            "fwd_readout": (B * (2 * N * F[-1] * E), R * (F[-1] * (4 + 1 + simg) + E * 4)),
-            "bwd_readout": (B * (2 * N * F[-1] * E * (2 if fused else 1)), R * (E * 4 + F[-1] * (4 + 1 + 4 + simg))),
-            "bwd_dy": (0, R * mid * (4 + 4 + 1 + 4)),
-        }.get(top)
-        if alg is not None:
-            flops_launch, bytes_launch = alg
-            if top == "bwd_dz":
-                # its L launches are not alike: the one for layer 0 has no dS product, no fused epilogue and a narrower S image.
-                # Use the mean algorithmic work per launch (sum over the L launches / L), matching the mean launch time below.
-                nL = len(F) - 1
-                light_b = R * (F[1] * 8 + (F[0] * simg if fused else F[1] * simg))
-                light_f = B * (2 * N * F[0] * F[1]) if fused else 0
-                bytes_launch = ((nL - 1) * bytes_launch + light_b) / nL
-                flops_launch = ((nL - 1) * flops_launch + light_f) / nL
-            t_hbm = bytes_launch / (peaks["hbm_gbs"] * 1e9)
-            t_tensor = flops_launch / (peaks["bf16_burst"] * 1e12)
-            traffic = None
-            tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-            if os.path.exists(tpath):
-                traffic = json.load(open(tpath)).get("%s/%s/%s" % (wname, args.precision, top))
-            tnote = "dram__bytes_read+write of ONE launch from the committed ncu --set full capture (profiles/r1_traffic.json); for bwd_dz that " \
-                    "is a full-layer launch, while achieved/algorithmic figures are means over the L launches (the layer-0 one is lighter)"
-            if t_hbm >= t_tensor:
-                ach = bytes_launch / (ms_launch * 1e-3) / 1e9
-                roofline = dict(bound="hbm", kernel=top, traffic_note=tnote, achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"],
-                                traffic=traffic, ms_per_launch=ms_launch, algorithmic_bytes_per_launch=bytes_launch,
-                                algorithmic_flops_per_launch=flops_launch, peak_source=peaks["source"] + ", STREAM-style copy")
+        flops_tab, bytes_tab = kernel_algorithmic_flops(w, B, fused_dw), kernel_boundary_bytes(w, B, tc, fused_dw)
+        top = max((k for k in kern if k in flops_tab), key=lambda k: kern[k][0], default=None)
+        if top is not None:
+            ms_launch = kern[top][0] / kern[top][1]
+            flops_launch = flops_tab[top]
+            comp_bytes_launch = B * work["bytes"] * flops_launch / (B * work["flops"])     # this launch's share of the step's compulsory bytes
+            t_tensor = flops_launch / (tensor_peak * 1e12)
+            t_hbm = comp_bytes_launch / (peaks["hbm_gbs"] * 1e9)
+            traffic = traffic_tab.get("%s/%s/%s" % (wname, args.precision, top))
+            if t_tensor >= t_hbm:
+                ach, peak, unit, bound = flops_launch / (ms_launch * 1e-3) / 1e12, tensor_peak, "TFLOP/s", "tensor"
             else:
-                ach = flops_launch / (ms_launch * 1e-3) / 1e12
-                roofline = dict(bound="tensor", kernel=top, traffic_note=tnote, achieved=ach, peak=peaks["bf16_burst"], unit="TFLOP/s", frac=ach / peaks["bf16_burst"],
-                                traffic=traffic, ms_per_launch=ms_launch, algorithmic_bytes_per_launch=bytes_launch,
-                                algorithmic_flops_per_launch=flops_launch, peak_source=peaks["source"] + ", burst bf16")
+                ach, peak, unit, bound = comp_bytes_launch / (ms_launch * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s", "hbm"
+            roofline = dict(bound=bound, kernel=top, achieved=ach, peak=peak, unit=unit, frac=ach / peak, traffic=traffic,
+                            ms_per_launch=ms_launch, algorithmic_flops_per_launch=flops_launch,
+                            compulsory_bytes_per_launch=comp_bytes_launch,
+                            peak_source=peaks["source"] + (", sustained bf16 (kernel timed inside the step)" if bound == "tensor" else ", STREAM-style copy"),
+                            hbm_achieved_gbs=(bytes_tab[top] / (ms_launch * 1e-3) / 1e9) if top in bytes_tab else None,
+                            implementation_bytes_per_launch=bytes_tab.get(top),
+                            traffic_ratio=(traffic / comp_bytes_launch) if traffic else None,
+                            note="frac = algorithmic dense-GEMM flops of one launch (mean over this kind's launches; split-operand passes and "
+                                 "recomputation not counted) / mean launch time / measured tensor peak. hbm_achieved_gbs = bytes of the boundary "
+                                 "tensors this implementation moves per launch / time; traffic = dram__bytes_read+write of one launch from "
+                                 "ncu --set full (profiles/r2_traffic.json); traffic_ratio = traffic / this launch's share of the compulsory bytes")
+    step_traffic = traffic_tab.get("%s/%s/step_total" % (wname, args.precision))
 
     # ---- secondary device-resident numbers for the other named configurations (BASELINE configs[0], [1], [4] shapes at
     # their per-GPU batch) with the same runtime ----
     others = {}
     if world == 1 and not args.no_extra:
-        for other, n_steps in (("c1_logp", 100), ("c2_tox21", 100), ("c5_large", 20)):
+        for other, n_steps in (("c1_logp", 100), ("c2_tox21", 100), ("c4_ddp", 30), ("c5_large", 20)):
             if other == wname:
                 continue
             try:
                 others[other] = measure_other(other, args, dev, steps=n_steps, warmup=10)
+                ow = algorithmic_work(WORKLOADS[other])
+                t_o = max(ow["bytes"] / (peaks["hbm_gbs"] * 1e9), ow["flops"] / (tensor_peak * 1e12))
+                others[other]["step_roofline"] = dict(frac=WORKLOADS[other]["batch"] * t_o / (others[other]["ms_per_step"] * 1e-3),
+                                                      t_roof_us=WORKLOADS[other]["batch"] * t_o * 1e6)
             except Exception as exc:  # noqa: BLE001 - secondary numbers must never cost the headline line
                 others[other] = dict(error=repr(exc)[:200])
             torch.cuda.empty_cache()
 
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_block(w, g, args.precision, dev)
+        except Exception as exc:  # noqa: BLE001
+            parity = dict(error=repr(exc)[:300])
+
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         r = cpu_reference_rate(w, steps=args.cpu_steps, warmup=1)
-        cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port",
-                   sample="%d steps of a %d-molecule chunk of %s, fwd+loss+bwd+Adam, reference op sequence on torch CPU (%d threads)" % (
-                       r["steps"], r["chunk"], wname, r["cores"]))
+        cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"] % wname)
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype={"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision],
@@ -506,20 +718,28 @@ def run_native(args, w, wname):
                 config=dict(workload=wname, per_gpu_batch=B, global_batch=B * world, n_max=w["n_max"], f0=w["f0"], hidden=w["hidden"],
                             encoder_dim=w["encoder_dim"], occupancy=args.occupancy, precision=args.precision, parallelism="dp%d" % world,
                             optimizer="Adam(fused)", runtime=runtime,
-                            head="openchem_b200 OpenChemMLP + criterion (libocgcn head kernels)" if args.head == "fused" else "torch modules", l2_policy="inputs+saved state per step (>1 GB at c3) exceed the 126 MB L2; no explicit flush"),
-                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps,
-                         feeder="openchem_b200.loader.DevicePrefetcher (pinned host -> device on a copy stream, one batch ahead)",
+                            head="openchem_b200 OpenChemMLP + criterion (libocgcn head kernels)" if args.head == "fused" else "torch modules",
+                            l2_policy="inputs+saved state per step (>1 GB at c3) exceed the 126 MB L2; no explicit flush",
+                            workload_note="N = 1: BASELINE config 3 (batch 4096 on one B200); N > 1: BASELINE config 4 (per-GPU batch 2048, "
+                                          "gradient all-reduce over NCCL); see single_gpu_same_workload for the matching 1-GPU figure"),
+                e2e=dict(value=world * B * args.steps / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=e2e_h2d[0], d2h_bytes_per_step=4,
+                         ms_per_step=ms_e2e / args.steps,
+                         feeder="openchem_b200.compact.CompactGraphDataset (host cache, packed once) -> per-step sampler + collate into pinned "
+                                "memory (loader.BackgroundIterator thread, 2 ahead) -> loader.DevicePrefetcher (copy stream, one batch ahead) -> "
+                                "ocgcn_expand_compact on the device; all inside the timed region",
                          loss_readback="every step's loss is copied to pinned host memory and read there, one step delayed "
                                        "(openchem_b200.step.DelayedLoss); the last read is inside the timed region"),
-                e2e_compact=dict(value=world * B * args.steps / (ms_e2e_compact * 1e-3), unit=UNIT, h2d_bytes_per_step=cb_host.nbytes(),
-                                 d2h_bytes_per_step=4, ms_per_step=ms_e2e_compact / args.steps,
-                                 format="openchem_b200.compact.CompactGraphBatch: bit-packed adj/features from pinned host memory, "
-                                        "expanded on the device (ocgcn_expand_compact) inside the timed region"),
+                e2e_dense=dict(value=world * B * args.steps / (ms_e2e_dense * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d_dense, d2h_bytes_per_step=4,
+                               ms_per_step=ms_e2e_dense / args.steps,
+                               format="the reference's host format: dense fp32 adj / features / labels from pinned memory (Graph2Label.cast_inputs layout)"),
                 gpu_launches=launches, clocks=clocks, roofline=roofline,
                 step_roofline=dict(frac=step_frac, t_roof_us=B * t_roof_mol * 1e6, flops_per_molecule=work["flops"],
                                    bytes_per_molecule=work["bytes"], tensor_peak_tflops=tensor_peak, hbm_gbs=peaks["hbm_gbs"],
-                                   peak_source=peaks["source"] + ", sustained bf16"),
-                kernels=shares, cpu_baseline=cpu, other_workloads=others)
+                                   peak_source=peaks["source"] + ", sustained bf16",
+                                   step_dram_bytes=step_traffic,
+                                   traffic_ratio=(step_traffic / (B * work["bytes"])) if step_traffic else None),
+                kernels=shares, parity=parity, replica_check=replica_check, single_gpu_same_workload=local_only, runtime_eager=eager,
+                cpu_baseline=cpu, other_workloads=others)
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     finish(world)
 
@@ -538,14 +758,16 @@ def main():
     ap.add_argument("--profile-steps", type=int, default=3)
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the secondary c2_tox21 measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads and the eager-runtime measurement")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity block (fp64 oracle on the timed configuration)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    # Headline: C3 (batch 4096 per B200). N>1 keeps the SAME per-GPU workload (weak scaling: global batch 4096*N), so the
-    # per-N values the driver compares are like for like; C4 (per-GPU batch 2048) is `--workload c4_ddp`.
-    wname = args.workload or "c3_synth"
+    # Headline: N = 1 -> BASELINE config 3 (batch 4096 on one B200); N > 1 -> BASELINE config 4 as stated (per-GPU batch 2048 at
+    # 2/4/8 GPUs, data-parallel with the gradient all-reduce). The N > 1 line also carries the same workload on one GPU without
+    # the exchange (single_gpu_same_workload).
+    wname = args.workload or ("c3_synth" if world == 1 else "c4_ddp")
     w = WORKLOADS[wname]
     if args.impl == "reference":
         run_reference_arm(args, w, wname)

@@ -207,3 +207,66 @@ class ResidentCompactDataset:
         if self.data.labels is not None:      # (clamped: an out-of-range entry was already flagged / expanded to zeros above)
             labels = self.data.labels.index_select(0, index.long().clamp(0, len(self) - 1))
         return x, adj, labels
+
+
+class CompactGraphDataset(torch.utils.data.Dataset):
+    """A featurised graph data set cached on the HOST in compact form ("cached / pre-featurised
+    GraphDataset" - the reference's GraphDataset re-parses and re-featurises every molecule in every __getitem__,
+    openchem/data/graph_data_layer.py:104-116).
+
+    Built ONCE from any map-style data set that yields the reference's sample dicts (or from dense arrays); afterwards a batch
+    is a row gather of 32-bit words: `collate(indices)` writes the selected molecules into one of a few pinned staging buffers
+    and returns a pinned CompactGraphBatch ready for a non-blocking upload (1 KiB per molecule at N = F0 = 64 instead of 32 KiB).
+    `__getitem__` keeps the reference's dict layout (dense fp32), so the object also works with run.py's stock DataLoader."""
+
+    def __init__(self, x_bits, adj_bits, n_features, labels=None, pinned_slots=4):
+        self.x_bits, self.adj_bits = torch.as_tensor(x_bits), torch.as_tensor(adj_bits)
+        self.labels = None if labels is None else torch.as_tensor(labels, dtype=torch.float32)
+        self.n_features = int(n_features)
+        CompactGraphBatch(self.x_bits, self.adj_bits, self.n_features, self.labels)      # shape / dtype validation
+        self.max_size = int(self.x_bits.shape[1])
+        self._slots, self._k, self._n_slots = {}, 0, int(pinned_slots)
+
+    @classmethod
+    def from_dense(cls, x, adj, labels=None, **kw):
+        cb = pack_graph_batch(x, adj, labels)
+        return cls(cb.x_bits, cb.adj_bits, cb.n_features, cb.labels, **kw)
+
+    @classmethod
+    def from_dataset(cls, dataset, chunk=1024, **kw):
+        """Featurise every sample of `dataset` once (e.g. the reference's GraphDataset) and keep only the packed words."""
+        parts = []
+        for lo in range(0, len(dataset), chunk):
+            parts.append(compact_collate([dataset[i] for i in range(lo, min(len(dataset), lo + chunk))]))
+        lab = None if parts[0].labels is None else torch.cat([p.labels for p in parts])
+        return cls(torch.cat([p.x_bits for p in parts]), torch.cat([p.adj_bits for p in parts]), parts[0].n_features, lab, **kw)
+
+    def __len__(self):
+        return self.x_bits.shape[0]
+
+    def __getitem__(self, i):
+        s = {"adj_matrix": unpack_bits_host(self.adj_bits[i].numpy(), self.max_size),
+             "node_feature_matrix": unpack_bits_host(self.x_bits[i].numpy(), self.n_features)}
+        if self.labels is not None:
+            s["labels"] = self.labels[i].numpy()
+        return s
+
+    def collate(self, indices):
+        """Gather the molecules `indices` (any 1-D integer sequence) into a pinned host CompactGraphBatch. The staging buffers
+        rotate through `pinned_slots` sets: a returned batch stays valid for the next pinned_slots - 1 calls."""
+        idx = torch.as_tensor(indices, dtype=torch.int64)
+        if idx.dim() != 1 or (idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= len(self))):
+            raise IndexError("openchem_b200.compact: batch indices out of range for a data set of %d molecules" % len(self))
+        n = idx.numel()
+        key = (n, self._k % self._n_slots)
+        self._k += 1
+        if key not in self._slots:
+            pin = torch.cuda.is_available()
+            mk = lambda src: torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, pin_memory=pin)  # noqa: E731
+            self._slots[key] = (mk(self.x_bits), mk(self.adj_bits), None if self.labels is None else mk(self.labels))
+        xs, as_, ls = self._slots[key]
+        torch.index_select(self.x_bits, 0, idx, out=xs)
+        torch.index_select(self.adj_bits, 0, idx, out=as_)
+        if ls is not None:
+            torch.index_select(self.labels, 0, idx, out=ls)
+        return CompactGraphBatch(xs, as_, self.n_features, ls)

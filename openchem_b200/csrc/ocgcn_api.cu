@@ -2,6 +2,7 @@
 // No torch types, no device allocation, no synchronisation: everything is enqueued on the caller's stream.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -67,6 +68,29 @@ struct ProfScope {
   } while (0)
 
 static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// Launch one kernel of a forward / backward call's chain. With programmatic dependent launch enabled (default; OCGCN_PDL=0
+// turns it off) the kernel may start its prologue while its predecessor on the stream drains; every kernel launched through
+// here calls pdl_wait() before its first global-memory access (ocgcn_common.cuh). Captured into CUDA graphs as programmatic edges.
+static bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("OCGCN_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+static bool tma_enabled() {
+  static const bool on = [] { const char* e = getenv("OCGCN_TMA"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  if (pdl_enabled()) { cfg.attrs = attr; cfg.numAttrs = 1; }
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 constexpr int kMaxPersistent = 2 * 148;   // tensor-core tile kernels: two resident CTAs per SM loop over the tiles
 
 // ---------------------------------------------------------------------------------------------------------
@@ -243,8 +267,43 @@ static int ensure_dynamic_smem(size_t smem) {
 // launch helpers
 // ---------------------------------------------------------------------------------------------------------
 static int mm_grid(int tiles) { return tiles < kMaxPersistent ? tiles : kMaxPersistent; }
+// ---- TMA tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// row-major fp32 matrix [rows][cols] -> map with a 128-row x 64-column box, no swizzle (dense [128][64] image in shared memory)
+static bool make_chunk_map(const float* base, size_t rows, int cols, CUtensorMap* tm) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || rows < 128 || cols < 64 || (cols % 4) != 0 || ((uintptr_t)base & 15)) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)cols * 4};
+  const cuuint32_t box[2] = {64u, 128u};
+  const cuuint32_t estride[2] = {1u, 1u};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int TR, int PROD, int EPI, int MM>
-static int launch_tile_t(const TileArgs& a, int tiles, cudaStream_t st) {
+static int launch_tile_t(const TileArgs& a_in, int tiles, cudaStream_t st) {
+  TileArgs a = a_in;
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  // forward producers of the tensor-core engine read Zprev chunk by chunk: stage it with TMA when the shape allows (one column block,
+  // so buf1 is not needed for a second weight image; at least one full box in each dimension)
+  a.use_tma = (MM && (PROD == P_MID || PROD == P_RO) && a.ncb == 1 && tma_enabled() &&
+               make_chunk_map(a.in0, (size_t)a.B * a.N, a.K, &tm)) ? 1 : 0;
   constexpr int TC = tile_cols<TR>();
   constexpr int NT = MM ? kThreadsMM : kThreads;
   ProfScope prof(PROD == P_X ? KK_FWD_FIRST : PROD == P_MID ? KK_FWD_MID : PROD == P_RO ? KK_FWD_READOUT : PROD == P_DZ ? KK_BWD_DZ : KK_BWD_READOUT, st);
@@ -253,7 +312,7 @@ static int launch_tile_t(const TileArgs& a, int tiles, cudaStream_t st) {
   ST_TRY((ensure_dynamic_smem<tile_kernel<TR, TC, PROD, EPI, MM, NT>>(smem)));
   // persistent (two CTAs per SM looping over tiles) only where the CTA accumulates the weight gradient across its tiles;
   // everything else launches one CTA per tile (dynamic scheduling balances and de-phases the co-resident CTAs better)
-  kern<<<((MM && a.dw_img) ? mm_grid(tiles) : tiles), NT, smem, st>>>(a);
+  CU_TRY(launch_chain(kern, dim3((MM && a.dw_img) ? mm_grid(tiles) : tiles), dim3(NT), smem, st, a, tm));
   LAUNCH_CHECK();
   return OCGCN_OK;
 }
@@ -284,7 +343,7 @@ static int run_dw_mma(const Layout& lo, const void* Aimg, const void* Bimg, int 
   g.stages = stages;
   const size_t smem = stage * stages + (size_t)(2 * stages + 1) * 8 + 16;
   ST_TRY((ensure_dynamic_smem<dw_mma_kernel>(smem)));
-  dw_mma_kernel<<<splits, 128, smem, st>>>(g);
+  CU_TRY(launch_chain(dw_mma_kernel, dim3(splits), dim3(128), smem, st, g));
   LAUNCH_CHECK();
   *splits_out = splits;
   return OCGCN_OK;
@@ -298,7 +357,7 @@ static int run_wprep(const WPrepJobs& jobs, int n, cudaStream_t st) {
     const int p = ((jobs.K[j] + 63) / 64) * ((jobs.Nn[j] + 127) / 128);
     pieces = p > pieces ? p : pieces;
   }
-  wprep_kernel<<<dim3(8 * pieces, n), 256, 0, st>>>(jobs);
+  CU_TRY(launch_chain(wprep_kernel, dim3(8 * pieces, n), dim3(256), 0, st, jobs));
   LAUNCH_CHECK();
   return OCGCN_OK;
 }
@@ -337,10 +396,11 @@ static TileArgs base_tile_args(const ocgcn_desc* d, const Layout& lo, const floa
 
 static int run_adj_pack(const ocgcn_desc* d, const Layout& lo, const float* adj, char* saved, cudaStream_t st) {
   ProfScope prof(KK_ADJ_PACK, st);
-  adj_pack_kernel<<<d->B, kThreads, (size_t)2 * d->N * lo.NW * 8, st>>>(
+  CU_TRY(launch_chain(adj_pack_kernel, dim3(d->B), dim3(kThreads), (size_t)2 * d->N * lo.NW * 8, st,
+      
       adj, d->adj_stride[0], d->adj_stride[1], d->adj_stride[2], d->N, lo.NW, reinterpret_cast<u64*>(saved + lo.rowmask),
       reinterpret_cast<u64*>(saved + lo.colmask), reinterpret_cast<unsigned*>(saved + lo.molflag),
-      reinterpret_cast<uint4*>(saved + lo.nbr), reinterpret_cast<uint4*>(saved + lo.cnbr));
+      reinterpret_cast<uint4*>(saved + lo.nbr), reinterpret_cast<uint4*>(saved + lo.cnbr)));
   LAUNCH_CHECK();
   return OCGCN_OK;
 }
@@ -358,8 +418,8 @@ static int run_bn_finalize(const ocgcn_desc* d, const Layout& lo, const ocgcn_pa
   f.running_mean = p->running_mean[l]; f.running_var = p->running_var[l];
   f.nbt = reinterpret_cast<long long*>(p->num_batches_tracked[l]);
   f.mean = stats; f.invstd = stats + F; f.scale = stats + 2 * F; f.shift = stats + 3 * F;
-  if (d->training && chan_wide(lo.tiles)) bn_finalize_kernel<kChanColsWide><<<(F + kChanColsWide - 1) / kChanColsWide, kRedThreads, 0, st>>>(f);
-  else bn_finalize_kernel<kChanCols><<<(F + kChanCols - 1) / kChanCols, kRedThreads, 0, st>>>(f);
+  if (d->training && chan_wide(lo.tiles)) CU_TRY(launch_chain(bn_finalize_kernel<kChanColsWide>, dim3((F + kChanColsWide - 1) / kChanColsWide), dim3(kRedThreads), 0, st, f));
+  else CU_TRY(launch_chain(bn_finalize_kernel<kChanCols>, dim3((F + kChanCols - 1) / kChanCols), dim3(kRedThreads), 0, st, f));
   LAUNCH_CHECK();
   return OCGCN_OK;
 }
@@ -385,7 +445,7 @@ static void add_reduce(ReduceJobs& j, const float* partial, float* out, int P, i
 static int run_reduce(const ReduceJobs& j, cudaStream_t st) {
   if (j.n == 0) return OCGCN_OK;
   ProfScope prof(KK_REDUCE, st);
-  reduce_partials_kernel<<<j.first_cta[j.n], kRedThreads, 0, st>>>(j);
+  CU_TRY(launch_chain(reduce_partials_kernel, dim3(j.first_cta[j.n]), dim3(kRedThreads), 0, st, j));
   LAUNCH_CHECK();
   return OCGCN_OK;
 }
@@ -480,8 +540,8 @@ static int run_layer_backward(const ocgcn_desc* d, const Layout& lo, const float
   f.g = coef; f.c1 = coef + cstride; f.c2 = coef + 2 * cstride;
   {
     ProfScope prof(KK_BWD_FINALIZE, st);
-    if (chan_wide(lo.tiles)) bwd_finalize_kernel<kChanColsWide><<<(Fout + kChanColsWide - 1) / kChanColsWide, kRedThreads, 0, st>>>(f);
-    else bwd_finalize_kernel<kChanCols><<<(Fout + kChanCols - 1) / kChanCols, kRedThreads, 0, st>>>(f);
+    if (chan_wide(lo.tiles)) CU_TRY(launch_chain(bwd_finalize_kernel<kChanColsWide>, dim3((Fout + kChanColsWide - 1) / kChanColsWide), dim3(kRedThreads), 0, st, f));
+    else CU_TRY(launch_chain(bwd_finalize_kernel<kChanCols>, dim3((Fout + kChanCols - 1) / kChanCols), dim3(kRedThreads), 0, st, f));
     LAUNCH_CHECK();
   }
 
@@ -983,13 +1043,13 @@ int ocgcn_head_forward(const ocgcn_head_desc* d, const float* inp, const ocgcn_h
     auto kern = a.Nout > 128 ? head_fwd_kernel<2> : head_fwd_kernel<1>;
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_fwd_smem(kHeadMaxWidth, kHeadMaxWidth)));
     ProfScope prof(KK_HEAD_FWD, st);
-    kern<<<lo.grid, HT, smem, st>>>(a);
+    CU_TRY(launch_chain(kern, dim3(lo.grid), dim3(HT), smem, st, a));
     LAUNCH_CHECK();
   }
   if (d->loss != OCGCN_LOSS_NONE) {
     ProfScope prof(KK_HEAD_LOSS, st);
-    head_loss_kernel<<<1, HT, 0, st>>>(reinterpret_cast<const float*>(scratch + lo.loss_part), lo.ntiles, lo.T, d->B, d->loss, loss,
-                                       reinterpret_cast<float*>(saved + lo.ncount));
+    CU_TRY(launch_chain(head_loss_kernel, dim3(1), dim3(HT), 0, st, reinterpret_cast<const float*>(scratch + lo.loss_part), lo.ntiles, lo.T, d->B, d->loss, loss,
+                                       reinterpret_cast<float*>(saved + lo.ncount)));
     LAUNCH_CHECK();
   }
   return OCGCN_OK;
@@ -1054,7 +1114,7 @@ int ocgcn_head_backward(const ocgcn_head_desc* d, const float* grad, const float
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_bwd_smem(kHeadMaxWidth, kHeadMaxWidth)));
     {
       ProfScope prof(KK_HEAD_BWD, st);
-      kern<<<lo.grid, HT, smem, st>>>(a);
+      CU_TRY(launch_chain(kern, dim3(lo.grid), dim3(HT), smem, st, a));
       LAUNCH_CHECK();
     }
     add_reduce(rj, a.dWpart, g->dW[i], lo.grid, a.Nout * a.Kin, 1, 0);

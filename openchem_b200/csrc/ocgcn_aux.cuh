@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(kThreads) adj_pack_kernel(const float* __restr
                                                             long long as2, int N, int NW, u64* __restrict__ rowmask,
                                                             u64* __restrict__ colmask, unsigned* __restrict__ molflag,
                                                             uint4* __restrict__ nbr, uint4* __restrict__ cnbr) {
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64* sR = reinterpret_cast<u64*>(smem_raw);
   u64* sCm = sR + (size_t)N * NW;
@@ -242,6 +243,7 @@ constexpr int kChanColsWide = 2;  // ... or 2 channels x 512 row lanes when ther
 static inline bool chan_wide(int rows) { return rows >= 1024; }
 template <int COLS>
 __global__ void __launch_bounds__(kRedThreads) bn_finalize_kernel(const BnFinalizeArgs a) {
+  pdl_wait();
   if (!a.training) {   // eval: running statistics
     const int c = blockIdx.x * COLS + (threadIdx.x % COLS);
     if (threadIdx.x >= COLS || c >= a.F) return;
@@ -494,6 +496,7 @@ struct BwdFinJob {
 };
 template <int COLS>
 __global__ void __launch_bounds__(kRedThreads) bwd_finalize_kernel(const BwdFinalizeArgs a) {
+  pdl_wait();
   __shared__ double sbuf[wide_reduce_smem<2, COLS>()];
   BwdFinJob job{a};
   wide_reduce<2, COLS>(job, a.T, a.F, blockIdx.x, sbuf);
@@ -614,6 +617,7 @@ __device__ __forceinline__ void wide_reduce_vec4(const float* __restrict__ p, fl
 static inline bool reduce_job_vec4(int matrix, int tr_cols, int count) { return matrix && count % 4 == 0 && (tr_cols == 0 || (count / tr_cols) % 4 == 0); }
 
 __global__ void __launch_bounds__(kRedThreads) reduce_partials_kernel(const ReduceJobs jobs) {
+  pdl_wait();
   int jb = 0;
   while (jb + 1 < jobs.n && (int)blockIdx.x >= jobs.first_cta[jb + 1]) ++jb;
   const int cg = (int)blockIdx.x - jobs.first_cta[jb];

@@ -1,5 +1,6 @@
 // Shared definitions for the ocgcn kernels (sm_100a).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -15,6 +16,15 @@ constexpr int KCP = KC + 4;     // padded chunk row (floats): float4-aligned row
 constexpr int kMaxNbr = 13;     // neighbours held inline in a 16-byte row record (more -> bit-mask fallback)
 
 typedef unsigned long long u64;
+
+// Programmatic dependent launch (PDL). The kernels of one forward / backward call are launched back to back with the
+// programmatic-stream-serialization attribute (ocgcn_api.cu: launch_chain): a kernel may become resident while its predecessor
+// drains, runs its prologue (shared-memory carve-up, mbarrier init, TMEM allocation), and blocks in pdl_wait() until the
+// predecessor grid has COMPLETED and its memory is visible - so pdl_wait() comes before the first global-memory access.
+// pdl_trigger() marks the point after which a CTA no longer delays the dependent's launch (all CTAs triggered or exited).
+// Both are no-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- producer / epilogue kinds of the tile kernel ------------------------------------------------------------
 enum Prod : int {
@@ -84,6 +94,9 @@ struct TileArgs {
   int dw_chunks;        // 16-byte channel chunks of that image per tile (<= 16)
   int dw_M;             // true row extent of the gradient (F_in, or F_L for the readout)
   float* dw_partial;    // [gridDim.x][dw_M][K] per-CTA partial gradients
+  // TMA staging of the forward producers' input (P_MID / P_RO of the tensor-core engine): the 128-row x 64-channel fp32 chunk of
+  // Zprev arrives through the kernel's tensor map (cp.async.bulk.tensor) instead of per-thread loads
+  int use_tma;
 };
 
 // ---- 16-byte neighbour record of one adjacency row (built once per forward by adj_pack_kernel) ----------------

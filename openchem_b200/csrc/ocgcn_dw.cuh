@@ -27,6 +27,7 @@ struct WPrepJobs {
 // grid = (8 * max pieces, jobs): one CTA writes one 16-byte-chunk row block (k-chunk kc = blockIdx.x % 8) of the hi(/lo) piece pair
 // (q, cbi) — four elements per thread, so the kernel is one load latency deep instead of 32
 __global__ void __launch_bounds__(256) wprep_kernel(const WPrepJobs jobs) {
+  pdl_wait();
   const int jb = blockIdx.y;
   const int K = jobs.K[jb], Nn = jobs.Nn[jb], parts = jobs.parts[jb];
   const int nq = (K + 63) / 64, ncb = (Nn + 127) / 128;
@@ -70,6 +71,7 @@ static inline size_t dw_stage_bytes(int chA, int chB, int rows_per_stage) {
 }
 
 __global__ void __launch_bounds__(128) dw_mma_kernel(const DwArgs a) {
+  pdl_wait();
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int chA = a.chA, chB = a.chB, S = a.stages;

@@ -193,6 +193,7 @@ static inline size_t head_fwd_smem(int Kin, int Nout) {
 
 template <int NCP>
 __global__ void __launch_bounds__(HT, 2) head_fwd_kernel(const HeadFwdArgs a) {
+  pdl_wait();
   extern __shared__ __align__(16) float hsm[];
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int Kin = a.Kin, Nout = a.Nout, NP = head_pitch(Nout);
@@ -329,6 +330,7 @@ __global__ void __launch_bounds__(HT, 2) head_fwd_kernel(const HeadFwdArgs a) {
 // the backward.
 __global__ void __launch_bounds__(HT) head_loss_kernel(const float* __restrict__ part, int ntiles, int T, int B, int loss, float* __restrict__ out,
                                                        float* __restrict__ coef) {
+  pdl_wait();
   __shared__ double sv[kHeadMaxWidth];
   __shared__ double sn[kHeadMaxWidth];
   const int tid = threadIdx.x;
@@ -406,6 +408,7 @@ static inline size_t head_bwd_smem(int Kin, int Nout) {
 
 template <int NCP>
 __global__ void __launch_bounds__(HT, 2) head_bwd_kernel(const HeadBwdArgs a) {
+  pdl_wait();
   extern __shared__ __align__(16) float hsm[];
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int Kin = a.Kin, Nout = a.Nout;

@@ -128,6 +128,15 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
                : "memory");
 }
+// 2-D tiled TMA load (cp.async.bulk.tensor): box of the tensor map at element coordinates (c0 innermost, c1) -> dense
+// [box rows][box cols] image in shared memory (no swizzle); out-of-range elements arrive as zeros and count towards the
+// mbarrier's transaction bytes. smem_dst must be 128-byte aligned.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

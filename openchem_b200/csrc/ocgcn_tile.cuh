@@ -250,7 +250,7 @@ __device__ __forceinline__ void stg2(float* p, float2 v, bool v0, bool v1, bool 
 }
 
 template <int TR, int TC, int PROD, int EPI, int MM, int NT>
-__global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const TileArgs a) {
+__global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const TileArgs a, const __grid_constant__ CUtensorMap tm_in0) {
   constexpr int NWARP = NT / 32;
   constexpr int TYN = TR / 8;
   constexpr int TXN = TC / 8;
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
   // fp32-class values, so the pool arg-max decisions match an fp32 forward), backward products 3 (no lo.lo).
   constexpr int NPASS = (PROD == P_X || PROD == P_MID || PROD == P_RO) ? 4 : 3;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int N = a.N, NW = a.NW, K = a.K, NC = a.NC;
   // Layout: [records][main region][flags][warp partials][barriers][tmem slot][row masks][column masks]. Only the bit masks have
   // a run-time size (NW words per row); they come LAST so that every other region sits at a compile-time offset and its
@@ -305,6 +305,8 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
   const bool do_dw = MM && (PROD == P_DZ || PROD == P_DU) && a.dw_img != nullptr;
   const bool use_mma = MM && (!a.skip_gemm || do_dw);
   uint32_t tmem = 0, ph_w = 0, ph_w1 = 0, ph_mma = 0, ph_s = 0;
+  const bool use_tma = MM && (PROD == P_MID || PROD == P_RO) && a.use_tma;
+  constexpr uint32_t kZBoxBytes = 128u * KC * 4u;
   const uint32_t tcols = (MM && (a.ncb > 1 || do_dw)) ? 2 * kTmemCols : kTmemCols;   // <= 2 accumulators of 128 columns
   bool mma_pending = false, store_pending = false;
 
@@ -314,6 +316,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
       tc::mbar_init(&bars[1], 1);
       tc::mbar_init(&bars[2], 1);
       tc::mbar_init(&bars[3], 1);
+      tc::mbar_init(&bars[5], 1);   // [5]: TMA-staged producer input chunk landed (bars[4] holds the TMEM slot)
       tc::mbar_init_fence();
     }
     if (warp == 0) {
@@ -327,6 +330,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
     tc::fence_after_sync();
     tmem = *tslot;
   }
+  pdl_wait();   // everything above touched only shared memory / TMEM; the predecessor kernel's results are needed from here on
 
   // persistent over tiles (MM launches use at most two CTAs per SM; the exact-fp32 engine launches one CTA per tile)
   int tile_iter = 0;
@@ -346,6 +350,11 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
   const float* const o_t = (PROD == P_DU) ? a.in2 + (size_t)mol0 * K : nullptr;
   const float* const do_t = (PROD == P_DU) ? a.in1 + (size_t)mol0 * K : nullptr;
 
+  if (use_tma && tid == 0) {   // first channel chunk of Zprev -> buf1 (free: the previous tile ended with a barrier), overlapping the staging below
+    tc::fence_async_smem();
+    tc::mbar_expect_tx(&bars[5], kZBoxBytes);
+    tc::tma_load_2d(buf1, &tm_in0, 0, (int)row0, &bars[5]);
+  }
   // ---- stage neighbour records (made tile-relative), masks and per-molecule flags ---------------------------
   int simple = 1;   // every row AND column of the tile is a binary record with <= kMaxNbr neighbours (any molecular graph)
   for (int r = tid; r < TR; r += NT) {
@@ -397,6 +406,11 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
         // ONE warp polls the mbarrier, everybody else parks at the hardware barrier: waiting warps then take no issue slots from the
         // co-resident CTA (16 polling warps were 7-10 % of the executed instructions)
         bool resync = false;
+        if (use_tma) {   // this chunk's TMA box has landed in buf1
+          // (one box per chunk since the kernel started: the phase parity follows from the chunk count, no register carried)
+          if (warp == 0) tc::mbar_wait(&bars[5], (uint32_t)(tile_iter * ((K + KC - 1) / KC) + k0 / KC) & 1u);
+          resync = true;
+        }
         if (mma_pending) {
           if (warp == 0) tc::mbar_wait(&bars[1], ph_mma);
           ph_mma ^= 1;
@@ -512,12 +526,18 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
           sc4.x *= kTanhScale; sc4.y *= kTanhScale; sc4.z *= kTanhScale; sc4.w *= kTanhScale;
           sh4.x *= kTanhScale; sh4.y *= kTanhScale; sh4.z *= kTanhScale; sh4.w *= kTanhScale;
           float4 v[RPW / 2];
+          if (!use_tma) {
 #pragma unroll
-          for (int sI = 0; sI < RPW / 2; ++sI) {
-            const int r = warp + (2 * sI + hh) * NWARP;
-            v[sI] = (r < rows && cv) ? __ldg(reinterpret_cast<const float4*>(&in0_t[r * K + c4])) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int sI = 0; sI < RPW / 2; ++sI) {
+              const int r = warp + (2 * sI + hh) * NWARP;
+              v[sI] = (r < rows && cv) ? __ldg(reinterpret_cast<const float4*>(&in0_t[r * K + c4])) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
           chunk_sync();
+          if (use_tma) {   // the chunk sits in buf1 as a dense [128][64] box (P_RO: tanh happens in place, bufT == buf1)
+#pragma unroll
+            for (int sI = 0; sI < RPW / 2; ++sI) v[sI] = *reinterpret_cast<const float4*>(&buf1[(warp + (2 * sI + hh) * NWARP) * BS + 4 * hl]);
+          }
 #pragma unroll
           for (int sI = 0; sI < RPW / 2; ++sI) {
             const int r = warp + (2 * sI + hh) * NWARP;
@@ -557,7 +577,8 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
         __syncthreads();
         // neighbour max-pool: P[i,c] = max_j A[i,j]*T[j,c], first index wins ties (gcn_encoder.py:44-50)
         if (MM && fast4) {
-#pragma unroll
+          // (readout producer: the operand split and image stores sit inside this loop, two row pairs in flight fit the 64 registers)
+#pragma unroll(PROD == P_RO ? 2 : RPW / 2)
           for (int sI = 0; sI < RPW / 2; ++sI) {
             const int r = warp + (2 * sI + hh) * NWARP;
             float bq[4] = {0.f, 0.f, 0.f, 0.f};
@@ -566,11 +587,14 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
               const int mb = rec_m(rec) * N;
               int aq[4];
               rec_max4_padded<BS>(rec, &bufT[4 * hl], bq, aq);
-              if (rec_has_zero(rec)) {  // a zero entry A[i,jz] contributes the candidate 0*T = 0
+              if (rec_has_zero(rec)) {  // a zero entry A[i,jz] contributes the candidate 0*T = 0 (first index wins an exact tie)
                 const int jz = mb + rec_jz(rec);
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (!(bq[e] > 0.f)) { if (bq[e] < 0.f || jz < aq[e]) aq[e] = jz; bq[e] = 0.f; }
+                for (int e = 0; e < 4; ++e) {
+                  const bool keep = bq[e] > 0.f || (bq[e] == 0.f && aq[e] < jz);
+                  aq[e] = keep ? aq[e] : jz;
+                  bq[e] = fmaxf(bq[e], 0.f);
+                }
               }
               if (first_pass && cv)
                 *reinterpret_cast<uchar4*>(argo_t + (r * K + c4)) =
@@ -946,6 +970,11 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
               }
             }
             tc::mma_commit(&bars[1]);
+          }
+          if (use_tma && k0 + KC < K) {   // next channel chunk of Zprev -> buf1: its last readers finished before the barrier above
+            tc::fence_async_smem();
+            tc::mbar_expect_tx(&bars[5], kZBoxBytes);
+            tc::tma_load_2d(buf1, &tm_in0, k0 + KC, (int)row0, &bars[5]);
           }
           if (first_pass && a.prod_img) {
             // the hi image of this chunk is the formatted operand of the weight-gradient GEMM: tile image [K/8][128][8] bf16
@@ -1485,6 +1514,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
   }   // column passes
   __syncthreads();   // the next tile restages the neighbour records and reuses every buffer
   }   // tiles of this CTA
+  pdl_trigger();
 
   if (do_dw) {
     // this CTA's partial weight gradient: TMEM columns [128, 256) -> dw_partial[cta][m][n] (merged in fixed order afterwards)

@@ -56,3 +56,39 @@ class DevicePrefetcher:
         batch = self.slots[k]
         self._preload()
         return batch
+
+
+class BackgroundIterator:
+    """Runs an iterator (e.g. sampler + `CompactGraphDataset.collate`, or a DataLoader) in a daemon thread, `depth` items ahead,
+    so the host-side batch assembly of step t+1.. overlaps the Python / launch work of step t instead of sitting between two
+    launches. Exceptions raised by the producer are re-raised at the consumer."""
+
+    _END = object()
+
+    def __init__(self, iterable, depth=2):
+        import queue
+        import threading
+        self.q = queue.Queue(maxsize=max(int(depth), 1))
+        self.exc = None
+
+        def run():
+            try:
+                for item in iterable:
+                    self.q.put(item)
+            except BaseException as e:  # noqa: BLE001 - handed to the consumer
+                self.exc = e
+            self.q.put(self._END)
+
+        self.thread = threading.Thread(target=run, daemon=True)
+        self.thread.start()
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        item = self.q.get()
+        if item is self._END:
+            if self.exc is not None:
+                raise self.exc
+            raise StopIteration
+        return item

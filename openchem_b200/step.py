@@ -47,7 +47,7 @@ class DelayedLoss:
 
 
 class TrainStep:
-    def __init__(self, model, criterion, make_optimizer, example_batch, use_graph=True, warmup=3, loss_fn=None):
+    def __init__(self, model, criterion, make_optimizer, example_batch, use_graph=True, warmup=3, loss_fn=None, exchange=True):
         """model((x, adj)) -> predictions; criterion(pred, y) -> scalar; make_optimizer(params) -> torch optimizer that is
         CUDA-graph capturable (e.g. Adam(fused=True, capturable=True)); example_batch = (x, adj, y) device tensors.
         loss_fn(model, (x, adj), y) -> scalar, optional: replaces criterion(model(inp), y), e.g. to evaluate the criterion
@@ -56,6 +56,8 @@ class TrainStep:
         given (see the snapshot note below): the first __call__ is training step 1."""
         self.model, self.criterion, self.loss_fn = model, criterion, loss_fn
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if not exchange:      # a purely local step (no gradient all-reduce, no initial broadcast): single-GPU timing inside a multi-rank job
+            self.world = 1
         dev = example_batch[0].device
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.flat_grad = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
