@@ -123,6 +123,16 @@ int ocgcn_layer_backward(const ocgcn_desc* desc, const float* grad_y, const floa
                          const ocgcn_params* params, const ocgcn_grads* grads, float* grad_x, void* saved,
                          void* scratch, void* stream);
 
+/* tanh + neighbour max-pool as a stand-alone differentiable op (replaces torch.tanh + x.repeat/view/expand/max(dim=2) of
+ * openchem/modules/encoders/edge_attention_encoder.py:54-61 and gcn_encoder.py:43-50 for callers that chain GraphConvolution layers
+ * themselves): pooled[b,i,c] = max_j adj[b,i,j] * tanh(y[b,j,c]), first index on ties; argmax (B,N,D) uint8 is the saved routing.
+ * backward: grad_y = (scatter of grad_pooled through argmax, times adj) * (1 - tanh(y)^2). y / pooled / grads contiguous (B,N,D);
+ * adj (B,N,N) with element strides adj_stride[3]; N <= OCGCN_MAX_ATOMS. Exact fp32, fixed summation order. */
+int ocgcn_pool_forward(int B, int N, int D, const float* y, const float* adj, const int64_t* adj_stride, float* pooled,
+                       uint8_t* argmax, void* stream);
+int ocgcn_pool_backward(int B, int N, int D, const float* y, const float* adj, const int64_t* adj_stride, const uint8_t* argmax,
+                        const float* grad_pooled, float* grad_y, void* stream);
+
 /* Compact batch format (replaces the dense fp32 upload of Graph2Label.cast_inputs, openchem/models/Graph2Label.py:41-57,
  * for 0/1 adjacency and 0/1 node features — what utils/graph.py:57-63,80-84 produces). Bit (c & 31) of word
  * bits[(mol*N + row)*ceil(C/32) + (c >> 5)] is set iff dense[mol][row][c] == 1.0f; C = N for adj_bits, F0 for x_bits.
@@ -211,9 +221,8 @@ int ocgcn_last_launch_count(void);
 int ocgcn_last_cuda_error(void);
 const char* ocgcn_status_string(int status);
 /* ABI version; bumped whenever a struct above changes. */
-/* Bumped whenever a struct layout or an entry-point signature changes (2: ocgcn_expand_compact gained n_src / index_oob;
- * head and compact entry points exist). Bindings must refuse a library that reports another value. */
-#define OCGCN_ABI_VERSION 2
+/* Bumped whenever a struct layout or an entry-point signature changes (2: ocgcn_expand_compact gained n_src / index_oob; 3: ocgcn_pool_forward / _backward). Bindings must refuse a library that reports another value. */
+#define OCGCN_ABI_VERSION 3
 int ocgcn_abi_version(void);
 
 #ifdef __cplusplus

@@ -14,6 +14,7 @@
 #include "ocgcn_compact.cuh"
 #include "ocgcn_dw.cuh"
 #include "ocgcn_head.cuh"
+#include "ocgcn_pool.cuh"
 #include "ocgcn_tile.cuh"
 
 namespace ocgcn {
@@ -24,11 +25,11 @@ static thread_local int tl_cuda_err = 0;
 // ---- opt-in per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream ----------
 enum KernelKind : int {
   KK_ADJ_PACK = 0, KK_TRANSPOSE, KK_FWD_FIRST, KK_FWD_MID, KK_BN_FINALIZE, KK_FWD_READOUT, KK_BWD_READOUT, KK_BWD_DY,
-  KK_BWD_FINALIZE, KK_BWD_DZ, KK_GEMM_TN, KK_REDUCE, KK_BN_APPLY, KK_WPREP, KK_DW_MMA, KK_EXPAND, KK_PACK, KK_HEAD_FWD, KK_HEAD_LOSS, KK_HEAD_BWD, KK_COUNT
+  KK_BWD_FINALIZE, KK_BWD_DZ, KK_GEMM_TN, KK_REDUCE, KK_BN_APPLY, KK_WPREP, KK_DW_MMA, KK_EXPAND, KK_PACK, KK_HEAD_FWD, KK_HEAD_LOSS, KK_HEAD_BWD, KK_POOL_FWD, KK_POOL_BWD, KK_COUNT
 };
 static const char* const kKindNames[KK_COUNT] = {"adj_pack", "transpose", "fwd_first", "fwd_mid", "bn_finalize", "fwd_readout",
                                                  "bwd_readout", "bwd_dy", "bwd_finalize", "bwd_dz", "gemm_tn", "reduce", "bn_apply",
-                                                 "wprep", "dw_mma", "expand_compact", "pack_compact", "head_fwd", "head_loss", "head_bwd"};
+                                                 "wprep", "dw_mma", "expand_compact", "pack_compact", "head_fwd", "head_loss", "head_bwd", "pool_fwd", "pool_bwd"};
 struct ProfRec { int kind; cudaEvent_t e0, e1; };
 // process-wide (autograd runs backward on its own thread), guarded by a mutex; off by default
 static std::atomic<bool> g_prof_on{false};
@@ -894,6 +895,53 @@ int ocgcn_expand_compact(int B, int N, int F0, const uint32_t* x_bits, const uin
     expand_bits_kernel<<<bits_grid(rows * ((F0 + 3) / 4)), 256, 0, st>>>(x_bits, index, n_src, index_oob, N, F0, (F0 + 31) / 32, rows, x);
     LAUNCH_CHECK();
   }
+  return OCGCN_OK;
+}
+
+static int pool_args(int B, int N, int D, const float* y, const float* adj, const int64_t* adj_stride, PoolArgs* a) {
+  if (B <= 0 || N <= 0 || D <= 0 || !adj_stride) return OCGCN_EINVAL;
+  if (N > OCGCN_MAX_ATOMS) return OCGCN_EUNSUPPORTED;
+  ST_TRY(check_device());
+  ST_TRY(check_device_ptr(y));
+  ST_TRY(check_device_ptr(adj));
+  memset(a, 0, sizeof(*a));
+  a->B = B; a->N = N; a->D = D; a->y = y; a->adj = adj;
+  a->as0 = adj_stride[0]; a->as1 = adj_stride[1]; a->as2 = adj_stride[2];
+  return OCGCN_OK;
+}
+
+int ocgcn_pool_forward(int B, int N, int D, const float* y, const float* adj, const int64_t* adj_stride, float* pooled, uint8_t* argmax,
+                       void* stream) {
+  tl_launches = 0;
+  PoolArgs a;
+  ST_TRY(pool_args(B, N, D, y, adj, adj_stride, &a));
+  ST_TRY(check_device_ptr(pooled));
+  if (!argmax) return OCGCN_EINVAL;
+  a.pooled = pooled; a.arg = argmax;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = pool_smem_bytes(N, false);
+  ST_TRY((ensure_dynamic_smem<pool_fwd_kernel>(smem)));
+  ProfScope ps(KK_POOL_FWD, st);
+  CU_TRY(launch_chain(pool_fwd_kernel, dim3((D + kPoolCols - 1) / kPoolCols, B), dim3(kPoolCols), smem, st, a));
+  LAUNCH_CHECK();
+  return OCGCN_OK;
+}
+
+int ocgcn_pool_backward(int B, int N, int D, const float* y, const float* adj, const int64_t* adj_stride, const uint8_t* argmax,
+                        const float* grad_pooled, float* grad_y, void* stream) {
+  tl_launches = 0;
+  PoolArgs a;
+  ST_TRY(pool_args(B, N, D, y, adj, adj_stride, &a));
+  ST_TRY(check_device_ptr(grad_pooled));
+  ST_TRY(check_device_ptr(grad_y));
+  if (!argmax) return OCGCN_EINVAL;
+  a.arg = const_cast<uint8_t*>(argmax); a.grad_pooled = grad_pooled; a.grad_y = grad_y;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = pool_smem_bytes(N, true);
+  ST_TRY((ensure_dynamic_smem<pool_bwd_kernel>(smem)));
+  ProfScope ps(KK_POOL_BWD, st);
+  CU_TRY(launch_chain(pool_bwd_kernel, dim3((D + kPoolCols - 1) / kPoolCols, B), dim3(kPoolCols), smem, st, a));
+  LAUNCH_CHECK();
   return OCGCN_OK;
 }
 

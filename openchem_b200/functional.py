@@ -391,3 +391,52 @@ class HeadFn(torch.autograd.Function):
                                                scratch.data_ptr(), _stream_ptr(inp.device)))
             _count(lib)
         return (gx, None, None, *gW, *gb, *gg, *gbt)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tanh + neighbour max-pool as a stand-alone op — ocgcn_pool_forward / ocgcn_pool_backward
+# ---------------------------------------------------------------------------------------------------------------------
+class PoolFn(torch.autograd.Function):
+    """pooled[b,i,c] = max_j adj[b,i,j] * tanh(y[b,j,c]) (first index on ties): the tanh + x.repeat/view/expand/max(dim=2) of
+    edge_attention_encoder.py:54-61 / gcn_encoder.py:43-50 without the (B,N,N,D) temporaries. Differentiable w.r.t. y."""
+
+    @staticmethod
+    def forward(ctx, y, adj):
+        lib = _lib.load()
+        _require_cuda(y, "y")
+        _require_cuda(adj, "adj")
+        if adj.requires_grad:
+            raise RuntimeError("openchem_b200: gradients w.r.t. the adjacency are not supported (no reference caller needs them)")
+        y = _f32(y.detach()).contiguous()
+        adj = _f32(adj)
+        B, N, D = y.shape
+        if tuple(adj.shape) != (B, N, N) or adj.device != y.device:
+            raise RuntimeError("openchem_b200: adj must be (B,N,N) on the device of y (B,N,D); got %s and %s" % (tuple(adj.shape), tuple(y.shape)))
+        pooled = torch.empty_like(y)
+        arg = torch.empty((B, N, D), dtype=torch.uint8, device=y.device)
+        strides = (ctypes.c_int64 * 3)(*adj.stride())
+        with torch.cuda.device(y.device):
+            _lib.check(lib.ocgcn_pool_forward(B, N, D, y.data_ptr(), adj.data_ptr(), strides, pooled.data_ptr(), arg.data_ptr(),
+                                              _stream_ptr(y.device)))
+            _count(lib)
+        ctx.save_for_backward(y, adj, arg)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, grad_pooled):
+        lib = _lib.load()
+        y, adj, arg = ctx.saved_tensors
+        B, N, D = y.shape
+        grad_pooled = _f32(grad_pooled).contiguous()
+        grad_y = torch.empty_like(y)
+        strides = (ctypes.c_int64 * 3)(*adj.stride())
+        with torch.cuda.device(y.device):
+            _lib.check(lib.ocgcn_pool_backward(B, N, D, y.data_ptr(), adj.data_ptr(), strides, arg.data_ptr(), grad_pooled.data_ptr(),
+                                               grad_y.data_ptr(), _stream_ptr(y.device)))
+            _count(lib)
+        return grad_y, None
+
+
+def tanh_neighbour_max_pool(y, adj):
+    """Public name of PoolFn: tanh, then the neighbour max-pool over `adj`."""
+    return PoolFn.apply(y, adj)

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ocgcn_abi_version() == 2
+    assert lib.ocgcn_abi_version() == 3
     assert lib.ocgcn_status_string(0) == b"ok"
     assert b"unsupported" in lib.ocgcn_status_string(2)
 
@@ -217,3 +217,26 @@ int main(void) {
                                            ctypes.sizeof(_lib.HeadGrads)]
     assert sizes[4] == "0" and int(sizes[5]) > 0 and int(sizes[6]) > 0
     assert out[3].strip() == "2"      # head width > 256: OCGCN_EUNSUPPORTED
+
+
+def test_edge_attention_encoder_surface_and_init_order():
+    """Same constructor / attributes / state_dict keys as the reference's GraphEdgeAttentionEncoder, and the same initial weights
+    under the same seed (fixture written by oracle/make_golden_edge.py from the unmodified reference: dense first, then the layers)."""
+    import numpy as np
+    import torch
+    from _util import load_golden
+    from openchem_b200.modules.encoders.edge_attention_encoder import GraphEdgeAttentionEncoder
+    g = load_golden("edge_small")
+    hidden, sizes = [int(h) for h in g["hidden"]], [int(s) for s in g["sizes"]]
+    torch.manual_seed(5)
+    enc = GraphEdgeAttentionEncoder({"input_size": int(g["x"].shape[2]), "encoder_dim": int(g["dO"].shape[1]), "n_layers": len(hidden),
+                                     "hidden_size": hidden, "edge_attr_sizes": sizes}, False)
+    sd = enc.state_dict()
+    assert sorted(sd.keys()) == sorted(k[3:] for k in g if k.startswith("sd_"))
+    for k, v in sd.items():
+        if ".bn." not in k:          # (the fixture randomised the BatchNorm parameters after construction)
+            assert np.array_equal(v.numpy(), g["sd_" + k]), k
+    assert enc.attr_dim == sum(sizes) and len(enc.graph_conv) == len(hidden) * sum(sizes) and enc.hidden_size[0] == enc.input_size
+    assert GraphEdgeAttentionEncoder.get_required_params() == {"n_layers": int, "hidden_size": list, "edge_attr_sizes": list}
+    with pytest.raises(RuntimeError):        # no CPU fallback
+        enc((torch.from_numpy(g["x"]), torch.from_numpy(g["edge_attr"])))

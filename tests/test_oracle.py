@@ -197,3 +197,28 @@ def test_c_pool_scan_is_bit_identical_to_the_numpy_definition():
             d0 = orc.neighbour_max_pool_backward(dP, adj, a0, use_c=False)
             d1 = orc.neighbour_max_pool_backward(dP, adj, a0, use_c=True)
             assert np.array_equal(d0, d1)
+
+
+@pytest.mark.parametrize("case", ["edge_small", "edge_wide"])
+def test_edge_attention_oracle_matches_reference_fixture(case):
+    """oracle/edge_attention_oracle.py vs the unmodified reference's fp64 run of GraphEdgeAttentionEncoder (make_golden_edge.py)."""
+    from oracle import edge_attention_oracle as eo
+    g = load_golden(case)
+    L, A = len(g["hidden"]), int(g["sizes"].sum())
+    n = L * A
+    f64 = lambda k: g["sd_" + k].astype(np.float64)  # noqa: E731
+    p = dict(W=[f64("graph_conv.%d.weight" % k) for k in range(n)], b=[f64("graph_conv.%d.bias" % k) for k in range(n)],
+             gamma=[f64("graph_conv.%d.bn.weight" % k) for k in range(n)], beta=[f64("graph_conv.%d.bn.bias" % k) for k in range(n)],
+             running_mean=[f64("graph_conv.%d.bn.running_mean" % k) for k in range(n)],
+             running_var=[f64("graph_conv.%d.bn.running_var" % k) for k in range(n)], Wd=f64("dense.weight"), bd=f64("dense.bias"))
+    O, cache, rms, rvs = eo.forward(g["x"].astype(np.float64), g["edge_attr"].astype(np.float64), p, L, training=True)
+    gr = eo.backward(g["dO"].astype(np.float64), cache)
+    assert rel_l2(O, g["ref64_out_train"]) < 1e-10
+    assert rel_l2(gr["dWd"], g["ref64_grad_dense.weight"]) < 1e-10 and rel_l2(gr["dbd"], g["ref64_grad_dense.bias"]) < 1e-10
+    for k in range(n):
+        assert rel_l2(gr["dW"][k], g["ref64_grad_graph_conv.%d.weight" % k]) < 1e-10
+        assert rel_l2(gr["dgamma"][k], g["ref64_grad_graph_conv.%d.bn.weight" % k]) < 1e-10
+        assert rel_l2(gr["dbeta"][k], g["ref64_grad_graph_conv.%d.bn.bias" % k]) < 1e-10
+        assert rel_l2(rvs[k], g["ref64_buf_graph_conv.%d.bn.running_var" % k]) < 1e-10
+    Oe = eo.forward(g["x"].astype(np.float64), g["edge_attr"].astype(np.float64), dict(p, running_mean=rms, running_var=rvs), L, training=False)[0]
+    assert rel_l2(Oe, g["ref64_out_eval"]) < 1e-10
