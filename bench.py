@@ -280,14 +280,17 @@ def finish(world):
         os._exit(0)
 
 
-def measure_other(wname, args, dev, steps, warmup):
-    """Device-resident train-step rate of another named workload with the same runtime (one GPU, rank 0 only)."""
+def measure_other(wname, args, dev, steps, warmup, rank=0, world=1):
+    """Device-resident train-step rate of another named workload with the same runtime. world == 1: one GPU; world > 1: EVERY rank
+    calls this (the captured step contains the NCCL gradient all-reduce), per-rank shards, barrier + max over ranks."""
     import torch
+    import torch.distributed as dist
+    from openchem_b200 import dist as ocd
     from openchem_b200.step import TrainStep
     w = WORKLOADS[wname]
     B, T = w["batch"], w["mlp_hidden"][-1]
-    g = make_graph_batch(B, w["n_max"], w["f0"], occupancy="molecular" if wname in ("c1_logp", "c2_tox21") else "full", seed=99)
-    labels = make_labels(B, T, w["task"] if w["task"] == "multitask" else "regression", seed=98)
+    g = make_graph_batch(B, w["n_max"], w["f0"], occupancy="molecular" if wname in ("c1_logp", "c2_tox21") else "full", seed=99 + rank)
+    labels = make_labels(B, T, w["task"] if w["task"] == "multitask" else "regression", seed=98 + rank)
     x, adj, y = (torch.from_numpy(a).to(dev) for a in (g["x"], g["adj"], labels))
     model = build_model(w, args.precision, dev, args.head)
     crit = make_criterion(w)
@@ -295,16 +298,23 @@ def measure_other(wname, args, dev, steps, warmup):
                    use_graph=(args.runtime == "graph"), loss_fn=head_loss_fn(args, crit))
     for _ in range(warmup):
         st()
-    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     e0.record()
     for _ in range(steps):
         st()
     e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    return dict(value=B / (ms * 1e-3), unit=UNIT, ms_per_step=ms, per_gpu_batch=B, n_max=w["n_max"], f0=w["f0"], hidden=w["hidden"],
-                occupancy="molecular", steps=steps, graph=st.graph is not None)
+    barrier()
+    ms = ocd.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+    return dict(value=world * B / (ms * 1e-3), unit=UNIT, ms_per_step=ms, per_gpu_batch=B, global_batch=B * world, n_gpus=world, n_max=w["n_max"],
+                f0=w["f0"], hidden=w["hidden"], occupancy="molecular" if wname in ("c1_logp", "c2_tox21") else "full", steps=steps,
+                graph=st.graph is not None)
 
 
 def kernel_algorithmic_flops(w, B, fused_dw):
@@ -580,6 +590,25 @@ def run_native(args, w, wname):
                           what="one GPU, same per-GPU batch, no gradient exchange (slowest rank)")
         del lstep, lmodel
 
+    # ---- BASELINE config 4 as stated (per-GPU batch 2048, N ranks, gradient all-reduce inside the captured step), measured in the
+    # same job next to the headline so that every N > 1 line carries it together with its own single-GPU figure ----
+    c4_line = None
+    if world > 1 and wname != "c4_ddp" and stepper is not None:
+        from openchem_b200.step import TrainStep
+        c4_line = measure_other("c4_ddp", args, dev, steps=max(args.steps, 20), warmup=max(args.warmup, 5), rank=rank, world=world)
+        w4 = WORKLOADS["c4_ddp"]
+        g4 = make_graph_batch(w4["batch"], w4["n_max"], w4["f0"], occupancy="full", seed=99 + rank)
+        y4 = make_labels(w4["batch"], w4["mlp_hidden"][-1], "regression", seed=98 + rank)
+        torch.manual_seed(0)
+        m4 = build_model(w4, args.precision, dev, args.head)
+        s4 = TrainStep(m4, crit, adam, tuple(torch.from_numpy(a).to(dev) for a in (g4["x"], g4["adj"], y4)), loss_fn=head_loss_fn(args, crit), exchange=False)
+        for _ in range(5):
+            s4()
+        ms4 = timed(s4, 20) / 20
+        c4_line["single_gpu_same_workload"] = dict(value=w4["batch"] / (ms4 * 1e-3), unit=UNIT, ms_per_step=ms4,
+                                                   what="one GPU, per-GPU batch 2048, no gradient exchange (slowest rank)")
+        del s4, m4
+
     # the clock / throttle sampler (nvidia-smi, ~20 Hz at best) ran through the device-resident AND the end-to-end timed
     # regions: the same load, enough samples for a median even when K steps last only tens of milliseconds
     clocks = sampler.stop() if rank == 0 else None
@@ -720,8 +749,9 @@ def run_native(args, w, wname):
                             optimizer="Adam(fused)", runtime=runtime,
                             head="openchem_b200 OpenChemMLP + criterion (libocgcn head kernels)" if args.head == "fused" else "torch modules",
                             l2_policy="inputs+saved state per step (>1 GB at c3) exceed the 126 MB L2; no explicit flush",
-                            workload_note="N = 1: BASELINE config 3 (batch 4096 on one B200); N > 1: BASELINE config 4 (per-GPU batch 2048, "
-                                          "gradient all-reduce over NCCL); see single_gpu_same_workload for the matching 1-GPU figure"),
+                            workload_note="BASELINE config 3 (batch 4096 per B200) at every N: weak scaling of the headline workload, so the per-N "
+                                          "values are like for like; BASELINE config 4 (per-GPU batch 2048 at 2/4/8 GPUs) is measured in the same job "
+                                          "under `c4_ddp` (N > 1) and under other_workloads.c4_ddp (N = 1)"),
                 e2e=dict(value=world * B * args.steps / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=e2e_h2d[0], d2h_bytes_per_step=4,
                          ms_per_step=ms_e2e / args.steps,
                          feeder="openchem_b200.compact.CompactGraphDataset (host cache, packed once) -> per-step sampler + collate into pinned "
@@ -738,7 +768,7 @@ def run_native(args, w, wname):
                                    peak_source=peaks["source"] + ", sustained bf16",
                                    step_dram_bytes=step_traffic,
                                    traffic_ratio=(step_traffic / (B * work["bytes"])) if step_traffic else None),
-                kernels=shares, parity=parity, replica_check=replica_check, single_gpu_same_workload=local_only, runtime_eager=eager,
+                kernels=shares, parity=parity, replica_check=replica_check, single_gpu_same_workload=local_only, c4_ddp=c4_line, runtime_eager=eager,
                 cpu_baseline=cpu, other_workloads=others)
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     finish(world)
@@ -764,10 +794,10 @@ def main():
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    # Headline: N = 1 -> BASELINE config 3 (batch 4096 on one B200); N > 1 -> BASELINE config 4 as stated (per-GPU batch 2048 at
-    # 2/4/8 GPUs, data-parallel with the gradient all-reduce). The N > 1 line also carries the same workload on one GPU without
-    # the exchange (single_gpu_same_workload).
-    wname = args.workload or ("c3_synth" if world == 1 else "c4_ddp")
+    # Headline: BASELINE config 3 (batch 4096 per B200) at every N - weak scaling, so the driver's per-N values compare the same
+    # per-GPU work. BASELINE config 4 as stated (per-GPU batch 2048 at 2/4/8 GPUs, gradient all-reduce) is measured in the same job and
+    # reported under `c4_ddp` with its own single-GPU figure; `--workload c4_ddp` makes it the headline.
+    wname = args.workload or "c3_synth"
     w = WORKLOADS[wname]
     if args.impl == "reference":
         run_reference_arm(args, w, wname)

@@ -9,7 +9,8 @@ RDKit installed, swap the two dataset lines for the reference's GraphDataset cal
 Run with the UNMODIFIED reference drivers (reference checkout on PYTHONPATH after this repo):
     python <OpenChem>/run.py --config_file=configs/logp_gcnn_b200.py --mode=train_eval
     python <OpenChem>/launch.py --nproc_per_node=8 <OpenChem>/run.py --config_file=configs/logp_gcnn_b200.py --mode=train_eval
-Environment knobs (tests): OCB200_TRAIN / OCB200_VAL (data set sizes), OCB200_EPOCHS, OCB200_LOGDIR, OCB200_PRECISION,
+Environment knobs: OCB200_DATA=logp_csv (the reference's logP_labels.csv under $OPENCHEM_ROOT instead of synthetic graphs),
+OCB200_TRAIN / OCB200_VAL (synthetic data set sizes), OCB200_EPOCHS, OCB200_LOGDIR, OCB200_PRECISION,
 OCB200_NMAX, OCB200_BATCH.
 """
 import os
@@ -26,9 +27,16 @@ from torch.optim import Adam
 from torch.optim.lr_scheduler import StepLR
 from sklearn.metrics import r2_score
 
-_n = int(os.environ.get("OCB200_NMAX", "85"))
-train_dataset = SyntheticGraphDataset(int(os.environ.get("OCB200_TRAIN", "11340")), _n, 33, seed=1)
-test_dataset = SyntheticGraphDataset(int(os.environ.get("OCB200_VAL", "2836")), _n, 33, seed=2)
+if os.environ.get("OCB200_DATA", "synthetic") == "logp_csv":
+    # the reference's own data set (benchmark_datasets/logp_dataset/logP_labels.csv), same 80/20 split as logp_gcnn_config.py:51-58,
+    # featurised without RDKit (openchem_b200/smiles.py: exact topology, approximate valence / hybridisation)
+    from openchem_b200.smiles import logp_csv_datasets
+    _root = os.environ.get("OPENCHEM_ROOT", ".")
+    train_dataset, test_dataset = logp_csv_datasets(os.path.join(_root, "benchmark_datasets", "logp_dataset", "logP_labels.csv"))
+else:
+    _n = int(os.environ.get("OCB200_NMAX", "85"))
+    train_dataset = SyntheticGraphDataset(int(os.environ.get("OCB200_TRAIN", "11340")), _n, 33, seed=1)
+    test_dataset = SyntheticGraphDataset(int(os.environ.get("OCB200_VAL", "2836")), _n, 33, seed=2)
 
 model = Graph2Label
 
@@ -39,8 +47,8 @@ model_params = {
     'batch_size': int(os.environ.get("OCB200_BATCH", "256")),
     'num_epochs': int(os.environ.get("OCB200_EPOCHS", "101")),
     'logdir': os.environ.get("OCB200_LOGDIR", 'logs/logp_gcnn_b200_logs'),
-    'print_every': 1,
-    'save_every': 1,
+    'print_every': int(os.environ.get("OCB200_PRINT_EVERY", "1")),
+    'save_every': int(os.environ.get("OCB200_SAVE_EVERY", "1")),
     'train_data_layer': train_dataset,
     'val_data_layer': test_dataset,
     'eval_metrics': r2_score,

@@ -33,8 +33,35 @@ torch.Tensor.cuda = lambda self, *a, **k: self      # MultitaskLoss hard-codes .
 
 from openchem_b200.synthetic import make_graph_batch, make_labels  # noqa: E402
 
+from openchem_b200.smiles import smiles_batch  # noqa: E402
+
 OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def csv_molecules(kind, B, n_max):
+    """The first B molecules (that fit n_max atoms) of the reference's own benchmark CSVs, featurised without RDKit
+    (openchem_b200/smiles.py: exact topology / element / charge / aromaticity, approximate valence and hybridisation) in the logP
+    config's 33-feature layout, with the CSV's labels (Tox21: empty cells -> 9 = ignore_index, tox21_rnn_config.py pattern)."""
+    import csv
+    if kind == "logp":
+        rows = list(csv.reader(open(os.path.join(REF, "benchmark_datasets", "logp_dataset", "logP_labels.csv"))))[1:]
+        smiles, labels = [r[1] for r in rows], np.asarray([[float(r[2])] for r in rows], dtype=np.float32)
+    else:
+        rows = list(csv.reader(open(os.path.join(REF, "benchmark_datasets", "tox21", "tox21.csv"))))[1:]
+        smiles = [r[13] for r in rows]
+        labels = np.asarray([[9.0 if v == "" else float(v) for v in r[:12]] for r in rows], dtype=np.float32)
+    g = smiles_batch(smiles[:4 * B], n_max)
+    keep = g["kept"][:B]
+    assert len(keep) == B
+    return dict(x=g["x"][:B], adj=g["adj"][:B], n_atoms=g["n_atoms"][:B]), labels[keep]
+
+
 CASES = {
+    # the named configurations at their real widths and batch size, on the first 256 molecules of the reference's own data sets:
+    # BASELINE config 1 (logp_gcnn_config.py: 33 -> 5x128, E 128, MLP [128,1], MSELoss, N = 85 = the data set's largest molecule)
+    "g2l_logp_c1": dict(B=256, N=85, F0=33, hidden=[128] * 5, E=128, mlp=[128, 1], task="regression", data="logp"),
+    # BASELINE config 2 (Tox21-shaped: 12 tasks, max_atoms 50, sigmoid head, MultitaskLoss(ignore_index=9))
+    "g2l_tox21_c2": dict(B=256, N=50, F0=33, hidden=[128] * 5, E=128, mlp=[128, 12], task="multitask", data="tox21"),
     # logp_gcnn_config.py shape, narrower: regression head + MSELoss
     "g2l_logp": dict(B=20, N=30, F0=33, hidden=[64, 64, 64], E=64, mlp=[64, 1], task="regression"),
     # Tox21-style: 12 tasks, sigmoid head, MultitaskLoss(ignore_index=9)
@@ -59,9 +86,14 @@ def build(case, dtype):
 def main():
     os.makedirs(OUT, exist_ok=True)
     for name, case in CASES.items():
-        g = make_graph_batch(case["B"], case["N"], case["F0"], occupancy="molecular", seed=21)
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
         T = case["mlp"][-1]
-        y = make_labels(case["B"], T, "multitask" if case["task"] == "multitask" else "regression", seed=22)
+        if "data" in case:
+            g, y = csv_molecules(case["data"], case["B"], case["N"])
+        else:
+            g = make_graph_batch(case["B"], case["N"], case["F0"], occupancy="molecular", seed=21)
+            y = make_labels(case["B"], T, "multitask" if case["task"] == "multitask" else "regression", seed=22)
         out = dict(x=g["x"], adj=g["adj"], y=y, hidden=np.asarray(case["hidden"]), E=np.asarray(case["E"]), mlp=np.asarray(case["mlp"]),
                    task=np.asarray(case["task"]))
         for tag, dtype in (("ref32", torch.float32), ("ref64", torch.float64)):

@@ -36,7 +36,10 @@ def _rel(a, b, scale=0.0):
 
 @pytest.mark.parametrize("fused_loss", [True, False])
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 1e-2)])
-@pytest.mark.parametrize("name", ["g2l_logp", "g2l_tox21"])
+# g2l_*_c1 / _c2: BASELINE configs 1 and 2 at their real widths (5x128, encoder 128, MLP [128,1] / [128,12]) and batch size 256, on the
+# first 256 molecules of the reference's own logP / Tox21 CSVs (featurised without RDKit, openchem_b200/smiles.py); the others are
+# small synthetic cases of the same two model shapes.
+@pytest.mark.parametrize("name", ["g2l_logp_c1", "g2l_tox21_c2", "g2l_logp", "g2l_tox21"])
 def test_model_step_matches_reference_graph2label(name, precision, tol, fused_loss):
     from openchem_b200.criterion.multitask_loss import MultitaskLoss
     from openchem_b200.modules.mlp.openchem_mlp import fused_head_loss
