@@ -745,7 +745,10 @@ def run_native(args, w, wname):
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype={"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision],
                 data="synthetic",
                 config=dict(workload=wname, per_gpu_batch=B, global_batch=B * world, n_max=w["n_max"], f0=w["f0"], hidden=w["hidden"],
-                            encoder_dim=w["encoder_dim"], occupancy=args.occupancy, precision=args.precision, parallelism="dp%d" % world,
+                            encoder_dim=w["encoder_dim"], occupancy=args.occupancy, precision=args.precision,
+                            precision_engine={"fp32": "exact fp32 FFMA", "bf16": "tcgen05 kind::f16, bf16 hi+lo split operands (4 passes forward, 3 backward, 1 for dW)",
+                                              "tf32": "same bf16-split tcgen05 engine as 'bf16' (no kind::tf32 MMA is issued)"}[args.precision],
+                            parallelism="dp%d" % world,
                             optimizer="Adam(fused)", runtime=runtime,
                             head="openchem_b200 OpenChemMLP + criterion (libocgcn head kernels)" if args.head == "fused" else "torch modules",
                             l2_policy="inputs+saved state per step (>1 GB at c3) exceed the 126 MB L2; no explicit flush",
