@@ -444,7 +444,7 @@ def run_native(args, w, wname):
         # the package's step runtime: fwd + loss + bwd + NCCL grad all-reduce + Adam captured in one CUDA graph
         from openchem_b200.step import TrainStep
         stepper = TrainStep(model, crit, adam, (x, adj, y), loss_fn=head_loss_fn(args, crit))
-        runtime = "openchem_b200.step.TrainStep: one CUDA graph per step (flat-gradient NCCL all-reduce inside)" if stepper.graph is not None \
+        runtime = ("openchem_b200.step.TrainStep: one CUDA graph per step (flat-gradient all-reduce inside: %s)" % stepper.exchange_kind) if stepper.graph is not None \
             else "openchem_b200.step.TrainStep eager (graph capture failed: %s)" % stepper.graph_error
         opt = stepper.opt
 

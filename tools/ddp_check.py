@@ -92,7 +92,7 @@ def main():
     rel_nb = float(torch.linalg.norm(((flat - flat_emu) * keep).double()) / torch.linalg.norm((flat_emu * keep).double()))
     ok = identical and rel_nb < 1e-4
     if rank == 0:
-        print(json.dumps(dict(world=world, precision=precision, steps=K, graph=step.graph is not None, replicas_bit_identical=identical,
+        print(json.dumps(dict(world=world, precision=precision, steps=K, graph=step.graph is not None, exchange=step.exchange_kind, replicas_bit_identical=identical,
                               rel_l2_vs_single_gpu_emulation=rel, rel_l2_without_zero_gradient_biases=rel_nb, losses_rank0=losses, ok=ok)), flush=True)
     torch.cuda.synchronize()
     sys.stdout.flush()
