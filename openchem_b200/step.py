@@ -6,8 +6,8 @@ torch DDP, run.py:235-236); at the 1-3 ms steps of the B200 path that host work 
 show up on the critical path. `TrainStep` captures the whole step — including the all-reduce — in ONE CUDA graph:
 
 * gradients live in one flat fp32 buffer (every `p.grad` is a view), so the exchange is a single all-reduce of 0.4 MB issued
-  inside the graph right after backward - over NVLink peer memory (symmetric-memory one-shot: each rank sums all peers' buffers
-  in rank order) when available, else NCCL;
+  inside the graph right after backward (NCCL; symmetric-memory one-shot / NVLS multimem variants over NVLink peer memory are
+  selectable, see `_symmetric_flat_grad`);
 * BatchNorm statistics stay per rank (plain BatchNorm1d semantics, as under the reference's DDP); running buffers are not
   re-broadcast every step — rank 0's are the ones a checkpoint written by rank 0 holds, as in the reference;
 * inputs are read from static device buffers (`.inputs`); copy a new batch into them (any stream-ordered copy) and replay.
@@ -132,10 +132,13 @@ class TrainStep:
         """The gradient exchange is ONE latency-bound 0.4 MB all-reduce per step. Over NVLink / NVSwitch it does not need NCCL's ring:
         with the flat gradient in symmetric (peer-mapped) memory every rank can read all peers' buffers directly (`one_shot`: sum in
         rank order, identical on every rank) or let the switch reduce (`multimem`, NVLS). `allreduce` / $OCB200_ALLREDUCE selects
-        'nccl' | 'one_shot' | 'multimem' | 'auto' (default: one_shot when the symmetric-memory rendezvous works, else nccl)."""
+        'nccl' (default) | 'one_shot' | 'multimem'. Measured at 2 B200 (c4, 30 steps): 1.223 ms per step with NCCL, 1.233 one_shot,
+        1.228 multimem, against 1.192 without any exchange - the ~30 us are the per-step wait for the slower rank (every exchange
+        is a synchronisation point), not transfer time, so the direct-access variants buy nothing here; they stay selectable and
+        covered by tests/test_gpu_dist.py."""
         import os
-        kind = (allreduce or os.environ.get("OCB200_ALLREDUCE", "auto")).lower()
-        if kind == "nccl":
+        kind = (allreduce or os.environ.get("OCB200_ALLREDUCE", "nccl")).lower()
+        if kind in ("nccl", "auto"):
             return None
         try:
             import torch.distributed._symmetric_memory as symm
@@ -148,10 +151,7 @@ class TrainStep:
             self._reduced = torch.empty(numel, dtype=torch.float32, device=dev)
             return buf
         except Exception as exc:  # noqa: BLE001 - any failure of the optional fast path falls back to the NCCL all-reduce
-            if kind not in ("auto",):
-                raise
-            self.exchange_error = repr(exc)[:200]
-            return None
+            raise RuntimeError("openchem_b200.TrainStep: allreduce=%r needs torch symmetric memory over NVLink peers: %r" % (kind, exc))
 
     def _exchange(self):
         if self.exchange_kind == "nccl":

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("precision,allreduce", [("bf16", "auto"), ("fp32", "nccl"), ("bf16", "one_shot")])
+@pytest.mark.parametrize("precision,allreduce", [("bf16", "nccl"), ("fp32", "nccl"), ("bf16", "one_shot"), ("bf16", "multimem")])
 def test_two_rank_train_step_matches_single_gpu_emulation(precision, allreduce):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29741", os.path.join(ROOT, "tools", "ddp_check.py")]
