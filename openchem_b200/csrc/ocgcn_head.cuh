@@ -235,9 +235,32 @@ __global__ void __launch_bounds__(HT, 2) head_fwd_kernel(const HeadFwdArgs a) {
     }
     __syncthreads();
   }
+  const bool vecA = (Kin % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
+  const bool vecW = (Kin % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.W) & 15) == 0);
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const int row0 = tile * HR, nv = min(HR, a.B - row0);
-    // A tile, k-major: lane = row (conflict-free stores; the strided global reads of one warp are re-used from L1 by the next k)
+    // A tile, k-major in shared memory. Rows are read with 16-byte loads along k (coalesced: one row = consecutive threads) and
+    // transposed by the stores; widths that are not a multiple of four (or a misaligned input) take the scalar lane = row loop.
+    if (vecA) {
+      const int K4 = Kin >> 2;
+      for (int e = tid; e < HR * K4; e += HT) {
+        const int r = e / K4, k = (e - r * K4) << 2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nv) {
+          v = __ldg(reinterpret_cast<const float4*>(&a.in[(size_t)(row0 + r) * Kin + k]));
+          if (a.prev_bn) {
+            v.x = head_act(fmaf(v.x, sScale[k], sShift[k]), a.bn.act);
+            v.y = head_act(fmaf(v.y, sScale[k + 1], sShift[k + 1]), a.bn.act);
+            v.z = head_act(fmaf(v.z, sScale[k + 2], sShift[k + 2]), a.bn.act);
+            v.w = head_act(fmaf(v.w, sScale[k + 3], sShift[k + 3]), a.bn.act);
+          }
+        }
+        sAk[k * HAP + r] = v.x;
+        sAk[(k + 1) * HAP + r] = v.y;
+        sAk[(k + 2) * HAP + r] = v.z;
+        sAk[(k + 3) * HAP + r] = v.w;
+      }
+    } else
     for (int e = tid; e < HR * Kin; e += HT) {
       const int r = e & (HR - 1), k = e >> 5;
       float v = 0.f;
@@ -254,6 +277,17 @@ __global__ void __launch_bounds__(HT, 2) head_fwd_kernel(const HeadFwdArgs a) {
       for (int c = 0; c < 4 * NCP; ++c) acc[r][c] = 0.f;
     for (int k0 = 0; k0 < Kin; k0 += HKC) {
       __syncthreads();
+      if (vecW) {     // W rows (nn.Linear layout (Nout, Kin)) read 16 bytes along k, transposed by the stores; zero padding beyond Nout
+        for (int e = tid; e < CW * (HKC / 4); e += HT) {
+          const int o = e / (HKC / 4), kk = (e - o * (HKC / 4)) << 2;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (o < Nout && k0 + kk < Kin) v = __ldg(reinterpret_cast<const float4*>(&a.W[(size_t)o * Kin + k0 + kk]));
+          sBk[kk * BP + o] = v.x;
+          sBk[(kk + 1) * BP + o] = v.y;
+          sBk[(kk + 2) * BP + o] = v.z;
+          sBk[(kk + 3) * BP + o] = v.w;
+        }
+      } else
       for (int e = tid; e < HKC * CW; e += HT) {     // lane = output column: conflict-free stores, zero padding beyond Nout / Kin
         const int o = e % CW, kk = e / CW;
         sBk[kk * BP + o] = (o < Nout && k0 + kk < Kin) ? __ldg(&a.W[(size_t)o * Kin + k0 + kk]) : 0.f;
