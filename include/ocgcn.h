@@ -123,6 +123,16 @@ int ocgcn_layer_backward(const ocgcn_desc* desc, const float* grad_y, const floa
                          const ocgcn_params* params, const ocgcn_grads* grads, float* grad_x, void* saved,
                          void* scratch, void* stream);
 
+/* Single-kernel EVAL forward (desc->training == 0) of the whole encoder, gcn_encoder.py:38-53 with BatchNorm on its running
+ * statistics: every layer of a molecule tile runs inside one persistent CTA and the activations stay on the SM between layers
+ * (csrc/ocgcn_fused.cuh). Nothing is saved for a backward pass: a caller that later needs gradients re-runs ocgcn_encoder_forward
+ * (same results, bit for bit) and then ocgcn_encoder_backward. Served: tensor-core classes, N <= 128, every width and E <= 128,
+ * L <= 8; anything else returns OCGCN_EUNSUPPORTED from both functions and the caller uses ocgcn_encoder_forward.
+ * `workspace` (ocgcn_query_eval_workspace bytes, 256-byte aligned) holds the packed adjacency and the weight images for the call. */
+int ocgcn_query_eval_workspace(const ocgcn_desc* desc, size_t* bytes);
+int ocgcn_encoder_forward_eval(const ocgcn_desc* desc, const float* x, const float* adj, const ocgcn_params* params, void* workspace,
+                               float* out, void* stream);
+
 /* tanh + neighbour max-pool as a stand-alone differentiable op (replaces torch.tanh + x.repeat/view/expand/max(dim=2) of
  * openchem/modules/encoders/edge_attention_encoder.py:54-61 and gcn_encoder.py:43-50 for callers that chain GraphConvolution layers
  * themselves): pooled[b,i,c] = max_j adj[b,i,j] * tanh(y[b,j,c]), first index on ties; argmax (B,N,D) uint8 is the saved routing.
@@ -221,8 +231,8 @@ int ocgcn_last_launch_count(void);
 int ocgcn_last_cuda_error(void);
 const char* ocgcn_status_string(int status);
 /* ABI version; bumped whenever a struct above changes. */
-/* Bumped whenever a struct layout or an entry-point signature changes (2: ocgcn_expand_compact gained n_src / index_oob; 3: ocgcn_pool_forward / _backward). Bindings must refuse a library that reports another value. */
-#define OCGCN_ABI_VERSION 3
+/* Bumped whenever a struct layout or an entry-point signature changes (2: ocgcn_expand_compact gained n_src / index_oob; 3: ocgcn_pool_forward / _backward; 4: ocgcn_encoder_forward_eval). Bindings must refuse a library that reports another value. */
+#define OCGCN_ABI_VERSION 4
 int ocgcn_abi_version(void);
 
 #ifdef __cplusplus

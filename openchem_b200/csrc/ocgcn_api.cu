@@ -13,6 +13,7 @@
 #include "ocgcn_common.cuh"
 #include "ocgcn_compact.cuh"
 #include "ocgcn_dw.cuh"
+#include "ocgcn_fused.cuh"
 #include "ocgcn_head.cuh"
 #include "ocgcn_pool.cuh"
 #include "ocgcn_tile.cuh"
@@ -25,11 +26,11 @@ static thread_local int tl_cuda_err = 0;
 // ---- opt-in per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream ----------
 enum KernelKind : int {
   KK_ADJ_PACK = 0, KK_TRANSPOSE, KK_FWD_FIRST, KK_FWD_MID, KK_BN_FINALIZE, KK_FWD_READOUT, KK_BWD_READOUT, KK_BWD_DY,
-  KK_BWD_FINALIZE, KK_BWD_DZ, KK_GEMM_TN, KK_REDUCE, KK_BN_APPLY, KK_WPREP, KK_DW_MMA, KK_EXPAND, KK_PACK, KK_HEAD_FWD, KK_HEAD_LOSS, KK_HEAD_BWD, KK_POOL_FWD, KK_POOL_BWD, KK_COUNT
+  KK_BWD_FINALIZE, KK_BWD_DZ, KK_GEMM_TN, KK_REDUCE, KK_BN_APPLY, KK_WPREP, KK_DW_MMA, KK_EXPAND, KK_PACK, KK_HEAD_FWD, KK_HEAD_LOSS, KK_HEAD_BWD, KK_POOL_FWD, KK_POOL_BWD, KK_FUSED_EVAL, KK_COUNT
 };
 static const char* const kKindNames[KK_COUNT] = {"adj_pack", "transpose", "fwd_first", "fwd_mid", "bn_finalize", "fwd_readout",
                                                  "bwd_readout", "bwd_dy", "bwd_finalize", "bwd_dz", "gemm_tn", "reduce", "bn_apply",
-                                                 "wprep", "dw_mma", "expand_compact", "pack_compact", "head_fwd", "head_loss", "head_bwd", "pool_fwd", "pool_bwd"};
+                                                 "wprep", "dw_mma", "expand_compact", "pack_compact", "head_fwd", "head_loss", "head_bwd", "pool_fwd", "pool_bwd", "fused_eval"};
 struct ProfRec { int kind; cudaEvent_t e0, e1; };
 // process-wide (autograd runs backward on its own thread), guarded by a mutex; off by default
 static std::atomic<bool> g_prof_on{false};
@@ -716,6 +717,100 @@ int ocgcn_encoder_forward(const ocgcn_desc* d, const float* x, const float* adj,
   }
   ST_TRY((launch_tile<P_RO, E_READOUT>(lo, a, st)));
   CU_TRY(cudaMemcpyAsync(saved + lo.O, out, (size_t)d->B * d->E * 4, cudaMemcpyDeviceToDevice, st));
+  return OCGCN_OK;
+}
+
+// ---- single-kernel eval forward (ocgcn_fused.cuh) --------------------------------------------------------------------------
+struct EvalLayout {
+  size_t rowmask, colmask, molflag, nbr, cnbr, Wf[OCGCN_MAX_LAYERS + 1], total;
+  int NW, MT, tiles;
+};
+// the fused eval kernel serves the tensor-core classes in eval mode when every width fits one 128-column block
+static int make_eval_layout(const ocgcn_desc* d, EvalLayout* lo) {
+  memset(lo, 0, sizeof(*lo));
+  if (!d || d->B <= 0 || d->N <= 0 || d->L <= 0 || d->E <= 0) return OCGCN_EINVAL;
+  if (d->mode != OCGCN_TF32 && d->mode != OCGCN_BF16) return OCGCN_EUNSUPPORTED;
+  if (d->training || d->N > 128 || d->L > kFusedMaxLayers || d->E > 128) return OCGCN_EUNSUPPORTED;
+  for (int l = 0; l <= d->L; ++l) {
+    if (d->F[l] <= 0) return OCGCN_EINVAL;
+    if (d->F[l] > 128) return OCGCN_EUNSUPPORTED;
+  }
+  if ((size_t)d->B * d->N >= (size_t)1 << 31) return OCGCN_EUNSUPPORTED;
+  lo->NW = (d->N + 63) / 64;
+  lo->MT = 128 / d->N;
+  lo->tiles = (d->B + lo->MT - 1) / lo->MT;
+  const size_t rows = (size_t)d->B * d->N;
+  size_t off = 0;
+  auto take = [&off](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+  lo->rowmask = take(rows * lo->NW * 8);
+  lo->colmask = take(rows * lo->NW * 8);
+  lo->molflag = take((size_t)d->B * 4);
+  lo->nbr = take(rows * 16);
+  lo->cnbr = take(rows * 16);
+  for (int l = 0; l < d->L; ++l) lo->Wf[l] = take(wimg_bytes(d->F[l], d->F[l + 1], 2));
+  lo->Wf[d->L] = take(wimg_bytes(d->F[d->L], d->E, 2));
+  lo->total = off;
+  return OCGCN_OK;
+}
+
+int ocgcn_query_eval_workspace(const ocgcn_desc* desc, size_t* bytes) {
+  EvalLayout lo;
+  ST_TRY(make_eval_layout(desc, &lo));
+  if (bytes) *bytes = lo.total;
+  return OCGCN_OK;
+}
+
+int ocgcn_encoder_forward_eval(const ocgcn_desc* d, const float* x, const float* adj, const ocgcn_params* p, void* workspace_v,
+                               float* out, void* stream) {
+  tl_launches = 0;
+  EvalLayout lo;
+  ST_TRY(make_eval_layout(d, &lo));
+  ST_TRY(validate_params(d, p, false));
+  if (!workspace_v || !out) return OCGCN_EINVAL;
+  ST_TRY(check_device());
+  ST_TRY(check_device_ptr(x));
+  ST_TRY(check_device_ptr(adj));
+  ST_TRY(check_device_ptr(out));
+  if ((uintptr_t)workspace_v & 255) return OCGCN_EALIGN;
+  char* ws = static_cast<char*>(workspace_v);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int L = d->L;
+  {
+    ProfScope prof(KK_ADJ_PACK, st);
+    CU_TRY(launch_chain(adj_pack_kernel, dim3(d->B), dim3(kThreads), (size_t)2 * d->N * lo.NW * 8, st, adj, (long long)d->adj_stride[0],
+                        (long long)d->adj_stride[1], (long long)d->adj_stride[2], d->N, lo.NW, reinterpret_cast<u64*>(ws + lo.rowmask),
+                        reinterpret_cast<u64*>(ws + lo.colmask), reinterpret_cast<unsigned*>(ws + lo.molflag),
+                        reinterpret_cast<uint4*>(ws + lo.nbr), reinterpret_cast<uint4*>(ws + lo.cnbr)));
+    LAUNCH_CHECK();
+  }
+  WPrepJobs wj;
+  memset(&wj, 0, sizeof(wj));
+  int nj = 0;
+  for (int l = 0; l < L; ++l) add_wprep(wj, nj, p->W[l], ws + lo.Wf[l], d->F[l], d->F[l + 1], 0, 2);
+  add_wprep(wj, nj, p->Wd, ws + lo.Wf[L], d->F[L], d->E, 1, 2);
+  ST_TRY(run_wprep(wj, nj, st));
+
+  FusedEvalArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = d->B; a.N = d->N; a.MT = lo.MT; a.ntiles = lo.tiles; a.L = L; a.E = d->E; a.eps = d->eps;
+  for (int l = 0; l <= L; ++l) a.F[l] = d->F[l];
+  a.x = x; a.xs0 = d->x_stride[0]; a.xs1 = d->x_stride[1]; a.xs2 = d->x_stride[2];
+  a.adj = adj; a.as0 = d->adj_stride[0]; a.as1 = d->adj_stride[1]; a.as2 = d->adj_stride[2];
+  a.nbr = reinterpret_cast<const uint4*>(ws + lo.nbr);
+  for (int l = 0; l < L; ++l) {
+    a.wimg[l] = ws + lo.Wf[l];
+    a.bias[l] = d->has_bias ? p->b[l] : nullptr;
+    a.gamma[l] = p->gamma[l]; a.beta[l] = p->beta[l];
+    a.running_mean[l] = p->running_mean[l]; a.running_var[l] = p->running_var[l];
+  }
+  a.wimg[L] = ws + lo.Wf[L];
+  a.bias[L] = p->bd;
+  a.out = out;
+  const size_t smem = fused_eval_smem_bytes();
+  ST_TRY((ensure_dynamic_smem<encoder_eval_fused_kernel>(smem)));
+  ProfScope prof(KK_FUSED_EVAL, st);
+  CU_TRY(launch_chain(encoder_eval_fused_kernel, dim3(lo.tiles < 148 ? lo.tiles : 148), dim3(kFusedThreads), smem, st, a));
+  LAUNCH_CHECK();
   return OCGCN_OK;
 }
 

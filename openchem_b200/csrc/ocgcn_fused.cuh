@@ -1,0 +1,353 @@
+// Single-kernel EVAL forward of the whole GraphCNNEncoder stack (tensor-core engine): every layer of a molecule tile runs inside one
+// persistent CTA and the activations never leave the SM between layers.
+//
+// In eval mode BatchNorm uses its running statistics (gcn.py:25,40 with self.training False), so no grid-wide reduction separates
+// the layers: the accumulator of layer l (TMEM) is read back once, bias + BatchNorm(running) + tanh are applied in registers and
+// T_l is written straight into the shared-memory buffers the next layer's max-pool reads. Per layer and 64-channel chunk:
+//     pool(T chunk) -> H (shared)  |  S = A.H gather -> bf16 hi/lo operand images  |  tcgen05.mma (4 passes) with the chunk's weight
+//     image (bulk-copied into a two-slot ring, the next piece is in flight while this one is consumed)
+// then the epilogue above; the last pooled H feeds the readout GEMM directly, D = tanh(H.Wd^T + bd), O = tanh(sum_i D) (unmasked sum,
+// gcn_encoder.py:51-53). Global traffic per molecule: its features, its 16-byte neighbour records, the weight images (L2) and E outputs.
+//
+// Same arithmetic, in the same order, as the layer-by-layer kernels (ocgcn_tile.cuh) run in eval mode: results are bit-identical
+// (tests/test_gpu_fused_eval.py). Rows whose adjacency row is not a <= 13-neighbour 0/1 record (hub atoms, float adjacencies) take a
+// dense scan over the molecule's columns with the reference's candidate order.
+//
+// One CTA per SM (about 205 KB of shared memory, 128 TMEM columns), 512 threads; launched for tiles <= a few waves per SM, where the
+// layered path is bound by one tile's latency and the launch count (Tox21 / logP-sized evaluation batches).
+#pragma once
+#include "ocgcn_common.cuh"
+#include "ocgcn_tc.cuh"
+#include "ocgcn_tile.cuh"
+
+namespace ocgcn {
+
+constexpr int kFusedMaxLayers = 8;
+constexpr int kFusedThreads = 512;
+constexpr int kFusedBS = KC + 4;                    // padded row of the T / H chunk buffers: conflict-free 16-byte row = lane stores
+constexpr int kFusedRows = 129;                     // 128 tile rows + the neutral dummy row of the padded neighbour records
+constexpr int kFusedStage = 128 * (128 + 4);        // floats of the readout staging tile
+
+struct FusedEvalArgs {
+  int B, N, MT, ntiles, L;
+  int F[kFusedMaxLayers + 1];                       // F[0] = input width, F[l+1] = width of layer l; all <= 128
+  int E;                                            // encoder_dim <= 128
+  float eps;
+  const float* x;
+  long long xs0, xs1, xs2;
+  const float* adj;                                 // dense adjacency (rows that do not fit a neighbour record)
+  long long as0, as1, as2;
+  const uint4* nbr;                                 // [B*N] row records
+  const void* wimg[kFusedMaxLayers + 1];            // forward weight images (wprep_kernel), [L] = readout
+  const float* bias[kFusedMaxLayers + 1];           // b_l or null, [L] = bd
+  const float* gamma[kFusedMaxLayers];
+  const float* beta[kFusedMaxLayers];
+  const float* running_mean[kFusedMaxLayers];
+  const float* running_var[kFusedMaxLayers];
+  float* out;                                       // [B][E]
+};
+
+static inline size_t fused_eval_smem_bytes() {
+  size_t main_f = (size_t)3 * kFusedRows * kFusedBS;                          // T0, T1, H
+  if ((size_t)kFusedStage > main_f) main_f = kFusedStage;
+  return (size_t)128 * 16 + main_f * 4 + (size_t)2 * 8 * kImgPitch + (size_t)2 * 2 * kWPiece + (size_t)2 * kFusedMaxLayers * 128 * 4 + 128;
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1) encoder_eval_fused_kernel(const FusedEvalArgs a) {
+  constexpr int NT = kFusedThreads, NWARP = NT / 32, TR = 128, BS = kFusedBS, RPW = TR / NWARP;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint4* sRec = reinterpret_cast<uint4*>(smem_raw);
+  float* mainp = reinterpret_cast<float*>(sRec + TR);
+  float* sT0 = mainp;
+  float* sT1 = sT0 + kFusedRows * BS;
+  float* sH = sT1 + kFusedRows * BS;
+  float* sD = mainp;                                                          // readout staging [128][132], aliases T0 / T1 / H
+  constexpr size_t main_f = ((size_t)3 * kFusedRows * kFusedBS > (size_t)kFusedStage) ? (size_t)3 * kFusedRows * kFusedBS : (size_t)kFusedStage;
+  unsigned char* imgHi = reinterpret_cast<unsigned char*>(mainp + main_f);
+  unsigned char* imgLo = imgHi + 8 * kImgPitch;
+  unsigned char* wRing = imgLo + 8 * kImgPitch;                               // two slots of (hi, lo) pieces
+  float* sScale = reinterpret_cast<float*>(wRing + 2 * 2 * kWPiece);          // [L][128] BatchNorm(running) scale * 2log2(e)
+  float* sShift = sScale + kFusedMaxLayers * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sShift + kFusedMaxLayers * 128);   // [0],[1]: weight ring slots landed, [2]: MMAs complete
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int hl = lane & 15, hh = lane >> 4;
+  const int N = a.N, L = a.L;
+  const uint32_t img_lane_off4 = (uint32_t)(hl >> 1) * kImgPitch + (uint32_t)(hl & 1) * 8;
+
+  if (tid == 0) {
+    tc::mbar_init(&bars[0], 1);
+    tc::mbar_init(&bars[1], 1);
+    tc::mbar_init(&bars[2], 1);
+    tc::mbar_init_fence();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tc::tmem_alloc(tslot, 128);
+  }
+  // dummy rows: -inf never wins a max (T buffers), 0 adds nothing (H buffer). The epilogues only ever write rows 0..127.
+  for (int i = tid; i < BS; i += NT) {
+    sT0[TR * BS + i] = -INFINITY;
+    sT1[TR * BS + i] = -INFINITY;
+    sH[TR * BS + i] = 0.f;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tslot;
+  pdl_wait();
+  // BatchNorm in eval mode: y = (z - running_mean) / sqrt(running_var + eps) * gamma + beta = z*scale + shift (same rounding as
+  // bn_finalize_kernel's eval branch); the 2*log2(e) factor of the exp2-based tanh is folded in, as in the layered kernels
+  for (int i = tid; i < L * 128; i += NT) {
+    const int l = i >> 7, c = i & 127;
+    float sc = 0.f, sh = 0.f;
+    if (c < a.F[l + 1]) {
+      const float invstd = (float)(1.0 / sqrt((double)a.running_var[l][c] + (double)a.eps));
+      sc = a.gamma[l][c] * invstd;
+      sh = a.beta[l][c] - (float)((double)a.running_mean[l][c]) * sc;
+    }
+    sScale[i] = sc * kTanhScale;
+    sShift[i] = sh * kTanhScale;
+  }
+
+  uint32_t w_issued = 0, w_used = 0, mma_cnt = 0;   // weight pieces requested / consumed, commits waited for (phase parities follow)
+  // the sequence of weight pieces is the same for every tile: layer-major, chunk-minor
+  auto piece_src = [&](uint32_t seq) -> const unsigned char* {   // seq counts pieces within one tile
+    int l = 0;
+    uint32_t s = seq;
+    for (;; ++l) {
+      const uint32_t nch = (uint32_t)((a.F[l] + KC - 1) / KC);
+      if (s < nch) break;
+      s -= nch;
+    }
+    return reinterpret_cast<const unsigned char*>(a.wimg[l]) + (size_t)s * 2 * kWPiece;
+  };
+  uint32_t pieces_per_tile = 0;
+  for (int l = 0; l <= L; ++l) pieces_per_tile += (uint32_t)((a.F[l] + KC - 1) / KC);
+  auto issue_piece = [&]() {   // thread 0 only: next piece of this CTA's sequence -> ring slot (w_issued & 1)
+    const uint32_t slot = w_issued & 1u;
+    unsigned char* dst = wRing + (size_t)slot * 2 * kWPiece;
+    const unsigned char* src = piece_src(w_issued % pieces_per_tile);
+    tc::fence_async_smem();
+    tc::mbar_expect_tx(&bars[slot], 2 * kWPiece);
+    tc::bulk_g2s(dst, src, kWPiece, &bars[slot]);
+    tc::bulk_g2s(dst + kWPiece, src + kWPiece, kWPiece, &bars[slot]);
+  };
+  const uint32_t my_tiles = ((uint32_t)a.ntiles > blockIdx.x) ? ((uint32_t)a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+  const uint32_t total_pieces = my_tiles * pieces_per_tile;
+  if (tid == 0) {
+    if (w_issued < total_pieces) { issue_piece(); }
+  }
+  if (total_pieces > 0) ++w_issued;
+  if (tid == 0) {
+    if (w_issued < total_pieces) { issue_piece(); }
+  }
+  if (w_issued < total_pieces) ++w_issued;
+
+  auto put_operand4 = [&](int r, const float4& val) {
+    uint2 hi, lo;
+    tc::split4_bf16(val, hi, lo);
+    const uint32_t off = img_lane_off4 + (uint32_t)r * 16;
+    *reinterpret_cast<uint2*>(imgHi + off) = hi;
+    *reinterpret_cast<uint2*>(imgLo + off) = lo;
+  };
+
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    const int mol0 = tile * a.MT;
+    const int nm = min(a.MT, a.B - mol0);
+    const int rows = nm * N;
+    const size_t row0 = (size_t)mol0 * N;
+    __syncthreads();   // the previous tile's readout staging (aliases T0 / T1 / H) and records are consumed
+    for (int r = tid; r < TR; r += NT) {
+      uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+      if (r < rows) {
+        const int m = r / N;
+        rec = rec_stage_padded(__ldg(&a.nbr[row0 + r]), m, m * N, TR);
+      }
+      sRec[r] = rec;
+    }
+    if (tid < BS) {   // the staging tile of the previous tile overwrote the dummy rows
+      sT0[TR * BS + tid] = -INFINITY;
+      sT1[TR * BS + tid] = -INFINITY;
+      sH[TR * BS + tid] = 0.f;
+    }
+    __syncthreads();
+
+    for (int l = 0; l <= L; ++l) {
+      const int K = a.F[l], NC = (l < L) ? a.F[l + 1] : a.E;
+      const int nch = (K + KC - 1) / KC;
+      for (int ch = 0; ch < nch; ++ch) {
+        const int k0 = ch * KC;
+        const int c4 = k0 + 4 * hl;
+        const bool cv = c4 < K;   // (K % 4 == 0 for l >= 1; layer 0 masks its tail channels when loading x)
+        float* const bufT = ch ? sT1 : sT0;
+        if (l == 0) {
+          // H = x: strided scalar loads (two adjacent channels per lane), zero beyond the valid rows / channels
+          const int c = k0 + 2 * lane;
+          const bool v0 = c < K, v1 = c + 1 < K;
+#pragma unroll
+          for (int q = 0; q < RPW; ++q) {
+            const int r = warp + q * NWARP;
+            float2 v = make_float2(0.f, 0.f);
+            if (r < rows && v0) {
+              const int m = rec_m(sRec[r]), i = r - m * N;
+              const float* px = a.x + (long long)(mol0 + m) * a.xs0 + (long long)i * a.xs1 + (long long)c * a.xs2;
+              v.x = __ldg(px);
+              if (v1) v.y = __ldg(px + a.xs2);
+            }
+            *reinterpret_cast<float2*>(&sH[r * BS + 2 * lane]) = v;
+          }
+          __syncthreads();
+        } else {
+          // neighbour max-pool of T_{l-1} (gcn_encoder.py:44-50); first index wins ties, a zero entry contributes the candidate 0
+#pragma unroll 2
+          for (int sI = 0; sI < RPW / 2; ++sI) {
+            const int r = warp + (2 * sI + hh) * NWARP;
+            float bq[4] = {0.f, 0.f, 0.f, 0.f};
+            if (r < rows && cv) {
+              const uint4 rec = sRec[r];
+              const int mb = rec_m(rec) * N;
+              if (rec_binary(rec) && !rec_fallback(rec)) {
+                int aq[4];
+                rec_max4_padded<BS>(rec, &bufT[4 * hl], bq, aq);
+                if (rec_has_zero(rec)) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) bq[e] = fmaxf(bq[e], 0.f);
+                }
+              } else {   // dense scan in the reference's candidate order (float adjacency, or more neighbours than a record holds)
+                const float* arow = a.adj + (long long)(mol0 + rec_m(rec)) * a.as0 + (long long)(r - mb) * a.as1;
+                const float a00 = __ldg(&arow[0]);
+                const float4 t0 = *reinterpret_cast<const float4*>(&bufT[mb * BS + 4 * hl]);
+                bq[0] = a00 * t0.x; bq[1] = a00 * t0.y; bq[2] = a00 * t0.z; bq[3] = a00 * t0.w;
+                for (int j = 1; j < N; ++j) {
+                  const float aj = __ldg(&arow[(long long)j * a.as2]);
+                  const float4 t = *reinterpret_cast<const float4*>(&bufT[(mb + j) * BS + 4 * hl]);
+                  bq[0] = fmaxf(bq[0], aj * t.x); bq[1] = fmaxf(bq[1], aj * t.y);
+                  bq[2] = fmaxf(bq[2], aj * t.z); bq[3] = fmaxf(bq[3], aj * t.w);
+                }
+              }
+            }
+            const float4 h4 = make_float4(bq[0], bq[1], bq[2], bq[3]);
+            if (l == L) put_operand4(r, h4);                                    // readout: the pooled H is the GEMM operand
+            else *reinterpret_cast<float4*>(&sH[r * BS + 4 * hl]) = h4;
+          }
+          if (l == L) tc::fence_async_smem();
+          __syncthreads();
+        }
+        if (l < L) {
+          // S = A.H for this chunk (gcn.py:34) -> operand images
+#pragma unroll 2
+          for (int sI = 0; sI < RPW / 2; ++sI) {
+            const int r = warp + (2 * sI + hh) * NWARP;
+            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < rows) {
+              const uint4 rec = sRec[r];
+              if (rec_binary(rec) && !rec_fallback(rec)) {
+                s4 = rec_sum4_padded<BS>(rec, &sH[4 * hl]);
+              } else {
+                const int mb = rec_m(rec) * N;
+                const float* arow = a.adj + (long long)(mol0 + rec_m(rec)) * a.as0 + (long long)(r - mb) * a.as1;
+                for (int j = 0; j < N; ++j) {
+                  const float aj = __ldg(&arow[(long long)j * a.as2]);
+                  const float4 hv = *reinterpret_cast<const float4*>(&sH[(mb + j) * BS + 4 * hl]);
+                  s4.x = fmaf(aj, hv.x, s4.x); s4.y = fmaf(aj, hv.y, s4.y); s4.z = fmaf(aj, hv.z, s4.z); s4.w = fmaf(aj, hv.w, s4.w);
+                }
+              }
+            }
+            put_operand4(r, s4);
+          }
+          tc::fence_async_smem();
+          __syncthreads();
+        }
+        // ---- GEMM chunk: acc (+)= image . W piece, 4 passes (hi.hi + lo.hi + hi.lo + lo.lo) ----
+        if (tid == 0) {
+          const uint32_t slot = w_used & 1u;
+          tc::mbar_wait(&bars[slot], (w_used >> 1) & 1u);
+          tc::fence_after_sync();
+          const int kleft = K - k0;
+          const int nks = (kleft >= KC) ? KC / 16 : (kleft + 15) / 16;
+          const uint32_t aHi = tc::smem_u32(imgHi), aLo = tc::smem_u32(imgLo);
+          const uint32_t bHi = tc::smem_u32(wRing + (size_t)slot * 2 * kWPiece), bLo = bHi + kWPiece;
+          constexpr uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, 128, false, false);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const uint32_t ab = (p & 1) ? aLo : aHi, bb = (p & 2) ? bLo : bHi;
+            uint64_t da = tc::make_desc(ab, kImgPitch, 128), db = tc::make_desc(bb, 128 * 16, 128);
+            for (int ks = 0; ks < nks; ++ks) {
+              tc::mma_ss<false>(tmem, da, db, idesc, (ch > 0 || p > 0 || ks > 0) ? 1u : 0u);
+              da += (uint64_t)((2 * kImgPitch) >> 4);
+              db += (uint64_t)((2 * 128 * 16) >> 4);
+            }
+          }
+          tc::mma_commit(&bars[2]);
+        }
+        ++w_used;
+        // the images, this ring slot and (last chunk) the accumulator are needed next: wait for the MMAs, then refill the slot
+        if (warp == 0) tc::mbar_wait(&bars[2], mma_cnt & 1u);
+        ++mma_cnt;
+        __syncthreads();
+        if (tid == 0) {
+          if (w_issued < total_pieces) { issue_piece(); }
+        }
+        if (w_issued < total_pieces) ++w_issued;
+      }   // chunks
+
+      // ---- epilogue: accumulator -> registers (thread = row, 32 columns per warp group) ----
+      tc::fence_after_sync();
+      const int q = warp & 3, hsel = warp >> 2;
+      const int row = q * 32 + lane;
+      const int cl = hsel * 32;
+      float v[32];
+      tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cl, v);
+      if (l < L) {
+        // Z = acc + b; T = tanh(BatchNorm_running(Z)) -> the next layer's T chunk buffers (columns >= NC stay unused)
+        float* dstT = (cl < KC ? sT0 : sT1) + row * BS + (cl & (KC - 1));
+        const float* bl = a.bias[l];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float t[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int gc = cl + i + e;
+            const float z = v[i + e] + ((bl && gc < NC) ? __ldg(&bl[gc]) : 0.f);
+            t[e] = fast_tanh_scaled(fmaf(z, sScale[l * 128 + gc], sShift[l * 128 + gc]));
+          }
+          *reinterpret_cast<float4*>(dstT + i) = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      } else {
+        const float* bd = a.bias[L];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float t[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int gc = cl + i + e;
+            t[e] = (row < rows && gc < NC) ? fast_tanh(v[i + e] + (bd ? __ldg(&bd[gc]) : 0.f)) : 0.f;   // gcn_encoder.py:51
+          }
+          *reinterpret_cast<float4*>(&sD[row * 132 + cl + i]) = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      }
+      tc::fence_before_sync();
+      __syncthreads();
+      if (l == L) {
+        // O[b,:] = tanh(sum over ALL N rows of D[b,i,:])  (unmasked, gcn_encoder.py:52-53)
+        for (int idx = tid; idx < nm * 128; idx += NT) {
+          const int m = idx >> 7, c = idx & 127;
+          if (c < NC) {
+            float s = 0.f;
+            for (int i = 0; i < N; ++i) s += sD[(m * N + i) * 132 + c];
+            a.out[(size_t)(mol0 + m) * NC + c] = fast_tanh(s);
+          }
+        }
+      }
+    }   // layers
+  }   // tiles
+  pdl_trigger();
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 128);
+}
+
+}  // namespace ocgcn

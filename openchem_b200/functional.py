@@ -6,6 +6,7 @@ the current stream, and the autograd graph. All arithmetic happens in libocgcn.s
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -124,6 +125,15 @@ def _count(lib):
     launch_counter["n"] += lib.ocgcn_last_launch_count()
 
 
+# single-kernel eval forward (csrc/ocgcn_fused.cuh): on by default for batches of at most `max_tiles` 128-row tiles (a few waves of
+# one-tile CTAs: the regime where the layer-by-layer path is bound by one tile's latency and the launch count)
+fused_eval = {"on": os.environ.get("OCB200_FUSED_EVAL", "1") != "0", "max_tiles": int(os.environ.get("OCB200_FUSED_EVAL_MAX_TILES", "592"))}
+
+
+def fused_eval_tiles(desc):
+    return (desc.B + (128 // desc.N) - 1) // (128 // desc.N) if 0 < desc.N <= 128 else 1 << 30
+
+
 SAVED_KINDS = {"Z": (0, torch.float32), "argmax": (1, torch.uint8), "S": (2, torch.float32), "stats": (3, torch.float32),
                "rowmask": (4, torch.int64), "molflag": (5, torch.int32)}
 debug_keep = {"on": False, "saved": None, "desc": None}     # tests only: keep the last forward's saved buffer
@@ -161,18 +171,32 @@ class EncoderFn(torch.autograd.Function):
         with torch.cuda.device(x.device):
             desc = _make_desc(spec, x, adj)
             params = _make_params(spec, Ws, bs, gammas, betas, Wd, bd)
-            sbytes, cbytes = _workspaces(desc, x.device)
-            saved = _alloc(sbytes, x.device)
-            scratch = _alloc(cbytes, x.device)
             out = torch.empty((x.shape[0], spec.encoder_dim), dtype=torch.float32, device=x.device)
-            _lib.check(lib.ocgcn_encoder_forward(ctypes.byref(desc), x.data_ptr(), adj.data_ptr(), ctypes.byref(params),
-                                                 saved.data_ptr(), scratch.data_ptr(), out.data_ptr(), _stream_ptr(x.device)))
-            _count(lib)
+            saved, cbytes = None, 0
+            ebytes = ctypes.c_size_t(0)
+            # eval mode: the whole stack in ONE kernel, activations stay on the SM between layers (csrc/ocgcn_fused.cuh). Nothing is
+            # saved; if a backward pass is requested later (the reference's evaluate() runs without no_grad) the saved state is
+            # rebuilt then by the layer-by-layer forward, which gives bit-identical results.
+            if (not spec.training and fused_eval["on"] and not debug_keep["on"]
+                    and lib.ocgcn_query_eval_workspace(ctypes.byref(desc), ctypes.byref(ebytes)) == 0
+                    and fused_eval_tiles(desc) <= fused_eval["max_tiles"]):
+                ws = _alloc(ebytes.value, x.device)
+                _lib.check(lib.ocgcn_encoder_forward_eval(ctypes.byref(desc), x.data_ptr(), adj.data_ptr(), ctypes.byref(params),
+                                                          ws.data_ptr(), out.data_ptr(), _stream_ptr(x.device)))
+                _count(lib)
+            else:
+                sbytes, cbytes = _workspaces(desc, x.device)
+                saved = _alloc(sbytes, x.device)
+                scratch = _alloc(cbytes, x.device)
+                _lib.check(lib.ocgcn_encoder_forward(ctypes.byref(desc), x.data_ptr(), adj.data_ptr(), ctypes.byref(params),
+                                                     saved.data_ptr(), scratch.data_ptr(), out.data_ptr(), _stream_ptr(x.device)))
+                _count(lib)
         if debug_keep["on"]:
             debug_keep["saved"], debug_keep["desc"] = saved, desc
         ctx.spec = spec
         ctx.cbytes = cbytes
-        ctx.save_for_backward(x, adj, saved, *[t for t in tensors if t is not None])
+        ctx.lazy = saved is None
+        ctx.save_for_backward(x, adj, *([] if saved is None else [saved]), *[t for t in tensors if t is not None])
         ctx.none_mask = [t is None for t in tensors]
         return out
 
@@ -181,7 +205,11 @@ class EncoderFn(torch.autograd.Function):
         lib = _lib.load()
         spec = ctx.spec
         L = len(spec.widths) - 1
-        x, adj, saved, *rest = ctx.saved_tensors
+        if ctx.lazy:
+            x, adj, *rest = ctx.saved_tensors
+            saved = None
+        else:
+            x, adj, saved, *rest = ctx.saved_tensors
         it = iter(rest)
         tensors = [None if isnone else next(it) for isnone in ctx.none_mask]
         Ws, bs, gammas, betas = tensors[0:4 * L:4], tensors[1:4 * L:4], tensors[2:4 * L:4], tensors[3:4 * L:4]
@@ -190,6 +218,14 @@ class EncoderFn(torch.autograd.Function):
         with torch.cuda.device(x.device):
             desc = _make_desc(spec, x, adj)
             params = _make_params(spec, Ws, bs, gammas, betas, Wd, bd)
+            if saved is None:     # the forward was the single-kernel eval forward: rebuild the saved state now (eval mode: no side effects)
+                sbytes, ctx.cbytes = _workspaces(desc, x.device)
+                saved = _alloc(sbytes, x.device)
+                tmp = torch.empty((x.shape[0], spec.encoder_dim), dtype=torch.float32, device=x.device)
+                _lib.check(lib.ocgcn_encoder_forward(ctypes.byref(desc), x.data_ptr(), adj.data_ptr(), ctypes.byref(params),
+                                                     saved.data_ptr(), _alloc(ctx.cbytes, x.device).data_ptr(), tmp.data_ptr(),
+                                                     _stream_ptr(x.device)))
+                _count(lib)
             grads = _lib.Grads()
             outs = []
             for l in range(L):
