@@ -125,9 +125,10 @@ def _count(lib):
     launch_counter["n"] += lib.ocgcn_last_launch_count()
 
 
-# single-kernel eval forward (csrc/ocgcn_fused.cuh): on by default for batches of at most `max_tiles` 128-row tiles (a few waves of
-# one-tile CTAs: the regime where the layer-by-layer path is bound by one tile's latency and the launch count)
-fused_eval = {"on": os.environ.get("OCB200_FUSED_EVAL", "1") != "0", "max_tiles": int(os.environ.get("OCB200_FUSED_EVAL_MAX_TILES", "592"))}
+# single-kernel eval forward (csrc/ocgcn_fused.cuh): on by default at every batch size (measured on a B200, bf16 class, eval forward
+# of the encoder: C2 60 vs 131 us layer by layer, C1 107 vs 164 us, C4 312 vs 480 us, C3 654 vs 870 us; profiles/r2_fused_eval.md);
+# OCB200_FUSED_EVAL=0 or `max_tiles` restrict it
+fused_eval = {"on": os.environ.get("OCB200_FUSED_EVAL", "1") != "0", "max_tiles": int(os.environ.get("OCB200_FUSED_EVAL_MAX_TILES", str(1 << 30)))}
 
 
 def fused_eval_tiles(desc):

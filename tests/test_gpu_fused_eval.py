@@ -47,7 +47,7 @@ def test_fused_eval_equals_layered_eval_and_oracle(shape):
     torch.cuda.synchronize()
     assert torch.equal(out_f, out_l), float((out_f - out_l).abs().max())
     O = orc.encoder_forward(g["x"].astype(np.float64), g["adj"].astype(np.float64), orc.cast_params(p, np.float64), training=False)[0]
-    assert rel_l2(out_f.cpu().numpy(), O) < 1e-3
+    assert rel_l2(out_f.detach().cpu().numpy(), O) < 1e-3
     # buffers untouched in eval mode
     assert int(enc.graph_convolutions[0].bn.num_batches_tracked) == 0
 
