@@ -729,6 +729,38 @@ def run_native(args, w, wname):
                 others[other] = dict(error=repr(exc)[:200])
             torch.cuda.empty_cache()
 
+    # ---- eval-mode forward of the encoder (inference: Graph2Label.forward(eval=True) / evaluate / predict): the single-kernel path
+    # (activations stay on the SM across all layers, csrc/ocgcn_fused.cuh) next to the layer-by-layer kernels, device-resident ----
+    eval_fwd = {}
+    if world == 1 and not args.no_extra and args.precision != "fp32":
+        from openchem_b200 import functional as fn_
+        for other in (wname, "c2_tox21"):
+            try:
+                wo = WORKLOADS[other]
+                go = make_graph_batch(wo["batch"], wo["n_max"], wo["f0"], occupancy="molecular" if other in ("c1_logp", "c2_tox21") else "full", seed=3)
+                enc = build_model(wo, args.precision, dev, args.head).Encoder.eval()
+                xo, ao = torch.from_numpy(go["x"]).to(dev), torch.from_numpy(go["adj"]).to(dev)
+                res = {}
+                for mode, on in (("fused", True), ("layer_by_layer", False)):
+                    fn_.fused_eval["on"] = on
+                    with torch.no_grad():
+                        for _ in range(3):
+                            o_ = enc((xo, ao))
+                        gr_ = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(gr_):
+                            o_ = enc((xo, ao))
+                        ms_ = timed(gr_.replay, 30) / 30
+                    res[mode] = (ms_, o_.clone())
+                fn_.fused_eval["on"] = True
+                eval_fwd[other] = dict(fused_us=res["fused"][0] * 1e3, layer_by_layer_us=res["layer_by_layer"][0] * 1e3,
+                                       molecules_per_s=wo["batch"] / (res["fused"][0] * 1e-3), bit_identical=bool(torch.equal(res["fused"][1], res["layer_by_layer"][1])))
+                del enc, gr_
+            except Exception as exc:  # noqa: BLE001
+                eval_fwd[other] = dict(error=repr(exc)[:200])
+            finally:
+                fn_.fused_eval["on"] = True
+            torch.cuda.empty_cache()
+
     parity = None
     if not args.no_parity:
         try:
@@ -771,7 +803,7 @@ def run_native(args, w, wname):
                                    peak_source=peaks["source"] + ", sustained bf16",
                                    step_dram_bytes=step_traffic,
                                    traffic_ratio=(step_traffic / (B * work["bytes"])) if step_traffic else None),
-                kernels=shares, parity=parity, replica_check=replica_check, single_gpu_same_workload=local_only, c4_ddp=c4_line, runtime_eager=eager,
+                kernels=shares, eval_forward=eval_fwd, parity=parity, replica_check=replica_check, single_gpu_same_workload=local_only, c4_ddp=c4_line, runtime_eager=eager,
                 cpu_baseline=cpu, other_workloads=others)
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     finish(world)
