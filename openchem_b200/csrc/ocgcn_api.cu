@@ -26,11 +26,11 @@ static thread_local int tl_cuda_err = 0;
 // ---- opt-in per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream ----------
 enum KernelKind : int {
   KK_ADJ_PACK = 0, KK_TRANSPOSE, KK_FWD_FIRST, KK_FWD_MID, KK_BN_FINALIZE, KK_FWD_READOUT, KK_BWD_READOUT, KK_BWD_DY,
-  KK_BWD_FINALIZE, KK_BWD_DZ, KK_GEMM_TN, KK_REDUCE, KK_BN_APPLY, KK_WPREP, KK_DW_MMA, KK_EXPAND, KK_PACK, KK_HEAD_FWD, KK_HEAD_LOSS, KK_HEAD_BWD, KK_POOL_FWD, KK_POOL_BWD, KK_FUSED_EVAL, KK_COUNT
+  KK_BWD_FINALIZE, KK_BWD_DZ, KK_GEMM_TN, KK_REDUCE, KK_BN_APPLY, KK_WPREP, KK_DW_MMA, KK_EXPAND, KK_PACK, KK_HEAD_FWD, KK_HEAD_LOSS, KK_HEAD_BWD, KK_POOL_FWD, KK_POOL_BWD, KK_FUSED_EVAL, KK_FUSED_TRAIN, KK_COUNT
 };
 static const char* const kKindNames[KK_COUNT] = {"adj_pack", "transpose", "fwd_first", "fwd_mid", "bn_finalize", "fwd_readout",
                                                  "bwd_readout", "bwd_dy", "bwd_finalize", "bwd_dz", "gemm_tn", "reduce", "bn_apply",
-                                                 "wprep", "dw_mma", "expand_compact", "pack_compact", "head_fwd", "head_loss", "head_bwd", "pool_fwd", "pool_bwd", "fused_eval"};
+                                                 "wprep", "dw_mma", "expand_compact", "pack_compact", "head_fwd", "head_loss", "head_bwd", "pool_fwd", "pool_bwd", "fused_eval", "fused_train_fwd"};
 struct ProfRec { int kind; cudaEvent_t e0, e1; };
 // process-wide (autograd runs backward on its own thread), guarded by a mutex; off by default
 static std::atomic<bool> g_prof_on{false};
@@ -269,6 +269,23 @@ static int ensure_dynamic_smem(size_t smem) {
 // launch helpers
 // ---------------------------------------------------------------------------------------------------------
 static int mm_grid(int tiles) { return tiles < kMaxPersistent ? tiles : kMaxPersistent; }
+// cooperative launch (grid-wide barrier inside the kernel: every CTA must be resident)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_cooperative(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+static bool fused_train_enabled() {
+  static const bool on = [] { const char* e = getenv("OCGCN_FUSED_TRAIN"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 // ---- TMA tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda dependency) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -695,6 +712,50 @@ int ocgcn_encoder_forward(const ocgcn_desc* d, const float* x, const float* adj,
     memset(&tj, 0, sizeof(tj));
     tj.in[0] = p->Wd; tj.out[0] = reinterpret_cast<float*>(scratch + lo.WdT); tj.R[0] = d->E; tj.C[0] = d->F[L];
     ST_TRY(run_transposes(tj, 1, st));
+  }
+  // Training batches of at most one tile per SM (the Tox21 shape, C2): the whole forward in ONE cooperative kernel, accumulators parked in
+  // TMEM across the per-layer grid barrier (ocgcn_fused.cuh); it writes the same saved state as the layer-by-layer kernels below.
+  {
+    bool fused = lo.mm && d->training && fused_train_enabled() && d->N <= 128 && L <= kFusedMaxLayers && d->E <= 128 && lo.tiles <= 148;
+    for (int l = 0; l <= L && fused; ++l) fused = d->F[l] <= 128 && (l == 0 || d->F[l] % 4 == 0);
+    if (fused) {
+      FusedTrainArgs t;
+      memset(&t, 0, sizeof(t));
+      FusedEvalArgs& a = t.e;
+      a.B = d->B; a.N = d->N; a.MT = lo.MT; a.ntiles = lo.tiles; a.L = L; a.E = d->E; a.eps = d->eps;
+      for (int l = 0; l <= L; ++l) { a.F[l] = d->F[l]; t.KP[l] = lo.KP[l]; }
+      a.x = x; a.xs0 = d->x_stride[0]; a.xs1 = d->x_stride[1]; a.xs2 = d->x_stride[2];
+      a.adj = adj; a.as0 = d->adj_stride[0]; a.as1 = d->adj_stride[1]; a.as2 = d->adj_stride[2];
+      a.nbr = reinterpret_cast<const uint4*>(saved + lo.nbr);
+      for (int l = 0; l < L; ++l) {
+        a.wimg[l] = scratch + lo.Wf[l];
+        a.bias[l] = d->has_bias ? p->b[l] : nullptr;
+        a.gamma[l] = p->gamma[l]; a.beta[l] = p->beta[l];
+        a.running_mean[l] = p->running_mean[l]; a.running_var[l] = p->running_var[l];
+        t.rm[l] = p->running_mean[l]; t.rv[l] = p->running_var[l];
+        t.nbt[l] = reinterpret_cast<long long*>(p->num_batches_tracked[l]);
+        t.Z[l] = reinterpret_cast<float*>(saved + lo.Z[l]);
+        t.arg[l] = reinterpret_cast<unsigned char*>(saved + lo.arg[l]);
+        t.S[l] = saved + lo.S[l];
+        t.stats[l] = reinterpret_cast<float*>(saved + lo.stats[l]);
+      }
+      a.wimg[L] = scratch + lo.Wro;
+      a.bias[L] = p->bd;
+      a.out = out;
+      t.S[L] = saved + lo.HL;
+      t.D = reinterpret_cast<float*>(saved + lo.D);
+      t.partials = reinterpret_cast<float*>(scratch + lo.partials);
+      t.momentum = d->momentum;
+      const size_t smem = fused_train_smem_bytes();
+      ST_TRY((ensure_dynamic_smem<encoder_train_fused_kernel>(smem)));
+      {
+        ProfScope prof(KK_FUSED_TRAIN, st);
+        CU_TRY(launch_cooperative(encoder_train_fused_kernel, dim3(lo.tiles < 148 ? lo.tiles : 148), dim3(kFusedThreads), smem, st, t));
+        LAUNCH_CHECK();
+      }
+      CU_TRY(cudaMemcpyAsync(saved + lo.O, out, (size_t)d->B * d->E * 4, cudaMemcpyDeviceToDevice, st));
+      return OCGCN_OK;
+    }
   }
   for (int l = 0; l < L; ++l) ST_TRY(run_layer_forward(d, lo, x, adj, p, l, saved, scratch, st));
 
