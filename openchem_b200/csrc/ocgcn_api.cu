@@ -281,6 +281,10 @@ static cudaError_t launch_cooperative(void (*kern)(KArgs...), dim3 grid, dim3 bl
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
+static bool fused_layer_enabled() {
+  static const bool on = [] { const char* e = getenv("OCGCN_FUSED_LAYER"); return e && e[0] == '1'; }();   // experimental: off unless asked for
+  return on;
+}
 static bool fused_train_enabled() {
   static const bool on = [] { const char* e = getenv("OCGCN_FUSED_TRAIN"); return !(e && e[0] == '0'); }();
   return on;
@@ -716,9 +720,11 @@ int ocgcn_encoder_forward(const ocgcn_desc* d, const float* x, const float* adj,
   // Training batches of at most one tile per SM (the Tox21 shape, C2): the whole forward in ONE cooperative kernel, accumulators parked in
   // TMEM across the per-layer grid barrier (ocgcn_fused.cuh); it writes the same saved state as the layer-by-layer kernels below.
   {
-    bool fused = lo.mm && d->training && fused_train_enabled() && d->N <= 128 && L <= kFusedMaxLayers && d->E <= 128 && lo.tiles <= 148;
+    bool fused = lo.mm && d->training && fused_train_enabled() && d->N <= 128 && L <= kFusedMaxLayers && d->E <= 128;
     for (int l = 0; l <= L && fused; ++l) fused = d->F[l] <= 128 && (l == 0 || d->F[l] % 4 == 0);
-    if (fused) {
+    const bool coop = fused && lo.tiles <= 148;                    // one tile per SM: all stages in one cooperative launch
+    const bool per_layer = fused && !coop && fused_layer_enabled(); // larger batches: the same kernel, one persistent launch per stage
+    if (coop || per_layer) {
       FusedTrainArgs t;
       memset(&t, 0, sizeof(t));
       FusedEvalArgs& a = t.e;
@@ -748,10 +754,21 @@ int ocgcn_encoder_forward(const ocgcn_desc* d, const float* x, const float* adj,
       t.momentum = d->momentum;
       const size_t smem = fused_train_smem_bytes();
       ST_TRY((ensure_dynamic_smem<encoder_train_fused_kernel>(smem)));
-      {
+      if (coop) {
+        t.l_begin = 0; t.l_end = L + 1;
         ProfScope prof(KK_FUSED_TRAIN, st);
-        CU_TRY(launch_cooperative(encoder_train_fused_kernel, dim3(lo.tiles < 148 ? lo.tiles : 148), dim3(kFusedThreads), smem, st, t));
+        CU_TRY(launch_cooperative(encoder_train_fused_kernel, dim3(lo.tiles), dim3(kFusedThreads), smem, st, t));
         LAUNCH_CHECK();
+      } else {
+        for (int l = 0; l <= L; ++l) {
+          t.l_begin = l; t.l_end = l + 1;
+          {
+            ProfScope prof(l == 0 ? KK_FWD_FIRST : l < L ? KK_FWD_MID : KK_FWD_READOUT, st);
+            CU_TRY(launch_chain(encoder_train_fused_kernel, dim3(148), dim3(kFusedThreads), smem, st, t));
+            LAUNCH_CHECK();
+          }
+          if (l < L) ST_TRY(run_bn_finalize(d, lo, p, l, saved, scratch, st));
+        }
       }
       CU_TRY(cudaMemcpyAsync(saved + lo.O, out, (size_t)d->B * d->E * 4, cudaMemcpyDeviceToDevice, st));
       return OCGCN_OK;

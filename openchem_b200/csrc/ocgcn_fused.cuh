@@ -378,6 +378,10 @@ struct FusedTrainArgs {
   float* stats[kFusedMaxLayers];           // [4][F[l+1]] mean, invstd, scale, shift
   float* D;                                // [rows][E]
   float* partials;                         // [tiles][2][F[l+1]] per-tile (mean, M2), reused by every layer
+  // stage range [l_begin, l_end) of this launch (stages 0..L-1 = layers, L = readout). The cooperative launch runs all stages with a
+  // grid barrier + statistics fold after every layer; a one-stage launch (any number of tiles per CTA, no barrier) is the persistent
+  // per-layer forward of large batches: its input T comes from the saved Z of the previous layer and that layer's statistics.
+  int l_begin, l_end;
 };
 
 static inline size_t fused_train_smem_bytes() { return fused_eval_smem_bytes() + (size_t)2 * 4 * 128 * 4; }
@@ -411,7 +415,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) encoder_train_fused_kernel(c
   const uint32_t img_lane_off4 = (uint32_t)(hl >> 1) * kImgPitch + (uint32_t)(hl & 1) * 8;
   const int G = (int)gridDim.x;
   const int nk = ((int)blockIdx.x < a.ntiles) ? (a.ntiles - (int)blockIdx.x + G - 1) / G : 0;   // tiles of this CTA (<= 4)
-  const uint32_t tcols = nk <= 1 ? 128u : nk <= 2 ? 256u : 512u;
+  const bool park = (t.l_end - t.l_begin) > 1;   // several stages in one launch: accumulators stay parked in TMEM across the grid barrier
+  const uint32_t tcols = (!park || nk <= 1) ? 128u : nk <= 2 ? 256u : 512u;
 
   if (tid == 0) {
     tc::mbar_init(&bars[0], 1);
@@ -431,9 +436,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) encoder_train_fused_kernel(c
 
   uint32_t w_issued = 0, w_used = 0, mma_cnt = 0;
   uint32_t total_pieces = 0;
-  for (int l = 0; l <= L; ++l) total_pieces += (uint32_t)(nk * ((a.F[l] + KC - 1) / KC));
+  for (int l = t.l_begin; l < t.l_end; ++l) total_pieces += (uint32_t)(nk * ((a.F[l] + KC - 1) / KC));
   auto piece_src = [&](uint32_t seq) -> const unsigned char* {   // layer-major, then this CTA's tiles, then channel chunks
-    int l = 0;
+    int l = t.l_begin;
     uint32_t s = seq;
     for (;; ++l) {
       const uint32_t cnt = (uint32_t)(nk * ((a.F[l] + KC - 1) / KC));
@@ -464,7 +469,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) encoder_train_fused_kernel(c
     *reinterpret_cast<uint2*>(imgLo + off) = lo;
   };
 
-  for (int l = 0; l <= L; ++l) {
+  if (!park && t.l_begin > 0) {   // one-stage launch: BatchNorm scale / shift of the previous layer from its saved statistics
+    const int Fp = a.F[t.l_begin];
+    const float* st = t.stats[t.l_begin - 1];
+    for (int c = tid; c < 128; c += NT) {
+      sScale[c] = c < Fp ? __ldg(&st[2 * Fp + c]) * kTanhScale : 0.f;
+      sShift[c] = c < Fp ? __ldg(&st[3 * Fp + c]) * kTanhScale : 0.f;
+    }
+  }
+  for (int l = t.l_begin; l < t.l_end; ++l) {
     const int K = a.F[l], NC = (l < L) ? a.F[l + 1] : a.E;
     const int nch = (K + KC - 1) / KC;
     for (int k = 0; k < nk; ++k) {
@@ -473,7 +486,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) encoder_train_fused_kernel(c
       const int nm = min(a.MT, a.B - mol0);
       const int rows = nm * N;
       const size_t row0 = (size_t)mol0 * N;
-      const uint32_t acc = tmem + (uint32_t)(k * 128);
+      const uint32_t acc = tmem + (uint32_t)(park ? k * 128 : 0);
       __syncthreads();   // the staging tile of the previous epilogue (aliases T0 / T1 / H) and the records are consumed
       for (int r = tid; r < TR; r += NT) {
         uint4 rec = make_uint4(0u, 0u, 0u, 0u);
@@ -488,7 +501,34 @@ __global__ void __launch_bounds__(kFusedThreads, 1) encoder_train_fused_kernel(c
         sT1[TR * BS + tid] = -INFINITY;
         sH[TR * BS + tid] = 0.f;
       }
-      if (l > 0) {
+      if (l > 0 && l == t.l_begin) {
+        // one-stage launch: T = tanh(BatchNorm(Z_{l-1})) from the saved pre-BatchNorm activations (coalesced 16-byte loads, half a warp per row)
+        const float* zin = t.Z[l - 1] + row0 * K;
+#pragma unroll
+        for (int chh = 0; chh < 2; ++chh) {
+          const int c4 = chh * KC + 4 * hl;
+          float* const bufT = chh ? sT1 : sT0;
+          if (chh * KC < K) {
+            const float4 sc4 = *reinterpret_cast<const float4*>(&sScale[c4]), sh4 = *reinterpret_cast<const float4*>(&sShift[c4]);
+            float4 zv[RPW / 2];
+#pragma unroll
+            for (int sI = 0; sI < RPW / 2; ++sI) {
+              const int r = warp + (2 * sI + hh) * NWARP;
+              zv[sI] = (r < rows && c4 < K) ? __ldg(reinterpret_cast<const float4*>(&zin[r * K + c4])) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int sI = 0; sI < RPW / 2; ++sI) {
+              const int r = warp + (2 * sI + hh) * NWARP;
+              float4 tv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (r < rows && c4 < K) {
+                tv.x = fast_tanh_scaled(fmaf(zv[sI].x, sc4.x, sh4.x)); tv.y = fast_tanh_scaled(fmaf(zv[sI].y, sc4.y, sh4.y));
+                tv.z = fast_tanh_scaled(fmaf(zv[sI].z, sc4.z, sh4.z)); tv.w = fast_tanh_scaled(fmaf(zv[sI].w, sc4.w, sh4.w));
+              }
+              *reinterpret_cast<float4*>(&bufT[r * BS + 4 * hl]) = tv;
+            }
+          }
+        }
+      } else if (l > 0) {
         // second half of layer l-1's epilogue, after the grid barrier: parked accumulator -> + bias -> BatchNorm (batch statistics)
         // -> tanh -> the T chunk buffers this layer's max-pool reads
         tc::fence_after_sync();
@@ -729,7 +769,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) encoder_train_fused_kernel(c
       }
     }   // tiles of this CTA
 
-    if (l < L) {
+    if (l < L && l + 1 < t.l_end) {
       // ---- grid-wide BatchNorm statistics of layer l: barrier, then EVERY CTA folds all per-tile partials in the same fixed order ----
       __threadfence();
       grid.sync();
