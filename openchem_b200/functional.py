@@ -125,6 +125,28 @@ def _count(lib):
     launch_counter["n"] += lib.ocgcn_last_launch_count()
 
 
+# Gradient sinks (openchem_b200.step.TrainStep): inside a sink scope the backward kernels write each parameter gradient straight into a
+# caller-registered buffer (a view of the step's flat gradient) and return that view, so a `torch.autograd.grad` call needs no
+# per-parameter accumulate / copy kernel (28 tiny launches per step at the GraphCNN shapes). The decision is taken at FORWARD time in
+# the calling thread; outside a scope (plain `loss.backward()`, run.py's train_step) fresh tensors are returned as autograd expects.
+from torch.utils.weak import WeakIdKeyDictionary  # noqa: E402  (keys compared by identity: Tensor.__eq__ is elementwise)
+
+grad_sinks = WeakIdKeyDictionary()            # nn.Parameter -> destination tensor (same shape, contiguous, same device)
+sink_scope = {"on": False}
+
+
+def _sinks_for(params):
+    if not sink_scope["on"]:
+        return None
+    return [None if t is None else grad_sinks.get(t) for t in params]
+
+
+def _grad_buffer(like, sinks, i):
+    if sinks is not None and sinks[i] is not None:
+        return sinks[i]
+    return torch.empty_like(like)
+
+
 # single-kernel eval forward (csrc/ocgcn_fused.cuh): on by default at every batch size (measured on a B200, bf16 class, eval forward
 # of the encoder: C2 60 vs 131 us layer by layer, C1 107 vs 164 us, C4 312 vs 480 us, C3 654 vs 870 us; profiles/r2_fused_eval.md);
 # OCB200_FUSED_EVAL=0 or `max_tiles` restrict it
@@ -163,6 +185,7 @@ class EncoderFn(torch.autograd.Function):
                                "use GraphConvolution layers if you need d/dx")
         L = len(spec.widths) - 1
         x, adj = _f32(x), _f32(adj)
+        ctx.sinks = _sinks_for(tensors)
         tensors = [None if t is None else t.detach().contiguous() for t in tensors]
         Ws, bs, gammas, betas = tensors[0:4 * L:4], tensors[1:4 * L:4], tensors[2:4 * L:4], tensors[3:4 * L:4]
         Wd, bd = tensors[4 * L], tensors[4 * L + 1]
@@ -229,13 +252,14 @@ class EncoderFn(torch.autograd.Function):
                 _count(lib)
             grads = _lib.Grads()
             outs = []
+            sk = ctx.sinks
             for l in range(L):
-                gW, gg, gb_ = torch.empty_like(Ws[l]), torch.empty_like(gammas[l]), torch.empty_like(betas[l])
-                gbias = torch.empty_like(bs[l]) if bs[l] is not None else None
+                gW, gg, gb_ = _grad_buffer(Ws[l], sk, 4 * l), _grad_buffer(gammas[l], sk, 4 * l + 2), _grad_buffer(betas[l], sk, 4 * l + 3)
+                gbias = _grad_buffer(bs[l], sk, 4 * l + 1) if bs[l] is not None else None
                 grads.dW[l], grads.dgamma[l], grads.dbeta[l] = gW.data_ptr(), gg.data_ptr(), gb_.data_ptr()
                 grads.db[l] = gbias.data_ptr() if gbias is not None else None
                 outs += [gW, gbias, gg, gb_]
-            gWd, gbd = torch.empty_like(Wd), torch.empty_like(bd)
+            gWd, gbd = _grad_buffer(Wd, sk, 4 * L), _grad_buffer(bd, sk, 4 * L + 1)
             grads.dWd, grads.dbd = gWd.data_ptr(), gbd.data_ptr()
             scratch = _alloc(ctx.cbytes, x.device)
             _lib.check(lib.ocgcn_encoder_backward(ctypes.byref(desc), grad_out.data_ptr(), x.data_ptr(), adj.data_ptr(),
@@ -357,6 +381,7 @@ class HeadFn(torch.autograd.Function):
         inp = _f32(inp.detach()).contiguous()
         if inp.dim() != 2 or inp.shape[1] != spec.widths[0]:
             raise RuntimeError("openchem_b200: MLP input must be (B, %d); got %s" % (spec.widths[0], tuple(inp.shape)))
+        ctx.sinks = _sinks_for(tensors)
         tensors = [None if t is None else t.detach().contiguous() for t in tensors]
         Ws, bs = tensors[0:L], tensors[L:2 * L]
         gammas, betas = tensors[2 * L:3 * L - 1], tensors[3 * L - 1:4 * L - 2]
@@ -411,10 +436,11 @@ class HeadFn(torch.autograd.Function):
             desc = _head_desc(spec, inp.shape[0], ctx.need_dx)
             params = _head_params(spec, Ws, bs, gammas, betas)
             grads = _lib.HeadGrads()
-            gW = [torch.empty_like(w) for w in Ws]
-            gb = [None if b is None else torch.empty_like(b) for b in bs]
-            gg = [torch.empty_like(t) for t in gammas]
-            gbt = [torch.empty_like(t) for t in betas]
+            sk = ctx.sinks
+            gW = [_grad_buffer(w, sk, i) for i, w in enumerate(Ws)]
+            gb = [None if b is None else _grad_buffer(b, sk, L + i) for i, b in enumerate(bs)]
+            gg = [_grad_buffer(t, sk, 2 * L + i) for i, t in enumerate(gammas)]
+            gbt = [_grad_buffer(t, sk, 3 * L - 1 + i) for i, t in enumerate(betas)]
             for i in range(L):
                 grads.dW[i] = gW[i].data_ptr()
                 grads.db[i] = gb[i].data_ptr() if gb[i] is not None else None

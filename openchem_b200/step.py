@@ -72,9 +72,13 @@ class TrainStep:
             if self.world > 1:
                 self.exchange_kind = "nccl"
         off = 0
+        self.views = []
+        from . import functional
         for p in self.params:
             n = p.numel()
             p.grad = self.flat_grad[off:off + n].view_as(p)
+            self.views.append(p.grad)
+            functional.grad_sinks[p] = p.grad     # the package's backward kernels write the gradient straight into this view
             off += n
         self.opt = make_optimizer(self.params)
         self.inputs = tuple(torch.empty_like(t) for t in example_batch)
@@ -119,10 +123,21 @@ class TrainStep:
         torch.cuda.synchronize(dev)
 
     def _body(self):
-        self.flat_grad.zero_()
+        from . import functional
         x, adj, y = self.inputs
-        loss = self.loss_fn(self.model, (x, adj), y) if self.loss_fn is not None else self.criterion(self.model((x, adj)), y)
-        loss.backward()
+        functional.sink_scope["on"] = True        # (decided at forward time; see functional.grad_sinks)
+        try:
+            loss = self.loss_fn(self.model, (x, adj), y) if self.loss_fn is not None else self.criterion(self.model((x, adj)), y)
+        finally:
+            functional.sink_scope["on"] = False
+        # torch.autograd.grad instead of .backward(): no AccumulateGrad node runs. Gradients the package's kernels produced are already
+        # in the flat buffer (the returned tensor IS the view); anything else (torch modules in the model) is copied, unused -> zero
+        grads = torch.autograd.grad(loss, self.params, allow_unused=True)
+        for view, g in zip(self.views, grads):
+            if g is None:
+                view.zero_()
+            elif g.data_ptr() != view.data_ptr():
+                view.copy_(g)
         if self.world > 1:
             self._exchange()
         self.opt.step()
