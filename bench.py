@@ -13,6 +13,7 @@ all-reduce over NCCL when N > 1) -> Adam step. Rank 0 prints ONE JSON line.
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import math
 import os
@@ -65,36 +66,89 @@ def measured_peaks():
 # clocks sampling during the timed region
 # --------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed regions (B200_PROFILING.md's clocks line). The samples come from NVML, the
+    library nvidia-smi itself reads, polled every few milliseconds by a thread of this process and only inside `window()`, i.e.
+    while a timed region runs: the regions last tens of milliseconds, shorter than one `nvidia-smi` process start, and a fork
+    per sample stalls the launching thread for a millisecond or more each time, which the end-to-end region (at most one step
+    ahead of the device) cannot hide. Without NVML bindings: one `nvidia-smi -lms 100` process for the whole span."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
-        self.index, self.samples, self.stop_flag, self.thread = index, [], threading.Event(), None
+        self.index, self.samples, self.proc, self.log = index, [], None, None
+        self.thread, self.stop_flag, self.active, self.source = None, threading.Event(), threading.Event(), None
 
-    def _loop(self):
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:  # noqa: BLE001
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+
+    def _loop(self, nv, h):
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
         while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
-            except Exception:  # noqa: BLE001
-                pass
-            self.stop_flag.wait(0.1)
+            if self.active.is_set():
+                try:
+                    sm, r = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(reasons_fn(h))
+                    self.samples.append([str(sm), str(mx), ""] + ["Active" if r & b else "Not Active" for _, b in bits])
+                except Exception:  # noqa: BLE001
+                    pass
+                self.stop_flag.wait(0.004)
+            else:
+                self.stop_flag.wait(0.001)
 
     def start(self):
-        self.thread = threading.Thread(target=self._loop, daemon=True)
-        self.thread.start()
+        try:
+            nv, h = self._nvml_handle()
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.source = "NVML (pynvml), polled every 4 ms inside the timed regions only"
+            self.thread = threading.Thread(target=self._loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            pass
+        import tempfile
+        self.source = "nvidia-smi -lms 100, one process over the whole span of the timed regions"
+        self.log = tempfile.TemporaryFile(mode="w+")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=self.log, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    @contextlib.contextmanager
+    def window(self):
+        self.active.set()
+        try:
+            yield
+        finally:
+            self.active.clear()
 
     def stop(self):
         self.stop_flag.set()
-        if self.thread:
+        if self.thread is not None:
             self.thread.join(timeout=6)
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=6)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.log.seek(0)
+            self.samples = [[t.strip() for t in line.split(",")] for line in self.log.read().splitlines() if line.strip()]
+            self.log.close()
         sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
         mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for s in self.samples if len(s) >= 7 for i in range(4) if s[3 + i].lower() == "active"})
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm),
+                    source=self.source)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -498,7 +552,8 @@ def run_native(args, w, wname):
     if rank == 0:
         sampler.start()
     functional.launch_counter["n"] = 0
-    ms_total = timed(lambda: step(x, adj, y), args.steps)
+    with sampler.window():
+        ms_total = timed(lambda: step(x, adj, y), args.steps)
     launches = functional.launch_counter["n"]
     if stepper is not None and stepper.graph is not None:
         launches = launches_per_body * args.steps     # replays re-issue the captured launches; count them from one eager body
@@ -554,26 +609,56 @@ def run_native(args, w, wname):
             yield host_set.collate(perm.permutation(n_set)[:B]).tensors()      # per-step host work: the sampler + the collate
 
     from openchem_b200.loader import BackgroundIterator
-    feed_c = DevicePrefetcher(BackgroundIterator(compact_batches(2 + args.steps), depth=2), dev)
     e2e_h2d = [0]
 
-    def compact_step():
-        xbits, abits, yb = next(feed_c)
-        e2e_h2d[0] = (xbits.numel() + abits.numel()) * 4 + yb.numel() * 4
-        cb = CompactGraphBatch(xbits, abits, w["f0"], yb)
-        if stepper is not None:
-            stepper.load_compact(cb)
-            return stepper()
-        xe, ae = cb.expand()
-        return step(xe, ae, yb)
+    # The step of the compact route is captured ON the bit words: its static inputs are (x_bits, adj_bits, labels) and the captured
+    # kernels read the words themselves (ocgcn_encoder_forward_compact / _backward_compact; GraphCNNEncoder.forward given int32 words).
+    # Same model class, same initial weights, its own optimizer state; under N > 1 it carries the same in-graph gradient all-reduce.
+    cstepper = None
+    if stepper is not None:
+        from openchem_b200.step import TrainStep
+        torch.manual_seed(0)
+        cmodel = build_model(w, args.precision, dev, args.head)
+        c0 = host_set.collate(perm.permutation(n_set)[:B]).to(dev)
+        cstepper = TrainStep(cmodel, crit, adam, (c0.x_bits, c0.adj_bits, c0.labels), loss_fn=head_loss_fn(args, crit))
+        assert cstepper.graph is not None, getattr(cstepper, "graph_error", None)
 
-    ms_e2e = e2e_region(compact_step)
+    def compact_step_via(st_words, st_dense, feed):
+        def one():
+            xbits, abits, yb = next(feed)
+            e2e_h2d[0] = (xbits.numel() + abits.numel()) * 4 + yb.numel() * 4
+            cb = CompactGraphBatch(xbits, abits, w["f0"], yb)
+            if st_words is not None:
+                st_words.load_compact(cb)          # three small device copies into the static word buffers
+                return st_words()
+            if st_dense is not None:
+                st_dense.load_compact(cb)          # ocgcn_expand_compact into the static dense inputs
+                return st_dense()
+            xe, ae = cb.expand()
+            return step(xe, ae, yb)
+        return one
+
+    feed_c = DevicePrefetcher(BackgroundIterator(compact_batches(2 + args.steps), depth=2), dev)
+    with sampler.window():
+        ms_e2e = e2e_region(compact_step_via(cstepper, stepper, feed_c))
+    if world > 1 and cstepper is not None:
+        flat = torch.cat([q.detach().reshape(-1).double() for q in cmodel.parameters()])
+        mine = torch.stack([flat.sum(), (flat * flat).sum(), flat.abs().max()])
+        allv = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        assert all(torch.equal(v, allv[0]) for v in allv), "data-parallel replicas of the compact-route step diverged"
+    # the earlier form of the compact route, kept for comparison: the words are expanded on the device into the dense step's inputs
+    ms_e2e_expand = None
+    if cstepper is not None and not args.no_extra:
+        feed_x = DevicePrefetcher(BackgroundIterator(compact_batches(2 + args.steps), depth=2), dev)
+        ms_e2e_expand = e2e_region(compact_step_via(None, stepper, feed_x))
 
     # ---- e2e_dense: the same region fed in the REFERENCE's host format (dense fp32 adjacency / features / labels from pinned
     # memory, Graph2Label.cast_inputs' layout) through the same feeder ----
     h2d_dense = hx.numel() * 4 + hadj.numel() * 4 + hy.numel() * 4
     feed = DevicePrefetcher([(hx, hadj, hy)] * (2 + args.steps), dev)
-    ms_e2e_dense = e2e_region(lambda: step(*next(feed)))
+    with sampler.window():
+        ms_e2e_dense = e2e_region(lambda: step(*next(feed)))
 
     # ---- the same per-GPU workload without the gradient exchange (N > 1 only): every rank steps a purely local replica.
     # This is the single-GPU number the N-GPU value should be read against (BASELINE config 4 is quoted at 2048 per GPU) ----
@@ -609,11 +694,11 @@ def run_native(args, w, wname):
                                                    what="one GPU, per-GPU batch 2048, no gradient exchange (slowest rank)")
         del s4, m4
 
-    # the clock / throttle sampler (nvidia-smi, ~20 Hz at best) ran through the device-resident AND the end-to-end timed
-    # regions: the same load, enough samples for a median even when K steps last only tens of milliseconds
+    # the clock / throttle sampler polled inside the device-resident AND the end-to-end timed regions (ClockSampler.window):
+    # the same load, enough samples for a median even when K steps last only tens of milliseconds
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
-        clocks["window"] = "device-resident + end-to-end timed regions"
+        clocks["window"] = "inside the device-resident + end-to-end timed regions"
 
     # ---- per-kernel timing (CUDA events around every launch, on the launching stream) ----
     # (every rank runs the steps - they contain the DDP all-reduce - but only rank 0 records events)
@@ -791,7 +876,11 @@ def run_native(args, w, wname):
                          ms_per_step=ms_e2e / args.steps,
                          feeder="openchem_b200.compact.CompactGraphDataset (host cache, packed once) -> per-step sampler + collate into pinned "
                                 "memory (loader.BackgroundIterator thread, 2 ahead) -> loader.DevicePrefetcher (copy stream, one batch ahead) -> "
-                                "ocgcn_expand_compact on the device; all inside the timed region",
+                                + ("TrainStep captured on the bit words: ocgcn_encoder_forward_compact reads them directly (no dense x / adj on the "
+                                   "device)" if cstepper is not None else "ocgcn_expand_compact on the device") + "; all inside the timed region",
+                         via_dense_expand=(dict(value=world * B * args.steps / (ms_e2e_expand * 1e-3), ms_per_step=ms_e2e_expand / args.steps,
+                                                what="same feed, words expanded by ocgcn_expand_compact into the dense step's inputs")
+                                           if ms_e2e_expand else None),
                          loss_readback="every step's loss is copied to pinned host memory and read there, one step delayed "
                                        "(openchem_b200.step.DelayedLoss); the last read is inside the timed region"),
                 e2e_dense=dict(value=world * B * args.steps / (ms_e2e_dense * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d_dense, d2h_bytes_per_step=4,

@@ -159,6 +159,18 @@ int ocgcn_expand_compact(int B, int N, int F0, const uint32_t* x_bits, const uin
 int ocgcn_pack_compact(int B, int N, int F0, const float* x, const int64_t* x_stride, const float* adj,
                        const int64_t* adj_stride, uint32_t* x_bits, uint32_t* adj_bits, int32_t* nonbinary, void* stream);
 
+/* The encoder entry points fed with the bit words themselves (same layout as above; desc->x_stride / adj_stride are ignored): the
+ * neighbour records are built straight from adj_bits and the first layer reads x_bits, so the dense fp32 x / adj (8*N*N bytes per
+ * molecule written by ocgcn_expand_compact and read again by the forward) never exist. Results are bit-identical to
+ * ocgcn_expand_compact followed by the dense entry point (GraphCNNEncoder.forward on the same batch, gcn_encoder.py:38-53).
+ * The backward of a *_forward_compact call is ocgcn_encoder_backward_compact (same `saved`); it needs neither x nor adj. */
+int ocgcn_encoder_forward_compact(const ocgcn_desc* desc, const uint32_t* x_bits, const uint32_t* adj_bits,
+                                  const ocgcn_params* params, void* saved, void* scratch, float* out, void* stream);
+int ocgcn_encoder_forward_eval_compact(const ocgcn_desc* desc, const uint32_t* x_bits, const uint32_t* adj_bits,
+                                       const ocgcn_params* params, void* workspace, float* out, void* stream);
+int ocgcn_encoder_backward_compact(const ocgcn_desc* desc, const float* grad_out, const ocgcn_params* params,
+                                   const ocgcn_grads* grads, void* saved, void* scratch, void* stream);
+
 /* ---- MLP head + loss (Graph2Label.forward's `self.MLP(output)` and the criterion `fit` applies to it) -------------------
  * ocgcn_head_forward   <- OpenChemMLP.forward                      openchem/modules/mlp/openchem_mlp.py:51-61
  *                         (+ nn.MSELoss / MultitaskLoss.forward    openchem/criterion/multitask_loss.py:40-49 when loss != NONE)
@@ -231,8 +243,8 @@ int ocgcn_last_launch_count(void);
 int ocgcn_last_cuda_error(void);
 const char* ocgcn_status_string(int status);
 /* ABI version; bumped whenever a struct above changes. */
-/* Bumped whenever a struct layout or an entry-point signature changes (2: ocgcn_expand_compact gained n_src / index_oob; 3: ocgcn_pool_forward / _backward; 4: ocgcn_encoder_forward_eval). Bindings must refuse a library that reports another value. */
-#define OCGCN_ABI_VERSION 4
+/* Bumped whenever a struct layout or an entry-point signature changes (2: ocgcn_expand_compact gained n_src / index_oob; 3: ocgcn_pool_forward / _backward; 4: ocgcn_encoder_forward_eval; 5: ocgcn_encoder_*_compact). Bindings must refuse a library that reports another value. */
+#define OCGCN_ABI_VERSION 5
 int ocgcn_abi_version(void);
 
 #ifdef __cplusplus

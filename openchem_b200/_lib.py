@@ -82,6 +82,7 @@ EXPORTS = [
     "ocgcn_saved_tensor", "ocgcn_expand_compact", "ocgcn_pack_compact",
     "ocgcn_head_query_workspace", "ocgcn_head_forward", "ocgcn_head_backward", "ocgcn_pool_forward", "ocgcn_pool_backward",
     "ocgcn_query_eval_workspace", "ocgcn_encoder_forward_eval",
+    "ocgcn_encoder_forward_compact", "ocgcn_encoder_forward_eval_compact", "ocgcn_encoder_backward_compact",
 ]
 
 
@@ -99,7 +100,7 @@ def _stale():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-ABI_VERSION = 4     # include/ocgcn.h OCGCN_ABI_VERSION: bump both whenever a struct layout or an entry-point signature changes
+ABI_VERSION = 5     # include/ocgcn.h OCGCN_ABI_VERSION: bump both whenever a struct layout or an entry-point signature changes
 
 
 def build(force=False, verbose=False):
@@ -173,6 +174,11 @@ def load():
         lib.ocgcn_query_eval_workspace.argtypes = [ctypes.POINTER(Desc), ctypes.POINTER(ctypes.c_size_t)]
         lib.ocgcn_encoder_forward_eval.argtypes = [ctypes.POINTER(Desc), vp, vp, ctypes.POINTER(Params), vp, vp, vp]
         lib.ocgcn_query_eval_workspace.restype = lib.ocgcn_encoder_forward_eval.restype = ctypes.c_int
+        lib.ocgcn_encoder_forward_compact.argtypes = [ctypes.POINTER(Desc), vp, vp, ctypes.POINTER(Params), vp, vp, vp, vp]
+        lib.ocgcn_encoder_forward_eval_compact.argtypes = [ctypes.POINTER(Desc), vp, vp, ctypes.POINTER(Params), vp, vp, vp]
+        lib.ocgcn_encoder_backward_compact.argtypes = [ctypes.POINTER(Desc), vp, ctypes.POINTER(Params), ctypes.POINTER(Grads), vp, vp, vp]
+        for name in ("ocgcn_encoder_forward_compact", "ocgcn_encoder_forward_eval_compact", "ocgcn_encoder_backward_compact"):
+            getattr(lib, name).restype = ctypes.c_int
         lib.ocgcn_pool_forward.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, i64p, vp, vp, vp]
         lib.ocgcn_pool_backward.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, i64p, vp, vp, vp, vp]
         lib.ocgcn_pool_forward.restype = lib.ocgcn_pool_backward.restype = ctypes.c_int

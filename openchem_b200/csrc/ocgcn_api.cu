@@ -417,15 +417,59 @@ static TileArgs base_tile_args(const ocgcn_desc* d, const Layout& lo, const floa
   return a;
 }
 
-static int run_adj_pack(const ocgcn_desc* d, const Layout& lo, const float* adj, char* saved, cudaStream_t st) {
+// The batch as the caller handed it over: dense fp32 x / adj with the strides of the descriptor, or the bit words of a compact batch
+// (ocgcn_*_compact entry points; exact 0/1 matrices, ocgcn_pack_compact's layout).
+struct GraphIn {
+  const float* x;
+  const float* adj;
+  const uint32_t* x_bits;
+  const uint32_t* adj_bits;
+  bool compact() const { return adj_bits != nullptr; }
+};
+
+static int check_graph_in(const GraphIn& gi) {
+  if (gi.compact()) {
+    if (!gi.x_bits) return OCGCN_EINVAL;
+    ST_TRY(check_device_ptr(gi.adj_bits));
+    ST_TRY(check_device_ptr(gi.x_bits));
+    if (((uintptr_t)gi.adj_bits & 3) || ((uintptr_t)gi.x_bits & 3)) return OCGCN_EALIGN;
+    return OCGCN_OK;
+  }
+  ST_TRY(check_device_ptr(gi.x));
+  ST_TRY(check_device_ptr(gi.adj));
+  return OCGCN_OK;
+}
+
+static int launch_adj_pack(const ocgcn_desc* d, const GraphIn& gi, int NW, u64* rowmask, u64* colmask, unsigned* molflag, uint4* nbr,
+                           uint4* cnbr, cudaStream_t st) {
   ProfScope prof(KK_ADJ_PACK, st);
-  CU_TRY(launch_chain(adj_pack_kernel, dim3(d->B), dim3(kThreads), (size_t)2 * d->N * lo.NW * 8, st,
-      
-      adj, d->adj_stride[0], d->adj_stride[1], d->adj_stride[2], d->N, lo.NW, reinterpret_cast<u64*>(saved + lo.rowmask),
-      reinterpret_cast<u64*>(saved + lo.colmask), reinterpret_cast<unsigned*>(saved + lo.molflag),
-      reinterpret_cast<uint4*>(saved + lo.nbr), reinterpret_cast<uint4*>(saved + lo.cnbr)));
+  const size_t smem = (size_t)2 * d->N * NW * 8;
+  const float* no_adj = nullptr;
+  const uint32_t* no_bits = nullptr;
+  const long long s0 = d->adj_stride[0], s1 = d->adj_stride[1], s2 = d->adj_stride[2];
+  if (NW == 1) {      // N <= 64: one warp per molecule
+    const dim3 grid((d->B + kWarps - 1) / kWarps);
+    if (gi.compact())
+      CU_TRY(launch_chain(adj_pack_warp_kernel<true>, grid, dim3(kThreads), 0, st, no_adj, 0ll, 0ll, 0ll, gi.adj_bits, d->B, d->N, rowmask, colmask,
+                          molflag, nbr, cnbr));
+    else
+      CU_TRY(launch_chain(adj_pack_warp_kernel<false>, grid, dim3(kThreads), 0, st, gi.adj, s0, s1, s2, no_bits, d->B, d->N, rowmask, colmask,
+                          molflag, nbr, cnbr));
+  } else if (gi.compact()) {
+    CU_TRY(launch_chain(adj_pack_kernel<true>, dim3(d->B), dim3(kThreads), smem, st, no_adj, 0ll, 0ll, 0ll, gi.adj_bits, d->N, NW, rowmask, colmask,
+                        molflag, nbr, cnbr));
+  } else {
+    CU_TRY(launch_chain(adj_pack_kernel<false>, dim3(d->B), dim3(kThreads), smem, st, gi.adj, s0, s1, s2, no_bits, d->N, NW, rowmask, colmask,
+                        molflag, nbr, cnbr));
+  }
   LAUNCH_CHECK();
   return OCGCN_OK;
+}
+
+static int run_adj_pack(const ocgcn_desc* d, const Layout& lo, const GraphIn& gi, char* saved, cudaStream_t st) {
+  return launch_adj_pack(d, gi, lo.NW, reinterpret_cast<u64*>(saved + lo.rowmask), reinterpret_cast<u64*>(saved + lo.colmask),
+                         reinterpret_cast<unsigned*>(saved + lo.molflag), reinterpret_cast<uint4*>(saved + lo.nbr),
+                         reinterpret_cast<uint4*>(saved + lo.cnbr), st);
 }
 
 static int run_bn_finalize(const ocgcn_desc* d, const Layout& lo, const ocgcn_params* p, int l, char* saved, char* scratch,
@@ -493,9 +537,9 @@ static int validate_params(const ocgcn_desc* d, const ocgcn_params* p, bool laye
 }
 
 // The forward of one graph-conv layer's GEMM stage (producer P_X for l==0, P_MID otherwise) + BN statistics.
-static int run_layer_forward(const ocgcn_desc* d, const Layout& lo, const float* x, const float* adj, const ocgcn_params* p, int l,
+static int run_layer_forward(const ocgcn_desc* d, const Layout& lo, const GraphIn& gi, const ocgcn_params* p, int l,
                              char* saved, char* scratch, cudaStream_t st) {
-  TileArgs a = base_tile_args(d, lo, adj, saved);
+  TileArgs a = base_tile_args(d, lo, gi.adj, saved);
   a.K = d->F[l]; a.NC = d->F[l + 1];
   a.Bm = p->W[l];
   a.bias = d->has_bias ? p->b[l] : nullptr;
@@ -508,7 +552,8 @@ static int run_layer_forward(const ocgcn_desc* d, const Layout& lo, const float*
     a.wimg = scratch + lo.Wf[l]; a.ncb = (d->F[l + 1] + 127) / 128;
   }
   if (l == 0) {
-    a.in0 = x; a.xs0 = d->x_stride[0]; a.xs1 = d->x_stride[1]; a.xs2 = d->x_stride[2];
+    a.in0 = gi.x; a.xs0 = d->x_stride[0]; a.xs1 = d->x_stride[1]; a.xs2 = d->x_stride[2];
+    a.x_bits = gi.x_bits; a.xw = (d->F[0] + 31) / 32;
     ST_TRY((launch_tile<P_X, E_ZSTATS>(lo, a, st)));
   } else {
     const float* stats = reinterpret_cast<const float*>(saved + lo.stats[l - 1]);
@@ -684,16 +729,15 @@ int ocgcn_query_workspace(const ocgcn_desc* desc, size_t* saved_bytes, size_t* s
   return OCGCN_OK;
 }
 
-int ocgcn_encoder_forward(const ocgcn_desc* d, const float* x, const float* adj, const ocgcn_params* p, void* saved_v,
-                          void* scratch_v, float* out, void* stream) {
+static int encoder_forward_impl(const ocgcn_desc* d, const GraphIn& gi, const ocgcn_params* p, void* saved_v, void* scratch_v, float* out,
+                                void* stream) {
   tl_launches = 0;
   Layout lo;
   ST_TRY(make_layout(d, false, &lo));
   ST_TRY(validate_params(d, p, false));
   if (!saved_v || !scratch_v || !out) return OCGCN_EINVAL;
   ST_TRY(check_device());
-  ST_TRY(check_device_ptr(x));
-  ST_TRY(check_device_ptr(adj));
+  ST_TRY(check_graph_in(gi));
   ST_TRY(check_device_ptr(out));
   if (((uintptr_t)saved_v & 255) || ((uintptr_t)scratch_v & 255)) return OCGCN_EALIGN;
   char* saved = static_cast<char*>(saved_v);
@@ -701,7 +745,7 @@ int ocgcn_encoder_forward(const ocgcn_desc* d, const float* x, const float* adj,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int L = d->L;
 
-  ST_TRY(run_adj_pack(d, lo, adj, saved, st));
+  ST_TRY(run_adj_pack(d, lo, gi, saved, st));
   if (lo.mm) {
     WPrepJobs wj;
     memset(&wj, 0, sizeof(wj));
@@ -730,8 +774,9 @@ int ocgcn_encoder_forward(const ocgcn_desc* d, const float* x, const float* adj,
       FusedEvalArgs& a = t.e;
       a.B = d->B; a.N = d->N; a.MT = lo.MT; a.ntiles = lo.tiles; a.L = L; a.E = d->E; a.eps = d->eps;
       for (int l = 0; l <= L; ++l) { a.F[l] = d->F[l]; t.KP[l] = lo.KP[l]; }
-      a.x = x; a.xs0 = d->x_stride[0]; a.xs1 = d->x_stride[1]; a.xs2 = d->x_stride[2];
-      a.adj = adj; a.as0 = d->adj_stride[0]; a.as1 = d->adj_stride[1]; a.as2 = d->adj_stride[2];
+      a.x = gi.x; a.xs0 = d->x_stride[0]; a.xs1 = d->x_stride[1]; a.xs2 = d->x_stride[2];
+      a.adj = gi.adj; a.as0 = d->adj_stride[0]; a.as1 = d->adj_stride[1]; a.as2 = d->adj_stride[2];
+      a.x_bits = gi.x_bits; a.adj_bits = gi.adj_bits; a.xw = (d->F[0] + 31) / 32; a.aw = (d->N + 31) / 32;
       a.nbr = reinterpret_cast<const uint4*>(saved + lo.nbr);
       for (int l = 0; l < L; ++l) {
         a.wimg[l] = scratch + lo.Wf[l];
@@ -774,10 +819,10 @@ int ocgcn_encoder_forward(const ocgcn_desc* d, const float* x, const float* adj,
       return OCGCN_OK;
     }
   }
-  for (int l = 0; l < L; ++l) ST_TRY(run_layer_forward(d, lo, x, adj, p, l, saved, scratch, st));
+  for (int l = 0; l < L; ++l) ST_TRY(run_layer_forward(d, lo, gi, p, l, saved, scratch, st));
 
   // readout: H_L = pool(tanh(BN(Z_L))), D = tanh(H_L Wd^T + bd), O = tanh(sum_i D)
-  TileArgs a = base_tile_args(d, lo, adj, saved);
+  TileArgs a = base_tile_args(d, lo, gi.adj, saved);
   const float* stats = reinterpret_cast<const float*>(saved + lo.stats[L - 1]);
   a.K = d->F[L]; a.NC = d->E;
   a.in0 = reinterpret_cast<const float*>(saved + lo.Z[L - 1]);
@@ -796,6 +841,19 @@ int ocgcn_encoder_forward(const ocgcn_desc* d, const float* x, const float* adj,
   ST_TRY((launch_tile<P_RO, E_READOUT>(lo, a, st)));
   CU_TRY(cudaMemcpyAsync(saved + lo.O, out, (size_t)d->B * d->E * 4, cudaMemcpyDeviceToDevice, st));
   return OCGCN_OK;
+}
+
+int ocgcn_encoder_forward(const ocgcn_desc* d, const float* x, const float* adj, const ocgcn_params* p, void* saved_v,
+                          void* scratch_v, float* out, void* stream) {
+  const GraphIn gi = {x, adj, nullptr, nullptr};
+  return encoder_forward_impl(d, gi, p, saved_v, scratch_v, out, stream);
+}
+
+int ocgcn_encoder_forward_compact(const ocgcn_desc* d, const uint32_t* x_bits, const uint32_t* adj_bits, const ocgcn_params* p,
+                                  void* saved_v, void* scratch_v, float* out, void* stream) {
+  if (!x_bits || !adj_bits) return OCGCN_EINVAL;
+  const GraphIn gi = {nullptr, nullptr, x_bits, adj_bits};
+  return encoder_forward_impl(d, gi, p, saved_v, scratch_v, out, stream);
 }
 
 // ---- single-kernel eval forward (ocgcn_fused.cuh) --------------------------------------------------------------------------
@@ -838,29 +896,23 @@ int ocgcn_query_eval_workspace(const ocgcn_desc* desc, size_t* bytes) {
   return OCGCN_OK;
 }
 
-int ocgcn_encoder_forward_eval(const ocgcn_desc* d, const float* x, const float* adj, const ocgcn_params* p, void* workspace_v,
-                               float* out, void* stream) {
+static int encoder_forward_eval_impl(const ocgcn_desc* d, const GraphIn& gi, const ocgcn_params* p, void* workspace_v, float* out,
+                                     void* stream) {
   tl_launches = 0;
   EvalLayout lo;
   ST_TRY(make_eval_layout(d, &lo));
   ST_TRY(validate_params(d, p, false));
   if (!workspace_v || !out) return OCGCN_EINVAL;
   ST_TRY(check_device());
-  ST_TRY(check_device_ptr(x));
-  ST_TRY(check_device_ptr(adj));
+  ST_TRY(check_graph_in(gi));
   ST_TRY(check_device_ptr(out));
   if ((uintptr_t)workspace_v & 255) return OCGCN_EALIGN;
   char* ws = static_cast<char*>(workspace_v);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int L = d->L;
-  {
-    ProfScope prof(KK_ADJ_PACK, st);
-    CU_TRY(launch_chain(adj_pack_kernel, dim3(d->B), dim3(kThreads), (size_t)2 * d->N * lo.NW * 8, st, adj, (long long)d->adj_stride[0],
-                        (long long)d->adj_stride[1], (long long)d->adj_stride[2], d->N, lo.NW, reinterpret_cast<u64*>(ws + lo.rowmask),
-                        reinterpret_cast<u64*>(ws + lo.colmask), reinterpret_cast<unsigned*>(ws + lo.molflag),
-                        reinterpret_cast<uint4*>(ws + lo.nbr), reinterpret_cast<uint4*>(ws + lo.cnbr)));
-    LAUNCH_CHECK();
-  }
+  ST_TRY(launch_adj_pack(d, gi, lo.NW, reinterpret_cast<u64*>(ws + lo.rowmask), reinterpret_cast<u64*>(ws + lo.colmask),
+                         reinterpret_cast<unsigned*>(ws + lo.molflag), reinterpret_cast<uint4*>(ws + lo.nbr),
+                         reinterpret_cast<uint4*>(ws + lo.cnbr), st));
   WPrepJobs wj;
   memset(&wj, 0, sizeof(wj));
   int nj = 0;
@@ -872,8 +924,9 @@ int ocgcn_encoder_forward_eval(const ocgcn_desc* d, const float* x, const float*
   memset(&a, 0, sizeof(a));
   a.B = d->B; a.N = d->N; a.MT = lo.MT; a.ntiles = lo.tiles; a.L = L; a.E = d->E; a.eps = d->eps;
   for (int l = 0; l <= L; ++l) a.F[l] = d->F[l];
-  a.x = x; a.xs0 = d->x_stride[0]; a.xs1 = d->x_stride[1]; a.xs2 = d->x_stride[2];
-  a.adj = adj; a.as0 = d->adj_stride[0]; a.as1 = d->adj_stride[1]; a.as2 = d->adj_stride[2];
+  a.x = gi.x; a.xs0 = d->x_stride[0]; a.xs1 = d->x_stride[1]; a.xs2 = d->x_stride[2];
+  a.adj = gi.adj; a.as0 = d->adj_stride[0]; a.as1 = d->adj_stride[1]; a.as2 = d->adj_stride[2];
+  a.x_bits = gi.x_bits; a.adj_bits = gi.adj_bits; a.xw = (d->F[0] + 31) / 32; a.aw = (d->N + 31) / 32;
   a.nbr = reinterpret_cast<const uint4*>(ws + lo.nbr);
   for (int l = 0; l < L; ++l) {
     a.wimg[l] = ws + lo.Wf[l];
@@ -892,9 +945,23 @@ int ocgcn_encoder_forward_eval(const ocgcn_desc* d, const float* x, const float*
   return OCGCN_OK;
 }
 
-int ocgcn_encoder_backward(const ocgcn_desc* d, const float* grad_out, const float* x, const float* adj, const ocgcn_params* p,
-                           const ocgcn_grads* g, void* saved_v, void* scratch_v, void* stream) {
-  (void)x;
+int ocgcn_encoder_forward_eval(const ocgcn_desc* d, const float* x, const float* adj, const ocgcn_params* p, void* workspace_v,
+                               float* out, void* stream) {
+  const GraphIn gi = {x, adj, nullptr, nullptr};
+  return encoder_forward_eval_impl(d, gi, p, workspace_v, out, stream);
+}
+
+int ocgcn_encoder_forward_eval_compact(const ocgcn_desc* d, const uint32_t* x_bits, const uint32_t* adj_bits, const ocgcn_params* p,
+                                       void* workspace_v, float* out, void* stream) {
+  if (!x_bits || !adj_bits) return OCGCN_EINVAL;
+  const GraphIn gi = {nullptr, nullptr, x_bits, adj_bits};
+  return encoder_forward_eval_impl(d, gi, p, workspace_v, out, stream);
+}
+
+// adj == nullptr: the forward call was ocgcn_encoder_forward_compact (every molecule's adjacency is exactly 0/1, so the kernels walk the
+// packed records / masks in `saved` and never touch the dense tensor)
+static int encoder_backward_impl(const ocgcn_desc* d, const float* grad_out, const float* adj, const ocgcn_params* p,
+                                 const ocgcn_grads* g, void* saved_v, void* scratch_v, void* stream) {
   tl_launches = 0;
   Layout lo;
   ST_TRY(make_layout(d, false, &lo));
@@ -904,7 +971,7 @@ int ocgcn_encoder_backward(const ocgcn_desc* d, const float* grad_out, const flo
     if (!g->dW[l] || !g->dgamma[l] || !g->dbeta[l]) return OCGCN_EINVAL;
   ST_TRY(check_device());
   ST_TRY(check_device_ptr(grad_out));
-  ST_TRY(check_device_ptr(adj));
+  if (adj) ST_TRY(check_device_ptr(adj));
   if (((uintptr_t)saved_v & 255) || ((uintptr_t)scratch_v & 255)) return OCGCN_EALIGN;
   char* saved = static_cast<char*>(saved_v);
   char* scratch = static_cast<char*>(scratch_v);
@@ -969,6 +1036,18 @@ int ocgcn_encoder_backward(const ocgcn_desc* d, const float* grad_out, const flo
   return run_reduce(rj, st);   // every dW_l, db_l, dWd, dbd in one fixed-order reduction launch
 }
 
+int ocgcn_encoder_backward(const ocgcn_desc* d, const float* grad_out, const float* x, const float* adj, const ocgcn_params* p,
+                           const ocgcn_grads* g, void* saved_v, void* scratch_v, void* stream) {
+  (void)x;
+  if (!adj) return OCGCN_EINVAL;
+  return encoder_backward_impl(d, grad_out, adj, p, g, saved_v, scratch_v, stream);
+}
+
+int ocgcn_encoder_backward_compact(const ocgcn_desc* d, const float* grad_out, const ocgcn_params* p, const ocgcn_grads* g, void* saved_v,
+                                   void* scratch_v, void* stream) {
+  return encoder_backward_impl(d, grad_out, nullptr, p, g, saved_v, scratch_v, stream);
+}
+
 int ocgcn_layer_forward(const ocgcn_desc* d, const float* x, const float* adj, const ocgcn_params* p, void* saved_v, void* scratch_v,
                         float* y, void* stream) {
   tl_launches = 0;
@@ -980,11 +1059,12 @@ int ocgcn_layer_forward(const ocgcn_desc* d, const float* x, const float* adj, c
   ST_TRY(check_device_ptr(x));
   ST_TRY(check_device_ptr(adj));
   ST_TRY(check_device_ptr(y));
+  const GraphIn gi = {x, adj, nullptr, nullptr};
   if (((uintptr_t)saved_v & 255) || ((uintptr_t)scratch_v & 255)) return OCGCN_EALIGN;
   char* saved = static_cast<char*>(saved_v);
   char* scratch = static_cast<char*>(scratch_v);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  ST_TRY(run_adj_pack(d, lo, adj, saved, st));
+  ST_TRY(run_adj_pack(d, lo, gi, saved, st));
   if (lo.mm) {
     WPrepJobs wj;
     memset(&wj, 0, sizeof(wj));
@@ -993,7 +1073,7 @@ int ocgcn_layer_forward(const ocgcn_desc* d, const float* x, const float* adj, c
     if (d->need_dx) add_wprep(wj, nj, p->W[0], saved + lo.Wb[0], d->F[1], d->F[0], 1, 2);
     ST_TRY(run_wprep(wj, nj, st));
   }
-  ST_TRY(run_layer_forward(d, lo, x, adj, p, 0, saved, scratch, st));
+  ST_TRY(run_layer_forward(d, lo, gi, p, 0, saved, scratch, st));
   const int F = d->F[1];
   const float* stats = reinterpret_cast<const float*>(saved + lo.stats[0]);
   const size_t total = lo.rows * F;

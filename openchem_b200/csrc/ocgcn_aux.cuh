@@ -33,10 +33,14 @@ __device__ __forceinline__ uint4 build_record(const u64* mk, int NW, int N, bool
   return make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
 }
 
+// BITS: the adjacency arrives as the bit words of a compact batch (compact.py: bit (j & 31) of word adj_bits[(b*N + i)*AW + (j >> 5)],
+// AW = ceil(N/32)); the row masks are those words, and every entry is 0 or 1 by construction. Otherwise `adj` is dense fp32.
+template <bool BITS>
 __global__ void __launch_bounds__(kThreads) adj_pack_kernel(const float* __restrict__ adj, long long as0, long long as1,
-                                                            long long as2, int N, int NW, u64* __restrict__ rowmask,
-                                                            u64* __restrict__ colmask, unsigned* __restrict__ molflag,
-                                                            uint4* __restrict__ nbr, uint4* __restrict__ cnbr) {
+                                                            long long as2, const uint32_t* __restrict__ adj_bits, int N, int NW,
+                                                            u64* __restrict__ rowmask, u64* __restrict__ colmask,
+                                                            unsigned* __restrict__ molflag, uint4* __restrict__ nbr,
+                                                            uint4* __restrict__ cnbr) {
   pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64* sR = reinterpret_cast<u64*>(smem_raw);
@@ -44,6 +48,20 @@ __global__ void __launch_bounds__(kThreads) adj_pack_kernel(const float* __restr
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* ab = adj + (long long)b * as0;
   int nonbin = 0;
+  if (BITS) {
+    const int AW = (N + 31) >> 5;
+    const uint32_t* wb = adj_bits + (size_t)b * N * AW;
+    const uint32_t tail = (N & 31) ? ((1u << (N & 31)) - 1u) : 0xffffffffu;    // bits beyond column N - 1 are ignored
+    for (int idx = tid; idx < N * NW; idx += kThreads) {
+      const int i = idx / NW, w = idx - i * NW;
+      uint32_t lo = 0u, hi = 0u;
+      if (2 * w < AW) { lo = __ldg(&wb[i * AW + 2 * w]); if (2 * w == AW - 1) lo &= tail; }
+      if (2 * w + 1 < AW) { hi = __ldg(&wb[i * AW + 2 * w + 1]); if (2 * w + 1 == AW - 1) hi &= tail; }
+      const u64 m = (u64)lo | ((u64)hi << 32);
+      sR[idx] = m;
+      rowmask[(size_t)b * N * NW + idx] = m;
+    }
+  } else
   // Row masks. Rows in batches of four per warp: the 8*NW loads of a batch are in flight together (the kernel is latency-bound
   // otherwise). The ballots of a batch are parked in lanes 0 .. 4*NW-1 (slot = u*NW + w) and written with ONE store each to
   // shared and global memory per batch instead of one predicated lane-0 store per word.
@@ -113,6 +131,82 @@ __global__ void __launch_bounds__(kThreads) adj_pack_kernel(const float* __restr
     else cnbr[(size_t)b * N + (i - N)] = build_record(&sCm[(i - N) * NW], NW, N, !nonbin);
   }
   if (tid == 0) molflag[b] = nonbin ? 0u : 1u;
+}
+
+// N <= 64 (one 64-bit mask word per row, NW == 1): one WARP per molecule, no shared memory, no block barrier. Lane t owns rows /
+// columns t and t + 32: the row masks are read (bit words) or voted (dense fp32, eight rows = 16 loads in flight per lane), the column
+// masks are their bit transpose by 64 ballot pairs, and every lane builds the records of its own rows and columns. Same outputs as
+// adj_pack_kernel, bit for bit; the molecule-per-CTA kernel is latency-bound at these sizes (three barriers for ~1 KB of work).
+template <bool BITS>
+__global__ void __launch_bounds__(kThreads) adj_pack_warp_kernel(const float* __restrict__ adj, long long as0, long long as1,
+                                                                 long long as2, const uint32_t* __restrict__ adj_bits, int B, int N,
+                                                                 u64* __restrict__ rowmask, u64* __restrict__ colmask,
+                                                                 unsigned* __restrict__ molflag, uint4* __restrict__ nbr,
+                                                                 uint4* __restrict__ cnbr) {
+  pdl_wait();
+  const int lane = threadIdx.x & 31, b = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  if (b >= B) return;   // warp-uniform
+  u64 rm0 = 0, rm1 = 0;
+  int nonbin = 0;
+  if (BITS) {
+    const int AW = (N + 31) >> 5;
+    const uint32_t* wb = adj_bits + (size_t)b * N * AW;
+    const uint32_t tail = (N & 31) ? ((1u << (N & 31)) - 1u) : 0xffffffffu;    // bits beyond column N - 1 are ignored
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = lane + 32 * h;
+      u64 m = 0;
+      if (r < N) {
+        uint32_t lo = __ldg(&wb[r * AW]), hi = 0u;
+        if (AW == 1) lo &= tail;
+        else hi = __ldg(&wb[r * AW + 1]) & tail;
+        m = (u64)lo | ((u64)hi << 32);
+      }
+      if (h == 0) rm0 = m; else rm1 = m;
+    }
+  } else {
+    const float* ab = adj + (long long)b * as0;
+    const long long o0 = (long long)lane * as2, o1 = (long long)(lane + 32) * as2;
+    for (int i0 = 0; i0 < N; i0 += 8) {
+      float v0[8], v1[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u;
+        const float* rp = ab + (long long)i * as1;
+        v0[u] = (i < N && lane < N) ? __ldg(rp + o0) : 0.f;
+        v1[u] = (i < N && lane + 32 < N) ? __ldg(rp + o1) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u;
+        nonbin |= (fabsf(v0[u] * (v0[u] - 1.f)) + fabsf(v1[u] * (v1[u] - 1.f)) != 0.f);
+        const unsigned b0 = __ballot_sync(0xffffffffu, v0[u] != 0.f), b1 = __ballot_sync(0xffffffffu, v1[u] != 0.f);
+        const u64 m = (u64)b0 | ((u64)b1 << 32);
+        if (lane == (i & 31)) { if (i < 32) rm0 = m; else rm1 = m; }
+      }
+    }
+    nonbin = __any_sync(0xffffffffu, nonbin);
+  }
+  u64 cm0 = 0, cm1 = 0;
+#pragma unroll 8
+  for (int j = 0; j < 32; ++j) {
+    const unsigned c0 = __ballot_sync(0xffffffffu, (unsigned)(rm0 >> j) & 1u), c1 = __ballot_sync(0xffffffffu, (unsigned)(rm1 >> j) & 1u);
+    const unsigned d0 = __ballot_sync(0xffffffffu, (unsigned)(rm0 >> (j + 32)) & 1u), d1 = __ballot_sync(0xffffffffu, (unsigned)(rm1 >> (j + 32)) & 1u);
+    if (lane == j) { cm0 = (u64)c0 | ((u64)c1 << 32); cm1 = (u64)d0 | ((u64)d1 << 32); }
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = lane + 32 * h;
+    if (r < N) {
+      const u64 rmask = h ? rm1 : rm0, cmask = h ? cm1 : cm0;
+      const size_t o = (size_t)b * N + r;
+      rowmask[o] = rmask;
+      colmask[o] = cmask;
+      nbr[o] = build_record(&rmask, 1, N, !nonbin);
+      cnbr[o] = build_record(&cmask, 1, N, !nonbin);
+    }
+  }
+  if (lane == 0) molflag[b] = nonbin ? 0u : 1u;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -57,6 +57,8 @@ struct TileArgs {
   // producer inputs
   const float* in0;  // P_X: x | P_MID/P_RO: Zprev | P_DZ: dY | P_DU: D
   long long xs0, xs1, xs2;
+  const uint32_t* x_bits;  // P_X, compact batch: bit (c & 31) of word x_bits[(mol*N + i)*xw + (c >> 5)] is x[mol,i,c] (in0 is null)
+  int xw;                  // words per row of x_bits = ceil(F0/32)
   const float* in1;   // P_DZ: Z | P_DU: dO
   const float* in2;   // P_DU: O
   const float* vec0;  // P_MID/P_RO: scale | P_DZ: g = gamma*invstd
@@ -98,6 +100,38 @@ struct TileArgs {
   // Zprev arrives through the kernel's tensor map (cp.async.bulk.tensor) instead of per-thread loads
   int use_tma;
 };
+
+// x[mol, i, c] and x[mol, i, c + 1] (c even) of the first layer's input: from the dense fp32 tensor, or from the bit words of a
+// compact batch (compact.py; the two bits share a word). `second` = channel c + 1 exists.
+__device__ __forceinline__ float2 load_x_pair(const float* __restrict__ x, long long xs0, long long xs1, long long xs2,
+                                              const uint32_t* __restrict__ x_bits, int xw, int N, long long mol, int i, int c, bool second) {
+  if (x_bits) {
+    const uint32_t w = __ldg(&x_bits[((size_t)mol * N + i) * xw + (c >> 5)]) >> (c & 31);
+    return make_float2((float)(w & 1u), second ? (float)((w >> 1) & 1u) : 0.f);
+  }
+  const float* px = x + mol * xs0 + (long long)i * xs1 + (long long)c * xs2;
+  float2 v;
+  v.x = __ldg(px);
+  v.y = second ? __ldg(px + xs2) : 0.f;
+  return v;
+}
+
+// one adjacency row adj[mol, i, :] of a dense fp32 tensor, or of the bit words of a compact batch (exact 0/1 entries)
+struct AdjRow {
+  const float* p;
+  long long s;
+  const uint32_t* w;
+};
+__device__ __forceinline__ AdjRow adj_row(const float* __restrict__ adj, long long as0, long long as1, long long as2,
+                                          const uint32_t* __restrict__ adj_bits, int aw, int N, long long mol, int i) {
+  AdjRow r;
+  if (adj_bits) { r.p = nullptr; r.s = 0; r.w = adj_bits + ((size_t)mol * N + i) * aw; }
+  else { r.p = adj + mol * as0 + (long long)i * as1; r.s = as2; r.w = nullptr; }
+  return r;
+}
+__device__ __forceinline__ float adj_at(const AdjRow& r, int j) {
+  return r.w ? (float)((__ldg(&r.w[j >> 5]) >> (j & 31)) & 1u) : __ldg(&r.p[(long long)j * r.s]);
+}
 
 // ---- 16-byte neighbour record of one adjacency row (built once per forward by adj_pack_kernel) ----------------
 // byte 0: count (bits 0-3, <= kMaxNbr) | 0x20 if the molecule's adjacency is exactly 0/1 | 0x40 if the row has a

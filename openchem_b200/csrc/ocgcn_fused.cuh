@@ -30,6 +30,28 @@ constexpr int kFusedBS = KC + 4;                    // padded row of the T / H c
 constexpr int kFusedRows = 129;                     // 128 tile rows + the neutral dummy row of the padded neighbour records
 constexpr int kFusedStage = 128 * (128 + 4);        // floats of the readout staging tile
 
+// layer 0 of a compact batch: x[mol, i, c], x[mol, i, c + 1] (c = 2*lane even) of this warp's rows from the bit words. All words are
+// requested first and converted afterwards, so the loads of a warp's rows overlap.
+template <int RPW_, int NWARP_, int BS_>
+__device__ __forceinline__ void stage_x_words(const uint32_t* __restrict__ x_bits, int xw, int N, long long mol0, const uint4* sRec, int rows,
+                                              int warp, int lane, int c, bool v0, bool v1, float* sH) {
+  uint32_t wv[RPW_];
+#pragma unroll
+  for (int q = 0; q < RPW_; ++q) {
+    const int r = warp + q * NWARP_;
+    wv[q] = 0u;
+    if (r < rows && v0) {
+      const int m = rec_m(sRec[r]), i = r - m * N;
+      wv[q] = __ldg(&x_bits[((size_t)(mol0 + m) * N + i) * xw + (c >> 5)]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < RPW_; ++q) {
+    const uint32_t w = wv[q] >> (c & 31);
+    *reinterpret_cast<float2*>(&sH[(warp + q * NWARP_) * BS_ + 2 * lane]) = make_float2((float)(w & 1u), v1 ? (float)((w >> 1) & 1u) : 0.f);
+  }
+}
+
 struct FusedEvalArgs {
   int B, N, MT, ntiles, L;
   int F[kFusedMaxLayers + 1];                       // F[0] = input width, F[l+1] = width of layer l; all <= 128
@@ -39,6 +61,9 @@ struct FusedEvalArgs {
   long long xs0, xs1, xs2;
   const float* adj;                                 // dense adjacency (rows that do not fit a neighbour record)
   long long as0, as1, as2;
+  const uint32_t* x_bits;                           // compact batch (compact.py): bit words in place of x / adj (then both null)
+  const uint32_t* adj_bits;
+  int xw, aw;                                       // words per row: ceil(F[0]/32), ceil(N/32)
   const uint4* nbr;                                 // [B*N] row records
   const void* wimg[kFusedMaxLayers + 1];            // forward weight images (wprep_kernel), [L] = readout
   const float* bias[kFusedMaxLayers + 1];           // b_l or null, [L] = bd
@@ -189,17 +214,19 @@ __global__ void __launch_bounds__(kFusedThreads, 1) encoder_eval_fused_kernel(co
           // H = x: strided scalar loads (two adjacent channels per lane), zero beyond the valid rows / channels
           const int c = k0 + 2 * lane;
           const bool v0 = c < K, v1 = c + 1 < K;
+          if (a.x_bits) {
+            stage_x_words<RPW, NWARP, BS>(a.x_bits, a.xw, N, mol0, sRec, rows, warp, lane, c, v0, v1, sH);
+          } else {
 #pragma unroll
-          for (int q = 0; q < RPW; ++q) {
-            const int r = warp + q * NWARP;
-            float2 v = make_float2(0.f, 0.f);
-            if (r < rows && v0) {
-              const int m = rec_m(sRec[r]), i = r - m * N;
-              const float* px = a.x + (long long)(mol0 + m) * a.xs0 + (long long)i * a.xs1 + (long long)c * a.xs2;
-              v.x = __ldg(px);
-              if (v1) v.y = __ldg(px + a.xs2);
+            for (int q = 0; q < RPW; ++q) {
+              const int r = warp + q * NWARP;
+              float2 v = make_float2(0.f, 0.f);
+              if (r < rows && v0) {
+                const int m = rec_m(sRec[r]), i = r - m * N;
+                v = load_x_pair(a.x, a.xs0, a.xs1, a.xs2, nullptr, 0, N, mol0 + m, i, c, v1);
+              }
+              *reinterpret_cast<float2*>(&sH[r * BS + 2 * lane]) = v;
             }
-            *reinterpret_cast<float2*>(&sH[r * BS + 2 * lane]) = v;
           }
           __syncthreads();
         } else {
@@ -219,12 +246,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) encoder_eval_fused_kernel(co
                   for (int e = 0; e < 4; ++e) bq[e] = fmaxf(bq[e], 0.f);
                 }
               } else {   // dense scan in the reference's candidate order (float adjacency, or more neighbours than a record holds)
-                const float* arow = a.adj + (long long)(mol0 + rec_m(rec)) * a.as0 + (long long)(r - mb) * a.as1;
-                const float a00 = __ldg(&arow[0]);
+                const AdjRow arow = adj_row(a.adj, a.as0, a.as1, a.as2, a.adj_bits, a.aw, N, mol0 + rec_m(rec), r - mb);
+                const float a00 = adj_at(arow, 0);
                 const float4 t0 = *reinterpret_cast<const float4*>(&bufT[mb * BS + 4 * hl]);
                 bq[0] = a00 * t0.x; bq[1] = a00 * t0.y; bq[2] = a00 * t0.z; bq[3] = a00 * t0.w;
                 for (int j = 1; j < N; ++j) {
-                  const float aj = __ldg(&arow[(long long)j * a.as2]);
+                  const float aj = adj_at(arow, j);
                   const float4 t = *reinterpret_cast<const float4*>(&bufT[(mb + j) * BS + 4 * hl]);
                   bq[0] = fmaxf(bq[0], aj * t.x); bq[1] = fmaxf(bq[1], aj * t.y);
                   bq[2] = fmaxf(bq[2], aj * t.z); bq[3] = fmaxf(bq[3], aj * t.w);
@@ -250,9 +277,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) encoder_eval_fused_kernel(co
                 s4 = rec_sum4_padded<BS>(rec, &sH[4 * hl]);
               } else {
                 const int mb = rec_m(rec) * N;
-                const float* arow = a.adj + (long long)(mol0 + rec_m(rec)) * a.as0 + (long long)(r - mb) * a.as1;
+                const AdjRow arow = adj_row(a.adj, a.as0, a.as1, a.as2, a.adj_bits, a.aw, N, mol0 + rec_m(rec), r - mb);
                 for (int j = 0; j < N; ++j) {
-                  const float aj = __ldg(&arow[(long long)j * a.as2]);
+                  const float aj = adj_at(arow, j);
                   const float4 hv = *reinterpret_cast<const float4*>(&sH[(mb + j) * BS + 4 * hl]);
                   s4.x = fmaf(aj, hv.x, s4.x); s4.y = fmaf(aj, hv.y, s4.y); s4.z = fmaf(aj, hv.z, s4.z); s4.w = fmaf(aj, hv.w, s4.w);
                 }
@@ -561,17 +588,19 @@ __global__ void __launch_bounds__(kFusedThreads, 1) encoder_train_fused_kernel(c
         if (l == 0) {
           const int c = k0 + 2 * lane;
           const bool v0 = c < K, v1 = c + 1 < K;
+          if (a.x_bits) {
+            stage_x_words<RPW, NWARP, BS>(a.x_bits, a.xw, N, mol0, sRec, rows, warp, lane, c, v0, v1, sH);
+          } else {
 #pragma unroll
-          for (int q = 0; q < RPW; ++q) {
-            const int r = warp + q * NWARP;
-            float2 v = make_float2(0.f, 0.f);
-            if (r < rows && v0) {
-              const int m = rec_m(sRec[r]), i = r - m * N;
-              const float* px = a.x + (long long)(mol0 + m) * a.xs0 + (long long)i * a.xs1 + (long long)c * a.xs2;
-              v.x = __ldg(px);
-              if (v1) v.y = __ldg(px + a.xs2);
+            for (int q = 0; q < RPW; ++q) {
+              const int r = warp + q * NWARP;
+              float2 v = make_float2(0.f, 0.f);
+              if (r < rows && v0) {
+                const int m = rec_m(sRec[r]), i = r - m * N;
+                v = load_x_pair(a.x, a.xs0, a.xs1, a.xs2, nullptr, 0, N, mol0 + m, i, c, v1);
+              }
+              *reinterpret_cast<float2*>(&sH[r * BS + 2 * lane]) = v;
             }
-            *reinterpret_cast<float2*>(&sH[r * BS + 2 * lane]) = v;
           }
           __syncthreads();
         } else {
@@ -597,13 +626,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) encoder_train_fused_kernel(c
                   }
                 }
               } else {   // dense scan in the reference's candidate order
-                const float* arow = a.adj + (long long)(mol0 + rec_m(rec)) * a.as0 + (long long)(r - mb) * a.as1;
-                const float a00 = __ldg(&arow[0]);
+                const AdjRow arow = adj_row(a.adj, a.as0, a.as1, a.as2, a.adj_bits, a.aw, N, mol0 + rec_m(rec), r - mb);
+                const float a00 = adj_at(arow, 0);
                 const float4 t0 = *reinterpret_cast<const float4*>(&bufT[mb * BS + 4 * hl]);
                 bq[0] = a00 * t0.x; bq[1] = a00 * t0.y; bq[2] = a00 * t0.z; bq[3] = a00 * t0.w;
                 aq[0] = aq[1] = aq[2] = aq[3] = mb;
                 for (int j = 1; j < N; ++j) {
-                  const float aj = __ldg(&arow[(long long)j * a.as2]);
+                  const float aj = adj_at(arow, j);
                   const float4 tv = *reinterpret_cast<const float4*>(&bufT[(mb + j) * BS + 4 * hl]);
                   const float cnd[4] = {aj * tv.x, aj * tv.y, aj * tv.z, aj * tv.w};
 #pragma unroll
@@ -632,9 +661,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) encoder_train_fused_kernel(c
                 s4 = rec_sum4_padded<BS>(rec, &sH[4 * hl]);
               } else {
                 const int mb = rec_m(rec) * N;
-                const float* arow = a.adj + (long long)(mol0 + rec_m(rec)) * a.as0 + (long long)(r - mb) * a.as1;
+                const AdjRow arow = adj_row(a.adj, a.as0, a.as1, a.as2, a.adj_bits, a.aw, N, mol0 + rec_m(rec), r - mb);
                 for (int j = 0; j < N; ++j) {
-                  const float aj = __ldg(&arow[(long long)j * a.as2]);
+                  const float aj = adj_at(arow, j);
                   const float4 hv = *reinterpret_cast<const float4*>(&sH[(mb + j) * BS + 4 * hl]);
                   s4.x = fmaf(aj, hv.x, s4.x); s4.y = fmaf(aj, hv.y, s4.y); s4.z = fmaf(aj, hv.z, s4.z); s4.w = fmaf(aj, hv.w, s4.w);
                 }

@@ -493,6 +493,29 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
 
       // =========================== PRODUCER ===========================
       if (PROD == P_X) {
+        if (a.x_bits) {
+          // compact batch: the row's bit word now, shift + convert after the wait (a use inside the loop would serialise the loads)
+#pragma unroll
+          for (int h = 0; h < RPW / 8; ++h) {
+            uint32_t wv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int r = warp + (h * 8 + q) * NWARP;
+              wv[q] = 0u;
+              if (r < rows && v0) {
+                const int m = rec_m(sRec[r]), i = r - m * N;
+                wv[q] = __ldg(&a.x_bits[((size_t)(mol0 + m) * N + i) * a.xw + (c >> 5)]);
+              }
+            }
+            if (h == 0) chunk_sync();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint32_t w = wv[q] >> (c & 31);     // c is even: channels c and c + 1 share the word
+              *reinterpret_cast<float2*>(&buf1[(warp + (h * 8 + q) * NWARP) * BS + 2 * lane]) =
+                  make_float2((float)(w & 1u), v1 ? (float)((w >> 1) & 1u) : 0.f);
+            }
+          }
+        } else {
 #pragma unroll
         for (int h = 0; h < RPW / 8; ++h) {
           float2 v[8];
@@ -511,6 +534,7 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float2*>(&buf1[(warp + (h * 8 + q) * NWARP) * BS + 2 * lane]) = v[q];
+        }
         }
         if (MM && warp == 0) *reinterpret_cast<float2*>(&buf1[TR * BS + 2 * lane]) = make_float2(0.f, 0.f);   // dummy row of the padded records
         __syncthreads();

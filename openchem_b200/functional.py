@@ -70,11 +70,23 @@ class LayerSpec:
         self.nbt = nbt
 
 
+def is_compact_pair(x, adj):
+    """(x, adj) are the int32 bit words of an openchem_b200.compact.CompactGraphBatch rather than dense fp32 tensors."""
+    return x.dtype == torch.int32 and adj.dtype == torch.int32
+
+
 def _make_desc(spec, x, adj, need_dx=False):
     d = _lib.Desc()
-    B, N, F0 = x.shape
-    if adj.dim() != 3 or adj.shape[0] != B or adj.shape[1] != N or adj.shape[2] != N:
-        raise RuntimeError("openchem_b200: adj must be (B,N,N) matching x (B,N,F); got %s and %s" % (tuple(adj.shape), tuple(x.shape)))
+    if is_compact_pair(x, adj):      # bit words (B,N,ceil(F0/32)) and (B,N,ceil(N/32)); the strides in the descriptor are not used
+        B, N, XW = x.shape
+        F0 = spec.widths[0]
+        if tuple(adj.shape) != (B, N, (N + 31) // 32) or XW != (F0 + 31) // 32 or not x.is_contiguous() or not adj.is_contiguous():
+            raise RuntimeError("openchem_b200: compact batch needs contiguous x_bits (B,N,ceil(F0/32)) and adj_bits (B,N,ceil(N/32)) "
+                               "with F0 = %d; got %s and %s" % (F0, tuple(x.shape), tuple(adj.shape)))
+    else:
+        B, N, F0 = x.shape
+        if adj.dim() != 3 or adj.shape[0] != B or adj.shape[1] != N or adj.shape[2] != N:
+            raise RuntimeError("openchem_b200: adj must be (B,N,N) matching x (B,N,F); got %s and %s" % (tuple(adj.shape), tuple(x.shape)))
     if F0 != spec.widths[0]:
         raise RuntimeError("openchem_b200: x has %d features, layer expects %d" % (F0, spec.widths[0]))
     d.B, d.N, d.L, d.E = B, N, len(spec.widths) - 1, spec.encoder_dim
@@ -88,6 +100,9 @@ def _make_desc(spec, x, adj, need_dx=False):
     for i in range(3):
         d.x_stride[i] = x.stride(i)
         d.adj_stride[i] = adj.stride(i)
+    if is_compact_pair(x, adj):
+        for i, (sx, sa) in enumerate(((N * F0, N * N), (F0, N), (1, 1))):
+            d.x_stride[i], d.adj_stride[i] = sx, sa
     return d
 
 
@@ -159,6 +174,7 @@ def fused_eval_tiles(desc):
 
 SAVED_KINDS = {"Z": (0, torch.float32), "argmax": (1, torch.uint8), "S": (2, torch.float32), "stats": (3, torch.float32),
                "rowmask": (4, torch.int64), "molflag": (5, torch.int32)}
+compact_direct = {"on": True}    # GraphCNNEncoder.forward(CompactGraphBatch): feed the bit words to the kernels (off: expand to dense first)
 debug_keep = {"on": False, "saved": None, "desc": None}     # tests only: keep the last forward's saved buffer
 
 
@@ -173,7 +189,8 @@ def saved_tensor(kind, layer=0):
 
 class EncoderFn(torch.autograd.Function):
     """GraphCNNEncoder.forward (gcn_encoder.py:38-53) as ONE autograd node. inputs: x, adj, spec, then per layer
-    W, b, gamma, beta (b may be None) and finally Wd, bd."""
+    W, b, gamma, beta (b may be None) and finally Wd, bd. (x, adj) may also be the int32 bit words of a compact batch
+    (compact.CompactGraphBatch.x_bits / .adj_bits): the ocgcn_encoder_*_compact entry points then read the words directly."""
 
     @staticmethod
     def forward(ctx, x, adj, spec, *tensors):
@@ -184,7 +201,9 @@ class EncoderFn(torch.autograd.Function):
             raise RuntimeError("openchem_b200: the fused encoder treats x and adj as data (no gradient); "
                                "use GraphConvolution layers if you need d/dx")
         L = len(spec.widths) - 1
-        x, adj = _f32(x), _f32(adj)
+        compact = is_compact_pair(x, adj)
+        if not compact:
+            x, adj = _f32(x), _f32(adj)
         ctx.sinks = _sinks_for(tensors)
         tensors = [None if t is None else t.detach().contiguous() for t in tensors]
         Ws, bs, gammas, betas = tensors[0:4 * L:4], tensors[1:4 * L:4], tensors[2:4 * L:4], tensors[3:4 * L:4]
@@ -205,15 +224,17 @@ class EncoderFn(torch.autograd.Function):
                     and lib.ocgcn_query_eval_workspace(ctypes.byref(desc), ctypes.byref(ebytes)) == 0
                     and fused_eval_tiles(desc) <= fused_eval["max_tiles"]):
                 ws = _alloc(ebytes.value, x.device)
-                _lib.check(lib.ocgcn_encoder_forward_eval(ctypes.byref(desc), x.data_ptr(), adj.data_ptr(), ctypes.byref(params),
-                                                          ws.data_ptr(), out.data_ptr(), _stream_ptr(x.device)))
+                fwd_eval = lib.ocgcn_encoder_forward_eval_compact if compact else lib.ocgcn_encoder_forward_eval
+                _lib.check(fwd_eval(ctypes.byref(desc), x.data_ptr(), adj.data_ptr(), ctypes.byref(params),
+                                    ws.data_ptr(), out.data_ptr(), _stream_ptr(x.device)))
                 _count(lib)
             else:
                 sbytes, cbytes = _workspaces(desc, x.device)
                 saved = _alloc(sbytes, x.device)
                 scratch = _alloc(cbytes, x.device)
-                _lib.check(lib.ocgcn_encoder_forward(ctypes.byref(desc), x.data_ptr(), adj.data_ptr(), ctypes.byref(params),
-                                                     saved.data_ptr(), scratch.data_ptr(), out.data_ptr(), _stream_ptr(x.device)))
+                fwd = lib.ocgcn_encoder_forward_compact if compact else lib.ocgcn_encoder_forward
+                _lib.check(fwd(ctypes.byref(desc), x.data_ptr(), adj.data_ptr(), ctypes.byref(params),
+                               saved.data_ptr(), scratch.data_ptr(), out.data_ptr(), _stream_ptr(x.device)))
                 _count(lib)
         if debug_keep["on"]:
             debug_keep["saved"], debug_keep["desc"] = saved, desc
@@ -246,9 +267,9 @@ class EncoderFn(torch.autograd.Function):
                 sbytes, ctx.cbytes = _workspaces(desc, x.device)
                 saved = _alloc(sbytes, x.device)
                 tmp = torch.empty((x.shape[0], spec.encoder_dim), dtype=torch.float32, device=x.device)
-                _lib.check(lib.ocgcn_encoder_forward(ctypes.byref(desc), x.data_ptr(), adj.data_ptr(), ctypes.byref(params),
-                                                     saved.data_ptr(), _alloc(ctx.cbytes, x.device).data_ptr(), tmp.data_ptr(),
-                                                     _stream_ptr(x.device)))
+                fwd = lib.ocgcn_encoder_forward_compact if is_compact_pair(x, adj) else lib.ocgcn_encoder_forward
+                _lib.check(fwd(ctypes.byref(desc), x.data_ptr(), adj.data_ptr(), ctypes.byref(params),
+                               saved.data_ptr(), _alloc(ctx.cbytes, x.device).data_ptr(), tmp.data_ptr(), _stream_ptr(x.device)))
                 _count(lib)
             grads = _lib.Grads()
             outs = []
@@ -262,9 +283,14 @@ class EncoderFn(torch.autograd.Function):
             gWd, gbd = _grad_buffer(Wd, sk, 4 * L), _grad_buffer(bd, sk, 4 * L + 1)
             grads.dWd, grads.dbd = gWd.data_ptr(), gbd.data_ptr()
             scratch = _alloc(ctx.cbytes, x.device)
-            _lib.check(lib.ocgcn_encoder_backward(ctypes.byref(desc), grad_out.data_ptr(), x.data_ptr(), adj.data_ptr(),
-                                                  ctypes.byref(params), ctypes.byref(grads), saved.data_ptr(), scratch.data_ptr(),
-                                                  _stream_ptr(x.device)))
+            if is_compact_pair(x, adj):
+                _lib.check(lib.ocgcn_encoder_backward_compact(ctypes.byref(desc), grad_out.data_ptr(), ctypes.byref(params),
+                                                              ctypes.byref(grads), saved.data_ptr(), scratch.data_ptr(),
+                                                              _stream_ptr(x.device)))
+            else:
+                _lib.check(lib.ocgcn_encoder_backward(ctypes.byref(desc), grad_out.data_ptr(), x.data_ptr(), adj.data_ptr(),
+                                                      ctypes.byref(params), ctypes.byref(grads), saved.data_ptr(), scratch.data_ptr(),
+                                                      _stream_ptr(x.device)))
             _count(lib)
         return (None, None, None, *outs, gWd, gbd)
 

@@ -15,7 +15,7 @@ from __future__ import annotations
 import torch.nn as nn
 
 from ...compact import CompactGraphBatch
-from ...functional import EncoderFn, LayerSpec
+from ...functional import EncoderFn, LayerSpec, compact_direct
 from ...layers.gcn import GraphConvolution
 from ...utils import check_params
 from .openchem_encoder import OpenChemEncoder
@@ -47,10 +47,12 @@ class GraphCNNEncoder(OpenChemEncoder):
         return {"n_layers": int, "hidden_size": list}
 
     def forward(self, inp):
-        if isinstance(inp, CompactGraphBatch):   # bit-packed batch: rebuilt as dense fp32 on the device (bit-exact)
-            x, adj = inp.expand()
+        if isinstance(inp, CompactGraphBatch):
+            # bit-packed batch: the kernels read the words themselves (ocgcn_encoder_*_compact); `compact_direct["on"] = False`
+            # rebuilds the dense fp32 tensors on the device first (bit-exact, same results)
+            x, adj = (inp.x_bits.contiguous(), inp.adj_bits.contiguous()) if compact_direct["on"] else inp.expand()
         else:
-            x, adj = inp[0], inp[1]
+            x, adj = inp[0], inp[1]           # dense fp32 tensors, or a (x_bits, adj_bits) pair of int32 bit words
         gcs = list(self.graph_convolutions)
         bn0 = gcs[0].bn
         spec = LayerSpec(self.hidden_size, self.encoder_dim, self.precision, self.training, gcs[0].bias is not None,

@@ -185,9 +185,15 @@ class TrainStep:
                 dst.copy_(src, non_blocking=True)
 
     def load_compact(self, batch):
-        """Expand a device CompactGraphBatch (openchem_b200.compact) straight into the static dense inputs: no dense
-        staging copy, and only the bit words crossed the host link."""
-        batch.expand(out=(self.inputs[0], self.inputs[1]))
+        """Feed a device CompactGraphBatch (openchem_b200.compact); only the bit words crossed the host link.
+        A step built on a compact example batch (`example_batch = (x_bits, adj_bits, labels)`, int32 words) keeps the words as
+        its static inputs and the captured kernels read them directly (ocgcn_encoder_forward_compact): three small copies.
+        A step built on dense tensors gets the batch expanded straight into its static dense inputs (no staging copy)."""
+        if self.inputs[0].dtype == torch.int32:
+            self.inputs[0].copy_(batch.x_bits, non_blocking=True)
+            self.inputs[1].copy_(batch.adj_bits, non_blocking=True)
+        else:
+            batch.expand(out=(self.inputs[0], self.inputs[1]))
         if batch.labels is not None:
             self.inputs[2].copy_(batch.labels, non_blocking=True)
 

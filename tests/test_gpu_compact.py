@@ -72,24 +72,64 @@ def test_device_pack_rejects_non_binary():
         compact.pack_graph_batch_device(torch.from_numpy(x).to(_dev()), torch.from_numpy(adj).to(_dev()))
 
 
+def _star_batch(B, N, F0, seed):
+    """Molecules whose atom 0 is bonded to every other atom: more neighbours than a 16-byte record holds, so those rows take the
+    kernels' mask / dense fallback paths (which read the bit words themselves on the compact route)."""
+    g = make_graph_batch(B, N, F0, occupancy="full", seed=seed)
+    g["adj"][:, 0, :] = 1.0
+    g["adj"][:, :, 0] = 1.0
+    return g
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_encoder_accepts_compact_batch_with_identical_results(precision):
-    g, p, cfg = _case(B=12, N=30, F0=33, hidden=(64, 64), E=32, seed=2)
+@pytest.mark.parametrize("shape", ["small", "odd_words", "many_tiles", "star"])
+@pytest.mark.parametrize("training", [True, False])
+def test_encoder_reads_compact_words_with_identical_results(precision, shape, training):
+    """GraphCNNEncoder.forward(CompactGraphBatch) feeds the bit words to ocgcn_encoder_*_compact (no dense tensors): outputs and
+    every gradient are bit-identical to the dense route, for the cooperative fused forward (few tiles), the layer-by-layer kernels
+    (> 148 tiles), the single-kernel eval forward, word counts that are odd, and rows that overflow a neighbour record."""
+    from openchem_b200 import functional
+    B, N, F0, hidden, E = {"small": (12, 30, 33, (64, 64), 32), "odd_words": (9, 70, 75, (64, 128), 64),
+                           "many_tiles": (330, 64, 64, (128, 128), 128), "star": (10, 40, 33, (64, 64), 32)}[shape]
+    g, p, cfg = _case(B=B, N=N, F0=F0, hidden=hidden, E=E, seed=2)
+    if shape == "star":
+        g = _star_batch(B, N, F0, 3)
     dev = _dev()
-    enc = build_encoder(cfg, p, dev, precision=precision).train()
+    enc = build_encoder(cfg, p, dev, precision=precision)
+    enc.train(training)
     x, adj = torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["adj"]).to(dev)
     state = {k: v.clone() for k, v in enc.state_dict().items()}
     out_d = enc((x, adj))
     out_d.sum().backward()
     gd = [q.grad.clone() for q in enc.parameters()]
-    enc.load_state_dict(state)
-    enc.zero_grad()
+    stats_d = {k: v.clone() for k, v in enc.state_dict().items() if "running" in k}
     cb = compact.pack_graph_batch(g["x"], g["adj"]).to(dev)
-    out_c = enc(cb)
-    out_c.sum().backward()
-    assert torch.equal(out_c, out_d)
-    for a, b in zip(gd, [q.grad for q in enc.parameters()]):
-        assert torch.equal(a, b)
+    for direct, inp in ((True, cb), (True, (cb.x_bits, cb.adj_bits)), (False, cb)):
+        enc.load_state_dict(state)
+        enc.zero_grad()
+        functional.compact_direct["on"] = direct
+        try:
+            n0 = functional.launch_counter["n"]
+            out_c = enc(inp)
+            out_c.sum().backward()
+        finally:
+            functional.compact_direct["on"] = True
+        assert functional.launch_counter["n"] > n0
+        assert torch.equal(out_c, out_d)
+        for a, b in zip(gd, [q.grad for q in enc.parameters()]):
+            assert torch.equal(a, b)
+        for k, v in stats_d.items():
+            assert torch.equal(enc.state_dict()[k], v), k
+
+
+def test_compact_route_rejects_mismatched_words():
+    g, p, cfg = _case(B=4, N=30, F0=33, hidden=(32,), E=16, seed=2)
+    enc = build_encoder(cfg, p, _dev(), precision="bf16")
+    cb = compact.pack_graph_batch(g["x"], g["adj"]).to(_dev())
+    with pytest.raises(RuntimeError, match="compact batch needs"):
+        enc((cb.x_bits[:, :, :1], cb.adj_bits))          # F0 = 33 needs two words per row
+    with pytest.raises(RuntimeError, match="compact batch needs"):
+        enc((cb.x_bits, cb.adj_bits[:, :-1]))
 
 
 class _Model(torch.nn.Module):
@@ -117,6 +157,38 @@ def test_train_step_load_compact_equals_dense_load():
         assert step.graph is not None, step.graph_error
         run = []
         for data in (g2, g):
+            if use_compact:
+                step.load_compact(compact.pack_graph_batch(data["x"], data["adj"], y).to(dev))
+                run.append(float(step()))
+            else:
+                run.append(float(step(torch.from_numpy(data["x"]).to(dev), torch.from_numpy(data["adj"]).to(dev), y.to(dev))))
+        losses.append(run)
+    assert losses[0] == losses[1], losses
+
+
+def test_train_step_built_on_compact_words_equals_dense_step():
+    """A TrainStep whose static inputs ARE the bit words (captured ocgcn_encoder_forward_compact / _backward_compact) takes the same
+    steps, bit for bit, as the dense one."""
+    from openchem_b200.step import TrainStep
+    g, p, cfg = _case(16, 20, 16, (32,), 16, seed=4)
+    g2 = make_graph_batch(16, 20, 16, seed=9)
+    dev = _dev()
+    y = torch.from_numpy(np.random.RandomState(1).randn(16, 1).astype(np.float32))
+    losses = []
+    for use_compact in (False, True):
+        torch.manual_seed(0)
+        model = _Model(build_encoder(cfg, p, dev, precision="bf16"), 16).to(dev).train()
+        if use_compact:
+            c0 = compact.pack_graph_batch(g["x"], g["adj"], y).to(dev)
+            ex = (c0.x_bits, c0.adj_bits, c0.labels)
+        else:
+            ex = (torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["adj"]).to(dev), y.to(dev))
+        step = TrainStep(model, torch.nn.MSELoss(), lambda ps: torch.optim.Adam(ps, lr=1e-3, fused=True, capturable=True), ex,
+                         use_graph=True, warmup=1)
+        assert step.graph is not None, step.graph_error
+        assert (step.inputs[0].dtype == torch.int32) == use_compact
+        run = []
+        for data in (g2, g, g2):
             if use_compact:
                 step.load_compact(compact.pack_graph_batch(data["x"], data["adj"], y).to(dev))
                 run.append(float(step()))

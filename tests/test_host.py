@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ocgcn_abi_version() == 4
+    assert lib.ocgcn_abi_version() == 5
     assert lib.ocgcn_status_string(0) == b"ok"
     assert b"unsupported" in lib.ocgcn_status_string(2)
 
