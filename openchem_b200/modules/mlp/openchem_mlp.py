@@ -11,6 +11,7 @@ reference's configs use, recognised by name), inactive dropout (p = 0 or eval mo
 reference). Anything else raises at construction / call time: there is no silent fallback.
 
 `fused_head_loss(mlp, inp, target, criterion)` additionally runs nn.MSELoss() or MultitaskLoss inside the last kernel.
+`OpenChemMLPSimple` (:64-111: Linear -> activation per layer, no BatchNorm) is mirrored on the same kernels.
 """
 from __future__ import annotations
 
@@ -91,6 +92,52 @@ class OpenChemMLP(nn.Module):
 
     def forward(self, inp):
         return HeadFn.apply(inp, None, self._spec(), *self._tensors())
+
+
+class OpenChemMLPSimple(nn.Module):
+    """OpenChemMLPSimple with the reference's surface (openchem/modules/mlp/openchem_mlp.py:64-111): every layer is
+    Linear -> activation[i], no BatchNorm, no dropout; optional 'init': 'xavier_uniform' (gain of relu) applied to every Linear in
+    module order (:86-94). Same attributes and `state_dict` keys (`layers.{i}.weight/bias`). Each layer runs as one head kernel per
+    direction (a one-layer ocgcn_head_forward / ocgcn_head_backward call whose epilogue applies the activation)."""
+
+    def __init__(self, params):
+        super().__init__()
+        check_params(params, self.get_required_params(), self.get_optional_params())
+        self.params = params
+        self.hidden_size = self.params["hidden_size"]
+        self.input_size = [self.params["input_size"]] + self.hidden_size[:-1]
+        self.n_layers = self.params["n_layers"]
+        self.activation = self.params["activation"]
+        if type(self.activation) is list:
+            assert len(self.activation) == self.n_layers
+        else:
+            self.activation = [self.activation] * self.n_layers
+        self.layers = nn.ModuleList([])
+        for i in range(self.n_layers):
+            self.layers.append(nn.Linear(in_features=self.input_size[i], out_features=self.hidden_size[i]))
+        if "init" in self.params.keys():
+            if self.params["init"] == "xavier_uniform":
+                for m in self.modules():
+                    if isinstance(m, nn.Linear):
+                        nn.init.xavier_uniform_(m.weight, gain=nn.init.calculate_gain("relu"))
+            else:
+                raise NotImplementedError("Only xavier_uniform initialization is supported now in OpenChemMLPSimple")
+        self._acts = [_act_name(a) for a in self.activation]
+
+    @staticmethod
+    def get_required_params():
+        return {"input_size": int, "n_layers": int, "hidden_size": list, "activation": None}
+
+    @staticmethod
+    def get_optional_params():
+        return {"init": str}
+
+    def forward(self, inp):
+        output = inp
+        for i, layer in enumerate(self.layers):
+            spec = HeadSpec([self.input_size[i], self.hidden_size[i]], [self._acts[i]], self.training, 1e-5, 0.1, [], [], [])
+            output = HeadFn.apply(output, None, spec, layer.weight, layer.bias)
+        return output
 
 
 def fused_head_loss(mlp, inp, target, criterion):

@@ -147,6 +147,29 @@ def test_head_vs_oracle(B, widths, acts, loss_kind):
     _compare(res, ref, len(widths) - 1, True, (B, widths), tol=1e-4 if B == 2 else 2e-5 if B > 4000 else TOL)
 
 
+@pytest.mark.parametrize("name", ["mlp_simple_xavier", "mlp_simple_default", "mlp_simple_single"])
+def test_mlp_simple_vs_reference_golden(name):
+    """OpenChemMLPSimple (openchem_mlp.py:64-111: Linear -> activation per layer) on the head kernels against the unmodified
+    reference's fp64 run: outputs, input gradient and every parameter gradient within the fp32 class (1e-5 rel-L2)."""
+    from test_head_host import build_simple
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    mlp, w = build_simple(z)
+    mlp = mlp.to(_dev()).train()
+    x = torch.from_numpy(z["inp"]).to(_dev()).requires_grad_(True)
+    y = mlp(x)
+    (y * torch.from_numpy(z["gout"]).to(_dev())).sum().backward()
+
+    def rel(a, b):
+        b = np.asarray(b, dtype=np.float64)
+        return float(np.linalg.norm(a.detach().double().cpu().numpy() - b) / max(np.linalg.norm(b), 1e-30))
+    assert rel(y, z["out_f64"]) < 1e-5 and rel(x.grad, z["dx_f64"]) < 1e-5
+    for i, l in enumerate(mlp.layers):
+        assert rel(l.weight.grad, z[f"dW{i}_f64"]) < 1e-5, i
+        assert rel(l.bias.grad, z[f"db{i}_f64"]) < 1e-5, i
+    # eval mode: same function (no BatchNorm, no dropout)
+    assert torch.equal(mlp.eval()(x.detach()), y.detach())
+
+
 def test_head_is_deterministic_and_rejects_bad_input():
     from openchem_b200.modules.mlp.openchem_mlp import fused_head_loss
     p, inp, target, gpred, _ = _oracle_case(700, [64, 96, 4], ["relu", "identity"], "mse", seed=3)

@@ -77,6 +77,42 @@ def test_module_surface_and_init_order():
         drop.train()(torch.zeros(4, 8))
 
 
+SIMPLE_CASES = ["mlp_simple_xavier", "mlp_simple_default", "mlp_simple_single"]
+ACT_FN = {"identity": "identity", "relu": F.relu, "sigmoid": torch.sigmoid, "tanh": torch.tanh}
+
+
+def build_simple(z):
+    """openchem_b200's OpenChemMLPSimple built under the fixture's seed, the way oracle/make_golden_mlp_simple.py built the reference's."""
+    from openchem_b200.modules.mlp.openchem_mlp import OpenChemMLPSimple
+    w = [int(v) for v in z["widths"]]
+    params = {"input_size": w[0], "n_layers": len(w) - 1, "hidden_size": w[1:], "activation": [ACT_FN[str(a)] for a in z["acts"]]}
+    if str(z["init"]):
+        params["init"] = str(z["init"])
+    torch.manual_seed(int(z["seed"]))
+    return OpenChemMLPSimple(params), w
+
+
+@pytest.mark.parametrize("name", SIMPLE_CASES)
+def test_mlp_simple_surface_and_init_order(name):
+    """Same constructor arguments and seed as the reference's OpenChemMLPSimple (openchem_mlp.py:64-94) -> bit-identical initial
+    weights (default nn.Linear init and the xavier_uniform branch), same state_dict keys and attributes; no CPU path."""
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    mlp, w = build_simple(z)
+    L = len(w) - 1
+    assert set(mlp.state_dict().keys()) == {"layers.%d.%s" % (i, k) for i in range(L) for k in ("weight", "bias")}
+    for i in range(L):
+        assert np.array_equal(mlp.layers[i].weight.detach().numpy(), z[f"W{i}"]), i
+        assert np.array_equal(mlp.layers[i].bias.detach().numpy(), z[f"b{i}"]), i
+    assert mlp.hidden_size == w[1:] and mlp.input_size == w[:-1] and mlp.n_layers == L and len(mlp.activation) == L
+    with pytest.raises(RuntimeError):
+        mlp(torch.zeros(4, w[0]))
+    from openchem_b200.modules.mlp.openchem_mlp import OpenChemMLPSimple
+    with pytest.raises(NotImplementedError):
+        OpenChemMLPSimple({"input_size": 4, "n_layers": 1, "hidden_size": [3], "activation": F.relu, "init": "kaiming"})
+    with pytest.raises(ValueError):
+        OpenChemMLPSimple({"input_size": 4, "n_layers": 1, "hidden_size": [3]})      # 'activation' is required (check_params)
+
+
 def test_multitask_criterion_class_matches_oracle():
     from openchem_b200.criterion.multitask_loss import MultitaskLoss
     rng = np.random.RandomState(0)
