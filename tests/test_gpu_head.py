@@ -1,6 +1,8 @@
 """MLP head + criteria on the B200 (ocgcn_head_forward / ocgcn_head_backward through the module surface) against fixtures
 of the unmodified reference (fp64-promoted run) and against the oracle at sizes the fixtures do not cover.
 Tolerance: 1e-5 relative (exact-fp32 class), written below."""
+import os
+
 import numpy as np
 import pytest
 import torch
