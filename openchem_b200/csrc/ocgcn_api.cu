@@ -447,7 +447,7 @@ static int launch_adj_pack(const ocgcn_desc* d, const GraphIn& gi, int NW, u64* 
   const float* no_adj = nullptr;
   const uint32_t* no_bits = nullptr;
   const long long s0 = d->adj_stride[0], s1 = d->adj_stride[1], s2 = d->adj_stride[2];
-  if (NW == 1) {      // N <= 64: one warp per molecule
+  if (NW == 1 && d->B >= 1024) {      // N <= 64, large batch: one warp per molecule (small batches need the CTA kernel's parallelism per molecule)
     const dim3 grid((d->B + kWarps - 1) / kWarps);
     if (gi.compact())
       CU_TRY(launch_chain(adj_pack_warp_kernel<true>, grid, dim3(kThreads), 0, st, no_adj, 0ll, 0ll, 0ll, gi.adj_bits, d->B, d->N, rowmask, colmask,

@@ -82,7 +82,7 @@ def _star_batch(B, N, F0, seed):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("shape", ["small", "odd_words", "many_tiles", "star"])
+@pytest.mark.parametrize("shape", ["small", "odd_words", "many_tiles", "star", "warp_pack"])
 @pytest.mark.parametrize("training", [True, False])
 def test_encoder_reads_compact_words_with_identical_results(precision, shape, training):
     """GraphCNNEncoder.forward(CompactGraphBatch) feeds the bit words to ocgcn_encoder_*_compact (no dense tensors): outputs and
@@ -90,10 +90,14 @@ def test_encoder_reads_compact_words_with_identical_results(precision, shape, tr
     (> 148 tiles), the single-kernel eval forward, word counts that are odd, and rows that overflow a neighbour record."""
     from openchem_b200 import functional
     B, N, F0, hidden, E = {"small": (12, 30, 33, (64, 64), 32), "odd_words": (9, 70, 75, (64, 128), 64),
-                           "many_tiles": (330, 64, 64, (128, 128), 128), "star": (10, 40, 33, (64, 64), 32)}[shape]
+                           "many_tiles": (330, 64, 64, (128, 128), 128), "star": (10, 40, 33, (64, 64), 32),
+                           "warp_pack": (1030, 20, 16, (32,), 16)}[shape]      # B >= 1024: the warp-per-molecule adjacency packing
     g, p, cfg = _case(B=B, N=N, F0=F0, hidden=hidden, E=E, seed=2)
     if shape == "star":
         g = _star_batch(B, N, F0, 3)
+    if shape == "warp_pack":        # a few hub atoms with more neighbours than a record holds, inside the large batch
+        g["adj"][:3, 0, :] = 1.0
+        g["adj"][:3, :, 0] = 1.0
     dev = _dev()
     enc = build_encoder(cfg, p, dev, precision=precision)
     enc.train(training)
