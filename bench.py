@@ -726,8 +726,8 @@ def run_native(args, w, wname):
         eopt = torch.optim.Adam(emodel.parameters(), lr=5e-4)
         eloss = head_loss_fn(args, crit)
 
-        def eager_step():
-            with torch.autograd.set_detect_anomaly(True):        # openchem_model.py:103
+        def eager_step(anomaly=True):
+            with torch.autograd.set_detect_anomaly(anomaly):     # openchem_model.py:103
                 eopt.zero_grad()
                 loss = crit(estep_model((x, adj)), y)
                 loss.backward()
@@ -736,10 +736,16 @@ def run_native(args, w, wname):
 
         for _ in range(3):
             eager_step()
-        ms_eager = timed(eager_step, max(args.steps // 2, 5))
-        eager = dict(value=world * B * max(args.steps // 2, 5) / (ms_eager * 1e-3), unit=UNIT, ms_per_step=ms_eager / max(args.steps // 2, 5),
+        n_eager = max(args.steps // 2, 5)
+        ms_eager = timed(eager_step, n_eager)
+        ms_plain = timed(lambda: eager_step(False), n_eager)
+        eager = dict(value=world * B * n_eager / (ms_eager * 1e-3), unit=UNIT, ms_per_step=ms_eager / n_eager,
                      what="device-resident batch; eager autograd + torch Adam + anomaly mode + loss.item() every step, as the reference's "
-                          "train_step/fit drive the model (DistributedDataParallel when N > 1)")
+                          "train_step/fit drive the model (DistributedDataParallel when N > 1)",
+                     without_anomaly_mode=dict(ms_per_step=ms_plain / n_eager, value=world * B * n_eager / (ms_plain * 1e-3),
+                                               what="same loop without torch.autograd.set_detect_anomaly: the difference is the reference's own "
+                                                    "train_step setting (a Python stack capture per autograd node and a device sync per "
+                                                    "gradient for the NaN check), not this package"))
         del eloss, estep_model, emodel
 
     if rank != 0:
