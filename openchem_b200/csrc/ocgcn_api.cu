@@ -335,7 +335,9 @@ static int launch_tile_t(const TileArgs& a_in, int tiles, cudaStream_t st) {
   ST_TRY((ensure_dynamic_smem<tile_kernel<TR, TC, PROD, EPI, MM, NT>>(smem)));
   // persistent (two CTAs per SM looping over tiles) only where the CTA accumulates the weight gradient across its tiles;
   // everything else launches one CTA per tile (dynamic scheduling balances and de-phases the co-resident CTAs better)
-  CU_TRY(launch_chain(kern, dim3((MM && a.dw_img) ? mm_grid(tiles) : tiles), dim3(NT), smem, st, a, tm));
+  // forward kernels with the TMA-staged input run persistent too: a CTA requests its next tile's first input chunk during the epilogue
+  static const bool persist_fwd = [] { const char* e = getenv("OCGCN_PERSIST_FWD"); return !(e && e[0] == '0'); }();
+  CU_TRY(launch_chain(kern, dim3((MM && (a.dw_img || (persist_fwd && a.use_tma))) ? mm_grid(tiles) : tiles), dim3(NT), smem, st, a, tm));
   LAUNCH_CHECK();
   return OCGCN_OK;
 }

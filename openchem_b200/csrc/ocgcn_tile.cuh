@@ -277,6 +277,8 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
   float* sW = buf1 + TR * BS;                                          // MM == 0: weight chunk
   unsigned char* imgHi = reinterpret_cast<unsigned char*>(mainp + TR * TCP);  // MM == 1: operand images [8][kImgPitch], after the staging tile
   unsigned char* imgLo = imgHi + 8 * kImgPitch;
+  float* const zbox0 = reinterpret_cast<float*>(imgHi);   // TMA landing buffer of a tile's first Zprev chunk (see use_tma below)
+  static_assert(!MM || (size_t)128 * KC * 4 <= (size_t)2 * 8 * kImgPitch, "the Zprev box fits the operand-image region");
   unsigned char* wHi = reinterpret_cast<unsigned char*>(buf0);                 // MM == 1: weight image pieces (hi, lo) alias buf0
   float* sC = mainp;  // epilogue staging, aliases buf0/buf1/sW
   constexpr size_t main_a = MM ? (size_t)TR * TCP + (size_t)2 * 8 * kImgPitch / 4 : (size_t)2 * TR * KCP + (size_t)KC * TC;
@@ -350,10 +352,13 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
   const float* const o_t = (PROD == P_DU) ? a.in2 + (size_t)mol0 * K : nullptr;
   const float* const do_t = (PROD == P_DU) ? a.in1 + (size_t)mol0 * K : nullptr;
 
-  if (use_tma && tid == 0) {   // first channel chunk of Zprev -> buf1 (free: the previous tile ended with a barrier), overlapping the staging below
+  // First channel chunk of Zprev -> zbox0, the operand-image region (dead between the last MMA of a tile and the first gather of the
+  // next one). The first tile of this CTA asks for it here; every later tile's box was requested during the previous tile's
+  // epilogue (below), so it has landed by the time the tanh stage wants it.
+  if (use_tma && tid == 0 && tile_iter == 0) {
     tc::fence_async_smem();
     tc::mbar_expect_tx(&bars[5], kZBoxBytes);
-    tc::tma_load_2d(buf1, &tm_in0, 0, (int)row0, &bars[5]);
+    tc::tma_load_2d(zbox0, &tm_in0, 0, (int)row0, &bars[5]);
   }
   // ---- stage neighbour records (made tile-relative), masks and per-molecule flags ---------------------------
   int simple = 1;   // every row AND column of the tile is a binary record with <= kMaxNbr neighbours (any molecular graph)
@@ -558,9 +563,10 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
             }
           }
           chunk_sync();
-          if (use_tma) {   // the chunk sits in buf1 as a dense [128][64] box (P_RO: tanh happens in place, bufT == buf1)
+          if (use_tma) {   // the chunk sits in shared memory as a dense [128][64] box: chunk 0 in zbox0, later chunks in buf1 (P_RO: tanh in place there)
+            const float* const zsrc = (k0 == 0) ? zbox0 : buf1;
 #pragma unroll
-            for (int sI = 0; sI < RPW / 2; ++sI) v[sI] = *reinterpret_cast<const float4*>(&buf1[(warp + (2 * sI + hh) * NWARP) * BS + 4 * hl]);
+            for (int sI = 0; sI < RPW / 2; ++sI) v[sI] = *reinterpret_cast<const float4*>(&zsrc[(warp + (2 * sI + hh) * NWARP) * BS + 4 * hl]);
           }
 #pragma unroll
           for (int sI = 0; sI < RPW / 2; ++sI) {
@@ -1048,6 +1054,13 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
         if (warp == 0) tc::mbar_wait(&bars[1], ph_mma);
         ph_mma ^= 1;
         mma_pending = false;
+        // every MMA of this tile has read its operand images (and the bulk store of the hi image was drained above): the image
+        // region is free. Persistent forward CTAs request the NEXT tile's first Zprev chunk into it now; it lands under the epilogue.
+        if (use_tma && tid == 0 && tile + (int)gridDim.x < a.ntiles) {
+          tc::fence_async_smem();
+          tc::mbar_expect_tx(&bars[5], kZBoxBytes);
+          tc::tma_load_2d(zbox0, &tm_in0, 0, (int)((size_t)(tile + (int)gridDim.x) * a.MT * N), &bars[5]);
+        }
         __syncthreads();
       }
       tc::fence_after_sync();
