@@ -790,6 +790,13 @@ def run_native(args, w, wname):
                 ach, peak, unit, bound = flops_launch / (ms_launch * 1e-3) / 1e12, tensor_peak, "TFLOP/s", "tensor"
             else:
                 ach, peak, unit, bound = comp_bytes_launch / (ms_launch * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s", "hbm"
+            # the same two fractions for EVERY tile-kernel kind of the step (the dominant one is `roofline` itself)
+            for k in kern:
+                if k in flops_tab and kern[k][1]:
+                    ms_k = kern[k][0] / kern[k][1]
+                    shares[k]["tensor_frac"] = flops_tab[k] / (ms_k * 1e-3) / 1e12 / tensor_peak
+                    if k in bytes_tab:
+                        shares[k]["implementation_hbm_frac"] = bytes_tab[k] / (ms_k * 1e-3) / 1e9 / peaks["hbm_gbs"]
             roofline = dict(bound=bound, kernel=top, achieved=ach, peak=peak, unit=unit, frac=ach / peak, traffic=traffic,
                             ms_per_launch=ms_launch, algorithmic_flops_per_launch=flops_launch,
                             compulsory_bytes_per_launch=comp_bytes_launch,
