@@ -20,6 +20,7 @@
 
 namespace ocgcn {
 
+static thread_local int tl_tile_parity = 0;
 static thread_local int tl_launches = 0;
 static thread_local int tl_cuda_err = 0;
 
@@ -327,6 +328,9 @@ static int launch_tile_t(const TileArgs& a_in, int tiles, cudaStream_t st) {
   // so buf1 is not needed for a second weight image; at least one full box in each dimension)
   a.use_tma = (MM && (PROD == P_MID || PROD == P_RO) && a.ncb == 1 && tma_enabled() &&
                make_chunk_map(a.in0, (size_t)a.B * a.N, a.K, &tm)) ? 1 : 0;
+  // consecutive tile launches of a call alternate the direction they walk the batch in (thread-local parity, reset per API call)
+  static const bool zigzag = [] { const char* e = getenv("OCGCN_ZIGZAG"); return !(e && e[0] == '0'); }();
+  a.reverse = (MM && zigzag) ? (tl_tile_parity++ & 1) : 0;
   constexpr int TC = tile_cols<TR>();
   constexpr int NT = MM ? kThreadsMM : kThreads;
   ProfScope prof(PROD == P_X ? KK_FWD_FIRST : PROD == P_MID ? KK_FWD_MID : PROD == P_RO ? KK_FWD_READOUT : PROD == P_DZ ? KK_BWD_DZ : KK_BWD_READOUT, st);
@@ -734,6 +738,7 @@ int ocgcn_query_workspace(const ocgcn_desc* desc, size_t* saved_bytes, size_t* s
 static int encoder_forward_impl(const ocgcn_desc* d, const GraphIn& gi, const ocgcn_params* p, void* saved_v, void* scratch_v, float* out,
                                 void* stream) {
   tl_launches = 0;
+  tl_tile_parity = 0;
   Layout lo;
   ST_TRY(make_layout(d, false, &lo));
   ST_TRY(validate_params(d, p, false));
@@ -901,6 +906,7 @@ int ocgcn_query_eval_workspace(const ocgcn_desc* desc, size_t* bytes) {
 static int encoder_forward_eval_impl(const ocgcn_desc* d, const GraphIn& gi, const ocgcn_params* p, void* workspace_v, float* out,
                                      void* stream) {
   tl_launches = 0;
+  tl_tile_parity = 0;
   EvalLayout lo;
   ST_TRY(make_eval_layout(d, &lo));
   ST_TRY(validate_params(d, p, false));
@@ -965,6 +971,7 @@ int ocgcn_encoder_forward_eval_compact(const ocgcn_desc* d, const uint32_t* x_bi
 static int encoder_backward_impl(const ocgcn_desc* d, const float* grad_out, const float* adj, const ocgcn_params* p,
                                  const ocgcn_grads* g, void* saved_v, void* scratch_v, void* stream) {
   tl_launches = 0;
+  tl_tile_parity = d ? ((d->L + 1) & 1) : 0;   // the forward's L + 1 tile launches ended on parity L & 1: start on the other direction
   Layout lo;
   ST_TRY(make_layout(d, false, &lo));
   ST_TRY(validate_params(d, p, false));
@@ -1053,6 +1060,7 @@ int ocgcn_encoder_backward_compact(const ocgcn_desc* d, const float* grad_out, c
 int ocgcn_layer_forward(const ocgcn_desc* d, const float* x, const float* adj, const ocgcn_params* p, void* saved_v, void* scratch_v,
                         float* y, void* stream) {
   tl_launches = 0;
+  tl_tile_parity = 0;
   Layout lo;
   ST_TRY(make_layout(d, true, &lo));
   ST_TRY(validate_params(d, p, true));
@@ -1093,6 +1101,7 @@ int ocgcn_layer_backward(const ocgcn_desc* d, const float* grad_y, const float* 
                          const ocgcn_grads* g, float* grad_x, void* saved_v, void* scratch_v, void* stream) {
   (void)x;
   tl_launches = 0;
+  tl_tile_parity = 0;
   Layout lo;
   ST_TRY(make_layout(d, true, &lo));
   ST_TRY(validate_params(d, p, true));
@@ -1129,6 +1138,7 @@ static int bits_grid(long long work_items) {
 int ocgcn_expand_compact(int B, int N, int F0, const uint32_t* x_bits, const uint32_t* adj_bits, const int32_t* index, int n_src,
                          int32_t* index_oob, float* x, float* adj, void* stream) {
   tl_launches = 0;
+  tl_tile_parity = 0;
   if (B <= 0 || N <= 0 || F0 <= 0) return OCGCN_EINVAL;
   if ((x != nullptr) != (x_bits != nullptr) || (adj != nullptr) != (adj_bits != nullptr) || (!x && !adj)) return OCGCN_EINVAL;
   if (index && (n_src <= 0 || !index_oob)) return OCGCN_EINVAL;
@@ -1168,6 +1178,7 @@ static int pool_args(int B, int N, int D, const float* y, const float* adj, cons
 int ocgcn_pool_forward(int B, int N, int D, const float* y, const float* adj, const int64_t* adj_stride, float* pooled, uint8_t* argmax,
                        void* stream) {
   tl_launches = 0;
+  tl_tile_parity = 0;
   PoolArgs a;
   ST_TRY(pool_args(B, N, D, y, adj, adj_stride, &a));
   ST_TRY(check_device_ptr(pooled));
@@ -1185,6 +1196,7 @@ int ocgcn_pool_forward(int B, int N, int D, const float* y, const float* adj, co
 int ocgcn_pool_backward(int B, int N, int D, const float* y, const float* adj, const int64_t* adj_stride, const uint8_t* argmax,
                         const float* grad_pooled, float* grad_y, void* stream) {
   tl_launches = 0;
+  tl_tile_parity = 0;
   PoolArgs a;
   ST_TRY(pool_args(B, N, D, y, adj, adj_stride, &a));
   ST_TRY(check_device_ptr(grad_pooled));
@@ -1203,6 +1215,7 @@ int ocgcn_pool_backward(int B, int N, int D, const float* y, const float* adj, c
 int ocgcn_pack_compact(int B, int N, int F0, const float* x, const int64_t* x_stride, const float* adj, const int64_t* adj_stride,
                        uint32_t* x_bits, uint32_t* adj_bits, int32_t* nonbinary, void* stream) {
   tl_launches = 0;
+  tl_tile_parity = 0;
   if (B <= 0 || N <= 0 || F0 <= 0 || !nonbinary) return OCGCN_EINVAL;
   if ((x != nullptr) != (x_bits != nullptr) || (adj != nullptr) != (adj_bits != nullptr) || (!x && !adj)) return OCGCN_EINVAL;
   if ((x && !x_stride) || (adj && !adj_stride)) return OCGCN_EINVAL;
@@ -1309,6 +1322,7 @@ int ocgcn_head_query_workspace(const ocgcn_head_desc* desc, size_t* saved_bytes,
 int ocgcn_head_forward(const ocgcn_head_desc* d, const float* inp, const ocgcn_head_params* p, const float* target, void* saved_v,
                        void* scratch_v, float* pred, float* loss, void* stream) {
   tl_launches = 0;
+  tl_tile_parity = 0;
   HeadLayout lo;
   ST_TRY(head_layout(d, &lo));
   ST_TRY(head_validate(d, p));
@@ -1362,6 +1376,7 @@ int ocgcn_head_backward(const ocgcn_head_desc* d, const float* grad, const float
                         const ocgcn_head_params* p, const ocgcn_head_grads* g, float* grad_inp, void* saved_v, void* scratch_v,
                         void* stream) {
   tl_launches = 0;
+  tl_tile_parity = 0;
   HeadLayout lo;
   ST_TRY(head_layout(d, &lo));
   ST_TRY(head_validate(d, p));

@@ -99,6 +99,7 @@ struct TileArgs {
   // TMA staging of the forward producers' input (P_MID / P_RO of the tensor-core engine): the 128-row x 64-channel fp32 chunk of
   // Zprev arrives through the kernel's tensor map (cp.async.bulk.tensor) instead of per-thread loads
   int use_tma;
+  int reverse;   // tiles are visited last to first (see tile_kernel)
 };
 
 // x[mol, i, c] and x[mol, i, c + 1] (c even) of the first layer's input: from the dense fp32 tensor, or from the bit words of a

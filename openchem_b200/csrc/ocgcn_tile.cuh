@@ -336,7 +336,10 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
 
   // persistent over tiles (MM launches use at most two CTAs per SM; the exact-fp32 engine launches one CTA per tile)
   int tile_iter = 0;
-  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tile_iter) {
+  for (int tix = blockIdx.x; tix < a.ntiles; tix += gridDim.x, ++tile_iter) {
+  // a.reverse: walk the batch from its last tile to its first. Consecutive kernels of a pass alternate the direction, so each starts
+  // on the tiles its predecessor wrote LAST (the part of Z / dY that is still in the L2)
+  const int tile = a.reverse ? a.ntiles - 1 - tix : tix;
   const int mol0 = tile * a.MT;
   const int nm = min(a.MT, a.B - mol0);
   const int rows = nm * N;
@@ -1056,10 +1059,11 @@ __global__ void __launch_bounds__(NT, (TR == 128 ? 2 : 1)) tile_kernel(const Til
         mma_pending = false;
         // every MMA of this tile has read its operand images (and the bulk store of the hi image was drained above): the image
         // region is free. Persistent forward CTAs request the NEXT tile's first Zprev chunk into it now; it lands under the epilogue.
-        if (use_tma && tid == 0 && tile + (int)gridDim.x < a.ntiles) {
+        if (use_tma && tid == 0 && tix + (int)gridDim.x < a.ntiles) {
+          const int ntile = a.reverse ? a.ntiles - 1 - (tix + (int)gridDim.x) : tix + (int)gridDim.x;
           tc::fence_async_smem();
           tc::mbar_expect_tx(&bars[5], kZBoxBytes);
-          tc::tma_load_2d(zbox0, &tm_in0, 0, (int)((size_t)(tile + (int)gridDim.x) * a.MT * N), &bars[5]);
+          tc::tma_load_2d(zbox0, &tm_in0, 0, (int)((size_t)ntile * a.MT * N), &bars[5]);
         }
         __syncthreads();
       }
