@@ -330,7 +330,7 @@ static int launch_tile_t(const TileArgs& a_in, int tiles, cudaStream_t st) {
                make_chunk_map(a.in0, (size_t)a.B * a.N, a.K, &tm)) ? 1 : 0;
   // consecutive tile launches of a call alternate the direction they walk the batch in (thread-local parity, reset per API call)
   static const bool zigzag = [] { const char* e = getenv("OCGCN_ZIGZAG"); return !(e && e[0] == '0'); }();
-  a.reverse = (MM && zigzag) ? (tl_tile_parity++ & 1) : 0;
+  a.reverse = (MM && zigzag && tiles > kMaxPersistent) ? (tl_tile_parity++ & 1) : 0;   // (batches whose tiles are all co-resident gain nothing)
   constexpr int TC = tile_cols<TR>();
   constexpr int NT = MM ? kThreadsMM : kThreads;
   ProfScope prof(PROD == P_X ? KK_FWD_FIRST : PROD == P_MID ? KK_FWD_MID : PROD == P_RO ? KK_FWD_READOUT : PROD == P_DZ ? KK_BWD_DZ : KK_BWD_READOUT, st);
