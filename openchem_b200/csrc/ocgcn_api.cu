@@ -1356,11 +1356,17 @@ int ocgcn_head_forward(const ocgcn_head_desc* d, const float* inp, const ocgcn_h
       a.loss = d->loss; a.target = target; a.ignore = d->ignore_index;
       a.loss_part = reinterpret_cast<float*>(scratch + lo.loss_part);
     }
-    const size_t smem = head_fwd_smem(a.Kin, a.Nout);
-    auto kern = a.Nout > 128 ? head_fwd_kernel<2> : head_fwd_kernel<1>;
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_fwd_smem(kHeadMaxWidth, kHeadMaxWidth)));
     ProfScope prof(KK_HEAD_FWD, st);
-    CU_TRY(launch_chain(kern, dim3(lo.grid), dim3(HT), smem, st, a));
+    static const bool narrow = [] { const char* e = getenv("OCGCN_HEAD_NARROW"); return !(e && e[0] == '0'); }();
+    if (narrow && head_fwd_narrow_ok(a.Kin, a.Nout, a.has_bn, a.loss)) {     // 32-column CTAs: four times the CTAs of the wide kernel at width 128
+      ST_TRY((ensure_dynamic_smem<head_fwd_narrow_kernel>(head_fwd_narrow_smem(kHeadMaxWidth))));
+      CU_TRY(launch_chain(head_fwd_narrow_kernel, dim3(lo.grid, (a.Nout + HNC - 1) / HNC), dim3(HT), head_fwd_narrow_smem(a.Kin), st, a));
+    } else {
+      const size_t smem = head_fwd_smem(a.Kin, a.Nout);
+      auto kern = a.Nout > 128 ? head_fwd_kernel<2> : head_fwd_kernel<1>;
+      CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_fwd_smem(kHeadMaxWidth, kHeadMaxWidth)));
+      CU_TRY(launch_chain(kern, dim3(lo.grid), dim3(HT), smem, st, a));
+    }
     LAUNCH_CHECK();
   }
   if (d->loss != OCGCN_LOSS_NONE) {
@@ -1427,12 +1433,20 @@ int ocgcn_head_backward(const ocgcn_head_desc* d, const float* grad, const float
     }
     a.dWpart = reinterpret_cast<float*>(scratch + lo.dWpart[i]);
     a.dbpart = reinterpret_cast<float*>(scratch + lo.dbpart[i]);
-    const size_t smem = head_bwd_smem(a.Kin, a.Nout);
-    auto kern = a.Kin > 128 ? head_bwd_kernel<2> : head_bwd_kernel<1>;
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_bwd_smem(kHeadMaxWidth, kHeadMaxWidth)));
     {
       ProfScope prof(KK_HEAD_BWD, st);
-      CU_TRY(launch_chain(kern, dim3(lo.grid), dim3(HT), smem, st, a));
+      static const bool narrow = [] { const char* e = getenv("OCGCN_HEAD_NARROW"); return !(e && e[0] == '0'); }();
+      // 32-input-column CTAs (see head_bwd_narrow_kernel) for batches of at most 32 row tiles: each column block repeats the dU tile and
+      // the fold of the per-tile partials, which costs more than it hides once the row tiles alone fill the GPU (C3: 36 vs 28 us)
+      if (narrow && lo.ntiles <= 32 && head_bwd_narrow_ok(a.Kin, a.W)) {
+        ST_TRY((ensure_dynamic_smem<head_bwd_narrow_kernel>(head_bwd_narrow_smem(kHeadMaxWidth))));
+        CU_TRY(launch_chain(head_bwd_narrow_kernel, dim3(lo.grid, (a.Kin + HNC - 1) / HNC), dim3(HT), head_bwd_narrow_smem(a.Nout), st, a));
+      } else {
+        const size_t smem = head_bwd_smem(a.Kin, a.Nout);
+        auto kern = a.Kin > 128 ? head_bwd_kernel<2> : head_bwd_kernel<1>;
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_bwd_smem(kHeadMaxWidth, kHeadMaxWidth)));
+        CU_TRY(launch_chain(kern, dim3(lo.grid), dim3(HT), smem, st, a));
+      }
       LAUNCH_CHECK();
     }
     add_reduce(rj, a.dWpart, g->dW[i], lo.grid, a.Nout * a.Kin, 1, 0);

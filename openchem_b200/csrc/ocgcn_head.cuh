@@ -358,6 +358,189 @@ __global__ void __launch_bounds__(HT, 2) head_fwd_kernel(const HeadFwdArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Narrow forward kernel: a CTA computes 32 rows x HNC = 32 output columns (grid.y walks the column blocks), so a layer of width
+// 128 runs on four times as many CTAs as head_fwd_kernel, each fetching a quarter of the weight matrix in ONE round. The wide
+// kernel's time is a latency chain (four weight chunks with two barriers each, cold instruction fetch) on one CTA per SM at most;
+// here several CTAs share an SM and hide each other's latencies, and small batches (8 row tiles at B = 256) reach 32 SMs.
+// Both operands stay row-major in shared memory with a pitch of K + 4 floats: the weight block arrives by cp.async (requested
+// before the grid-dependency wait: parameters do not depend on the predecessor kernel), the A tile is a coalesced copy with
+// BatchNorm + activation applied on the way. Inner loop per four k: 4 broadcast LDS.128 (this thread's rows) + 1 conflict-free
+// LDS.128 (its column) for 16 FFMA, accumulated in the same k order as the wide kernel: results are bit-identical to it.
+// Not used for an MSE criterion over more than 32 outputs (the per-tile loss partial needs every column in one CTA).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int HNC = 32;
+static inline size_t head_fwd_narrow_smem(int Kin) {
+  const size_t pa = (size_t)(Kin + 4);
+  const size_t atile = (size_t)HR * pa * 4;
+  return (size_t)2 * kHeadMaxWidth * 4 + (atile > kHeadFoldBytes ? atile : kHeadFoldBytes) + (size_t)HNC * pa * 4 + (size_t)HR * (HNC + 1) * 4;
+}
+static inline bool head_fwd_narrow_ok(int Kin, int Nout, int has_bn, int loss) {
+  return (Kin % 4 == 0) && (has_bn || loss != HLOSS_MSE || Nout <= HNC);
+}
+
+__global__ void __launch_bounds__(HT, 2) head_fwd_narrow_kernel(const HeadFwdArgs a) {
+  extern __shared__ __align__(16) float hsm[];
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int Kin = a.Kin, Nout = a.Nout, PA = Kin + 4;
+  const int o0 = blockIdx.y * HNC, o = o0 + tx;
+  float* sScale = hsm;
+  float* sShift = sScale + kHeadMaxWidth;
+  float* sA = sShift + kHeadMaxWidth;                                       // [HR][PA]; the fold scratch aliases it before the first tile
+  const size_t atile = (size_t)HR * PA * 4;
+  float* sW = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sA) + (atile > kHeadFoldBytes ? atile : kHeadFoldBytes));   // [HNC][PA]
+  float* sO = sW + (size_t)HNC * PA;                                        // [HR][HNC + 1]
+  // weight block rows o0 .. o0 + 31 (nn.Linear layout (Nout, Kin)): straight 16-byte copies, zero rows beyond Nout
+  {
+    const int K4 = Kin >> 2;
+    const bool aligned = (reinterpret_cast<uintptr_t>(a.W) & 15) == 0;
+    for (int e = tid; e < HNC * K4; e += HT) {
+      const int oc = e / K4, k = (e - oc * K4) << 2;
+      float* dst = &sW[oc * PA + k];
+      if (o0 + oc < Nout) {
+        const float* src = &a.W[(size_t)(o0 + oc) * Kin + k];
+        if (aligned) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+        } else {
+          dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2); dst[3] = __ldg(src + 3);
+        }
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  pdl_wait();
+  const bool lead = blockIdx.x == 0 && blockIdx.y == 0;
+  if (a.prev_bn) {
+    double* sred = reinterpret_cast<double*>(sA);
+    double* f0 = sred + 16 * kHeadMaxWidth;
+    double* f1 = f0 + kHeadMaxWidth;
+    if (a.training) head_fold<true>(a.bn.part, a.ntiles, Kin, a.B, sred, f0, f1);
+    if (tid < Kin) {
+      const int c = tid;
+      float mean, invstd;
+      if (a.training) {
+        const double m = f0[c] / (double)a.B;
+        double m2 = f1[c] - f0[c] * m;
+        m2 = m2 > 0.0 ? m2 : 0.0;
+        const double var = m2 / (double)a.B;
+        mean = (float)m;
+        invstd = (float)(1.0 / sqrt(var + (double)a.eps));
+        if (lead) {
+          const float unb = (float)(m2 / (double)(a.B > 1 ? a.B - 1 : 1));
+          a.bn.running_mean[c] = (1.f - a.momentum) * a.bn.running_mean[c] + a.momentum * mean;
+          a.bn.running_var[c] = (1.f - a.momentum) * a.bn.running_var[c] + a.momentum * unb;
+          if (c == 0 && a.bn.nbt) *a.bn.nbt += 1;
+        }
+      } else {
+        mean = a.bn.running_mean[c];
+        invstd = (float)(1.0 / sqrt((double)a.bn.running_var[c] + (double)a.eps));
+      }
+      if (lead) { a.bn.stat[c] = mean; a.bn.stat[Kin + c] = invstd; }
+      const float sc = __ldg(&a.bn.gamma[c]) * invstd;
+      sScale[c] = sc;
+      sShift[c] = __ldg(&a.bn.beta[c]) - mean * sc;
+    }
+    __syncthreads();
+  }
+  const bool vecA = (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
+  const float bias = (a.b && o < Nout) ? __ldg(&a.b[o]) : 0.f;
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    const int row0 = tile * HR, nv = min(HR, a.B - row0);
+    {
+      const int K4 = Kin >> 2;
+      for (int e = tid; e < HR * K4; e += HT) {
+        const int r = e / K4, k = (e - r * K4) << 2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nv) {
+          const float* src = &a.in[(size_t)(row0 + r) * Kin + k];
+          if (vecA) v = __ldg(reinterpret_cast<const float4*>(src));
+          else v = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
+          if (a.prev_bn) {
+            v.x = head_act(fmaf(v.x, sScale[k], sShift[k]), a.bn.act);
+            v.y = head_act(fmaf(v.y, sScale[k + 1], sShift[k + 1]), a.bn.act);
+            v.z = head_act(fmaf(v.z, sScale[k + 2], sShift[k + 2]), a.bn.act);
+            v.w = head_act(fmaf(v.w, sScale[k + 3], sShift[k + 3]), a.bn.act);
+          }
+        }
+        *reinterpret_cast<float4*>(&sA[r * PA + k]) = v;
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* wrow = &sW[tx * PA];
+    const float* arow = &sA[(4 * ty) * PA];
+#pragma unroll 4
+    for (int k = 0; k < Kin; k += 4) {
+      const float4 w = *reinterpret_cast<const float4*>(&wrow[k]);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float4 av = *reinterpret_cast<const float4*>(&arow[r * PA + k]);
+        acc[r] = fmaf(av.x, w.x, acc[r]);
+        acc[r] = fmaf(av.y, w.y, acc[r]);
+        acc[r] = fmaf(av.z, w.z, acc[r]);
+        acc[r] = fmaf(av.w, w.w, acc[r]);
+      }
+    }
+    // epilogue: bias (+ activation), store, stage for the column reductions
+    if (o < Nout) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int rr = ty * 4 + r;
+        float u = acc[r] + bias;
+        if (!a.has_bn) u = head_act(u, a.act);
+        if (rr < nv) a.out[(size_t)(row0 + rr) * Nout + o] = u;
+        float staged = u;
+        if (!a.has_bn && a.loss != HLOSS_NONE && rr < nv) {
+          const float y = __ldg(&a.target[(size_t)(row0 + rr) * Nout + o]);
+          if (a.loss == HLOSS_MSE) {
+            staged = (u - y) * (u - y);
+          } else {
+            const float t = (y == a.ignore) ? 0.f : y;
+            staged = -(t * fmaxf(logf(u), -100.f) + (1.f - t) * fmaxf(logf(1.f - u), -100.f));
+          }
+        }
+        sO[rr * (HNC + 1) + tx] = staged;
+      }
+    }
+    __syncthreads();
+    if (a.has_bn) {
+      if (tid < HNC && o0 + tid < Nout) {     // per-tile mean and M2 over the valid rows (two passes over the staged tile)
+        float s = 0.f;
+        for (int r = 0; r < nv; ++r) s += sO[r * (HNC + 1) + tid];
+        const float mean = s / (float)nv;
+        float m2 = 0.f;
+        for (int r = 0; r < nv; ++r) { const float d = sO[r * (HNC + 1) + tid] - mean; m2 = fmaf(d, d, m2); }
+        a.part_out[((size_t)tile * 2) * Nout + o0 + tid] = mean;
+        a.part_out[((size_t)tile * 2 + 1) * Nout + o0 + tid] = m2;
+      }
+    } else if (a.loss == HLOSS_MSE) {
+      if (tid < 32) {       // (Nout <= 32 here) same order as the wide kernel: rows inside a column, then a shuffle tree over the columns
+        float s = 0.f;
+        if (tid < Nout)
+          for (int r = 0; r < nv; ++r) s += sO[r * (HNC + 1) + tid];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (tid == 0) a.loss_part[tile] = s;
+      }
+    } else if (a.loss == HLOSS_MULTITASK) {
+      if (tid < HNC && o0 + tid < Nout) {
+        float s = 0.f, cnt = 0.f;
+        for (int r = 0; r < nv; ++r) {
+          s += sO[r * (HNC + 1) + tid];
+          cnt += (__ldg(&a.target[(size_t)(row0 + r) * Nout + o0 + tid]) == a.ignore) ? 0.f : 1.f;
+        }
+        a.loss_part[((size_t)tile * 2) * Nout + o0 + tid] = s;
+        a.loss_part[((size_t)tile * 2 + 1) * Nout + o0 + tid] = cnt;
+      }
+    }
+    __syncthreads();
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");   // (a CTA without tiles still drains its copies before exiting)
+}
+
 // one CTA. MSE: mean over B*T. Multitask (multitask_loss.py:40-49 as executed): F.binary_cross_entropy is called with its default
 // 'mean' reduction (:46), so the criterion is  s * mean_j(n_j / n_j)  with s = mean BCE over ALL B*T entries (ignored labels counted as
 // class 0) and n_j = valid samples of task j — i.e. s, or nan when a task has no valid sample. coef = mean_j(n_j / n_j) is kept for
@@ -603,6 +786,186 @@ __global__ void __launch_bounds__(HT, 2) head_bwd_kernel(const HeadBwdArgs a) {
     }
     __syncthreads();
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Narrow backward kernel (same idea as head_fwd_narrow_kernel): a CTA owns 32 batch rows x HNC = 32 columns of the layer's INPUT
+// width (grid.y walks the column blocks). It rebuilds the full dU tile (elementwise, cheap), keeps its [Nout][32] block of W in shared
+// memory for all its tiles (cp.async, requested before the grid-dependency wait) and produces its 32 columns of dA / dY_{i-1}, of
+// the dW partial and of the dgamma / dbeta partials; db comes from the CTAs of column block 0. Summation orders (over the tile rows
+// for dW, over the output columns for dA) are those of head_bwd_kernel: bit-identical results.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int HNP = HNC + 4;     // pitch of the 32-column blocks in shared memory (16-byte rows, conflict-free lane = column reads)
+static inline size_t head_bwd_narrow_smem(int Nout) {
+  const size_t NO32 = (size_t)head_pad32(Nout), du = (size_t)HR * (NO32 + 4) * 4;
+  return (size_t)3 * kHeadMaxWidth * 4 + (du > kHeadFoldBytes ? du : kHeadFoldBytes) + NO32 * HNP * 4 + (size_t)HR * HNP * 4 + (size_t)HR * (HNC + 1) * 4;
+}
+static inline bool head_bwd_narrow_ok(int Kin, const void* W) { return (Kin % 4 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0); }
+
+__global__ void __launch_bounds__(HT, 2) head_bwd_narrow_kernel(const HeadBwdArgs a) {
+  extern __shared__ __align__(16) float hsm[];
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int Kin = a.Kin, Nout = a.Nout;
+  const int NO32 = (Nout + 31) / 32 * 32, NOP = NO32 + 4;
+  const int kb = blockIdx.y * HNC, kc = kb + tx;           // this thread's input column
+  const bool kvalid = kc < Kin;
+  float* sC0 = hsm;
+  float* sC1 = sC0 + kHeadMaxWidth;
+  float* sC2 = sC1 + kHeadMaxWidth;
+  float* sdUr = sC2 + kHeadMaxWidth;                        // [HR][NOP] dU tile, row-major, zero-padded to NO32 columns
+  const size_t du_bytes = (size_t)HR * NOP * 4;
+  float* sW = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sdUr) + (du_bytes > kHeadFoldBytes ? du_bytes : kHeadFoldBytes));   // [NO32][HNP]
+  float* sAp = sW + (size_t)NO32 * HNP;                     // [HR][HNP]  A_{i-1} block
+  float* sSt = sAp + (size_t)HR * HNP;                      // [HR][HNC + 1] dY_{i-1} staging
+  // W[:, kb .. kb + 31]: eight 16-byte pieces per output row, zero beyond Kin / Nout
+  for (int e = tid; e < NO32 * (HNC / 4); e += HT) {
+    const int oo = e / (HNC / 4), c4 = (e - oo * (HNC / 4)) << 2;
+    float* dst = &sW[oo * HNP + c4];
+    if (oo < Nout && kb + c4 < Kin)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(&a.W[(size_t)oo * Kin + kb + c4]) : "memory");
+    else
+      *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  pdl_wait();
+  const bool lead = blockIdx.x == 0 && blockIdx.y == 0;
+  const float inv_B = 1.f / (float)a.B;
+  if (a.has_bn) {
+    double* sred = reinterpret_cast<double*>(sdUr);
+    double* f0 = sred + 16 * kHeadMaxWidth;
+    double* f1 = f0 + kHeadMaxWidth;
+    head_fold<false>(a.dpart, a.ntiles, Nout, a.B, sred, f0, f1);
+    if (tid < Nout) {
+      const int c = tid;
+      const double dg = f0[c], db = f1[c];
+      if (lead) { a.dgamma[c] = (float)dg; a.dbeta[c] = (float)db; }
+      sC0[c] = __ldg(&a.gamma[c]) * __ldg(&a.stat[Nout + c]);
+      sC1[c] = a.training ? (float)db * inv_B : 0.f;
+      sC2[c] = a.training ? (float)dg * inv_B : 0.f;
+    }
+  }
+  const float gl = a.gloss ? __ldg(a.gloss) : 1.f;
+  float psc = 0.f, psh = 0.f, pmean = 0.f, pinv = 0.f;      // BatchNorm_{i-1} of this thread's input column
+  if (a.prev_bn && kvalid) {
+    pmean = __ldg(&a.pstat[kc]); pinv = __ldg(&a.pstat[Kin + kc]);
+    psc = __ldg(&a.pgamma[kc]) * pinv;
+    psh = __ldg(&a.pbeta[kc]) - pmean * psc;
+  }
+  __syncthreads();
+  float* dWp = a.dWpart + (size_t)blockIdx.x * Nout * Kin;
+  float* dbp = a.dbpart + (size_t)blockIdx.x * Nout;
+  int iter = 0;
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++iter) {
+    const int row0 = tile * HR, nv = min(HR, a.B - row0);
+    for (int e = tid; e < HR * NO32; e += HT) {
+      const int r = e / NO32, o = e - r * NO32;
+      float du = 0.f;
+      if (r < nv && o < Nout) {
+        const size_t g = (size_t)(row0 + r) * Nout + o;
+        if (a.has_bn) {
+          const float yhat = (__ldg(&a.U[g]) - __ldg(&a.stat[o])) * __ldg(&a.stat[Nout + o]);
+          du = sC0[o] * (__ldg(&a.dY[g]) - sC1[o] - yhat * sC2[o]);
+        } else {
+          const float p = __ldg(&a.pred[g]);
+          float dp;
+          if (a.loss == HLOSS_NONE) {
+            dp = __ldg(&a.grad_pred[g]);
+          } else if (a.loss == HLOSS_MSE) {
+            dp = gl * 2.f * (p - __ldg(&a.target[g])) / ((float)a.B * (float)Nout);
+          } else {
+            const float y = __ldg(&a.target[g]);
+            const float t = (y == a.ignore) ? 0.f : y;
+            dp = gl * __ldg(a.ncount) * (p - t) / fmaxf((1.f - p) * p, 1e-12f) / ((float)a.B * (float)Nout);
+          }
+          du = dp * head_act_grad(p, a.act);
+        }
+      }
+      sdUr[r * NOP + o] = du;
+    }
+    // this block's 32 columns of A_{i-1}: lane = column (128 contiguous bytes per row), four rows per thread
+    float uprev[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = ty + 8 * q;
+      uprev[q] = (r < nv && kvalid) ? __ldg(&a.prev[(size_t)(row0 + r) * Kin + kc]) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = ty + 8 * q;
+      float v = uprev[q];
+      if (a.prev_bn) v = (r < nv && kvalid) ? head_act(fmaf(v, psc, psh), a.pact) : 0.f;
+      sAp[r * HNP + tx] = v;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (blockIdx.y == 0 && tid < Nout) {
+      float s = 0.f;
+      for (int r = 0; r < nv; ++r) s += sdUr[r * NOP + tid];
+      dbp[tid] = iter ? dbp[tid] + s : s;
+    }
+    // dW partial: out[o][kc] = sum_r dU[r][o] * A[r][kc], 32 output rows per pass (thread: four o, one column)
+    for (int ob = 0; ob < NO32; ob += 32) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+      for (int r = 0; r < HR; ++r) {
+        const float4 du = *reinterpret_cast<const float4*>(&sdUr[r * NOP + ob + 4 * ty]);
+        const float av = sAp[r * HNP + tx];
+        acc[0] = fmaf(du.x, av, acc[0]); acc[1] = fmaf(du.y, av, acc[1]); acc[2] = fmaf(du.z, av, acc[2]); acc[3] = fmaf(du.w, av, acc[3]);
+      }
+      if (kvalid) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int o = ob + 4 * ty + j;
+          if (o < Nout) {
+            float* dst = &dWp[(size_t)o * Kin + kc];
+            *dst = iter ? *dst + acc[j] : acc[j];
+          }
+        }
+      }
+    }
+    if (a.dprev) {
+      // dA_{i-1}[r][kc] = sum_o dU[r][o] * W[o][kc]   (thread: rows 4*ty .. +3, one column)
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+      for (int o = 0; o < NO32; o += 4) {
+        const float w0 = sW[o * HNP + tx], w1 = sW[(o + 1) * HNP + tx], w2 = sW[(o + 2) * HNP + tx], w3 = sW[(o + 3) * HNP + tx];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float4 du = *reinterpret_cast<const float4*>(&sdUr[(4 * ty + r) * NOP + o]);
+          acc[r] = fmaf(du.x, w0, acc[r]);
+          acc[r] = fmaf(du.y, w1, acc[r]);
+          acc[r] = fmaf(du.z, w2, acc[r]);
+          acc[r] = fmaf(du.w, w3, acc[r]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int rr = 4 * ty + r;
+        float d = acc[r];
+        if (a.prev_bn) d *= head_act_grad(sAp[rr * HNP + tx], a.pact);
+        if (rr < nv && kvalid) a.dprev[(size_t)(row0 + rr) * Kin + kc] = d;
+        sSt[rr * (HNC + 1) + tx] = (rr < nv && kvalid) ? d : 0.f;
+      }
+      if (a.prev_bn) {
+        __syncthreads();
+        if (tid < HNC && kb + tid < Kin) {     // per-tile partial dgamma_{i-1} = sum_r dY * yhat, dbeta_{i-1} = sum_r dY
+          const int k = kb + tid;
+          const float mean = __ldg(&a.pstat[k]), invstd = __ldg(&a.pstat[Kin + k]);
+          float dg = 0.f, db = 0.f;
+          for (int r = 0; r < nv; ++r) {
+            const float d = sSt[r * (HNC + 1) + tid];
+            const float yhat = (__ldg(&a.prev[(size_t)(row0 + r) * Kin + k]) - mean) * invstd;
+            dg = fmaf(d, yhat, dg);
+            db += d;
+          }
+          a.dpart_out[((size_t)tile * 2) * Kin + k] = dg;
+          a.dpart_out[((size_t)tile * 2 + 1) * Kin + k] = db;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 }  // namespace ocgcn
