@@ -139,6 +139,14 @@ def test_cpu_tensors_raise_no_fallback():
         enc((torch.zeros(2, 5, 12), torch.zeros(2, 5, 5)))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         GraphConvolution(12, 4)(torch.zeros(2, 5, 12), torch.zeros(2, 5, 5))
+    # the compact route has no CPU path either: bit words on the host are refused, as is a host CompactGraphBatch
+    from openchem_b200 import compact, functional
+    cb = compact.pack_graph_batch(np.zeros((2, 5, 12), np.float32), np.eye(5, dtype=np.float32)[None].repeat(2, 0))
+    assert functional.is_compact_pair(cb.x_bits, cb.adj_bits) and not functional.is_compact_pair(torch.zeros(1), torch.zeros(1))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        enc((cb.x_bits, cb.adj_bits))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        enc(cb)
 
 
 def test_product_never_imports_the_oracle():
