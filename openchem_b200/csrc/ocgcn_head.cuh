@@ -620,7 +620,7 @@ struct HeadBwdArgs {
 static inline int head_pad32(int n) { return (n + 31) / 32 * 32; }
 static inline size_t head_bwd_smem(int Kin, int Nout) {
   const size_t gemm = ((size_t)HR * (head_pad32(Nout) + 4) + (size_t)head_pad32(Nout) * HAP + (size_t)2 * HR * (head_cw(Kin) + 4)) * 4;
-  return (size_t)4 * kHeadMaxWidth * 4 + (gemm > kHeadFoldBytes ? gemm : kHeadFoldBytes);
+  return (size_t)5 * kHeadMaxWidth * 4 + (gemm > kHeadFoldBytes ? gemm : kHeadFoldBytes);
 }
 
 template <int NCP>
@@ -634,8 +634,9 @@ __global__ void __launch_bounds__(HT, 2) head_bwd_kernel(const HeadBwdArgs a) {
   float* sC0 = hsm;                              // hidden: gamma*invstd          (per output column)
   float* sC1 = sC0 + kHeadMaxWidth;              // hidden: dbeta / B
   float* sC2 = sC1 + kHeadMaxWidth;              // hidden: dgamma / B
-  float* sPs = sC2 + kHeadMaxWidth;              // (spare)
-  float* sdUr = sPs + kHeadMaxWidth;             // [HR][NOP]   dU tile, row-major (= k-major for dW, k = row), zero-padded to NO32 columns
+  float* sPs = sC2 + kHeadMaxWidth;              // BatchNorm_{i-1} scale per input column (gamma * invstd)
+  float* sPt = sPs + kHeadMaxWidth;              // BatchNorm_{i-1} shift per input column (beta - mean * scale)
+  float* sdUr = sPt + kHeadMaxWidth;             // [HR][NOP]   dU tile, row-major (= k-major for dW, k = row), zero-padded to NO32 columns
   float* sdUk = sdUr + (size_t)HR * NOP;         // [NO32][HAP] dU tile, k-major for dA (k = output column)
   float* sAp = sdUk + (size_t)NO32 * HAP;        // [HR][BP]    A_{i-1} tile, row-major, zero-padded to CW columns
   float* sWc = sAp + (size_t)HR * BP;            // [HKC][BP]   chunk of W rows; reused as the dY_{i-1} staging tile
@@ -655,6 +656,11 @@ __global__ void __launch_bounds__(HT, 2) head_bwd_kernel(const HeadBwdArgs a) {
     }
   }
   const float gl = a.gloss ? __ldg(a.gloss) : 1.f;
+  if (a.prev_bn && tid < Kin) {     // once per CTA instead of three global loads per element of every A tile
+    const float sc = __ldg(&a.pgamma[tid]) * __ldg(&a.pstat[Kin + tid]);
+    sPs[tid] = sc;
+    sPt[tid] = __ldg(&a.pbeta[tid]) - __ldg(&a.pstat[tid]) * sc;
+  }
   __syncthreads();
   float* dWp = a.dWpart + (size_t)blockIdx.x * Nout * Kin;
   float* dbp = a.dbpart + (size_t)blockIdx.x * Nout;
@@ -695,10 +701,7 @@ __global__ void __launch_bounds__(HT, 2) head_bwd_kernel(const HeadBwdArgs a) {
       float v = 0.f;
       if (r < nv && k < Kin) {
         v = __ldg(&a.prev[(size_t)(row0 + r) * Kin + k]);
-        if (a.prev_bn) {
-          const float sc = __ldg(&a.pgamma[k]) * __ldg(&a.pstat[Kin + k]);
-          v = head_act(fmaf(v, sc, __ldg(&a.pbeta[k]) - __ldg(&a.pstat[k]) * sc), a.pact);
-        }
+        if (a.prev_bn) v = head_act(fmaf(v, sPs[k], sPt[k]), a.pact);
       }
       sAp[r * BP + k] = v;
     }
