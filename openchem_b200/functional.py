@@ -195,6 +195,9 @@ class EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, adj, spec, *tensors):
         lib = _lib.load()
+        if (x.dtype == torch.int32) != (adj.dtype == torch.int32):
+            raise RuntimeError("openchem_b200: x and adj must BOTH be int32 bit words of a compact batch or both dense tensors "
+                               "(got %s and %s)" % (x.dtype, adj.dtype))
         _require_cuda(x, "x")
         _require_cuda(adj, "adj")
         if x.requires_grad or adj.requires_grad:

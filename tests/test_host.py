@@ -147,6 +147,8 @@ def test_cpu_tensors_raise_no_fallback():
         enc((cb.x_bits, cb.adj_bits))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         enc(cb)
+    with pytest.raises(RuntimeError, match="BOTH be int32 bit words"):       # half a compact batch is a caller error, not dense data
+        enc((cb.x_bits, torch.zeros(2, 5, 5)))
 
 
 def test_product_never_imports_the_oracle():
